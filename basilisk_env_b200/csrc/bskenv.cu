@@ -1,0 +1,415 @@
+// bskenv.cu -- sm_100a kernels and the C ABI (include/bskenv.h) of the batched LEO environment step.
+//
+// Kernels:
+//   leo_step_kernel   one thread = one spacecraft; ONE launch = one decision interval for all envs
+//                     (replaces Basilisk ExecuteSimulation(), reference
+//                     basilisk_env/simulators/leoPowerAttitudeSimulator.py:590-595, and the gym
+//                     bookkeeping of basilisk_env/envs/leoPowerAttitudeEnvironment.py:65-145);
+//                     warp-shuffle reduction of the episode statistics; optional in-kernel auto-reset.
+//   leo_reset_kernel  simulator construction + initial observation (reference ...Simulator.py:67-117,
+//                     ...Environment.py:172-216) from explicit, stored or device-sampled ICs.
+//   fp64_peak_kernel  DFMA microbenchmark = the roofline denominator.
+// There is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/bskenv.h"
+#include "leo_core.cuh"
+#include "leo_host.h"
+
+#ifndef LEO_BLOCK
+#define LEO_BLOCK 128
+#endif
+#ifndef LEO_MIN_BLOCKS
+#define LEO_MIN_BLOCKS 1
+#endif
+
+namespace {
+
+enum { ST_RET = 0, ST_LEN, ST_COUNT, ST_WHEEL, ST_POWER, ST_DECAY, ST_MAXLEN, ST_STEPS, ST_N };
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NRW, bool J2>
+__global__ void __launch_bounds__(LEO_BLOCK, LEO_MIN_BLOCKS)
+leo_step_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+                int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
+                double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
+                double *__restrict__ term_obs, double *__restrict__ stats)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < n;
+    leo::StepOut o;
+    o.done = 0; o.reason = 0; o.reward = 0.;
+    double ep_ret = 0., ep_len = 0.;
+    if (valid) {
+        leo::leo_step_env<NRW, J2>(P, S, I, stride, e, actions[e], o);
+        reward[e] = o.reward;
+        done[e] = (uint8_t)o.done;
+        reason[e] = (uint8_t)o.reason;
+        if (o.done) {
+            ep_ret = S[(int64_t)F_EPRET * stride + e];
+            ep_len = (double)I[(int64_t)I_STEP * stride + e];
+            if (term_obs)
+                for (int k = 0; k < 5; k++) term_obs[e * 5 + k] = o.ob[k];
+            if (P.auto_reset) {
+                // SB-VecEnv convention: the returned observation is the first one of the next episode
+                int64_t ep = I[(int64_t)I_EPISODE * stride + e] + 1;
+                I[(int64_t)I_EPISODE * stride + e] = ep;
+                double ic[19];
+                leo::sample_ic(P, P.first_env_index + e, ep, ic);
+                for (int k = 0; k < 19; k++) ics[(int64_t)k * stride + e] = ic[k];
+                leo::leo_reset_env(P, S, I, stride, e, ic, o.ob);
+            }
+        }
+        for (int k = 0; k < 5; k++) obs[e * 5 + k] = o.ob[k];
+    }
+    // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
+    if (stats) {
+        const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
+        const int lane = threadIdx.x & 31;
+        if (any_done) {
+            double v_ret = warp_sum(o.done ? ep_ret : 0.), v_len = warp_sum(o.done ? ep_len : 0.);
+            int c_all = __popc(any_done);
+            int c_w = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
+            int c_p = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 4)));
+            int c_d = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 8)));
+            int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
+            if (lane == 0) {
+                atomicAdd(&stats[ST_RET], v_ret); atomicAdd(&stats[ST_LEN], v_len);
+                atomicAdd(&stats[ST_COUNT], (double)c_all); atomicAdd(&stats[ST_WHEEL], (double)c_w);
+                atomicAdd(&stats[ST_POWER], (double)c_p); atomicAdd(&stats[ST_DECAY], (double)c_d);
+                atomicAdd(&stats[ST_MAXLEN], (double)c_m);
+            }
+        }
+        const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
+        if (lane == 0 && c_valid) atomicAdd(&stats[ST_STEPS], (double)c_valid);
+    }
+}
+
+// mode 0: explicit ICs (row-major [n][19]); 1: stored ICs (reset_init); 2: device-sampled ICs
+__global__ void __launch_bounds__(256)
+leo_reset_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+                 int64_t stride, int64_t n, int mode, const double *__restrict__ ics_in, const uint8_t *__restrict__ mask,
+                 double *__restrict__ obs)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mask && !mask[e]) return;
+    double ic[19];
+    if (mode == 0) {
+        for (int k = 0; k < 19; k++) ic[k] = ics_in[e * 19 + k];
+    } else if (mode == 1) {
+        for (int k = 0; k < 19; k++) ic[k] = ics[(int64_t)k * stride + e];
+    } else {
+        int64_t ep = I[(int64_t)I_EPISODE * stride + e] + 1;
+        I[(int64_t)I_EPISODE * stride + e] = ep;
+        leo::sample_ic(P, P.first_env_index + e, ep, ic);
+    }
+    for (int k = 0; k < 19; k++) ics[(int64_t)k * stride + e] = ic[k];
+    double ob[5];
+    leo::leo_reset_env(P, S, I, stride, e, ic, ob);
+    if (obs)
+        for (int k = 0; k < 5; k++) obs[e * 5 + k] = ob[k];
+}
+
+__global__ void gather_ics_kernel(const double *__restrict__ ics, int64_t stride, int64_t n, double *__restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    for (int k = 0; k < 19; k++) out[e * 19 + k] = ics[(int64_t)k * stride + e];
+}
+// dense [fields][n] <-> padded [fields][stride]
+template <typename T>
+__global__ void copy_fields_kernel(const T *__restrict__ src, int64_t src_stride, T *__restrict__ dst, int64_t dst_stride,
+                                   int64_t n, int fields)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    for (int f = 0; f < fields; f++) dst[(int64_t)f * dst_stride + e] = src[(int64_t)f * src_stride + e];
+}
+
+// 8 independent DFMA chains per thread, everything in registers
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[(int64_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct bskenv_handle {
+    bskenv_config cfg;
+    LeoParams P;
+    int device;
+    int64_t n, stride;
+    double *S, *ics, *stats;
+    int64_t *I;
+    // staging for the host-buffer entry point
+    int32_t *d_act; double *d_obs, *d_rew; uint8_t *d_done, *d_reason;
+    int32_t *h_act; double *h_obs, *h_rew; uint8_t *h_done, *h_reason;
+    cudaStream_t own_stream;
+    int64_t launches;
+    std::string err;
+};
+
+#define CU_TRY(h, call)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                            \
+            return BSKENV_ECUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double *rew, uint8_t *done, uint8_t *reason,
+                       double *term_obs, cudaStream_t st)
+{
+    const int grid = (int)((h->n + LEO_BLOCK - 1) / LEO_BLOCK);
+    if (h->cfg.use_j2)
+        leo_step_kernel<3, true><<<grid, LEO_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs, h->stats);
+    else
+        leo_step_kernel<3, false><<<grid, LEO_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs, h->stats);
+    CU_TRY(h, cudaGetLastError());
+    h->launches++;
+    return BSKENV_OK;
+}
+
+extern "C" {
+
+int bskenv_abi_version(void) { return BSKENV_ABI_VERSION; }
+void bskenv_default_config(bskenv_config *cfg) { leo_host::default_config(cfg); }
+const char *bskenv_last_error(const bskenv_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+int64_t bskenv_num_envs(const bskenv_handle *h) { return h ? h->n : 0; }
+int64_t bskenv_launch_count(const bskenv_handle *h) { return h ? h->launches : 0; }
+double bskenv_flops_per_step(const bskenv_handle *h) { return h ? leo_host::flops_per_step(h->P) : 0.0; }
+
+int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t first_env_index, bskenv_handle **out)
+{
+    if (!cfg || !out || n_envs <= 0) { g_create_error = "bskenv_create: bad arguments"; return BSKENV_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        g_create_error = "bskenv_create: no CUDA device (this library has no CPU path)";
+        return BSKENV_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { g_create_error = "bskenv_create: device index out of range"; return BSKENV_EINVAL; }
+    bskenv_handle *h = new bskenv_handle();
+    h->cfg = *cfg;
+    std::string perr = leo_host::build_params(*cfg, h->P);
+    if (!perr.empty()) { g_create_error = "bskenv_create: " + perr; delete h; return BSKENV_EINVAL; }
+    h->P.first_env_index = first_env_index;
+    h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr;
+    h->d_act = nullptr; h->d_obs = h->d_rew = nullptr; h->d_done = h->d_reason = nullptr;
+    h->h_act = nullptr; h->h_obs = h->h_rew = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * LEO_ND * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * LEO_NI * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * 19 * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(double) * ST_N);
+    if (e == cudaSuccess) e = cudaMemset(h->S, 0, sizeof(double) * LEO_ND * h->stride);
+    if (e == cudaSuccess) e = cudaMemset(h->I, 0, sizeof(int64_t) * LEO_NI * h->stride);
+    if (e == cudaSuccess) e = cudaMemset(h->ics, 0, sizeof(double) * 19 * h->stride);
+    if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(double) * ST_N);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("bskenv_create: ") + cudaGetErrorString(e);
+        bskenv_destroy(h);
+        return BSKENV_ECUDA;
+    }
+    *out = h;
+    return BSKENV_OK;
+}
+
+int bskenv_destroy(bskenv_handle *h)
+{
+    if (!h) return BSKENV_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_reason);
+    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done); cudaFreeHost(h->h_reason);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return BSKENV_OK;
+}
+
+static int do_reset(bskenv_handle *h, int mode, const double *ics_in, const uint8_t *mask, double *obs, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int grid = (int)((h->n + 255) / 256);
+    leo_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, mode, ics_in, mask, obs);
+    CU_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+int bskenv_reset_seeded(bskenv_handle *h, uint64_t seed, const uint8_t *mask_dev, double *obs_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    h->P.seed = seed;
+    return do_reset(h, 2, nullptr, mask_dev, obs_dev, stream);
+}
+int bskenv_reset_ics(bskenv_handle *h, const double *ics_dev, const uint8_t *mask_dev, double *obs_dev, void *stream)
+{
+    if (!h || !ics_dev) { if (h) h->err = "bskenv_reset_ics: null ics"; return BSKENV_EINVAL; }
+    return do_reset(h, 0, ics_dev, mask_dev, obs_dev, stream);
+}
+int bskenv_reset_init(bskenv_handle *h, const uint8_t *mask_dev, double *obs_dev, void *stream)
+{
+    return do_reset(h, 1, nullptr, mask_dev, obs_dev, stream);
+}
+int bskenv_get_ics(bskenv_handle *h, double *ics_dev, void *stream)
+{
+    if (!h || !ics_dev) return BSKENV_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    gather_ics_kernel<<<(int)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->ics, h->stride, h->n, ics_dev);
+    CU_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+
+int bskenv_step(bskenv_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev,
+                uint8_t *done_reason_dev, double *term_obs_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev || !done_reason_dev) { h->err = "bskenv_step: null buffer"; return BSKENV_EINVAL; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    return launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, done_reason_dev, term_obs_dev, (cudaStream_t)stream);
+}
+
+int bskenv_step_host(bskenv_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done, uint8_t *done_reason)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!actions || !obs || !reward || !done || !done_reason) { h->err = "bskenv_step_host: null buffer"; return BSKENV_EINVAL; }
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    if (!h->own_stream) {
+        CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        CU_TRY(h, cudaMalloc(&h->d_act, n * sizeof(int32_t))); CU_TRY(h, cudaMalloc(&h->d_obs, n * 5 * sizeof(double)));
+        CU_TRY(h, cudaMalloc(&h->d_rew, n * sizeof(double))); CU_TRY(h, cudaMalloc(&h->d_done, n)); CU_TRY(h, cudaMalloc(&h->d_reason, n));
+        CU_TRY(h, cudaMallocHost(&h->h_act, n * sizeof(int32_t))); CU_TRY(h, cudaMallocHost(&h->h_obs, n * 5 * sizeof(double)));
+        CU_TRY(h, cudaMallocHost(&h->h_rew, n * sizeof(double))); CU_TRY(h, cudaMallocHost(&h->h_done, n)); CU_TRY(h, cudaMallocHost(&h->h_reason, n));
+    }
+    cudaStream_t st = h->own_stream;
+    memcpy(h->h_act, actions, n * sizeof(int32_t));
+    CU_TRY(h, cudaMemcpyAsync(h->d_act, h->h_act, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int rc = launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_reason, nullptr, st);
+    if (rc) return rc;
+    CU_TRY(h, cudaMemcpyAsync(h->h_obs, h->d_obs, n * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaMemcpyAsync(h->h_reason, h->d_reason, n, cudaMemcpyDeviceToHost, st));
+    CU_TRY(h, cudaStreamSynchronize(st));
+    memcpy(obs, h->h_obs, n * 5 * sizeof(double)); memcpy(reward, h->h_rew, n * sizeof(double));
+    memcpy(done, h->h_done, n); memcpy(done_reason, h->h_reason, n);
+    return BSKENV_OK;
+}
+
+int bskenv_state_dims(const bskenv_handle *h, int32_t *nd, int32_t *ni)
+{
+    (void)h;
+    if (nd) *nd = LEO_ND;
+    if (ni) *ni = LEO_NI;
+    return BSKENV_OK;
+}
+int bskenv_get_state(bskenv_handle *h, double *dstate_dev, int64_t *istate_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int grid = (int)((h->n + 255) / 256);
+    if (dstate_dev) copy_fields_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(h->S, h->stride, dstate_dev, h->n, h->n, LEO_ND);
+    if (istate_dev) copy_fields_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(h->I, h->stride, istate_dev, h->n, h->n, LEO_NI);
+    CU_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+int bskenv_set_state(bskenv_handle *h, const double *dstate_dev, const int64_t *istate_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    const int grid = (int)((h->n + 255) / 256);
+    if (dstate_dev) copy_fields_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(dstate_dev, h->n, h->S, h->stride, h->n, LEO_ND);
+    if (istate_dev) copy_fields_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(istate_dev, h->n, h->I, h->stride, h->n, LEO_NI);
+    CU_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+int bskenv_state_field(const char *name, int32_t *is_int)
+{
+    struct Ent { const char *n; int idx; int is_int; };
+    static const Ent tab[] = {
+        {"r_BN_N", F_R, 0}, {"v_BN_N", F_V, 0}, {"sigma_BN", F_SIG, 0}, {"omega_BN_B", F_OMG, 0}, {"Omega", F_WHL, 0},
+        {"u_current", F_UCUR, 0}, {"density", F_RHO, 0}, {"storedCharge", F_E, 0}, {"shadowFactor", F_SHADOW, 0},
+        {"extTorquePntB_B", F_LDIST, 0}, {"att_guidance", F_GUID, 0}, {"att_reference", F_REF, 0},
+        {"commandedControlTorque", F_LR, 0}, {"rwTorqueCommand", F_RWCMD, 0}, {"wheelDeltaH", F_DELTAH, 0},
+        {"ThrustOnCmd", F_THRON, 0}, {"ThrusterStartTime", F_THRSTART, 0}, {"thrOnTimeRemaining", F_THRREM, 0},
+        {"OnTimeRequest", F_THRCMD, 0}, {"reward_total", F_EPRET, 0}, {"sim_obs", F_OBS, 0},
+        {"tick", I_TICK, 1}, {"curr_step", I_STEP, 1}, {"task_mask", I_MASK, 1}, {"MRPSwitchCount", I_SWITCH, 1},
+        {"thrFactorMask", I_THRFACTOR, 1}, {"initRequest", I_INITREQ, 1}, {"thrDumpingCounter", I_DUMPCNT, 1},
+        {"dumpPriorTime", I_DUMPPRIOR, 1}, {"lastDeltaHInMsgTime", I_LASTDH, 1}, {"deltaHWriteTime", I_DHTIME, 1},
+        {"episode", I_EPISODE, 1}, {"fireCounter", I_FIRE, 1}, {"thrActive", I_THRACTIVE, 1}, {"episode_over", I_OVER, 1},
+        {"rwSat", I_RWSAT, 1}};
+    if (!name) return -1;
+    for (const Ent &t : tab)
+        if (!strcmp(t.n, name)) { if (is_int) *is_int = t.is_int; return t.idx; }
+    return -1;
+}
+
+int bskenv_episode_stats(bskenv_handle *h, double *stats_host)
+{
+    if (!h || !stats_host) return BSKENV_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaDeviceSynchronize());
+    CU_TRY(h, cudaMemcpy(stats_host, h->stats, sizeof(double) * ST_N, cudaMemcpyDeviceToHost));
+    CU_TRY(h, cudaMemset(h->stats, 0, sizeof(double) * ST_N));
+    return BSKENV_OK;
+}
+
+int bskenv_fp64_peak(int device, double seconds, double *tflops)
+{
+    if (!tflops) return BSKENV_EINVAL;
+    if (cudaSetDevice(device) != cudaSuccess) return BSKENV_ENODEV;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return BSKENV_ECUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * blocks * threads) != cudaSuccess) return BSKENV_ECUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    for (int w = 0; w < 3; w++) fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+    cudaDeviceSynchronize();
+    double best = 0.0, spent = 0.0;
+    const double flop = (double)blocks * threads * (double)iters * 64.0 * 2.0;
+    int reps = 0;
+    while ((spent < seconds || reps < 3) && reps < 10000) {
+        cudaEventRecord(a);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        double tf = flop / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+        spent += ms * 1e-3; reps++;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return BSKENV_ECUDA;
+    *tflops = best;
+    return BSKENV_OK;
+}
+
+}  // extern "C"

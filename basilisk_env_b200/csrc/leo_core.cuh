@@ -1,0 +1,836 @@
+// leo_core.cuh -- per-environment body of the fused LEO power/attitude decision step.
+//
+// One call of leo_step_env() replaces one `LEOPowerAttitudeSimulator.run_sim(action)`
+// (/root/reference/basilisk_env/simulators/leoPowerAttitudeSimulator.py:535-644, cited SIM:line) PLUS
+// the bookkeeping of `leoPowerAttEnv.step` (/root/reference/basilisk_env/envs/
+// leoPowerAttitudeEnvironment.py:65-145, cited ENV:line) for ONE spacecraft: the Basilisk scheduler,
+// message bus and 19 modules are flattened into a fixed schedule held in registers
+// (DESIGN.md "Fused schedule").  One CUDA thread owns one spacecraft.
+//
+// Everything here is __host__ __device__ so that tests/hostcore can compile the same source with
+// g++ and compare it with the independent oracle on a CPU-only box; the PRODUCT only ever runs it
+// on the GPU (leo_kernels.cu) -- there is no CPU fallback in the library.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include "leo_params.h"
+
+#if defined(__CUDACC__)
+#define LEO_HD __host__ __device__ __forceinline__
+#define LEO_HD_NOINLINE static __host__ __device__ __noinline__
+#else
+#define LEO_HD inline
+#define LEO_HD_NOINLINE static inline
+#endif
+
+#ifndef LEO_UNROLL_STAGES
+#define LEO_UNROLL_STAGES 1
+#endif
+
+namespace leo {
+
+// ------------------------------------------------------------------------------------------------
+// small vector algebra
+// ------------------------------------------------------------------------------------------------
+struct V3 { double x, y, z; };
+struct M3 { V3 a, b, c; };   // rows
+LEO_HD V3 mk(double x, double y, double z) { V3 v; v.x = x; v.y = y; v.z = z; return v; }
+LEO_HD V3 operator+(V3 p, V3 q) { return mk(p.x + q.x, p.y + q.y, p.z + q.z); }
+LEO_HD V3 operator-(V3 p, V3 q) { return mk(p.x - q.x, p.y - q.y, p.z - q.z); }
+LEO_HD V3 operator-(V3 p) { return mk(-p.x, -p.y, -p.z); }
+LEO_HD V3 operator*(V3 p, double s) { return mk(p.x * s, p.y * s, p.z * s); }
+LEO_HD V3 operator*(double s, V3 p) { return mk(p.x * s, p.y * s, p.z * s); }
+LEO_HD double dot(V3 p, V3 q) { return p.x * q.x + p.y * q.y + p.z * q.z; }
+LEO_HD V3 cross(V3 p, V3 q) { return mk(p.y * q.z - p.z * q.y, p.z * q.x - p.x * q.z, p.x * q.y - p.y * q.x); }
+LEO_HD double norm(V3 p) { return sqrt(dot(p, p)); }
+LEO_HD V3 mv(const M3 &m, V3 v) { return mk(dot(m.a, v), dot(m.b, v), dot(m.c, v)); }
+LEO_HD V3 mtv(const M3 &m, V3 v) { return m.a * v.x + m.b * v.y + m.c * v.z; }
+LEO_HD V3 mv9(const double *m, V3 v)
+{
+    return mk(m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z);
+}
+LEO_HD V3 arr(const double *p) { return mk(p[0], p[1], p[2]); }
+LEO_HD V3 unit_or_zero(V3 v)
+{ // Basilisk v3Normalize: scale by 1/|v|, zero vector below 1e-30
+    double n = norm(v);
+    return n > 1e-30 ? v * (1. / n) : mk(0., 0., 0.);
+}
+LEO_HD double rsq(double x)
+{
+#ifdef __CUDA_ARCH__
+    return rsqrt(x);
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+LEO_HD double clamp_asin(double x) { return x > 1. ? asin(1.) : (x < -1. ? asin(-1.) : asin(x)); }
+LEO_HD double clamp_acos(double x) { return x > 1. ? acos(1.) : (x < -1. ? acos(-1.) : acos(x)); }
+
+// Time arithmetic that feeds discrete decisions must round exactly like the scalar reference code:
+// keep the compiler from contracting it into FMAs.
+LEO_HD double t_mul(double p, double q)
+{
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(p, q);
+#else
+    return p * q;
+#endif
+}
+LEO_HD double t_add(double p, double q)
+{
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(p, q);
+#else
+    return p + q;
+#endif
+}
+LEO_HD double t_sub(double p, double q)
+{
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(p, q);
+#else
+    return p - q;
+#endif
+}
+LEO_HD double t_div(double p, double q)
+{
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(p, q);
+#else
+    return p / q;
+#endif
+}
+LEO_HD double ns2sec(int64_t ns) { return t_mul((double)ns, 1e-9); }   // CurrentSimNanos*NANO2SEC
+
+// ------------------------------------------------------------------------------------------------
+// attitude kinematics (Schaub & Junkins; same conventions as Basilisk RigidBodyKinematics)
+// ------------------------------------------------------------------------------------------------
+LEO_HD M3 mrp_to_BN(V3 q)
+{
+    double d1 = dot(q, q), S = 1. - d1, inv = 1. / ((1. + d1) * (1. + d1));
+    M3 C;
+    C.a = mk(4. * (2. * q.x * q.x - d1) + S * S, 8. * q.x * q.y + 4. * q.z * S, 8. * q.x * q.z - 4. * q.y * S) * inv;
+    C.b = mk(8. * q.y * q.x - 4. * q.z * S, 4. * (2. * q.y * q.y - d1) + S * S, 8. * q.y * q.z + 4. * q.x * S) * inv;
+    C.c = mk(8. * q.z * q.x + 4. * q.y * S, 8. * q.z * q.y - 4. * q.x * S, 4. * (2. * q.z * q.z - d1) + S * S) * inv;
+    return C;
+}
+LEO_HD V3 dcm_to_mrp(const M3 &C)
+{ // C2MRP via Sheppard's method (C2EP) with the non-negative scalar part
+    double tr = C.a.x + C.b.y + C.c.z;
+    double b2_0 = (1. + tr) / 4., b2_1 = (1. + 2. * C.a.x - tr) / 4., b2_2 = (1. + 2. * C.b.y - tr) / 4., b2_3 = (1. + 2. * C.c.z - tr) / 4.;
+    int i = 0;
+    double mx = b2_0;
+    if (b2_1 > mx) { i = 1; mx = b2_1; }
+    if (b2_2 > mx) { i = 2; mx = b2_2; }
+    if (b2_3 > mx) { i = 3; mx = b2_3; }
+    double b0, b1, b2, b3;
+    if (i == 0) {
+        b0 = sqrt(b2_0);
+        b1 = (C.b.z - C.c.y) / 4. / b0; b2 = (C.c.x - C.a.z) / 4. / b0; b3 = (C.a.y - C.b.x) / 4. / b0;
+    } else if (i == 1) {
+        b1 = sqrt(b2_1);
+        b0 = (C.b.z - C.c.y) / 4. / b1;
+        if (b0 < 0.) { b1 = -b1; b0 = -b0; }
+        b2 = (C.a.y + C.b.x) / 4. / b1; b3 = (C.c.x + C.a.z) / 4. / b1;
+    } else if (i == 2) {
+        b2 = sqrt(b2_2);
+        b0 = (C.c.x - C.a.z) / 4. / b2;
+        if (b0 < 0.) { b2 = -b2; b0 = -b0; }
+        b1 = (C.a.y + C.b.x) / 4. / b2; b3 = (C.b.z + C.c.y) / 4. / b2;
+    } else {
+        b3 = sqrt(b2_3);
+        b0 = (C.a.y - C.b.x) / 4. / b3;
+        if (b0 < 0.) { b3 = -b3; b0 = -b0; }
+        b1 = (C.c.x + C.a.z) / 4. / b3; b2 = (C.b.z + C.c.y) / 4. / b3;
+    }
+    return mk(b1 / (1. + b0), b2 / (1. + b0), b3 / (1. + b0));
+}
+LEO_HD V3 mrp_inner(V3 q)
+{
+    double m = dot(q, q);
+    return m > 1.0 ? q * (-1. / m) : q;
+}
+LEO_HD V3 mrp_sub(V3 q1, V3 q2)
+{ // sigma(q1 relative to q2) with the shadow-set guard near the singular denominator, mapped to |s|<=1
+    V3 s1 = q1;
+    double det = 1. + dot(s1, s1) * dot(q2, q2) + 2. * dot(s1, q2);
+    if (fabs(det) < 0.1) {
+        s1 = s1 * (-1.0 / dot(s1, s1));
+        det = 1. + dot(s1, s1) * dot(q2, q2) + 2. * dot(s1, q2);
+    }
+    V3 v1 = cross(s1, q2) * 2.;
+    V3 res = s1 * (1. - dot(q2, q2)) - q2 * (1. - dot(s1, s1)) + v1;
+    return mrp_inner(res * (1. / det));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sun ephemeris latch (SpiceTask, period = step_duration, SIM:102,357) with the eclipse constants that
+// only depend on the latched Sun position.  Analytic substitute for SPICE de430.
+// ------------------------------------------------------------------------------------------------
+struct SunLatch {
+    V3 r, v;            // Sun relative to Earth, inertial, at the message time
+    double hp2;         // |s_HP|^2
+    double inv_hp;      // 1/|s_HP|
+    double c1off, c2off, tan1, tan2;   // R_p/sin f_1, R_p/sin f_2, tan f_1, tan f_2
+    double et;          // J2000Current of the message
+};
+LEO_HD SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
+{
+    const double D2R = 3.14159265358979323846 / 180.0;
+    const double AUm = 149597870.693 * 1000.0;
+    double t = ns2sec(msg_ns);
+    double n = P.epoch_days + t / 86400.0;
+    double nd = 1.0 / 86400.0;
+    double L = (280.460 + 0.9856474 * n) * D2R, Ld = 0.9856474 * D2R * nd;
+    double g = (357.528 + 0.9856003 * n) * D2R, gd = 0.9856003 * D2R * nd;
+    double sg = sin(g), cg = cos(g), s2g = sin(2. * g), c2g = cos(2. * g);
+    double lam = L + (1.915 * sg + 0.020 * s2g) * D2R;
+    double lamd = Ld + (1.915 * cg + 0.040 * c2g) * D2R * gd;
+    double eps = (23.439 - 4e-7 * n) * D2R, epsd = -4e-7 * D2R * nd;
+    double R = (1.00014 - 0.01671 * cg - 0.00014 * c2g) * AUm;
+    double Rd = (0.01671 * sg + 0.00028 * s2g) * gd * AUm;
+    double sl = sin(lam), cl = cos(lam), se = sin(eps), ce = cos(eps);
+    V3 u = mk(cl, ce * sl, se * sl);
+    V3 ud = mk(-sl * lamd, ce * cl * lamd - se * sl * epsd, se * cl * lamd + ce * sl * epsd);
+    SunLatch s;
+    s.r = u * R;
+    s.v = u * Rd + ud * R;
+    s.et = P.epoch_days * 86400.0 + t;
+    s.hp2 = dot(s.r, s.r);
+    double hp = sqrt(s.hp2);
+    s.inv_hp = 1. / hp;
+    double f1 = asin((P.R_sun + P.R_planet) / hp), f2 = asin((P.R_sun - P.R_planet) / hp);
+    s.c1off = P.R_planet / sin(f1);
+    s.c2off = P.R_planet / sin(f2);
+    s.tan1 = tan(f1);
+    s.tan2 = tan(f2);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// integrated state and equations of motion
+// ------------------------------------------------------------------------------------------------
+template <int NRW>
+struct Dyn { V3 r, v, s, w; double W[NRW]; };
+
+template <int NRW>
+LEO_HD Dyn<NRW> axpy(const Dyn<NRW> &x, const Dyn<NRW> &k, double c)
+{ // x + c*k
+    Dyn<NRW> o;
+    o.r = x.r + k.r * c; o.v = x.v + k.v * c; o.s = x.s + k.s * c; o.w = x.w + k.w * c;
+#pragma unroll
+    for (int i = 0; i < NRW; i++) o.W[i] = x.W[i] + k.W[i] * c;
+    return o;
+}
+
+// Thruster force/torque at one RK stage (thrusterDynamicEffector::computeForceTorque without ramps).
+// Rare path (only while a desat pulse may still burn): state stays in global memory.
+LEO_HD_NOINLINE void thr_stage(const LeoParams &P, const double *S, int64_t stride, int64_t e, double tau, double dtFire,
+                               int &factor, int &active, V3 &F, V3 &L)
+{
+    double start = S[(int64_t)F_THRSTART * stride + e];
+    double tol = t_mul(-dtFire, 10E-10);
+    F = mk(0., 0., 0.); L = mk(0., 0., 0.);
+    int any = 0;
+    for (int k = 0; k < LEO_NTHR; k++) {
+        double on = S[(int64_t)(F_THRON + k) * stride + e];
+        bool fire = (t_sub(t_add(on, start), tau) >= tol) && (on > 0.0);
+        if (fire) {
+            factor |= (1 << k);
+            V3 f = arr(P.thr_dir[k]) * (P.thr_Fmax * 1.0);
+            F = f + F;
+            L = cross(arr(P.thr_loc[k]), f) + L;
+            any = 1;
+        } else {
+            factor &= ~(1 << k);
+        }
+    }
+    active = any;   // expiry is monotone in time: once nothing fires, nothing fires until the next command
+}
+
+template <int NRW, bool J2>
+LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, const SunLatch &sun, double dt_sun, double rho,
+                V3 tau_u, const double (&u)[NRW], V3 L_ext, V3 F_thr)
+{
+    // [BN] from sigma_BN
+    M3 BN = mrp_to_BN(x.s);
+    // gravity: central point mass + Sun third body with Euler-stepped Sun position (gravityEffector)
+    V3 g;
+    {
+        double ir = rsq(dot(x.r, x.r));
+        double ir3 = ir * ir * ir;
+        g = x.r * (-P.mu_c * ir3);
+        if (J2) {
+            double ir2 = ir * ir, z2 = 5. * x.r.z * x.r.z * ir2, kk = -P.j2k * ir3 * ir2;
+            g = g + mk(kk * x.r.x * (1. - z2), kk * x.r.y * (1. - z2), kk * x.r.z * (3. - z2));
+        }
+        if (P.use_sun3) {
+            V3 rs = sun.r + sun.v * dt_sun;
+            V3 d = x.r - rs;
+            double id = rsq(dot(d, d)), is = rsq(dot(rs, rs));
+            g = g + d * (-P.mu_sun * (id * id * id)) + rs * (-P.mu_sun * (is * is * is));
+        }
+    }
+    // facet drag with axis-aligned facets: F = -rho * S' * v_B, L = -rho * (M' x v_B)
+    V3 vB = mv(BN, x.v);
+    V3 F_B, L_B;
+    {
+        double ax = fabs(vB.x), ay = fabs(vB.y), az = fabs(vB.z);
+        int sx = vB.x > 0. ? 0 : 1, sy = vB.y > 0. ? 0 : 1, sz = vB.z > 0. ? 0 : 1;
+        // a zero component selects index 1 with weight |0| = 0: no contribution, like `projectedArea > 0`
+        double Sp = P.dragK[0][sx] * ax + P.dragK[1][sy] * ay + P.dragK[2][sz] * az;
+        V3 Mp = arr(P.dragM[0][sx]) * ax + arr(P.dragM[1][sy]) * ay + arr(P.dragM[2][sz]) * az;
+        F_B = vB * (-rho * Sp);
+        L_B = cross(Mp, vB) * (-rho);
+    }
+    F_B = F_B + F_thr;
+    // rotational EOM with balanced wheels (back-substitution, D constant):
+    //   [I - sum Js g g^T] wdot = -w x (I w + sum Js W g) - sum g u + L
+    V3 h = mv9(P.I, x.w);
+#pragma unroll
+    for (int i = 0; i < NRW; i++) h = h + arr(P.gs[i]) * (P.Js[i] * x.W[i]);
+    V3 rot = L_B + L_ext - tau_u - cross(x.w, h);
+    k.w = mv9(P.Dinv, rot);
+    k.v = mtv(BN, F_B * P.inv_mass) + g;
+    k.r = x.v;
+    { // sigma_dot = 1/4 [B(sigma)] omega
+        double s2 = dot(x.s, x.s), sw = dot(x.s, x.w);
+        k.s = (x.w * (1. - s2) + cross(x.s, x.w) * 2. + x.s * (2. * sw)) * 0.25;
+    }
+#pragma unroll
+    for (int i = 0; i < NRW; i++) k.W[i] = u[i] * P.invJs[i] - dot(arr(P.gs[i]), k.w);
+}
+
+// ------------------------------------------------------------------------------------------------
+// flight software, one pass per fswRate
+// ------------------------------------------------------------------------------------------------
+struct AttRef { V3 sigma_RN, omega_RN_N, domega_RN_N; };
+struct AttGuid { V3 sigma_BR, omega_BR_B, omega_RN_B, domega_RN_B; };
+
+LEO_HD AttRef hill_point(V3 r, V3 v, V3 cel_r, V3 cel_v)
+{ // hillPoint.computeHillPointingReference
+    V3 rel_r = r - cel_r, rel_v = v - cel_v;
+    M3 RN;
+    RN.a = unit_or_zero(rel_r);
+    V3 h = cross(rel_r, rel_v);
+    RN.c = unit_or_zero(h);
+    RN.b = cross(RN.c, RN.a);
+    AttRef o;
+    o.sigma_RN = dcm_to_mrp(RN);
+    double rm = norm(rel_r), hm = norm(h), dfdt = 0., ddfdt2 = 0.;
+    if (rm > 1.) {
+        dfdt = hm / (rm * rm);
+        ddfdt2 = -2.0 * dot(rel_v, RN.a) / rm * dfdt;
+    }
+    o.omega_RN_N = mtv(RN, mk(0., 0., dfdt));
+    o.domega_RN_N = mtv(RN, mk(0., 0., ddfdt2));
+    return o;
+}
+LEO_HD AttGuid att_tracking_error(V3 sigma_BN, V3 omega_BN_B, const AttRef &ref)
+{ // attTrackingError.computeAttitudeError with sigma_R0R = 0 (addMRP with zero is the identity + inner-set map)
+    AttGuid g;
+    V3 sigma_RN = mrp_inner(ref.sigma_RN);
+    g.sigma_BR = mrp_sub(sigma_BN, sigma_RN);
+    M3 BN = mrp_to_BN(sigma_BN);
+    g.omega_RN_B = mv(BN, ref.omega_RN_N);
+    g.omega_BR_B = omega_BN_B - g.omega_RN_B;
+    g.domega_RN_B = mv(BN, ref.domega_RN_N);
+    return g;
+}
+LEO_HD V3 mrp_feedback(const LeoParams &P, const AttGuid &g)
+{ // MRP_Feedback with Ki < 0 (integral off) and no wheel feed-forward wired (SIM:440-449)
+    V3 w = g.omega_BR_B + g.omega_RN_B;
+    V3 Lr = g.omega_BR_B * P.P + g.sigma_BR * P.K;
+    Lr = Lr - cross(g.omega_RN_B, mv9(P.I_fsw, w));
+    Lr = Lr - mv9(P.I_fsw, g.domega_RN_B - cross(w, g.omega_RN_B));
+    return -Lr;
+}
+
+// thrForceMapping.Update for the on-pulsing octet: minimum-norm impulses, subtract-min, saturation scaling
+LEO_HD_NOINLINE void thr_force_mapping(const LeoParams &P, V3 Lr, double (&F)[LEO_NTHR])
+{
+    double mn = 0.0;
+    for (int i = 0; i < LEO_NTHR; i++) {
+        F[i] = P.thr_W[i][0] * Lr.x + P.thr_W[i][1] * Lr.y + P.thr_W[i][2] * Lr.z;
+        if (F[i] < mn) mn = F[i];
+    }
+    if (P.thrForceSign > 0)
+        for (int i = 0; i < LEO_NTHR; i++) F[i] -= mn;
+    // computeTorqueAngErr
+    double ang = 0.0;
+    if (norm(Lr) > P.tfm_eps) {
+        V3 tau = mk(0., 0., 0.);
+        for (int i = 0; i < LEO_NTHR; i++) {
+            double f = fabs(F[i]) < P.thr_Fmax ? F[i] : P.thr_Fmax * fabs(F[i]) / F[i];
+            tau = tau + mk(P.thr_D[0][i], P.thr_D[1][i], P.thr_D[2][i]) * f;
+        }
+        double c = dot(unit_or_zero(Lr), unit_or_zero(tau));
+        if (c < 1.0) ang = clamp_acos(c);
+    }
+    if (ang > P.tfm_angErrThresh) {
+        double mx = 0.0;
+        for (int i = 0; i < LEO_NTHR; i++) {
+            double fr = fabs(F[i]) / P.thr_Fmax;
+            if (fr > mx) mx = fr;
+        }
+        if (mx > 1.0)
+            for (int i = 0; i < LEO_NTHR; i++) F[i] = (1.0 / mx) * F[i];
+    }
+}
+
+// rwDesatTask = thrMomentumManagement -> thrForceMapping -> thrMomentumDumping (SIM:488-490).
+// wheel speeds = the RWSpeed message of the previous dynamics tick (zeros before the first tick).
+template <int NRW>
+LEO_HD_NOINLINE void fsw_desat(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int64_t now_ns,
+                               const double (&ws)[NRW])
+{
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+    // thrMomentumManagement: one-shot after Reset
+    if (SI(I_INITREQ) == 1) {
+        V3 hs = mk(0., 0., 0.);
+        for (int i = 0; i < NRW; i++) hs = hs + arr(P.gs[i]) * (P.Js[i] * ws[i]);
+        double hm = norm(hs);
+        V3 dH = (hm < P.hs_min) ? mk(0., 0., 0.) : hs * (-(hm - P.hs_min) / hm);
+        SD(F_DELTAH) = dH.x; SD(F_DELTAH + 1) = dH.y; SD(F_DELTAH + 2) = dH.z;
+        SI(I_DHTIME) = now_ns;
+        SI(I_INITREQ) = 0;
+    }
+    // thrMomentumDumping (thrForceMapping evaluated lazily: its output is only consumed on a new Delta H)
+    double tOn[LEO_NTHR];
+    for (int k = 0; k < LEO_NTHR; k++) tOn[k] = 0.0;
+    int64_t prior = SI(I_DUMPPRIOR);
+    if (prior != 0) {
+        double dt = t_mul((double)(now_ns - prior), 1e-9);
+        if (dt < 0.0) dt = 0.0;
+        int64_t tdh = SI(I_DHTIME);
+        if (SI(I_LASTDH) != tdh) {
+            SI(I_LASTDH) = tdh;
+            SI(I_DUMPCNT) = 0;
+            double F[LEO_NTHR];
+            thr_force_mapping(P, mk(SD(F_DELTAH), SD(F_DELTAH + 1), SD(F_DELTAH + 2)), F);
+            for (int k = 0; k < LEO_NTHR; k++) SD(F_THRREM + k) = F[k] / P.thr_Fmax;
+        }
+        if (SI(I_DUMPCNT) <= 0) {
+            for (int k = 0; k < LEO_NTHR; k++) {
+                double rem = SD(F_THRREM + k);
+                tOn[k] = rem;
+                if (rem > 0.0) SD(F_THRREM + k) = t_sub(rem, dt);
+            }
+            SI(I_DUMPCNT) = P.maxCounterValue;
+        } else {
+            SI(I_DUMPCNT) -= 1;
+        }
+        for (int k = 0; k < LEO_NTHR; k++) {
+            if (tOn[k] < P.thrMinFireTime) tOn[k] = 0.0;
+            if (SD(F_THRREM + k) < 0.0) SD(F_THRREM + k) = 0.0;
+            if (tOn[k] >= dt) tOn[k] = dt;
+        }
+    }
+    SI(I_DUMPPRIOR) = now_ns;
+    for (int k = 0; k < LEO_NTHR; k++) SD(F_THRCMD + k) = tOn[k];
+#undef SD
+#undef SI
+}
+
+// thrusterDynamicEffector.UpdateState on a NEW on-time message (ConfigureThrustRequests)
+LEO_HD_NOINLINE int thr_latch(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int64_t cmd_ns, int factor)
+{
+    int any = 0;
+    for (int k = 0; k < LEO_NTHR; k++) {
+        double cmd = S[(int64_t)(F_THRCMD + k) * stride + e], on;
+        bool burning = (factor >> k) & 1;
+        if (cmd >= P.thr_MinOnTime) {
+            on = cmd;
+            if (!burning) I[(int64_t)(I_FIRE + k) * stride + e] += 1;
+        } else {
+            on = burning ? cmd : 0.0;
+        }
+        S[(int64_t)(F_THRON + k) * stride + e] = on;
+        if (on > 0.0) any = 1;
+    }
+    S[(int64_t)F_THRSTART * stride + e] = t_mul((double)cmd_ns, 1.0E-9);
+    return (any || factor != 0) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// eclipse (conical shadow model) and solar panel, per environment tick
+// ------------------------------------------------------------------------------------------------
+LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP)
+{ // eclipse.computePercentShadow
+    double nH = norm(r_HB), nB = norm(s_BP);
+    double a = clamp_asin(P.R_sun / nH), b = clamp_asin(P.R_planet / nB);
+    double c = clamp_acos((-dot(s_BP, r_HB)) / (nB * nH));
+    const double PI = 3.14159265358979323846;
+    double shadow = 1.0;
+    if (c < b - a) {
+        shadow = 0.0;
+    } else if (c < a - b) {
+        double area = PI * a * a - PI * b * b;
+        shadow = 1. - area / (PI * a * a);
+    } else if (c < a + b) {
+        double x = (c * c + a * a - b * b) / (2. * c);
+        double y = sqrt(a * a - x * x);
+        double area = a * a * clamp_acos(x / a) + b * b * clamp_acos((c - x) / b) - c * y;
+        shadow = 1. - area / (PI * a * a);
+    }
+    return shadow;
+}
+LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r)
+{ // planet at the origin (zeroBase earth); decisions on squared / algebraic forms, values by the reference formula
+    V3 r_HB = sun.r - r;
+    double hb2 = dot(r_HB, r_HB);
+    if (hb2 < sun.hp2) return 1.0;                    // spacecraft on the sunny side of the planet
+    double s2 = dot(r, r);
+    double s0 = -dot(r, sun.r) * sun.inv_hp;
+    double c1 = s0 + sun.c1off, c2 = s0 - sun.c2off;
+    double l = sqrt(s2 - s0 * s0);
+    double l1 = c1 * sun.tan1, l2 = c2 * sun.tan2;
+    if (!(fabs(l) < fabs(l2) || fabs(l) < fabs(l1))) return 1.0;
+    // inside the penumbra cone.  Umbra test c < b - a done algebraically (cos c > cos(b - a), all angles in
+    // [0, pi/2] x [0, pi]); the transcendental formula only runs in the partial band.
+    double inH = rsq(hb2), inB = rsq(s2);
+    double sa = P.R_sun * inH, sb = P.R_planet * inB;
+    if (sa < 1. && sb < 1. && sb > sa) {
+        double ca = sqrt(1. - sa * sa), cb = sqrt(1. - sb * sb);
+        double cc = -dot(r, r_HB) * inB * inH;
+        // guard band keeps the knife edge on the exact path
+        if (cc > cb * ca + sb * sa + 1e-12) return 0.0;
+    }
+    return penumbra_fraction(P, r_HB, r);
+}
+
+// ------------------------------------------------------------------------------------------------
+// counter-based RNG for device-side initial conditions (Philox4x32-10)
+// ------------------------------------------------------------------------------------------------
+LEO_HD void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t (&out)[4])
+{
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+struct IcRng {
+    uint64_t seed, env; uint32_t episode, block; uint32_t buf[4]; int have;
+    LEO_HD double u01()
+    { // 53-bit uniform in [0,1)
+        if (have == 0) {
+            philox4x32((uint32_t)env, (uint32_t)(env >> 32), episode, block++, (uint32_t)seed, (uint32_t)(seed >> 32), buf);
+            have = 2;
+        }
+        int j = 2 - have;
+        have--;
+        uint64_t x = ((uint64_t)buf[2 * j + 1] << 32) | buf[2 * j];
+        return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+    }
+    LEO_HD double uniform(double lo, double hi) { return lo + (hi - lo) * u01(); }
+};
+// Same distributions as the reference's sampler: leo_orbit.sampled_400km,
+// sc_attitudes.random_tumble(1e-5), set_ICs N(0,1)^3 / U(-800,800)^3 rpm / U(8,20) Wh.
+LEO_HD_NOINLINE void sample_ic(const LeoParams &P, int64_t global_env, int64_t episode, double (&ic)[19])
+{
+    IcRng g; g.seed = P.seed; g.env = (uint64_t)global_env; g.episode = (uint32_t)episode; g.block = 0; g.have = 0;
+    const double PI = 3.14159265358979323846, D2R = PI / 180.0;
+    double a = 6371 * 1000.0 + 500. * 1000;
+    double ecc = g.uniform(0, 0.05), inc = g.uniform(-90 * D2R, 90 * D2R);
+    double Om = g.uniform(0 * D2R, 360 * D2R), om = g.uniform(0 * D2R, 360 * D2R), f = g.uniform(0 * D2R, 360 * D2R);
+    { // orbitalMotion.elem2rv, non-rectilinear branch
+        double mu = P.mu_c, p = a * (1.0 - ecc * ecc), r = p / (1.0 + ecc * cos(f)), th = om + f, h = sqrt(mu * p);
+        ic[0] = r * (cos(th) * cos(Om) - cos(inc) * sin(th) * sin(Om));
+        ic[1] = r * (cos(th) * sin(Om) + cos(inc) * sin(th) * cos(Om));
+        ic[2] = r * (sin(th) * sin(inc));
+        ic[3] = -mu / h * (cos(Om) * (ecc * sin(om) + sin(th)) + cos(inc) * (ecc * cos(om) + cos(th)) * sin(Om));
+        ic[4] = -mu / h * (sin(Om) * (ecc * sin(om) + sin(th)) - cos(inc) * (ecc * cos(om) + cos(th)) * cos(Om));
+        ic[5] = mu / h * (ecc * cos(om) + cos(th)) * sin(inc);
+    }
+    for (int k = 0; k < 3; k++) ic[6 + k] = g.uniform(0, 1.0);
+    for (int k = 0; k < 3; k++) ic[9 + k] = g.uniform(-0.00001, 0.00001);
+    { // three standard normals by Box-Muller (the fourth is discarded)
+        double u1 = 1.0 - g.u01(), u2 = g.u01(), u3 = 1.0 - g.u01(), u4 = g.u01();
+        double r1 = sqrt(-2.0 * log(u1)), r2 = sqrt(-2.0 * log(u3));
+        ic[12] = r1 * cos(2. * PI * u2); ic[13] = r1 * sin(2. * PI * u2); ic[14] = r2 * cos(2. * PI * u4);
+    }
+    for (int k = 0; k < 3; k++) ic[15 + k] = g.uniform(-800, 800);
+    ic[18] = g.uniform(8. * 3600., 20. * 3600.);
+}
+
+// ------------------------------------------------------------------------------------------------
+// reset: LEOPowerAttitudeSimulator.__init__ (SIM:67-117) + InitializeSimulationAndDiscover, and the
+// initial observation of leoPowerAttEnv.reset (ENV:188-190)
+// ------------------------------------------------------------------------------------------------
+LEO_HD void leo_reset_env(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, const double (&ic)[19],
+                          double *obs /* 5, may be null */)
+{
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+    for (int f = 0; f < LEO_ND; f++) SD(f) = 0.0;
+    int64_t episode = SI(I_EPISODE);
+    for (int f = 0; f < LEO_NI; f++) SI(f) = 0;
+    SI(I_EPISODE) = episode;
+    for (int k = 0; k < 12; k++) SD(F_R + k) = ic[k];
+    for (int k = 0; k < 3; k++) SD(F_LDIST + k) = P.dist_mag * ic[12 + k];             // SIM:295 (quirk Q4: raw vector)
+    for (int k = 0; k < 3; k++) SD(F_WHL + k) = ic[15 + k] * P.wheel_rpm2rad;       // SIM:303-305
+    SD(F_E) = ic[18];
+    SI(I_TICK) = -1;
+    SI(I_MASK) = LEO_TASK_ALL;       // every task starts enabled
+    SI(I_INITREQ) = 1;               // Reset_thrMomentumManagement
+    if (obs) { // SIM:347-351 (wheel speeds in RPM, un-converted: SIM:306) then ENV:189-190
+        obs[0] = sqrt(ic[6] * ic[6] + ic[7] * ic[7] + ic[8] * ic[8]);
+        obs[1] = sqrt(ic[9] * ic[9] + ic[10] * ic[10] + ic[11] * ic[11]);
+        obs[2] = sqrt(ic[15] * ic[15] + ic[16] * ic[16] + ic[17] * ic[17]) / P.wheel_limit;
+        obs[3] = ic[18] / 3600.0 / P.power_max;
+        obs[4] = 0.0;
+    }
+#undef SD
+#undef SI
+}
+
+// ------------------------------------------------------------------------------------------------
+// one decision interval of one environment
+// ------------------------------------------------------------------------------------------------
+struct StepOut { double ob[5]; double reward; int done; int reason; };
+
+template <int NRW, bool J2>
+LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
+                         int action, StepOut &out)
+{
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+    // ---------------- load ----------------
+    Dyn<NRW> x;
+    x.r = mk(SD(F_R), SD(F_R + 1), SD(F_R + 2));
+    x.v = mk(SD(F_V), SD(F_V + 1), SD(F_V + 2));
+    x.s = mk(SD(F_SIG), SD(F_SIG + 1), SD(F_SIG + 2));
+    x.w = mk(SD(F_OMG), SD(F_OMG + 1), SD(F_OMG + 2));
+    double u[NRW];
+#pragma unroll
+    for (int i = 0; i < NRW; i++) { x.W[i] = SD(F_WHL + i); u[i] = SD(F_UCUR + i); }
+    double rho = SD(F_RHO), E = SD(F_E), shadow = SD(F_SHADOW);
+    const V3 L_ext = mk(SD(F_LDIST), SD(F_LDIST + 1), SD(F_LDIST + 2));
+    int64_t tick = SI(I_TICK);
+    int mask = (int)SI(I_MASK);
+    int thr_factor = (int)SI(I_THRFACTOR), thr_active = (int)SI(I_THRACTIVE), rw_sat = (int)SI(I_RWSAT);
+    int64_t nswitch = SI(I_SWITCH);
+
+    // ---------------- mode switch (SIM:543-588); modeRequest = str(action) ----------------
+    if (action == 0) mask = LEO_TASK_NADIR | LEO_TASK_MRP;
+    else if (action == 1) mask = LEO_TASK_SUN | LEO_TASK_MRP;
+    else if (action == 2) {
+        mask = LEO_TASK_SUN | LEO_TASK_MRP | LEO_TASK_DESAT;
+        SI(I_INITREQ) = 1;                                   // thrDesatControlWrap.Reset (SIM:580)
+        SI(I_DUMPPRIOR) = 0; SI(I_DUMPCNT) = 0; SI(I_LASTDH) = 0;   // thrDumpWrap.Reset (SIM:581)
+        for (int k = 0; k < LEO_NTHR; k++) SD(F_THRREM + k) = 0.0;
+    }
+
+    V3 tau_u = mk(0., 0., 0.);
+#pragma unroll
+    for (int i = 0; i < NRW; i++) tau_u = tau_u + arr(P.gs[i]) * u[i];
+
+    // the Sun message in force at the start of the interval was written at the previous decision boundary
+    const int64_t ticks_per_step = (int64_t)P.ticks_per_fsw * P.fsw_per_step;
+    int64_t n = tick + 1;                                       // next tick to execute
+    const int64_t n_end = (tick < 0 ? 0 : tick) + ticks_per_step;  // inclusive (ConfigureStopTime is inclusive)
+    int64_t sun_ns = (tick < 0 ? 0 : tick) * P.dyn_ns;
+    SunLatch sun = sun_latch(P, sun_ns);
+    int to_fsw = (int)(n % P.ticks_per_fsw);                    // ticks until the next FSW pass (0 = now)
+    to_fsw = to_fsw == 0 ? 0 : P.ticks_per_fsw - to_fsw;
+
+    for (; n <= n_end; n++) {
+        const int64_t now_ns = n * P.dyn_ns;
+        int desat_ran = 0;
+        // ================= flight software (priority 100/50 tasks run before DynTask) =================
+        if (to_fsw == 0) {
+            to_fsw = P.ticks_per_fsw;
+            // nav messages = state written by the previous dynamics tick; never written before tick 0
+            V3 nr = x.r, nv = x.v, ns = x.s, nw = x.w;
+            double ws[NRW];
+#pragma unroll
+            for (int i = 0; i < NRW; i++) ws[i] = x.W[i];
+            if (n == 0) {
+                nr = nv = ns = nw = mk(0., 0., 0.);
+#pragma unroll
+                for (int i = 0; i < NRW; i++) ws[i] = 0.0;
+            }
+            AttRef ref;
+            ref.sigma_RN = mk(SD(F_REF), SD(F_REF + 1), SD(F_REF + 2));
+            ref.omega_RN_N = mk(SD(F_REF + 3), SD(F_REF + 4), SD(F_REF + 5));
+            ref.domega_RN_N = mk(SD(F_REF + 6), SD(F_REF + 7), SD(F_REF + 8));
+            if (mask & LEO_TASK_SUN) {                       // inertial3D
+                ref.sigma_RN = arr(P.sigma_R0N);
+                ref.omega_RN_N = mk(0., 0., 0.); ref.domega_RN_N = mk(0., 0., 0.);
+            }
+            if (mask & LEO_TASK_NADIR) {                     // hillPoint
+                V3 cr = mk(0., 0., 0.), cv = mk(0., 0., 0.);
+                if (P.hill_cel_pun) cr.x = sun.et;           // r_BdyZero_N aliases {J2000Current, 0, 0}
+                ref = hill_point(nr, nv, cr, cv);
+            }
+            if (mask & (LEO_TASK_SUN | LEO_TASK_NADIR)) {
+                SD(F_REF) = ref.sigma_RN.x; SD(F_REF + 1) = ref.sigma_RN.y; SD(F_REF + 2) = ref.sigma_RN.z;
+                SD(F_REF + 3) = ref.omega_RN_N.x; SD(F_REF + 4) = ref.omega_RN_N.y; SD(F_REF + 5) = ref.omega_RN_N.z;
+                SD(F_REF + 6) = ref.domega_RN_N.x; SD(F_REF + 7) = ref.domega_RN_N.y; SD(F_REF + 8) = ref.domega_RN_N.z;
+            }
+            if (mask & LEO_TASK_DESAT) {
+                fsw_desat<NRW>(P, S, I, stride, e, now_ns, ws);
+                desat_ran = 1;
+            }
+            if (mask & LEO_TASK_MRP) {
+                // quirk Q1: MRP_Feedback runs BEFORE attTrackingError -> uses last pass's att_guidance
+                AttGuid g;
+                g.sigma_BR = mk(SD(F_GUID), SD(F_GUID + 1), SD(F_GUID + 2));
+                g.omega_BR_B = mk(SD(F_GUID + 3), SD(F_GUID + 4), SD(F_GUID + 5));
+                g.omega_RN_B = mk(SD(F_GUID + 6), SD(F_GUID + 7), SD(F_GUID + 8));
+                g.domega_RN_B = mk(SD(F_GUID + 9), SD(F_GUID + 10), SD(F_GUID + 11));
+                V3 Lr = mrp_feedback(P, g);
+                SD(F_LR) = Lr.x; SD(F_LR + 1) = Lr.y; SD(F_LR + 2) = Lr.z;
+                g = att_tracking_error(ns, nw, ref);
+                SD(F_GUID) = g.sigma_BR.x; SD(F_GUID + 1) = g.sigma_BR.y; SD(F_GUID + 2) = g.sigma_BR.z;
+                SD(F_GUID + 3) = g.omega_BR_B.x; SD(F_GUID + 4) = g.omega_BR_B.y; SD(F_GUID + 5) = g.omega_BR_B.z;
+                SD(F_GUID + 6) = g.omega_RN_B.x; SD(F_GUID + 7) = g.omega_RN_B.y; SD(F_GUID + 8) = g.omega_RN_B.z;
+                SD(F_GUID + 9) = g.domega_RN_B.x; SD(F_GUID + 10) = g.domega_RN_B.y; SD(F_GUID + 11) = g.domega_RN_B.z;
+                // rwMotorTorque: us = Umap (-Lr)
+                V3 mLr = -Lr;
+#pragma unroll
+                for (int i = 0; i < NRW; i++) SD(F_RWCMD + i) = P.Umap[i][0] * mLr.x + P.Umap[i][1] * mLr.y + P.Umap[i][2] * mLr.z;
+            }
+            rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
+            // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule)
+            if (n > 0 && n == n_end) { sun_ns = now_ns; sun = sun_latch(P, sun_ns); }
+        }
+        to_fsw--;
+
+        // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
+        const double newTime = ns2sec(now_ns);
+        const double prevTime = n > 0 ? ns2sec(now_ns - P.dyn_ns) : 0.0;
+        const double h = t_sub(newTime, prevTime);
+        const double tBefore = t_sub(newTime, h);
+        const bool sun_newer = sun_ns > (n > 0 ? now_ns - P.dyn_ns : 0);
+        const double sun_dt0 = t_mul((double)((n > 0 ? now_ns - P.dyn_ns : 0) - sun_ns), 1e-9);
+        {
+            const double hh = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
+            Dyn<NRW> xs = x, xo = x, k;
+            double tauPrev = 0.0;
+            if (thr_active) { // time of the previous equationsOfMotion call = last stage of the previous tick
+                if (n > 0) {
+                    const double pT = prevTime, ppT = n > 1 ? ns2sec(now_ns - 2 * P.dyn_ns) : 0.0;
+                    const double ph = t_sub(pT, ppT);
+                    tauPrev = t_add(t_sub(pT, ph), ph);
+                }
+            }
+#if LEO_UNROLL_STAGES
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+            for (int st = 0; st < 4; st++) {
+                const double coff = (st == 0) ? 0.0 : (st == 3 ? h : t_mul(h, 0.5));
+                const double tau = t_add(tBefore, coff);
+                V3 F_thr = mk(0., 0., 0.), L_tot = L_ext;
+                if (thr_active) {
+                    V3 Lt;
+                    thr_stage(P, S, stride, e, tau, t_sub(tau, tauPrev), thr_factor, thr_active, F_thr, Lt);
+                    L_tot = L_tot + Lt;
+                    tauPrev = tau;
+                }
+                double dts = sun_dt0 + coff;
+                if (sun_newer) {
+                    // quirk Q18: the Sun message is newer than the integration time; Basilisk's unsigned
+                    // (systemClock - WriteClockNanos) wraps.  Replicated bit for bit.
+                    uint64_t sys = (uint64_t)t_add((double)(now_ns - P.dyn_ns), t_div(t_sub(tau, prevTime), 1e-9));
+                    dts = t_mul((double)(sys - (uint64_t)sun_ns), 1e-9);
+                }
+                eom<NRW, J2>(P, xs, k, sun, dts, rho, tau_u, u, L_tot, F_thr);
+                const double wo = (st == 0 || st == 3) ? h6 : h3;
+                xo = axpy(xo, k, wo);
+                if (st < 3) xs = axpy(x, k, st == 2 ? h : hh);
+            }
+            x = xo;
+        }
+        // HubEffector::modifyStates -- MRP shadow-set switch
+        {
+            double s2 = dot(x.s, x.s);
+            if (sqrt(s2) > 1.) { x.s = x.s * (-1. / s2) ; nswitch++; }
+        }
+        // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
+        rho = P.rho0 * exp(-(norm(x.r) - P.Rp_atmo) * P.inv_H);
+        // reactionWheelStateEffector.UpdateState: re-latch only when the command is new or a speed limit is in play
+        {
+            int lim = 0;
+#pragma unroll
+            for (int i = 0; i < NRW; i++) lim |= (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
+            if (rw_sat | lim) {
+                tau_u = mk(0., 0., 0.);
+#pragma unroll
+                for (int i = 0; i < NRW; i++) {
+                    double uc = SD(F_RWCMD + i);
+                    if (P.u_max[i] > 0.) { if (uc > P.u_max[i]) uc = P.u_max[i]; else if (uc < -P.u_max[i]) uc = -P.u_max[i]; }
+                    if (fabs(uc) < P.u_min[i]) uc = 0.0;
+                    if (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && x.W[i] * uc >= 0.0) uc = 0.0;
+                    u[i] = uc;
+                    tau_u = tau_u + arr(P.gs[i]) * uc;
+                }
+                rw_sat = lim;
+            }
+        }
+        // thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters
+        if (desat_ran) thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor);
+
+        // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
+        shadow = eclipse_factor(P, sun, x.r);
+        {
+            V3 r_SB = sun.r - x.r;
+            double d2 = dot(r_SB, r_SB), id = rsq(d2);
+            M3 BN = mrp_to_BN(x.s);
+            V3 n_N = mtv(BN, arr(P.nHat_B));                   // panel normal in the inertial frame
+            double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
+            if (proj < 0.) proj = 0.;
+            double panel = P.panel_coef * proj * (id * id) * shadow;
+            if (n > 0) {                                       // quirk Q2: the sink message does not exist at tick 0
+                E = E + (panel + P.sink_power) * h;
+                if (E > P.capacity) E = P.capacity;
+                if (E < 0.) E = 0.;
+            }
+        }
+    }
+    tick = n_end;
+
+    // ---------------- observation sampling (SIM:598-642) + gym bookkeeping (ENV:98-145) ----------------
+    double ob0 = norm(mk(SD(F_GUID), SD(F_GUID + 1), SD(F_GUID + 2)));
+    double ob1 = norm(x.w);
+    double wn = 0.;
+#pragma unroll
+    for (int i = 0; i < NRW; i++) wn += x.W[i] * x.W[i];
+    double ob2 = sqrt(wn), ob3 = E / 3600., ob4 = shadow;
+    int sim_over = norm(x.r) < P.decay_radius;
+    int64_t curr_step = SI(I_STEP);
+    int over = (int)SI(I_OVER), reason = 0;
+    if (curr_step >= P.max_length) { over = 1; reason |= 1; }
+    double reward = 0.;
+    if (action == 0) reward = fabs(P.reward_mult / (1. + ob0 * ob0));
+    double ret = SD(F_EPRET) + reward;
+    SD(F_OBS) = ob0; SD(F_OBS + 1) = ob1; SD(F_OBS + 2) = ob2; SD(F_OBS + 3) = ob3; SD(F_OBS + 4) = ob4;
+    ob2 = ob2 / P.wheel_limit;
+    ob3 = ob3 / P.power_max;
+    if (ob2 > 1.) { over = 1; reward -= P.failure_penalty; ret -= P.failure_penalty; reason |= 2; }
+    if (ob3 == 0.) { over = 1; reward -= P.failure_penalty; ret -= P.failure_penalty; reason |= 4; }
+    if (sim_over) { over = 1; reason |= 8; }
+    out.ob[0] = ob0; out.ob[1] = ob1; out.ob[2] = ob2; out.ob[3] = ob3; out.ob[4] = ob4;
+    out.reward = reward; out.done = over; out.reason = reason;
+
+    // ---------------- store ----------------
+    SD(F_R) = x.r.x; SD(F_R + 1) = x.r.y; SD(F_R + 2) = x.r.z;
+    SD(F_V) = x.v.x; SD(F_V + 1) = x.v.y; SD(F_V + 2) = x.v.z;
+    SD(F_SIG) = x.s.x; SD(F_SIG + 1) = x.s.y; SD(F_SIG + 2) = x.s.z;
+    SD(F_OMG) = x.w.x; SD(F_OMG + 1) = x.w.y; SD(F_OMG + 2) = x.w.z;
+#pragma unroll
+    for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = x.W[i]; SD(F_UCUR + i) = u[i]; }
+    SD(F_RHO) = rho; SD(F_E) = E; SD(F_SHADOW) = shadow; SD(F_EPRET) = ret;
+    SI(I_TICK) = tick; SI(I_STEP) = curr_step + 1; SI(I_MASK) = mask; SI(I_SWITCH) = nswitch;
+    SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_OVER) = over; SI(I_RWSAT) = rw_sat;
+#undef SD
+#undef SI
+}
+
+}  // namespace leo

@@ -1,0 +1,115 @@
+// leo_params.h -- kernel parameter block and persistent-state layout of the fused LEO step.
+//
+// LeoParams is passed BY VALUE as a __grid_constant__ kernel parameter: every field is then a
+// constant-bank operand of the FP64 instructions (no registers, no loads).  It is derived on the
+// host from bskenv_config (include/bskenv.h) by leo_build_params(); the numbers come from
+//   /root/reference/basilisk_env/simulators/leoPowerAttitudeSimulator.py:127-191, 195-490 (SIM)
+//   /root/reference/basilisk_env/simulators/dynamics/effectorPrimatives/actuatorPrimatives.py (AP)
+//   /root/reference/basilisk_env/envs/leoPowerAttitudeEnvironment.py:25-42 (ENV)
+#pragma once
+#include <stdint.h>
+
+#define LEO_MAX_RW 4
+#define LEO_NTHR 8
+
+struct LeoParams {
+    // ---- task rates as integer nanoseconds (Basilisk sec2nano) and derived loop counts ----
+    int64_t dyn_ns, fsw_ns, step_ns;
+    int32_t ticks_per_fsw, fsw_per_step;
+    // ---- hub ----
+    double inv_mass;
+    double I[9];          // IHubPntBc_B (= ISCPntB_B: balanced wheels carry no mass properties)
+    double Dinv[9];       // inverse of  I - sum_i Js_i g_i g_i^T   (constant back-substitution matrix)
+    // ---- gravity ----
+    double mu_c, mu_sun;
+    double j2k;           // 1.5 * J2 * mu * Req^2 (only when the J2 template flag is on)
+    int32_t use_sun3, hill_cel_pun;
+    // ---- reaction wheels ----
+    int32_t nrw, pad0;
+    double gs[LEO_MAX_RW][3], Js[LEO_MAX_RW], invJs[LEO_MAX_RW];
+    double u_max[LEO_MAX_RW], u_min[LEO_MAX_RW], Om_max[LEO_MAX_RW];
+    double Umap[LEO_MAX_RW][3];   // rwMotorTorque: us = Umap * (-Lr) = CGs^T (CGs CGs^T)^-1 C (-Lr)
+    // ---- facet drag, facets with axis-aligned normals collapsed per axis and sign ----
+    double dragK[3][2];           // sum of 0.5*Cd*A over facets with normal (+/-) e_axis
+    double dragM[3][2][3];        // sum of 0.5*Cd*A*r_facet over the same facets
+    double dist_mag;              // disturbance_magnitude (2e-4)
+    // ---- exponential atmosphere ----
+    double rho0, inv_H, Rp_atmo;
+    // ---- eclipse ----
+    double R_sun, R_planet;
+    // ---- power ----
+    double nHat_B[3];
+    double panel_coef;            // eta * SOLAR_FLUX_EARTH * A * AU^2
+    double sink_power, capacity;
+    // ---- FSW ----
+    double K, P, Ki;
+    double I_fsw[9];
+    double sigma_R0N[3];
+    double hs_min;
+    double thr_loc[LEO_NTHR][3], thr_dir[LEO_NTHR][3];
+    double thr_D[3][LEO_NTHR];    // r_i x t_i
+    double thr_W[LEO_NTHR][3];    // D^T (D D^T)^-1  (minimum-norm map, thrForceMapping)
+    double thr_Fmax, thr_MinOnTime, thrMinFireTime;
+    double tfm_eps, tfm_angErrThresh;
+    int32_t thrForceSign, maxCounterValue;
+    // ---- gym layer ----
+    double wheel_limit, power_max, reward_mult, failure_penalty, decay_radius, wheel_rpm2rad;
+    int32_t max_length, auto_reset;
+    // ---- epoch (days of TT from J2000 at sim time 0) ----
+    double epoch_days;
+    // ---- IC sampling ----
+    uint64_t seed;
+    int64_t first_env_index;
+};
+
+// ---- persistent per-env state: double fields (SoA, field-major, stride = padded env count) ----
+enum LeoDField : int {
+    F_R = 0,         // r_BN_N[3]
+    F_V = 3,         // v_BN_N[3]
+    F_SIG = 6,       // sigma_BN[3]
+    F_OMG = 9,       // omega_BN_B[3]
+    F_WHL = 12,      // Omega[4]
+    F_UCUR = 16,     // RW u_current[4]
+    F_RHO = 20,      // latched neutral density
+    F_E = 21,        // storedCharge
+    F_SHADOW = 22,   // shadowFactor of the last env tick
+    F_LDIST = 23,    // extTorquePntB_B[3]
+    F_GUID = 26,     // att_guidance: sigma_BR, omega_BR_B, omega_RN_B, domega_RN_B
+    F_REF = 38,      // att_reference: sigma_RN, omega_RN_N, domega_RN_N
+    F_LR = 47,       // commandedControlTorque[3]
+    F_RWCMD = 50,    // rwTorqueCommand[4]
+    F_DELTAH = 54,   // wheelDeltaH[3]
+    F_THRON = 57,    // ThrustOnCmd[8]
+    F_THRSTART = 65, // ThrusterStartTime (shared by all thrusters of a command)
+    F_THRPREVFIRE = 66,
+    F_THRREM = 67,   // thrOnTimeRemaining[8]
+    F_THRCMD = 75,   // rwDesatTimeOnCmd OnTimeRequest[8]
+    F_EPRET = 83,    // reward_total of the running episode
+    F_OBS = 84,      // last un-normalised simulator obs[5]
+    LEO_ND = 89
+};
+// ---- persistent per-env state: int64 fields ----
+enum LeoIField : int {
+    I_TICK = 0,      // index of the last executed dynamics tick (-1 after reset)
+    I_STEP = 1,      // curr_step
+    I_MASK = 2,      // active tasks: 1 sunPoint, 2 nadirPoint, 4 mrpControl, 8 rwDesat
+    I_SWITCH = 3,    // MRPSwitchCount
+    I_THRFACTOR = 4, // bit i: ThrustFactor_i > 0
+    I_INITREQ = 5,   // thrMomentumManagement.initRequest
+    I_DUMPCNT = 6,   // thrMomentumDumping.thrDumpingCounter
+    I_DUMPPRIOR = 7, // thrMomentumDumping.priorTime [ns]
+    I_LASTDH = 8,    // thrMomentumDumping.lastDeltaHInMsgTime [ns]
+    I_DHTIME = 9,    // write time of wheelDeltaH [ns]; 0 when never written
+    I_EPISODE = 10,  // episode counter (keys the IC stream)
+    I_FIRE = 11,     // fireCounter[8]
+    I_THRACTIVE = 19,// any ThrustOnCmd > 0 or ThrustFactor > 0
+    I_OVER = 20,     // episode_over latch
+    I_RWSAT = 21,    // a wheel was speed-saturated at the last latch
+    LEO_NI = 22
+};
+
+#define LEO_TASK_SUN 1
+#define LEO_TASK_NADIR 2
+#define LEO_TASK_MRP 4
+#define LEO_TASK_DESAT 8
+#define LEO_TASK_ALL 15

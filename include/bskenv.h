@@ -1,0 +1,142 @@
+/*
+ * bskenv.h -- C ABI of the B200-native batched LEO power/attitude environment step.
+ *
+ * This is the drop-in boundary for ONE path of atharris/basilisk_env: everything below
+ * `LEOPowerAttitudeSimulator.run_sim(action)` (reference: basilisk_env/simulators/
+ * leoPowerAttitudeSimulator.py:535-644, i.e. the Basilisk `ExecuteSimulation()` call at :595 and the
+ * message sampling at :598-642), plus the gym bookkeeping of `leoPowerAttEnv.step`
+ * (basilisk_env/envs/leoPowerAttitudeEnvironment.py:65-145) and the simulator construction done in
+ * `reset` (:172-191, simulators/...Simulator.py:67-117), vectorised over N independent environments.
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  Device pointers are raw CUDA device
+ * addresses in the handle's device (e.g. torch `tensor.data_ptr()`), streams are `cudaStream_t`
+ * passed as `void*` (0 = legacy default stream).  Every function returns 0 on success or a negative
+ * BSKENV_E* code; `bskenv_last_error` gives the message.  Nothing throws across this boundary and
+ * there is NO CPU fallback: without a CUDA device `bskenv_create` fails.
+ */
+#ifndef BSKENV_H
+#define BSKENV_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSKENV_ABI_VERSION 1
+
+#define BSKENV_OK 0
+#define BSKENV_EINVAL (-1)   /* bad argument / unsupported configuration */
+#define BSKENV_ECUDA (-2)    /* CUDA runtime error (message in last_error) */
+#define BSKENV_ENODEV (-3)   /* no usable CUDA device */
+
+/* done_reason bitmask; replaces the reference's print() calls (envs/...Environment.py:110-127) */
+#define BSKENV_DONE_MAXLEN 1 /* curr_step >= max_length          (:98-99)  */
+#define BSKENV_DONE_WHEEL 2  /* ob[2] > 1, "wheel explosion"     (:110-115) */
+#define BSKENV_DONE_POWER 4  /* ob[3] == 0, "ran out of power"   (:119-123) */
+#define BSKENV_DONE_DECAY 8  /* sim_over, "orbit decayed"        (:125-127, simulators/...:641-642) */
+
+#define BSKENV_OBS_DIM 5     /* [|sigma_BR|, |omega_BN_B|, |Omega_rw|/wheel_limit, Wh/power_max, shadowFactor] */
+#define BSKENV_IC_DIM 19     /* rN(3) vN(3) sigma_init(3) omega_init(3) disturbance_vector(3) wheelSpeeds_rpm(3) storedCharge_Init */
+
+/*
+ * Batch-global configuration == the non-sampled entries of the reference's `initial_conditions`
+ * dict (simulators/leoPowerAttitudeSimulator.py:127-191), the constructor arguments (:67) and the
+ * env attributes (envs/leoPowerAttitudeEnvironment.py:25-42).  `bskenv_default_config` fills the
+ * reference values; only the fields below are tunable, the module graph itself is fixed.
+ */
+typedef struct bskenv_config {
+    int32_t abi_version;         /* BSKENV_ABI_VERSION */
+    int32_t reserved0;
+    /* LEOPowerAttitudeSimulator(dynRate, fswRate, step_duration) */
+    double dynRate;              /* 0.1 s   */
+    double fswRate;              /* 1.0 s   */
+    double step_duration;        /* 180. s  */
+    /* spacecraft ("mass", "width", "depth", "height") */
+    double mass, width, depth, height;
+    /* atmosphere ("planetRadius", "baseDensity", "scaleHeight") */
+    double planetRadius, baseDensity, scaleHeight;
+    double disturbance_magnitude;   /* 2e-4 */
+    /* power ("nHat_B", "panelArea", "panelEfficiency", "powerDraw", "storageCapacity") */
+    double nHat_B[3], panelArea, panelEfficiency, powerDraw, storageCapacity;
+    /* FSW ("sigma_R0N", "K", "Ki", "P", "hs_min", "thrForceSign", "maxCounterValue", "thrMinFireTime") */
+    double sigma_R0N[3], K, Ki, P, hs_min, thrMinFireTime;
+    int32_t thrForceSign, maxCounterValue;
+    /* env attributes */
+    int32_t max_length;          /* 540 */
+    int32_t auto_reset;          /* 0: gym single-env semantics; 1: re-sample ICs in-kernel when done */
+    double wheel_limit_rpm;      /* 3000 */
+    double power_max;            /* 20 */
+    double failure_penalty;      /* 1 */
+    /* documented deviations / switches: all 0 reproduces the reference wiring */
+    int32_t use_j2;              /* reference has no J2; 1 only for the stress config */
+    int32_t hill_cel_pun;        /* 1 = hillPoint reads the SPICE message as an ephemeris message */
+    int32_t reserved[8];
+} bskenv_config;
+
+typedef struct bskenv_handle bskenv_handle;
+
+int bskenv_abi_version(void);
+void bskenv_default_config(bskenv_config *cfg);
+
+/* One handle owns the persistent SoA state of `n_envs` environments on CUDA device `device`.
+ * `first_env_index` is the global index of env 0 of this shard: per-env random streams are keyed by
+ * (seed, global index, episode), so results do not depend on how envs are sharded across GPUs. */
+int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t first_env_index,
+                  bskenv_handle **out);
+int bskenv_destroy(bskenv_handle *h);
+const char *bskenv_last_error(const bskenv_handle *h); /* h may be NULL: last create() error */
+int64_t bskenv_num_envs(const bskenv_handle *h);
+
+/* reset(): sample fresh initial conditions on the device (distributions and clipping of
+ * initial_conditions/leo_orbit.py:25-39, sc_attitudes.py:3-13, simulators/...Simulator.py:152-167).
+ * `mask_dev` (uint8[n], may be NULL = all) selects the envs to reset.  `obs_dev` (double[n*5], may be
+ * NULL) receives the normalised initial observation of the reset envs. */
+int bskenv_reset_seeded(bskenv_handle *h, uint64_t seed, const uint8_t *mask_dev, double *obs_dev, void *stream);
+/* reset with explicit initial conditions: `ics_dev` is double[n*19] row-major (BSKENV_IC_DIM). */
+int bskenv_reset_ics(bskenv_handle *h, const double *ics_dev, const uint8_t *mask_dev, double *obs_dev, void *stream);
+/* reset_init(): rebuild from the stored initial conditions (envs/...Environment.py:202-216). */
+int bskenv_reset_init(bskenv_handle *h, const uint8_t *mask_dev, double *obs_dev, void *stream);
+int bskenv_get_ics(bskenv_handle *h, double *ics_dev, void *stream);
+
+/* step(): ONE kernel launch advances every env by one decision interval (step_duration of
+ * simulated time: 1800 RK4 ticks + 1800 environment ticks + 180 flight-software ticks at the
+ * reference rates) and evaluates reward/termination.  All buffers are caller-owned device memory:
+ *   actions int32[n]; obs double[n*5]; reward double[n]; done uint8[n]; done_reason uint8[n].
+ * With auto_reset, envs that finish are re-initialised inside the same launch; `obs` then holds the
+ * first observation of the new episode and `term_obs_dev` (double[n*5], may be NULL) the terminal one. */
+int bskenv_step(bskenv_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
+                uint8_t *done_dev, uint8_t *done_reason_dev, double *term_obs_dev, void *stream);
+/* Same call with HOST buffers (the reference-facing plugin path): copies actions to the device,
+ * launches, copies obs/reward/done/reason back through pinned staging owned by the handle, and
+ * synchronises.  This is what bench.py times as `e2e`. */
+int bskenv_step_host(bskenv_handle *h, const int32_t *actions, double *obs, double *reward,
+                     uint8_t *done, uint8_t *done_reason);
+
+/* Checkpoint / parity injection: the whole persistent state as two SoA blocks,
+ * double[n_double_fields][n] and int64[n_int_fields][n] (field-major). */
+int bskenv_state_dims(const bskenv_handle *h, int32_t *n_double_fields, int32_t *n_int_fields);
+int bskenv_get_state(bskenv_handle *h, double *dstate_dev, int64_t *istate_dev, void *stream);
+int bskenv_set_state(bskenv_handle *h, const double *dstate_dev, const int64_t *istate_dev, void *stream);
+/* index of a named state field (e.g. "r_BN_N", "sigma_BN", "Omega", "storedCharge"); -1 if unknown.
+ * `is_int` receives 1 for int64 fields. */
+int bskenv_state_field(const char *name, int32_t *is_int);
+
+/* Episode statistics of this shard since the last call (sum of returns, sum of lengths, episodes
+ * finished, finished by wheel / power / decay / max-length): int64/double[8] in `stats_host`.
+ * (An optional NCCL all-reduce of these eight numbers is the only collective of the design.) */
+int bskenv_episode_stats(bskenv_handle *h, double *stats_host);
+
+/* Number of step-path kernel launches issued through this handle (bench.py's gpu_launches). */
+int64_t bskenv_launch_count(const bskenv_handle *h);
+
+/* FP64 FMA-pipe microbenchmark used as the roofline denominator (MEASURED_PEAKS.json has none):
+ * returns achieved TFLOP/s of a register-resident DFMA chain kernel on `device`. */
+int bskenv_fp64_peak(int device, double seconds, double *tflops);
+
+/* ALGORITHMIC FP64 flop per env-decision-step for this configuration (DESIGN.md derivation). */
+double bskenv_flops_per_step(const bskenv_handle *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,72 @@
+// hostcore.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the device core (basilisk_env_b200/csrc/leo_core.cuh) for the HOST with g++ so that the
+// fused-schedule logic can be compared with the independent oracle on a CPU-only box (pytest -m "not gpu").
+// It is never loaded by the product: the library proper (libbskenv.so) has no CPU path.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+#include "../../basilisk_env_b200/csrc/leo_core.cuh"
+#include "../../basilisk_env_b200/csrc/leo_host.h"
+
+struct HC {
+    LeoParams P;
+    int64_t n;
+    std::vector<double> S, ics;
+    std::vector<int64_t> I;
+};
+
+extern "C" {
+void hc_default_config(bskenv_config *c) { leo_host::default_config(c); }
+HC *hc_create(const bskenv_config *cfg, int64_t n)
+{
+    HC *h = new HC();
+    std::string err = leo_host::build_params(*cfg, h->P);
+    if (!err.empty()) { delete h; return nullptr; }
+    h->n = n;
+    h->S.assign((size_t)LEO_ND * n, 0.0);
+    h->I.assign((size_t)LEO_NI * n, 0);
+    h->ics.assign((size_t)19 * n, 0.0);
+    return h;
+}
+void hc_destroy(HC *h) { delete h; }
+void hc_reset_ics(HC *h, const double *ics, double *obs)
+{
+    for (int64_t e = 0; e < h->n; e++) {
+        double ic[19];
+        for (int k = 0; k < 19; k++) { ic[k] = ics[e * 19 + k]; h->ics[e * 19 + k] = ic[k]; }
+        leo::leo_reset_env(h->P, h->S.data(), h->I.data(), h->n, e, ic, obs ? obs + 5 * e : nullptr);
+    }
+}
+void hc_reset_seeded(HC *h, uint64_t seed, int64_t first_env, double *ics_out, double *obs)
+{
+    h->P.seed = seed; h->P.first_env_index = first_env;
+    for (int64_t e = 0; e < h->n; e++) {
+        double ic[19];
+        leo::sample_ic(h->P, first_env + e, h->I[(size_t)I_EPISODE * h->n + e], ic);
+        for (int k = 0; k < 19; k++) { h->ics[e * 19 + k] = ic[k]; if (ics_out) ics_out[e * 19 + k] = ic[k]; }
+        leo::leo_reset_env(h->P, h->S.data(), h->I.data(), h->n, e, ic, obs ? obs + 5 * e : nullptr);
+    }
+}
+void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t *done, uint8_t *reason)
+{
+    for (int64_t e = 0; e < h->n; e++) {
+        leo::StepOut o;
+        leo::leo_step_env<3, false>(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o);
+        for (int k = 0; k < 5; k++) obs[5 * e + k] = o.ob[k];
+        reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
+    }
+}
+void hc_get_state(HC *h, double *S, int64_t *I)
+{
+    memcpy(S, h->S.data(), h->S.size() * sizeof(double));
+    memcpy(I, h->I.data(), h->I.size() * sizeof(int64_t));
+}
+int hc_dims(int *nd, int *ni) { *nd = LEO_ND; *ni = LEO_NI; return 0; }
+void hc_thr_force_mapping(HC *h, const double *Lr, double *F)
+{
+    double f[LEO_NTHR];
+    leo::thr_force_mapping(h->P, leo::mk(Lr[0], Lr[1], Lr[2]), f);
+    for (int i = 0; i < LEO_NTHR; i++) F[i] = f[i];
+}
+}
