@@ -181,7 +181,7 @@ void orc_addMRP(const double q1[3], const double q2[3], double result[3])
     v3Scale(1 - v3Dot(q2, q2), s1, res);
     v3Scale(1 - v3Dot(s1, s1), q2, v2);
     v3Add(res, v2, res);
-    v3Subtract(res, v1, res);
+    v3Add(res, v1, res);               /* [FN(Q)] = [FB(q2)][BN(q1)]: +2 q1 x q2 (Schaub & Junkins eq. 3.155) */
     v3Scale(1 / det, res, res);
     mag = v3Dot(res, res);
     if (mag > 1.0) v3Scale(-1. / mag, res, res);

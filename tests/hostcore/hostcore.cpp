@@ -43,7 +43,9 @@ void hc_reset_seeded(HC *h, uint64_t seed, int64_t first_env, double *ics_out, d
     h->P.seed = seed; h->P.first_env_index = first_env;
     for (int64_t e = 0; e < h->n; e++) {
         double ic[19];
-        leo::sample_ic(h->P, first_env + e, h->I[(size_t)I_EPISODE * h->n + e], ic);
+        int64_t ep = h->I[(size_t)I_EPISODE * h->n + e] + 1;     // as leo_reset_kernel mode 2
+        h->I[(size_t)I_EPISODE * h->n + e] = ep;
+        leo::sample_ic(h->P, first_env + e, ep, ic);
         for (int k = 0; k < 19; k++) { h->ics[e * 19 + k] = ic[k]; if (ics_out) ics_out[e * 19 + k] = ic[k]; }
         leo::leo_reset_env(h->P, h->S.data(), h->I.data(), h->n, e, ic, obs ? obs + 5 * e : nullptr);
     }

@@ -1,0 +1,70 @@
+"""TEST INFRASTRUCTURE: comparison of the SoA state of the CUDA path (or its host-compiled core)
+with the oracle's state at a decision boundary.
+
+Tolerances (north_star: discrete bit-exact, continuous <= 1e-9 relative per decision interval, FP64):
+  r, v, Omega : |delta| / |value|                      <= RTOL
+  sigma_BN    : |delta| (MRP, canonical |sigma| <= 1)  <= RTOL * max(1, |sigma|)
+  omega_BN_B  : |delta| <= RTOL * |omega| + OMEGA_ATOL   (rates settle to ~1e-8 rad/s under control, where
+                a relative measure of a difference of 1e-17 rad/s is meaningless)
+  storedCharge: relative; shadowFactor / obs[4]: absolute RTOL (it is a fraction in [0,1])
+"""
+import numpy as np
+
+from basilisk_env_b200 import _native
+
+RTOL = 1e-9
+OMEGA_ATOL = 1e-13
+
+
+def F(name):
+    return _native.state_field(name)[0]
+
+
+def vec_err(a, b, floor=0.0):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), floor, 1e-300))
+
+
+def compare_state(st, S, I, where=""):
+    """st: oracle LeoState; S, I: one env's column of the double / int64 state blocks."""
+    errs = {}
+    errs["r"] = vec_err(S[F("r_BN_N"):F("r_BN_N") + 3], st.r_BN_N[:])
+    errs["v"] = vec_err(S[F("v_BN_N"):F("v_BN_N") + 3], st.v_BN_N[:])
+    errs["sigma"] = vec_err(S[F("sigma_BN"):F("sigma_BN") + 3], st.sigma_BN[:], floor=1.0)
+    w_o = np.array(st.omega_BN_B[:]); w_k = S[F("omega_BN_B"):F("omega_BN_B") + 3]
+    errs["omega"] = float(np.linalg.norm(w_k - w_o) / (np.linalg.norm(w_o) + OMEGA_ATOL / RTOL))
+    errs["Omega"] = vec_err(S[F("Omega"):F("Omega") + 3], st.Omega[:3], floor=1.0)
+    errs["charge"] = abs(S[F("storedCharge")] - st.storedCharge) / max(abs(st.storedCharge), 1.0)
+    errs["shadow"] = abs(S[F("shadowFactor")] - st.shadowFactor)
+    errs["sigma_BR"] = vec_err(S[F("att_guidance"):F("att_guidance") + 3], st.sigma_BR[:], floor=1.0)
+    errs["u"] = vec_err(S[F("u_current"):F("u_current") + 3], st.u_current[:3], floor=1e-3)
+    for k, v in errs.items():
+        assert v <= RTOL, f"{where}: {k} differs by {v:.3e} (> {RTOL})"
+    # discrete quantities: bit-exact
+    assert int(I[F("MRPSwitchCount")]) == st.mrp_switch_count, f"{where}: MRP switch count"
+    assert int(I[F("task_mask")]) == st.task_mask, f"{where}: task mask"
+    assert int(I[F("thrFactorMask")]) == st.thr_factor_mask, f"{where}: thruster firing mask"
+    assert int(I[F("initRequest")]) == st.init_request, f"{where}: initRequest"
+    assert int(I[F("thrDumpingCounter")]) == st.dump_counter, f"{where}: dumping counter"
+    fc = [int(x) for x in I[F("fireCounter"):F("fireCounter") + 8]]
+    assert fc == list(st.thr_fire_count[:]), f"{where}: thruster fire counters {fc} vs {list(st.thr_fire_count[:])}"
+    assert int(I[F("tick")]) * 100000000 == st.sim_nanos, f"{where}: sim clock"
+    # commanded on-times are compared exactly as well: they gate discrete firing decisions
+    on_k = S[F("ThrustOnCmd"):F("ThrustOnCmd") + 8]
+    np.testing.assert_allclose(on_k, np.array(st.thrOnCmd[:]), rtol=1e-9, atol=1e-12, err_msg=f"{where}: ThrustOnCmd")
+    return errs
+
+
+def compare_obs(ob_k, ob_o, where=""):
+    ob_k = np.asarray(ob_k, float); ob_o = np.asarray(ob_o, float)
+    assert abs(ob_k[0] - ob_o[0]) <= RTOL * max(1.0, abs(ob_o[0])), f"{where}: obs[0] {ob_k[0]} vs {ob_o[0]}"
+    assert abs(ob_k[1] - ob_o[1]) <= RTOL * abs(ob_o[1]) + OMEGA_ATOL, f"{where}: obs[1] {ob_k[1]} vs {ob_o[1]}"
+    assert abs(ob_k[2] - ob_o[2]) <= RTOL * max(abs(ob_o[2]), 1e-3), f"{where}: obs[2] {ob_k[2]} vs {ob_o[2]}"
+    assert abs(ob_k[3] - ob_o[3]) <= RTOL * max(abs(ob_o[3]), 1e-3), f"{where}: obs[3] {ob_k[3]} vs {ob_o[3]}"
+    assert abs(ob_k[4] - ob_o[4]) <= RTOL, f"{where}: obs[4] {ob_k[4]} vs {ob_o[4]}"
+
+
+def sample_rows(orc, n, seed):
+    """n IC rows drawn from a seeded legacy numpy stream in the reference's draw order."""
+    rng = np.random.RandomState(seed)
+    return np.stack([orc.ic_to_row(orc.sample_ic_dict(rng)) for _ in range(n)])
