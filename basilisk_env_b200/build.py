@@ -8,7 +8,7 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libbskenv.so")
+LIB = os.environ.get("BSKENV_LIB") or os.path.join(HERE, "libbskenv.so")   # BSKENV_LIB: load a tuning variant instead
 SOURCES = ["bskenv.cu"]
 DEPS = ["bskenv.cu", "leo_core.cuh", "leo_params.h", "leo_host.h", os.path.join("..", "..", "include", "bskenv.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,14 +29,15 @@ def is_stale():
     return any(os.path.getmtime(os.path.join(CSRC, d)) > t for d in DEPS)
 
 
-def build(force=False, extra_flags=(), verbose=False):
-    if not force and not is_stale():
+def build(force=False, extra_flags=(), verbose=False, out=None):
+    if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    out = out or LIB
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(extra_flags) + ["-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         print(" ".join(cmd))
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -38,7 +38,7 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-template <int NRW, bool J2>
+template <int NRW, bool J2, bool DIAG>
 __global__ void __launch_bounds__(LEO_BLOCK, LEO_MIN_BLOCKS)
 leo_step_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                 int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
@@ -51,7 +51,7 @@ leo_step_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int
     o.done = 0; o.reason = 0; o.reward = 0.;
     double ep_ret = 0., ep_len = 0.;
     if (valid) {
-        leo::leo_step_env<NRW, J2>(P, S, I, stride, e, actions[e], o);
+        leo::leo_step_env<NRW, J2, DIAG>(P, S, I, stride, e, actions[e], o);
         reward[e] = o.reward;
         done[e] = (uint8_t)o.done;
         reason[e] = (uint8_t)o.reason;
@@ -183,10 +183,12 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
                        double *term_obs, cudaStream_t st)
 {
     const int grid = (int)((h->n + LEO_BLOCK - 1) / LEO_BLOCK);
-    if (h->cfg.use_j2)
-        leo_step_kernel<3, true><<<grid, LEO_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs, h->stats);
-    else
-        leo_step_kernel<3, false><<<grid, LEO_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs, h->stats);
+#define LEO_LAUNCH(J2, DIAG)                                                                                   \
+    leo_step_kernel<3, J2, DIAG><<<grid, LEO_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, \
+                                                             reason, term_obs, h->stats)
+    if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(true, true); else LEO_LAUNCH(true, false); }
+    else               { if (h->P.diag) LEO_LAUNCH(false, true); else LEO_LAUNCH(false, false); }
+#undef LEO_LAUNCH
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     return BSKENV_OK;

@@ -24,7 +24,7 @@
 #endif
 
 #ifndef LEO_UNROLL_STAGES
-#define LEO_UNROLL_STAGES 1
+#define LEO_UNROLL_STAGES 0
 #endif
 
 namespace leo {
@@ -213,24 +213,15 @@ LEO_HD SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
 template <int NRW>
 struct Dyn { V3 r, v, s, w; double W[NRW]; };
 
-template <int NRW>
-LEO_HD Dyn<NRW> axpy(const Dyn<NRW> &x, const Dyn<NRW> &k, double c)
-{ // x + c*k
-    Dyn<NRW> o;
-    o.r = x.r + k.r * c; o.v = x.v + k.v * c; o.s = x.s + k.s * c; o.w = x.w + k.w * c;
-#pragma unroll
-    for (int i = 0; i < NRW; i++) o.W[i] = x.W[i] + k.W[i] * c;
-    return o;
-}
-
 // Thruster force/torque at one RK stage (thrusterDynamicEffector::computeForceTorque without ramps).
 // Rare path (only while a desat pulse may still burn): state stays in global memory.
-LEO_HD_NOINLINE void thr_stage(const LeoParams &P, const double *S, int64_t stride, int64_t e, double tau, double dtFire,
-                               int &factor, int &active, V3 &F, V3 &L)
+struct ThrOut { V3 F, L; int factor, active; };
+LEO_HD_NOINLINE ThrOut thr_stage(const LeoParams &P, const double *S, int64_t stride, int64_t e, double tau, double dtFire, int factor)
 {
     double start = S[(int64_t)F_THRSTART * stride + e];
     double tol = t_mul(-dtFire, 10E-10);
-    F = mk(0., 0., 0.); L = mk(0., 0., 0.);
+    ThrOut o;
+    o.F = mk(0., 0., 0.); o.L = mk(0., 0., 0.);
     int any = 0;
     for (int k = 0; k < LEO_NTHR; k++) {
         double on = S[(int64_t)(F_THRON + k) * stride + e];
@@ -238,23 +229,53 @@ LEO_HD_NOINLINE void thr_stage(const LeoParams &P, const double *S, int64_t stri
         if (fire) {
             factor |= (1 << k);
             V3 f = arr(P.thr_dir[k]) * (P.thr_Fmax * 1.0);
-            F = f + F;
-            L = cross(arr(P.thr_loc[k]), f) + L;
+            o.F = f + o.F;
+            o.L = cross(arr(P.thr_loc[k]), f) + o.L;
             any = 1;
         } else {
             factor &= ~(1 << k);
         }
     }
-    active = any;   // expiry is monotone in time: once nothing fires, nothing fires until the next command
+    o.factor = factor;
+    o.active = any;   // expiry is monotone in time: once nothing fires, nothing fires until the next command
+    return o;
 }
 
-template <int NRW, bool J2>
-LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, const SunLatch &sun, double dt_sun, double rho,
-                V3 tau_u, const double (&u)[NRW], V3 L_ext, V3 F_thr)
+// MRP rotation without forming the DCM:  [BN] = I + (8 [s~]^2 - 4 (1 - s^2) [s~]) / (1 + s^2)^2
+struct MrpRot { double a8, b4; };       // 8/(1+s^2)^2 and 4(1-s^2)/(1+s^2)^2
+LEO_HD MrpRot mrp_rot(V3 s)
 {
-    // [BN] from sigma_BN
-    M3 BN = mrp_to_BN(x.s);
-    // gravity: central point mass + Sun third body with Euler-stepped Sun position (gravityEffector)
+    double s2 = dot(s, s), den = 1. + s2, inv = 1. / (den * den);
+    MrpRot m; m.a8 = 8. * inv; m.b4 = 4. * (1. - s2) * inv;
+    return m;
+}
+LEO_HD V3 rot_BN(const MrpRot &m, V3 s, V3 x)   // [BN] x   (inertial -> body)
+{
+    V3 t = cross(s, x), uu = cross(s, t);
+    return x + uu * m.a8 - t * m.b4;
+}
+LEO_HD V3 rot_NB(const MrpRot &m, V3 s, V3 x)   // [BN]^T x (body -> inertial)
+{
+    V3 t = cross(s, x), uu = cross(s, t);
+    return x + uu * m.a8 + t * m.b4;
+}
+
+// Sun "indirect" third-body term  -mu_sun * rs / |rs|^3  at Sun position rs (depends on time only)
+LEO_HD V3 sun_indirect(const LeoParams &P, V3 rs)
+{
+    double is = rsq(dot(rs, rs));
+    return rs * (-P.mu_sun * (is * is * is));
+}
+
+// One evaluation of SpacecraftPlus::equationsOfMotion for the scenario's effector set.
+//   rs     Sun position at the stage time (Euler-stepped from the latch), a_ind = sun_indirect(rs)
+//   DIAG   fast path of the reference configuration: diagonal hub inertia and three wheels along the
+//          body axes (AP:20-37) -- the same arithmetic with the structural zeros dropped
+template <int NRW, bool J2, bool DIAG>
+LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, V3 rs, V3 a_ind, double rho,
+                V3 tau_u, const double (&u)[NRW], V3 L_ext, bool thr_on, V3 F_thr)
+{
+    // gravity: central point mass (+J2) + Sun third body (gravityEffector)
     V3 g;
     {
         double ir = rsq(dot(x.r, x.r));
@@ -265,40 +286,51 @@ LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, const SunLat
             g = g + mk(kk * x.r.x * (1. - z2), kk * x.r.y * (1. - z2), kk * x.r.z * (3. - z2));
         }
         if (P.use_sun3) {
-            V3 rs = sun.r + sun.v * dt_sun;
             V3 d = x.r - rs;
-            double id = rsq(dot(d, d)), is = rsq(dot(rs, rs));
-            g = g + d * (-P.mu_sun * (id * id * id)) + rs * (-P.mu_sun * (is * is * is));
+            double id = rsq(dot(d, d));
+            g = g + d * (-P.mu_sun * (id * id * id)) + a_ind;
         }
     }
-    // facet drag with axis-aligned facets: F = -rho * S' * v_B, L = -rho * (M' x v_B)
-    V3 vB = mv(BN, x.v);
-    V3 F_B, L_B;
+    // facet drag with axis-aligned facets: F_B = -rho * S' * v_B (parallel to v_B, so [NB] F_B = -rho S' v_N),
+    // L_B = -rho * (M' x v_B)
+    MrpRot R = mrp_rot(x.s);
+    V3 vB = rot_BN(R, x.s, x.v);
+    V3 L_B;
+    double dragc;
     {
         double ax = fabs(vB.x), ay = fabs(vB.y), az = fabs(vB.z);
         int sx = vB.x > 0. ? 0 : 1, sy = vB.y > 0. ? 0 : 1, sz = vB.z > 0. ? 0 : 1;
         // a zero component selects index 1 with weight |0| = 0: no contribution, like `projectedArea > 0`
         double Sp = P.dragK[0][sx] * ax + P.dragK[1][sy] * ay + P.dragK[2][sz] * az;
         V3 Mp = arr(P.dragM[0][sx]) * ax + arr(P.dragM[1][sy]) * ay + arr(P.dragM[2][sz]) * az;
-        F_B = vB * (-rho * Sp);
+        dragc = -rho * Sp * P.inv_mass;
         L_B = cross(Mp, vB) * (-rho);
     }
-    F_B = F_B + F_thr;
+    k.v = g + x.v * dragc;
+    if (thr_on) k.v = k.v + rot_NB(R, x.s, F_thr * P.inv_mass);
+    k.r = x.v;
     // rotational EOM with balanced wheels (back-substitution, D constant):
     //   [I - sum Js g g^T] wdot = -w x (I w + sum Js W g) - sum g u + L
-    V3 h = mv9(P.I, x.w);
+    if (DIAG) {
+        V3 h = mk(P.I[0] * x.w.x + P.Js[0] * x.W[0], P.I[4] * x.w.y + P.Js[1] * x.W[1], P.I[8] * x.w.z + P.Js[2] * x.W[2]);
+        V3 rot = L_B + L_ext - tau_u - cross(x.w, h);
+        k.w = mk(rot.x * P.Dinv[0], rot.y * P.Dinv[4], rot.z * P.Dinv[8]);
+        k.W[0] = u[0] * P.invJs[0] - k.w.x;
+        k.W[1] = u[1] * P.invJs[1] - k.w.y;
+        k.W[2] = u[2] * P.invJs[2] - k.w.z;
+    } else {
+        V3 h = mv9(P.I, x.w);
 #pragma unroll
-    for (int i = 0; i < NRW; i++) h = h + arr(P.gs[i]) * (P.Js[i] * x.W[i]);
-    V3 rot = L_B + L_ext - tau_u - cross(x.w, h);
-    k.w = mv9(P.Dinv, rot);
-    k.v = mtv(BN, F_B * P.inv_mass) + g;
-    k.r = x.v;
+        for (int i = 0; i < NRW; i++) h = h + arr(P.gs[i]) * (P.Js[i] * x.W[i]);
+        V3 rot = L_B + L_ext - tau_u - cross(x.w, h);
+        k.w = mv9(P.Dinv, rot);
+#pragma unroll
+        for (int i = 0; i < NRW; i++) k.W[i] = u[i] * P.invJs[i] - dot(arr(P.gs[i]), k.w);
+    }
     { // sigma_dot = 1/4 [B(sigma)] omega
         double s2 = dot(x.s, x.s), sw = dot(x.s, x.w);
-        k.s = (x.w * (1. - s2) + cross(x.s, x.w) * 2. + x.s * (2. * sw)) * 0.25;
+        k.s = x.w * (0.25 * (1. - s2)) + cross(x.s, x.w) * 0.5 + x.s * (0.5 * sw);
     }
-#pragma unroll
-    for (int i = 0; i < NRW; i++) k.W[i] = u[i] * P.invJs[i] - dot(arr(P.gs[i]), k.w);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -456,8 +488,9 @@ LEO_HD_NOINLINE int thr_latch(const LeoParams &P, double *S, int64_t *I, int64_t
 // ------------------------------------------------------------------------------------------------
 // eclipse (conical shadow model) and solar panel, per environment tick
 // ------------------------------------------------------------------------------------------------
-LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP)
-{ // eclipse.computePercentShadow
+LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP, double l2sq, double p2, double u2)
+{ // eclipse.cpp: `if (fabs(l) < fabs(l_2) || fabs(l) < fabs(l_1))` gate, then computePercentShadow
+    if (!(sqrt(l2sq) < sqrt(u2) || sqrt(l2sq) < sqrt(p2))) return 1.0;
     double nH = norm(r_HB), nB = norm(s_BP);
     double a = clamp_asin(P.R_sun / nH), b = clamp_asin(P.R_planet / nB);
     double c = clamp_acos((-dot(s_BP, r_HB)) / (nB * nH));
@@ -476,28 +509,25 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP)
     }
     return shadow;
 }
-LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r)
-{ // planet at the origin (zeroBase earth); decisions on squared / algebraic forms, values by the reference formula
+// Shadow factor of the planet at the origin (zeroBase earth), eclipse.UpdateState + computePercentShadow.
+// Full sun / umbra are decided on squared cone radii (no sqrt, no transcendentals); a relative guard band of
+// ECL_BAND around both cone surfaces, and the penumbra itself, go through the reference formula.
+// The cone tests and the apparent-disk tests of computePercentShadow describe the same geometry (tangent
+// cones of two spheres), so outside the band both give exactly 0.0 or 1.0 (tests/test_hostcore_eclipse.py).
+#define ECL_BAND 1e-7
+LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r, double s2 /* = r.r */)
+{
     V3 r_HB = sun.r - r;
     double hb2 = dot(r_HB, r_HB);
     if (hb2 < sun.hp2) return 1.0;                    // spacecraft on the sunny side of the planet
-    double s2 = dot(r, r);
     double s0 = -dot(r, sun.r) * sun.inv_hp;
     double c1 = s0 + sun.c1off, c2 = s0 - sun.c2off;
-    double l = sqrt(s2 - s0 * s0);
+    double l2sq = s2 - s0 * s0;                       // l^2
     double l1 = c1 * sun.tan1, l2 = c2 * sun.tan2;
-    if (!(fabs(l) < fabs(l2) || fabs(l) < fabs(l1))) return 1.0;
-    // inside the penumbra cone.  Umbra test c < b - a done algebraically (cos c > cos(b - a), all angles in
-    // [0, pi/2] x [0, pi]); the transcendental formula only runs in the partial band.
-    double inH = rsq(hb2), inB = rsq(s2);
-    double sa = P.R_sun * inH, sb = P.R_planet * inB;
-    if (sa < 1. && sb < 1. && sb > sa) {
-        double ca = sqrt(1. - sa * sa), cb = sqrt(1. - sb * sb);
-        double cc = -dot(r, r_HB) * inB * inH;
-        // guard band keeps the knife edge on the exact path
-        if (cc > cb * ca + sb * sa + 1e-12) return 0.0;
-    }
-    return penumbra_fraction(P, r_HB, r);
+    double p2 = l1 * l1, u2 = l2 * l2;                // squared penumbra / umbra cone radii at this depth
+    if (l2sq > p2 * (1. + ECL_BAND) && l2sq > u2 * (1. + ECL_BAND)) return 1.0;     // outside both cones
+    if (l2sq < u2 * (1. - ECL_BAND) && c2 < 0. && P.R_sun > P.R_planet) return 0.0; // inside the umbra, before its apex
+    return penumbra_fraction(P, r_HB, r, l2sq, p2, u2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -593,7 +623,69 @@ LEO_HD void leo_reset_env(const LeoParams &P, double *S, int64_t *I, int64_t str
 // ------------------------------------------------------------------------------------------------
 struct StepOut { double ob[5]; double reward; int done; int reason; };
 
-template <int NRW, bool J2>
+// One flight-software pass at time now_ns (the priority 100/50 tasks run before DynTask at equal times).
+// nav = state written by the previous dynamics tick (zeros before tick 0: messages never written).
+template <int NRW>
+LEO_HD int fsw_pass(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e, int mask,
+                    int64_t n, int64_t now_ns, const Dyn<NRW> &x, double sun_et)
+{
+#define SD(f) S[(int64_t)(f) * stride + e]
+    V3 nr = x.r, nv = x.v, ns = x.s, nw = x.w;
+    double ws[NRW];
+#pragma unroll
+    for (int i = 0; i < NRW; i++) ws[i] = x.W[i];
+    if (n == 0) {
+        nr = nv = ns = nw = mk(0., 0., 0.);
+#pragma unroll
+        for (int i = 0; i < NRW; i++) ws[i] = 0.0;
+    }
+    AttRef ref;
+    ref.sigma_RN = mk(SD(F_REF), SD(F_REF + 1), SD(F_REF + 2));
+    ref.omega_RN_N = mk(SD(F_REF + 3), SD(F_REF + 4), SD(F_REF + 5));
+    ref.domega_RN_N = mk(SD(F_REF + 6), SD(F_REF + 7), SD(F_REF + 8));
+    if (mask & LEO_TASK_SUN) {                       // inertial3D
+        ref.sigma_RN = arr(P.sigma_R0N);
+        ref.omega_RN_N = mk(0., 0., 0.); ref.domega_RN_N = mk(0., 0., 0.);
+    }
+    if (mask & LEO_TASK_NADIR) {                     // hillPoint
+        V3 cr = mk(0., 0., 0.), cv = mk(0., 0., 0.);
+        if (P.hill_cel_pun) cr.x = sun_et;           // r_BdyZero_N aliases {J2000Current, 0, 0}
+        ref = hill_point(nr, nv, cr, cv);
+    }
+    if (mask & (LEO_TASK_SUN | LEO_TASK_NADIR)) {
+        SD(F_REF) = ref.sigma_RN.x; SD(F_REF + 1) = ref.sigma_RN.y; SD(F_REF + 2) = ref.sigma_RN.z;
+        SD(F_REF + 3) = ref.omega_RN_N.x; SD(F_REF + 4) = ref.omega_RN_N.y; SD(F_REF + 5) = ref.omega_RN_N.z;
+        SD(F_REF + 6) = ref.domega_RN_N.x; SD(F_REF + 7) = ref.domega_RN_N.y; SD(F_REF + 8) = ref.domega_RN_N.z;
+    }
+    int desat_ran = 0;
+    if (mask & LEO_TASK_DESAT) {
+        fsw_desat<NRW>(P, S, I, stride, e, now_ns, ws);
+        desat_ran = 1;
+    }
+    if (mask & LEO_TASK_MRP) {
+        // quirk Q1: MRP_Feedback runs BEFORE attTrackingError -> uses last pass's att_guidance
+        AttGuid g;
+        g.sigma_BR = mk(SD(F_GUID), SD(F_GUID + 1), SD(F_GUID + 2));
+        g.omega_BR_B = mk(SD(F_GUID + 3), SD(F_GUID + 4), SD(F_GUID + 5));
+        g.omega_RN_B = mk(SD(F_GUID + 6), SD(F_GUID + 7), SD(F_GUID + 8));
+        g.domega_RN_B = mk(SD(F_GUID + 9), SD(F_GUID + 10), SD(F_GUID + 11));
+        V3 Lr = mrp_feedback(P, g);
+        SD(F_LR) = Lr.x; SD(F_LR + 1) = Lr.y; SD(F_LR + 2) = Lr.z;
+        g = att_tracking_error(ns, nw, ref);
+        SD(F_GUID) = g.sigma_BR.x; SD(F_GUID + 1) = g.sigma_BR.y; SD(F_GUID + 2) = g.sigma_BR.z;
+        SD(F_GUID + 3) = g.omega_BR_B.x; SD(F_GUID + 4) = g.omega_BR_B.y; SD(F_GUID + 5) = g.omega_BR_B.z;
+        SD(F_GUID + 6) = g.omega_RN_B.x; SD(F_GUID + 7) = g.omega_RN_B.y; SD(F_GUID + 8) = g.omega_RN_B.z;
+        SD(F_GUID + 9) = g.domega_RN_B.x; SD(F_GUID + 10) = g.domega_RN_B.y; SD(F_GUID + 11) = g.domega_RN_B.z;
+        // rwMotorTorque: us = Umap (-Lr)
+        V3 mLr = -Lr;
+#pragma unroll
+        for (int i = 0; i < NRW; i++) SD(F_RWCMD + i) = P.Umap[i][0] * mLr.x + P.Umap[i][1] * mLr.y + P.Umap[i][2] * mLr.z;
+    }
+    return desat_ran;
+#undef SD
+}
+
+template <int NRW, bool J2, bool DIAG>
 LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
                          int action, StepOut &out)
 {
@@ -630,167 +722,149 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     for (int i = 0; i < NRW; i++) tau_u = tau_u + arr(P.gs[i]) * u[i];
 
     // the Sun message in force at the start of the interval was written at the previous decision boundary
-    const int64_t ticks_per_step = (int64_t)P.ticks_per_fsw * P.fsw_per_step;
+    const int tpf = P.ticks_per_fsw;
+    const int64_t ticks_per_step = (int64_t)tpf * P.fsw_per_step;
     int64_t n = tick + 1;                                       // next tick to execute
     const int64_t n_end = (tick < 0 ? 0 : tick) + ticks_per_step;  // inclusive (ConfigureStopTime is inclusive)
     int64_t sun_ns = (tick < 0 ? 0 : tick) * P.dyn_ns;
     SunLatch sun = sun_latch(P, sun_ns);
-    int to_fsw = (int)(n % P.ticks_per_fsw);                    // ticks until the next FSW pass (0 = now)
-    to_fsw = to_fsw == 0 ? 0 : P.ticks_per_fsw - to_fsw;
+    V3 A_prev = mk(0., 0., 0.);          // Sun indirect term at the end of the previous tick (= start of this one)
+    bool A_ok = false;
 
-    for (; n <= n_end; n++) {
-        const int64_t now_ns = n * P.dyn_ns;
+    while (n <= n_end) {
         int desat_ran = 0;
-        // ================= flight software (priority 100/50 tasks run before DynTask) =================
-        if (to_fsw == 0) {
-            to_fsw = P.ticks_per_fsw;
-            // nav messages = state written by the previous dynamics tick; never written before tick 0
-            V3 nr = x.r, nv = x.v, ns = x.s, nw = x.w;
-            double ws[NRW];
-#pragma unroll
-            for (int i = 0; i < NRW; i++) ws[i] = x.W[i];
-            if (n == 0) {
-                nr = nv = ns = nw = mk(0., 0., 0.);
-#pragma unroll
-                for (int i = 0; i < NRW; i++) ws[i] = 0.0;
-            }
-            AttRef ref;
-            ref.sigma_RN = mk(SD(F_REF), SD(F_REF + 1), SD(F_REF + 2));
-            ref.omega_RN_N = mk(SD(F_REF + 3), SD(F_REF + 4), SD(F_REF + 5));
-            ref.domega_RN_N = mk(SD(F_REF + 6), SD(F_REF + 7), SD(F_REF + 8));
-            if (mask & LEO_TASK_SUN) {                       // inertial3D
-                ref.sigma_RN = arr(P.sigma_R0N);
-                ref.omega_RN_N = mk(0., 0., 0.); ref.domega_RN_N = mk(0., 0., 0.);
-            }
-            if (mask & LEO_TASK_NADIR) {                     // hillPoint
-                V3 cr = mk(0., 0., 0.), cv = mk(0., 0., 0.);
-                if (P.hill_cel_pun) cr.x = sun.et;           // r_BdyZero_N aliases {J2000Current, 0, 0}
-                ref = hill_point(nr, nv, cr, cv);
-            }
-            if (mask & (LEO_TASK_SUN | LEO_TASK_NADIR)) {
-                SD(F_REF) = ref.sigma_RN.x; SD(F_REF + 1) = ref.sigma_RN.y; SD(F_REF + 2) = ref.sigma_RN.z;
-                SD(F_REF + 3) = ref.omega_RN_N.x; SD(F_REF + 4) = ref.omega_RN_N.y; SD(F_REF + 5) = ref.omega_RN_N.z;
-                SD(F_REF + 6) = ref.domega_RN_N.x; SD(F_REF + 7) = ref.domega_RN_N.y; SD(F_REF + 8) = ref.domega_RN_N.z;
-            }
-            if (mask & LEO_TASK_DESAT) {
-                fsw_desat<NRW>(P, S, I, stride, e, now_ns, ws);
-                desat_ran = 1;
-            }
-            if (mask & LEO_TASK_MRP) {
-                // quirk Q1: MRP_Feedback runs BEFORE attTrackingError -> uses last pass's att_guidance
-                AttGuid g;
-                g.sigma_BR = mk(SD(F_GUID), SD(F_GUID + 1), SD(F_GUID + 2));
-                g.omega_BR_B = mk(SD(F_GUID + 3), SD(F_GUID + 4), SD(F_GUID + 5));
-                g.omega_RN_B = mk(SD(F_GUID + 6), SD(F_GUID + 7), SD(F_GUID + 8));
-                g.domega_RN_B = mk(SD(F_GUID + 9), SD(F_GUID + 10), SD(F_GUID + 11));
-                V3 Lr = mrp_feedback(P, g);
-                SD(F_LR) = Lr.x; SD(F_LR + 1) = Lr.y; SD(F_LR + 2) = Lr.z;
-                g = att_tracking_error(ns, nw, ref);
-                SD(F_GUID) = g.sigma_BR.x; SD(F_GUID + 1) = g.sigma_BR.y; SD(F_GUID + 2) = g.sigma_BR.z;
-                SD(F_GUID + 3) = g.omega_BR_B.x; SD(F_GUID + 4) = g.omega_BR_B.y; SD(F_GUID + 5) = g.omega_BR_B.z;
-                SD(F_GUID + 6) = g.omega_RN_B.x; SD(F_GUID + 7) = g.omega_RN_B.y; SD(F_GUID + 8) = g.omega_RN_B.z;
-                SD(F_GUID + 9) = g.domega_RN_B.x; SD(F_GUID + 10) = g.domega_RN_B.y; SD(F_GUID + 11) = g.domega_RN_B.z;
-                // rwMotorTorque: us = Umap (-Lr)
-                V3 mLr = -Lr;
-#pragma unroll
-                for (int i = 0; i < NRW; i++) SD(F_RWCMD + i) = P.Umap[i][0] * mLr.x + P.Umap[i][1] * mLr.y + P.Umap[i][2] * mLr.z;
-            }
+        // ================= flight software every ticks_per_fsw-th tick =================
+        if (n % tpf == 0) {
+            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, mask, n, n * P.dyn_ns, x, sun.et);
             rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
             // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule)
-            if (n > 0 && n == n_end) { sun_ns = now_ns; sun = sun_latch(P, sun_ns); }
+            if (n > 0 && n == n_end) { sun_ns = n * P.dyn_ns; sun = sun_latch(P, sun_ns); A_ok = false; }
         }
-        to_fsw--;
+        int64_t m = (n / tpf + 1) * tpf - 1;                  // last tick before the next FSW pass
+        if (m > n_end) m = n_end;
 
-        // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
-        const double newTime = ns2sec(now_ns);
-        const double prevTime = n > 0 ? ns2sec(now_ns - P.dyn_ns) : 0.0;
-        const double h = t_sub(newTime, prevTime);
-        const double tBefore = t_sub(newTime, h);
-        const bool sun_newer = sun_ns > (n > 0 ? now_ns - P.dyn_ns : 0);
-        const double sun_dt0 = t_mul((double)((n > 0 ? now_ns - P.dyn_ns : 0) - sun_ns), 1e-9);
-        {
-            const double hh = 0.5 * h, h6 = h / 6.0, h3 = h / 3.0;
-            Dyn<NRW> xs = x, xo = x, k;
-            double tauPrev = 0.0;
-            if (thr_active) { // time of the previous equationsOfMotion call = last stage of the previous tick
-                if (n > 0) {
-                    const double pT = prevTime, ppT = n > 1 ? ns2sec(now_ns - 2 * P.dyn_ns) : 0.0;
-                    const double ph = t_sub(pT, ppT);
-                    tauPrev = t_add(t_sub(pT, ph), ph);
-                }
+#pragma unroll 1
+        for (; n <= m; n++) {
+            const int64_t now_ns = n * P.dyn_ns;
+            const int64_t prev_ns = n > 0 ? now_ns - P.dyn_ns : 0;
+            // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
+            const double newTime = ns2sec(now_ns);
+            const double prevTime = ns2sec(prev_ns);
+            const double h = t_sub(newTime, prevTime);
+            const double tBefore = t_sub(newTime, h);
+            const double hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
+            // Sun position is Euler-stepped from the latch: dt = (systemClock - WriteClockNanos) * 1e-9
+            double dts0, dts1, dtsm;
+            if (sun_ns > prev_ns) {
+                // quirk Q18: the Sun message is newer than the integration time; Basilisk's unsigned
+                // (systemClock - WriteClockNanos) wraps.  Replicated (last tick of every decision interval).
+                uint64_t s0 = (uint64_t)t_add((double)prev_ns, t_div(t_sub(tBefore, prevTime), 1e-9));
+                uint64_t sm = (uint64_t)t_add((double)prev_ns, t_div(t_sub(t_add(tBefore, t_mul(h, 0.5)), prevTime), 1e-9));
+                uint64_t s1 = (uint64_t)t_add((double)prev_ns, t_div(t_sub(t_add(tBefore, h), prevTime), 1e-9));
+                dts0 = t_mul((double)(s0 - (uint64_t)sun_ns), 1e-9);
+                dtsm = t_mul((double)(sm - (uint64_t)sun_ns), 1e-9);
+                dts1 = t_mul((double)(s1 - (uint64_t)sun_ns), 1e-9);
+                A_ok = false;
+            } else {
+                dts0 = t_mul((double)(prev_ns - sun_ns), 1e-9);
+                dtsm = dts0 + hh; dts1 = dts0 + h;
             }
+            // Sun indirect term: exact at both ends of the tick, mean at the two midpoint stages (|rs| changes by
+            // 1e-8 relative over a tick: the curvature left out is ~1e-16 relative)
+            V3 A0 = A_ok ? A_prev : sun_indirect(P, sun.r + sun.v * dts0);
+            V3 A1 = sun_indirect(P, sun.r + sun.v * dts1);
+            V3 Am = (A0 + A1) * 0.5;
+            // in the wrapped tick the stage clocks are not on a line (stage 4 may land exactly on the message
+            // time while stages 1-3 are 2^64 ns away): evaluate the midpoint exactly there
+            if (sun_ns > prev_ns) Am = sun_indirect(P, sun.r + sun.v * dtsm);
+            A_prev = A1; A_ok = !(sun_ns > prev_ns);
+            {
+                Dyn<NRW> xs = x, xo = x, k;
+                double tauPrev = 0.0;
+                if (thr_active) { // time of the previous equationsOfMotion call = last stage of the previous tick
+                    if (n > 0) {
+                        const double pT = prevTime, ppT = n > 1 ? ns2sec(now_ns - 2 * P.dyn_ns) : 0.0;
+                        const double ph = t_sub(pT, ppT);
+                        tauPrev = t_add(t_sub(pT, ph), ph);
+                    }
+                }
 #if LEO_UNROLL_STAGES
 #pragma unroll
 #else
 #pragma unroll 1
 #endif
-            for (int st = 0; st < 4; st++) {
-                const double coff = (st == 0) ? 0.0 : (st == 3 ? h : t_mul(h, 0.5));
-                const double tau = t_add(tBefore, coff);
-                V3 F_thr = mk(0., 0., 0.), L_tot = L_ext;
-                if (thr_active) {
-                    V3 Lt;
-                    thr_stage(P, S, stride, e, tau, t_sub(tau, tauPrev), thr_factor, thr_active, F_thr, Lt);
-                    L_tot = L_tot + Lt;
-                    tauPrev = tau;
-                }
-                double dts = sun_dt0 + coff;
-                if (sun_newer) {
-                    // quirk Q18: the Sun message is newer than the integration time; Basilisk's unsigned
-                    // (systemClock - WriteClockNanos) wraps.  Replicated bit for bit.
-                    uint64_t sys = (uint64_t)t_add((double)(now_ns - P.dyn_ns), t_div(t_sub(tau, prevTime), 1e-9));
-                    dts = t_mul((double)(sys - (uint64_t)sun_ns), 1e-9);
-                }
-                eom<NRW, J2>(P, xs, k, sun, dts, rho, tau_u, u, L_tot, F_thr);
-                const double wo = (st == 0 || st == 3) ? h6 : h3;
-                xo = axpy(xo, k, wo);
-                if (st < 3) xs = axpy(x, k, st == 2 ? h : hh);
-            }
-            x = xo;
-        }
-        // HubEffector::modifyStates -- MRP shadow-set switch
-        {
-            double s2 = dot(x.s, x.s);
-            if (sqrt(s2) > 1.) { x.s = x.s * (-1. / s2) ; nswitch++; }
-        }
-        // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
-        rho = P.rho0 * exp(-(norm(x.r) - P.Rp_atmo) * P.inv_H);
-        // reactionWheelStateEffector.UpdateState: re-latch only when the command is new or a speed limit is in play
-        {
-            int lim = 0;
+                for (int st = 0; st < 4; st++) {
+                    const double dts = (st == 0) ? dts0 : (st == 3 ? dts1 : dtsm);
+                    const V3 a_ind = (st == 0) ? A0 : (st == 3 ? A1 : Am);
+                    V3 F_thr = mk(0., 0., 0.), L_tot = L_ext;
+                    const bool thr_on = thr_active != 0;
+                    if (thr_on) {
+                        const double tau = t_add(tBefore, (st == 0) ? 0.0 : (st == 3 ? h : t_mul(h, 0.5)));
+                        ThrOut to = thr_stage(P, S, stride, e, tau, t_sub(tau, tauPrev), thr_factor);
+                        thr_factor = to.factor; thr_active = to.active;
+                        F_thr = to.F; L_tot = L_tot + to.L;
+                        tauPrev = tau;
+                    }
+                    eom<NRW, J2, DIAG>(P, xs, k, sun.r + sun.v * dts, a_ind, rho, tau_u, u, L_tot, thr_on, F_thr);
+                    const double wo = (st == 0 || st == 3) ? h6 : h3;
+                    const double cn = (st == 2) ? h : hh;
+                    xo.r = xo.r + k.r * wo; xo.v = xo.v + k.v * wo; xo.s = xo.s + k.s * wo; xo.w = xo.w + k.w * wo;
 #pragma unroll
-            for (int i = 0; i < NRW; i++) lim |= (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
-            if (rw_sat | lim) {
-                tau_u = mk(0., 0., 0.);
+                    for (int i = 0; i < NRW; i++) xo.W[i] = xo.W[i] + k.W[i] * wo;
+                    if (st < 3) {
+                        xs.r = x.r + k.r * cn; xs.v = x.v + k.v * cn; xs.s = x.s + k.s * cn; xs.w = x.w + k.w * cn;
 #pragma unroll
-                for (int i = 0; i < NRW; i++) {
-                    double uc = SD(F_RWCMD + i);
-                    if (P.u_max[i] > 0.) { if (uc > P.u_max[i]) uc = P.u_max[i]; else if (uc < -P.u_max[i]) uc = -P.u_max[i]; }
-                    if (fabs(uc) < P.u_min[i]) uc = 0.0;
-                    if (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && x.W[i] * uc >= 0.0) uc = 0.0;
-                    u[i] = uc;
-                    tau_u = tau_u + arr(P.gs[i]) * uc;
+                        for (int i = 0; i < NRW; i++) xs.W[i] = x.W[i] + k.W[i] * cn;
+                    }
                 }
-                rw_sat = lim;
+                x = xo;
             }
-        }
-        // thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters
-        if (desat_ran) thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor);
+            // HubEffector::modifyStates -- MRP shadow-set switch (|sigma| > 1)
+            {
+                double s2 = dot(x.s, x.s);
+                if (s2 > 1. && sqrt(s2) > 1.) { x.s = x.s * (-1. / s2); nswitch++; }
+            }
+            // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
+            const double r2 = dot(x.r, x.r);
+            // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
+            rho = P.rho0 * exp(-(sqrt(r2) - P.Rp_atmo) * P.inv_H);
+            // reactionWheelStateEffector.UpdateState: re-latch only when the command is new or a speed limit is in play
+            {
+                int lim = 0;
+#pragma unroll
+                for (int i = 0; i < NRW; i++) lim |= (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
+                if (rw_sat | lim) {
+                    tau_u = mk(0., 0., 0.);
+#pragma unroll
+                    for (int i = 0; i < NRW; i++) {
+                        double uc = SD(F_RWCMD + i);
+                        if (P.u_max[i] > 0.) { if (uc > P.u_max[i]) uc = P.u_max[i]; else if (uc < -P.u_max[i]) uc = -P.u_max[i]; }
+                        if (fabs(uc) < P.u_min[i]) uc = 0.0;
+                        if (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && x.W[i] * uc >= 0.0) uc = 0.0;
+                        u[i] = uc;
+                        tau_u = tau_u + arr(P.gs[i]) * uc;
+                    }
+                    rw_sat = lim;
+                }
+            }
+            // thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters
+            if (desat_ran) { thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor); desat_ran = 0; }
 
-        // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
-        shadow = eclipse_factor(P, sun, x.r);
-        {
-            V3 r_SB = sun.r - x.r;
-            double d2 = dot(r_SB, r_SB), id = rsq(d2);
-            M3 BN = mrp_to_BN(x.s);
-            V3 n_N = mtv(BN, arr(P.nHat_B));                   // panel normal in the inertial frame
-            double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
-            if (proj < 0.) proj = 0.;
-            double panel = P.panel_coef * proj * (id * id) * shadow;
-            if (n > 0) {                                       // quirk Q2: the sink message does not exist at tick 0
-                E = E + (panel + P.sink_power) * h;
-                if (E > P.capacity) E = P.capacity;
-                if (E < 0.) E = 0.;
+            // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
+            shadow = eclipse_factor(P, sun, x.r, r2);
+            {
+                V3 r_SB = sun.r - x.r;
+                double d2 = dot(r_SB, r_SB), id = rsq(d2);
+                MrpRot R = mrp_rot(x.s);
+                V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
+                double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
+                if (proj < 0.) proj = 0.;
+                double panel = P.panel_coef * proj * (id * id) * shadow;
+                if (n > 0) {                                       // quirk Q2: the sink message does not exist at tick 0
+                    E = E + (panel + P.sink_power) * h;
+                    if (E > P.capacity) E = P.capacity;
+                    if (E < 0.) E = 0.;
+                }
             }
         }
     }

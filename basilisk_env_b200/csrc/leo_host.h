@@ -77,6 +77,14 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
         for (int a = 0; a < 3; a++)
             for (int b = 0; b < 3; b++) D[3 * a + b] -= p.Js[i] * p.gs[i][a] * p.gs[i][b];
     if (!inv3(D, p.Dinv)) return "singular back-substitution matrix";
+    { // structural fast path: diagonal inertia and wheel i along body axis i
+        bool diag = p.nrw == 3;
+        for (int a = 0; a < 3 && diag; a++)
+            for (int b = 0; b < 3; b++)
+                if (a != b && (p.I[3 * a + b] != 0.0 || p.gs[a][b] != 0.0)) diag = false;
+        for (int a = 0; a < 3 && diag; a++) if (p.gs[a][a] != 1.0) diag = false;
+        p.diag = diag ? 1 : 0;
+    }
     { // rwMotorTorque map with controlAxes_B = identity (SIM:173-175): Umap = Gs^T (Gs Gs^T)^-1
         double M[9] = {0}, Mi[9];
         for (int a = 0; a < 3; a++)

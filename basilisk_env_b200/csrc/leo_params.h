@@ -24,6 +24,7 @@ struct LeoParams {
     double mu_c, mu_sun;
     double j2k;           // 1.5 * J2 * mu * Req^2 (only when the J2 template flag is on)
     int32_t use_sun3, hill_cel_pun;
+    int32_t diag, pad1;    // 1: diagonal hub inertia + three wheels along the body axes (the reference set-up): fast EOM path
     // ---- reaction wheels ----
     int32_t nrw, pad0;
     double gs[LEO_MAX_RW][3], Js[LEO_MAX_RW], invJs[LEO_MAX_RW];

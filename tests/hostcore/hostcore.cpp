@@ -14,6 +14,7 @@ struct HC {
     int64_t n;
     std::vector<double> S, ics;
     std::vector<int64_t> I;
+    int force_general = 0;
 };
 
 extern "C" {
@@ -54,7 +55,10 @@ void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t
 {
     for (int64_t e = 0; e < h->n; e++) {
         leo::StepOut o;
-        leo::leo_step_env<3, false>(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o);
+        if (h->P.diag && !h->force_general)
+            leo::leo_step_env<3, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o);
+        else
+            leo::leo_step_env<3, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o);
         for (int k = 0; k < 5; k++) obs[5 * e + k] = o.ob[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
     }
@@ -63,6 +67,17 @@ void hc_get_state(HC *h, double *S, int64_t *I)
 {
     memcpy(S, h->S.data(), h->S.size() * sizeof(double));
     memcpy(I, h->I.data(), h->I.size() * sizeof(int64_t));
+}
+void hc_force_general(HC *h, int on) { h->force_general = on; }
+// eclipse fast path (squared cone tests + guard band) for one Sun latch time and n spacecraft positions
+void hc_eclipse(HC *h, int64_t msg_ns, const double *r, int64_t n, double *out, double *sun_r)
+{
+    leo::SunLatch sun = leo::sun_latch(h->P, msg_ns);
+    for (int64_t i = 0; i < n; i++) {
+        leo::V3 p = leo::mk(r[3 * i], r[3 * i + 1], r[3 * i + 2]);
+        out[i] = leo::eclipse_factor(h->P, sun, p, leo::dot(p, p));
+    }
+    sun_r[0] = sun.r.x; sun_r[1] = sun.r.y; sun_r[2] = sun.r.z;
 }
 int hc_dims(int *nd, int *ni) { *nd = LEO_ND; *ni = LEO_NI; return 0; }
 void hc_thr_force_mapping(HC *h, const double *Lr, double *F)

@@ -39,6 +39,8 @@ def lib():
         L.hc_get_state.argtypes = [vp] * 3
         L.hc_dims.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.hc_thr_force_mapping.argtypes = [vp, vp, vp]
+        L.hc_force_general.argtypes = [vp, C.c_int]
+        L.hc_eclipse.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp]
         _LIB = L
     return _LIB
 
@@ -92,6 +94,16 @@ class HostCore:
         S = np.zeros((self.nd, self.n)); I = np.zeros((self.ni, self.n), np.int64)
         self.L.hc_get_state(self.h, S.ctypes.data, I.ctypes.data)
         return S, I
+
+    def force_general(self, on=True):
+        """Run the general (non-DIAG) EOM path even for the reference configuration."""
+        self.L.hc_force_general(self.h, int(on))
+
+    def eclipse(self, msg_ns, r):
+        r = np.ascontiguousarray(r, dtype=np.float64)
+        out = np.zeros(len(r)); sun = np.zeros(3)
+        self.L.hc_eclipse(self.h, int(msg_ns), r.ctypes.data, len(r), out.ctypes.data, sun.ctypes.data)
+        return out, sun
 
     def thr_force_mapping(self, Lr):
         Lr = np.ascontiguousarray(Lr, dtype=np.float64); F = np.zeros(8)
