@@ -55,12 +55,33 @@ LEO_HD V3 unit_or_zero(V3 v)
     double n = norm(v);
     return n > 1e-30 ? v * (1. / n) : mk(0., 0., 0.);
 }
+// Reciprocal square root / reciprocal of a finite, normal, positive operand: the MUFU seed (about 20 bits)
+// followed by one third-order correction (relative error ~2^-60 before the final rounding).  Unlike
+// rsqrt() / 1.0/x there is no special-operand test, hence no branch and no slow-path call in the hot loop.
 LEO_HD double rsq(double x)
 {
 #ifdef __CUDA_ARCH__
-    return rsqrt(x);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double t = y * y;
+    double e = fma(-x, t, 1.0);
+    double p = fma(e, 0.375, 0.5);
+    double q = y * e;
+    return fma(p, q, y);
 #else
     return 1.0 / sqrt(x);
+#endif
+}
+LEO_HD double frcp(double x)
+{
+#ifdef __CUDA_ARCH__
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    e = fma(e, e, e);
+    return fma(y, e, y);
+#else
+    return 1.0 / x;
 #endif
 }
 LEO_HD double clamp_asin(double x) { return x > 1. ? asin(1.) : (x < -1. ? asin(-1.) : asin(x)); }
@@ -172,9 +193,8 @@ struct SunLatch {
     double hp2;         // |s_HP|^2
     double inv_hp;      // 1/|s_HP|
     double c1off, c2off, tan1, tan2;   // R_p/sin f_1, R_p/sin f_2, tan f_1, tan f_2
-    double et;          // J2000Current of the message
 };
-LEO_HD SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
+LEO_HD_NOINLINE SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
 {
     const double D2R = 3.14159265358979323846 / 180.0;
     const double AUm = 149597870.693 * 1000.0;
@@ -195,7 +215,6 @@ LEO_HD SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
     SunLatch s;
     s.r = u * R;
     s.v = u * Rd + ud * R;
-    s.et = P.epoch_days * 86400.0 + t;
     s.hp2 = dot(s.r, s.r);
     double hp = sqrt(s.hp2);
     s.inv_hp = 1. / hp;
@@ -242,11 +261,11 @@ LEO_HD_NOINLINE ThrOut thr_stage(const LeoParams &P, const double *S, int64_t st
 }
 
 // MRP rotation without forming the DCM:  [BN] = I + (8 [s~]^2 - 4 (1 - s^2) [s~]) / (1 + s^2)^2
-struct MrpRot { double a8, b4; };       // 8/(1+s^2)^2 and 4(1-s^2)/(1+s^2)^2
+struct MrpRot { double a8, b4, oms2; };       // 8/(1+s^2)^2, 4(1-s^2)/(1+s^2)^2 and 1 - s^2
 LEO_HD MrpRot mrp_rot(V3 s)
 {
-    double s2 = dot(s, s), den = 1. + s2, inv = 1. / (den * den);
-    MrpRot m; m.a8 = 8. * inv; m.b4 = 4. * (1. - s2) * inv;
+    double s2 = dot(s, s), den = 1. + s2, inv = frcp(den * den);
+    MrpRot m; m.oms2 = 1. - s2; m.a8 = 8. * inv; m.b4 = 4. * m.oms2 * inv;
     return m;
 }
 LEO_HD V3 rot_BN(const MrpRot &m, V3 s, V3 x)   // [BN] x   (inertial -> body)
@@ -269,51 +288,56 @@ LEO_HD V3 sun_indirect(const LeoParams &P, V3 rs)
 
 // One evaluation of SpacecraftPlus::equationsOfMotion for the scenario's effector set.
 //   rs     Sun position at the stage time (Euler-stepped from the latch), a_ind = sun_indirect(rs)
-//   DIAG   fast path of the reference configuration: diagonal hub inertia and three wheels along the
-//          body axes (AP:20-37) -- the same arithmetic with the structural zeros dropped
+//   Lx     external body torque held over the step: extForceTorque (+ thrusters)
+//   Fm     thruster force in the body frame divided by the mass (only read when thr_on)
+//   DIAG   fast path of the reference configuration: diagonal hub inertia, three wheels along the body axes
+//          (AP:20-37) and drag facets located on their own normal axis (SIM:274-281) -- the same arithmetic
+//          with the structural zeros dropped
 template <int NRW, bool J2, bool DIAG>
 LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, V3 rs, V3 a_ind, double rho,
-                V3 tau_u, const double (&u)[NRW], V3 L_ext, bool thr_on, V3 F_thr)
+                V3 tau_u, const double (&u)[NRW], V3 Lx, bool thr_on, V3 Fm)
 {
     // gravity: central point mass (+J2) + Sun third body (gravityEffector)
     V3 g;
     {
         double ir = rsq(dot(x.r, x.r));
         double ir3 = ir * ir * ir;
-        g = x.r * (-P.mu_c * ir3);
+        V3 d = x.r - rs;
+        double id = rsq(dot(d, d));
+        g = a_ind + d * (-P.mu_sun * (id * id * id)) + x.r * (-P.mu_c * ir3);
         if (J2) {
             double ir2 = ir * ir, z2 = 5. * x.r.z * x.r.z * ir2, kk = -P.j2k * ir3 * ir2;
             g = g + mk(kk * x.r.x * (1. - z2), kk * x.r.y * (1. - z2), kk * x.r.z * (3. - z2));
         }
-        if (P.use_sun3) {
-            V3 d = x.r - rs;
-            double id = rsq(dot(d, d));
-            g = g + d * (-P.mu_sun * (id * id * id)) + a_ind;
-        }
     }
     // facet drag with axis-aligned facets: F_B = -rho * S' * v_B (parallel to v_B, so [NB] F_B = -rho S' v_N),
-    // L_B = -rho * (M' x v_B)
+    // L_B = -rho * (M' x v_B).  A facet contributes when its normal has a positive component along v_B:
+    // K(sign v) |v| = Ka |v| + Kd v with Ka/Kd the half sum / half difference of the +/- facets.
     MrpRot R = mrp_rot(x.s);
     V3 vB = rot_BN(R, x.s, x.v);
-    V3 L_B;
-    double dragc;
+    V3 Mp;
+    double Sp;
     {
         double ax = fabs(vB.x), ay = fabs(vB.y), az = fabs(vB.z);
-        int sx = vB.x > 0. ? 0 : 1, sy = vB.y > 0. ? 0 : 1, sz = vB.z > 0. ? 0 : 1;
-        // a zero component selects index 1 with weight |0| = 0: no contribution, like `projectedArea > 0`
-        double Sp = P.dragK[0][sx] * ax + P.dragK[1][sy] * ay + P.dragK[2][sz] * az;
-        V3 Mp = arr(P.dragM[0][sx]) * ax + arr(P.dragM[1][sy]) * ay + arr(P.dragM[2][sz]) * az;
-        dragc = -rho * Sp * P.inv_mass;
-        L_B = cross(Mp, vB) * (-rho);
+        Sp = P.dragKa[0] * ax + P.dragKa[1] * ay + P.dragKa[2] * az + P.dragKd[0] * vB.x + P.dragKd[1] * vB.y + P.dragKd[2] * vB.z;
+        if (DIAG) {
+            Mp = mk(P.dragMa[0][0] * ax + P.dragMd[0][0] * vB.x, P.dragMa[1][1] * ay + P.dragMd[1][1] * vB.y,
+                    P.dragMa[2][2] * az + P.dragMd[2][2] * vB.z);
+        } else {
+            Mp = arr(P.dragMa[0]) * ax + arr(P.dragMa[1]) * ay + arr(P.dragMa[2]) * az
+               + arr(P.dragMd[0]) * vB.x + arr(P.dragMd[1]) * vB.y + arr(P.dragMd[2]) * vB.z;
+        }
     }
-    k.v = g + x.v * dragc;
-    if (thr_on) k.v = k.v + rot_NB(R, x.s, F_thr * P.inv_mass);
+    const double mrho = -rho;
+    k.v = g + x.v * (mrho * Sp * P.inv_mass);
+    if (thr_on) k.v = k.v + rot_NB(R, x.s, Fm);
     k.r = x.v;
     // rotational EOM with balanced wheels (back-substitution, D constant):
     //   [I - sum Js g g^T] wdot = -w x (I w + sum Js W g) - sum g u + L
+    V3 rot = (Lx - tau_u) + cross(Mp, vB) * mrho;
     if (DIAG) {
         V3 h = mk(P.I[0] * x.w.x + P.Js[0] * x.W[0], P.I[4] * x.w.y + P.Js[1] * x.W[1], P.I[8] * x.w.z + P.Js[2] * x.W[2]);
-        V3 rot = L_B + L_ext - tau_u - cross(x.w, h);
+        rot = rot - cross(x.w, h);
         k.w = mk(rot.x * P.Dinv[0], rot.y * P.Dinv[4], rot.z * P.Dinv[8]);
         k.W[0] = u[0] * P.invJs[0] - k.w.x;
         k.W[1] = u[1] * P.invJs[1] - k.w.y;
@@ -322,14 +346,14 @@ LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, V3 rs, V3 a_
         V3 h = mv9(P.I, x.w);
 #pragma unroll
         for (int i = 0; i < NRW; i++) h = h + arr(P.gs[i]) * (P.Js[i] * x.W[i]);
-        V3 rot = L_B + L_ext - tau_u - cross(x.w, h);
+        rot = rot - cross(x.w, h);
         k.w = mv9(P.Dinv, rot);
 #pragma unroll
         for (int i = 0; i < NRW; i++) k.W[i] = u[i] * P.invJs[i] - dot(arr(P.gs[i]), k.w);
     }
     { // sigma_dot = 1/4 [B(sigma)] omega
-        double s2 = dot(x.s, x.s), sw = dot(x.s, x.w);
-        k.s = x.w * (0.25 * (1. - s2)) + cross(x.s, x.w) * 0.5 + x.s * (0.5 * sw);
+        double sw = dot(x.s, x.w);
+        k.s = x.w * (0.25 * R.oms2) + cross(x.s, x.w) * 0.5 + x.s * (0.5 * sw);
     }
 }
 
@@ -515,19 +539,20 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP, d
 // The cone tests and the apparent-disk tests of computePercentShadow describe the same geometry (tangent
 // cones of two spheres), so outside the band both give exactly 0.0 or 1.0 (tests/test_hostcore_eclipse.py).
 #define ECL_BAND 1e-7
-LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r, double s2 /* = r.r */)
+LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r, double s2 /* = r.r */, V3 r_HB /* = sun.r - r */,
+                             double hb2 /* = r_HB.r_HB */)
 {
-    V3 r_HB = sun.r - r;
-    double hb2 = dot(r_HB, r_HB);
-    if (hb2 < sun.hp2) return 1.0;                    // spacecraft on the sunny side of the planet
-    double s0 = -dot(r, sun.r) * sun.inv_hp;
-    double c1 = s0 + sun.c1off, c2 = s0 - sun.c2off;
-    double l2sq = s2 - s0 * s0;                       // l^2
-    double l1 = c1 * sun.tan1, l2 = c2 * sun.tan2;
-    double p2 = l1 * l1, u2 = l2 * l2;                // squared penumbra / umbra cone radii at this depth
-    if (l2sq > p2 * (1. + ECL_BAND) && l2sq > u2 * (1. + ECL_BAND)) return 1.0;     // outside both cones
-    if (l2sq < u2 * (1. - ECL_BAND) && c2 < 0. && P.R_sun > P.R_planet) return 0.0; // inside the umbra, before its apex
-    return penumbra_fraction(P, r_HB, r, l2sq, p2, u2);
+    const double s0 = -dot(r, sun.r) * sun.inv_hp;
+    const double c1 = s0 + sun.c1off, c2 = s0 - sun.c2off;
+    const double l2sq = s2 - s0 * s0;                       // l^2
+    const double l1 = c1 * sun.tan1, l2 = c2 * sun.tan2;
+    const double p2 = l1 * l1, u2 = l2 * l2;                // squared penumbra / umbra cone radii at this depth
+    const bool lit = (hb2 < sun.hp2)                        // spacecraft on the sunny side of the planet
+                     || (l2sq > p2 * (1. + ECL_BAND) && l2sq > u2 * (1. + ECL_BAND));       // outside both cones
+    const bool dark = l2sq < u2 * (1. - ECL_BAND) && c2 < 0. && P.R_sun > P.R_planet;      // inside the umbra, before its apex
+    double f = lit ? 1.0 : 0.0;
+    if (!lit && !dark) f = penumbra_fraction(P, r_HB, r, l2sq, p2, u2);
+    return f;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -625,9 +650,10 @@ struct StepOut { double ob[5]; double reward; int done; int reason; };
 
 // One flight-software pass at time now_ns (the priority 100/50 tasks run before DynTask at equal times).
 // nav = state written by the previous dynamics tick (zeros before tick 0: messages never written).
+// Out of line: it runs once per ticks_per_fsw dynamics ticks and must not bloat the hot tick loop.
 template <int NRW>
-LEO_HD int fsw_pass(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e, int mask,
-                    int64_t n, int64_t now_ns, const Dyn<NRW> &x, double sun_et)
+LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int mask,
+                             int64_t n, int64_t now_ns, Dyn<NRW> x, int64_t sun_ns)
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
     V3 nr = x.r, nv = x.v, ns = x.s, nw = x.w;
@@ -649,7 +675,8 @@ LEO_HD int fsw_pass(const LeoParams &P, double *__restrict__ S, int64_t *__restr
     }
     if (mask & LEO_TASK_NADIR) {                     // hillPoint
         V3 cr = mk(0., 0., 0.), cv = mk(0., 0., 0.);
-        if (P.hill_cel_pun) cr.x = sun_et;           // r_BdyZero_N aliases {J2000Current, 0, 0}
+        // r_BdyZero_N aliases {J2000Current, 0, 0} of the Sun message in force
+        if (P.hill_cel_pun) cr.x = P.epoch_days * 86400.0 + ns2sec(sun_ns);
         ref = hill_point(nr, nv, cr, cv);
     }
     if (mask & (LEO_TASK_SUN | LEO_TASK_NADIR)) {
@@ -685,6 +712,163 @@ LEO_HD int fsw_pass(const LeoParams &P, double *__restrict__ S, int64_t *__restr
 #undef SD
 }
 
+// Everything one RK4 step needs besides the parameter block.
+template <int NRW>
+struct StageIn {
+    Dyn<NRW> x;
+    double u[NRW];
+    V3 tau_u, Lx, Fm;              // wheel motor torque on the hub, held external torque, thrust / mass (body frame)
+    double rho, h;
+};
+
+// Classical RK4 over one dynamics tick.  The four stages run as ONE rolled loop whose body is a single block of
+// FP64 arithmetic small enough to stay resident in the SM sub-partition's L0 instruction cache (a fully
+// unrolled step streams ~20 KB of code per tick and the kernel becomes instruction-fetch bound: ncu
+// stall_no_instruction, profiles/).  No register copies cross the back edge: the stage input is rebuilt from
+// the tick-start state and the previous slope (xs = x + c k, with k = 0 before the first stage), and the
+// weighted slopes are summed separately and added once.
+//   Sun position at stage time: sun_r + sun_v * (dts0 + theta h); Sun indirect term: A0 + theta (A1 - A0)
+//   (theta = 0, 1/2, 1/2, 1; |r_sun| changes by 1e-8 relative over a tick: the curvature left out is ~1e-16).
+// The thrust is constant over the step here; steps in which a thruster may switch, and the step whose Sun
+// clock wraps, go through rk4_general() below.
+template <int NRW, bool J2, bool DIAG>
+LEO_HD Dyn<NRW> rk4_step(const LeoParams &P, const StageIn<NRW> &a, V3 sun_r, V3 sun_v, double dts0, V3 A0, V3 dA, bool thr_on)
+{
+    const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
+    const Dyn<NRW> &x = a.x;
+    Dyn<NRW> k, acc;
+    k.r = k.v = k.s = k.w = acc.r = acc.v = acc.s = acc.w = mk(0., 0., 0.);
+#pragma unroll
+    for (int i = 0; i < NRW; i++) k.W[i] = acc.W[i] = 0.;
+    double c = 0.;
+#pragma unroll 1
+    for (int st = 0; st < 4; st++) {
+        Dyn<NRW> xs;
+        xs.r = x.r + k.r * c; xs.v = x.v + k.v * c; xs.s = x.s + k.s * c; xs.w = x.w + k.w * c;
+#pragma unroll
+        for (int i = 0; i < NRW; i++) xs.W[i] = x.W[i] + k.W[i] * c;
+        const double theta = (st == 0) ? 0.0 : (st == 3 ? 1.0 : 0.5);
+        const double dts = dts0 + h * theta;
+        eom<NRW, J2, DIAG>(P, xs, k, sun_r + sun_v * dts, A0 + dA * theta, a.rho, a.tau_u, a.u, a.Lx, thr_on, a.Fm);
+        const double wo = (st == 0 || st == 3) ? h6 : h3;
+        acc.r = acc.r + k.r * wo; acc.v = acc.v + k.v * wo; acc.s = acc.s + k.s * wo; acc.w = acc.w + k.w * wo;
+#pragma unroll
+        for (int i = 0; i < NRW; i++) acc.W[i] = acc.W[i] + k.W[i] * wo;
+        c = (st == 2) ? h : hh;
+    }
+    Dyn<NRW> xo;
+    xo.r = x.r + acc.r; xo.v = x.v + acc.v; xo.s = x.s + acc.s; xo.w = x.w + acc.w;
+#pragma unroll
+    for (int i = 0; i < NRW; i++) xo.W[i] = x.W[i] + acc.W[i];
+    return xo;
+}
+
+// Explicit stage data of the general step
+struct SunStages { V3 sr0, srm, sr1, A0, Am, A1; };
+
+// The same RK4 step with explicit per-stage Sun data and thrusterDynamicEffector::computeForceTorque evaluated at
+// every stage time: used for the steps in which a thruster may start or stop burning (a new on-time command was
+// just latched, or a commanded burn expires within the step) and for the step whose Sun clock wraps (quirk Q18).
+// Out of line; classical accumulation order.
+template <int NRW>
+struct ThrEventOut { Dyn<NRW> x; int factor, active; };
+template <int NRW, bool J2, bool DIAG>
+LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S, int64_t stride, int64_t e, StageIn<NRW> a,
+                                             SunStages ss, V3 L_ext, double tBefore, double tauPrev, int thr_factor, int thr_active)
+{
+    const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
+    const Dyn<NRW> x = a.x;
+    Dyn<NRW> xs = x, xo = x, k;
+#pragma unroll 1
+    for (int st = 0; st < 4; st++) {
+        const V3 rs = (st == 0) ? ss.sr0 : (st == 3 ? ss.sr1 : ss.srm);
+        const V3 a_ind = (st == 0) ? ss.A0 : (st == 3 ? ss.A1 : ss.Am);
+        V3 Fm = mk(0., 0., 0.), Lx = L_ext;
+        const bool thr_on = thr_active != 0;
+        if (thr_on) {
+            const double tau = t_add(tBefore, (st == 0) ? 0.0 : (st == 3 ? h : t_mul(h, 0.5)));
+            ThrOut to = thr_stage(P, S, stride, e, tau, t_sub(tau, tauPrev), thr_factor);
+            thr_factor = to.factor; thr_active = to.active;
+            Fm = to.F * P.inv_mass; Lx = Lx + to.L;
+            tauPrev = tau;
+        }
+        eom<NRW, J2, DIAG>(P, xs, k, rs, a_ind, a.rho, a.tau_u, a.u, Lx, thr_on, Fm);
+        const double wo = (st == 0 || st == 3) ? h6 : h3;
+        const double cn = (st == 2) ? h : hh;
+        xo.r = xo.r + k.r * wo; xo.v = xo.v + k.v * wo; xo.s = xo.s + k.s * wo; xo.w = xo.w + k.w * wo;
+#pragma unroll
+        for (int i = 0; i < NRW; i++) xo.W[i] = xo.W[i] + k.W[i] * wo;
+        if (st < 3) {
+            xs.r = x.r + k.r * cn; xs.v = x.v + k.v * cn; xs.s = x.s + k.s * cn; xs.w = x.w + k.w * cn;
+#pragma unroll
+            for (int i = 0; i < NRW; i++) xs.W[i] = x.W[i] + k.W[i] * cn;
+        }
+    }
+    ThrEventOut<NRW> o;
+    o.x = xo; o.factor = thr_factor; o.active = thr_active;
+    return o;
+}
+
+// Force / torque of the thrusters that are burning (bit mask `factor`) and the earliest time at which one of
+// them stops: until then computeForceTorque returns the same sums at every stage (expiry is monotone in
+// time and the commanded on-times only change at the next command latch).
+struct ThrHold { V3 F, L; double t_next; };
+LEO_HD_NOINLINE ThrHold thr_hold(const LeoParams &P, const double *S, int64_t stride, int64_t e, int factor)
+{
+    ThrHold o;
+    o.F = mk(0., 0., 0.); o.L = mk(0., 0., 0.); o.t_next = 1e300;
+    double start = S[(int64_t)F_THRSTART * stride + e];
+    for (int k = 0; k < LEO_NTHR; k++) {
+        if (!((factor >> k) & 1)) continue;
+        V3 f = arr(P.thr_dir[k]) * (P.thr_Fmax * 1.0);
+        o.F = f + o.F;
+        o.L = cross(arr(P.thr_loc[k]), f) + o.L;
+        double t_off = t_add(S[(int64_t)(F_THRON + k) * stride + e], start);
+        if (t_off < o.t_next) o.t_next = t_off;
+    }
+    return o;
+}
+
+// Stage clocks of the step whose Sun message is newer than the integration time (quirk Q18): Basilisk's
+// unsigned (systemClock - WriteClockNanos) wraps.  Replicated (last tick of every decision interval).
+struct SunDt { double d0, dm, d1; };
+LEO_HD_NOINLINE SunDt sun_dt_wrapped(double prev_ns_d, double sun_ns_d, double tBefore, double prevTime, double h)
+{
+    SunDt o;
+    uint64_t sun_ns = (uint64_t)sun_ns_d;
+    uint64_t s0 = (uint64_t)t_add(prev_ns_d, t_div(t_sub(tBefore, prevTime), 1e-9));
+    uint64_t sm = (uint64_t)t_add(prev_ns_d, t_div(t_sub(t_add(tBefore, t_mul(h, 0.5)), prevTime), 1e-9));
+    uint64_t s1 = (uint64_t)t_add(prev_ns_d, t_div(t_sub(t_add(tBefore, h), prevTime), 1e-9));
+    o.d0 = t_mul((double)(s0 - sun_ns), 1e-9);
+    o.dm = t_mul((double)(sm - sun_ns), 1e-9);
+    o.d1 = t_mul((double)(s1 - sun_ns), 1e-9);
+    return o;
+}
+
+// reactionWheelStateEffector.UpdateState: latch the motor torque command (torque and speed saturation)
+template <int NRW>
+struct RwLatch { double u[NRW]; V3 tau_u; };
+template <int NRW>
+LEO_HD_NOINLINE RwLatch<NRW> rw_latch(const LeoParams &P, const double *S, int64_t stride, int64_t e, Dyn<NRW> x)
+{
+    RwLatch<NRW> o;
+    o.tau_u = mk(0., 0., 0.);
+#pragma unroll
+    for (int i = 0; i < NRW; i++) {
+        double uc = S[(int64_t)(F_RWCMD + i) * stride + e];
+        if (P.u_max[i] > 0.) { if (uc > P.u_max[i]) uc = P.u_max[i]; else if (uc < -P.u_max[i]) uc = -P.u_max[i]; }
+        if (fabs(uc) < P.u_min[i]) uc = 0.0;
+        if (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && x.W[i] * uc >= 0.0) uc = 0.0;
+        o.u[i] = uc;
+        o.tau_u = o.tau_u + arr(P.gs[i]) * uc;
+    }
+    return o;
+}
+
+// Margin [s] by which a burning thruster's expiry must lie beyond the end of a step for the step to take the
+// constant-thrust path (the exact test has a tolerance of 1e-9 * stage spacing around the expiry time).
+#define LEO_THR_MARGIN 1e-6
+
 template <int NRW, bool J2, bool DIAG>
 LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
                          int action, StepOut &out)
@@ -692,20 +876,21 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
     // ---------------- load ----------------
-    Dyn<NRW> x;
+    StageIn<NRW> a;
+    Dyn<NRW> &x = a.x;
     x.r = mk(SD(F_R), SD(F_R + 1), SD(F_R + 2));
     x.v = mk(SD(F_V), SD(F_V + 1), SD(F_V + 2));
     x.s = mk(SD(F_SIG), SD(F_SIG + 1), SD(F_SIG + 2));
     x.w = mk(SD(F_OMG), SD(F_OMG + 1), SD(F_OMG + 2));
-    double u[NRW];
 #pragma unroll
-    for (int i = 0; i < NRW; i++) { x.W[i] = SD(F_WHL + i); u[i] = SD(F_UCUR + i); }
-    double rho = SD(F_RHO), E = SD(F_E), shadow = SD(F_SHADOW);
+    for (int i = 0; i < NRW; i++) { x.W[i] = SD(F_WHL + i); a.u[i] = SD(F_UCUR + i); }
+    a.rho = SD(F_RHO);
+    double E = SD(F_E), shadow = SD(F_SHADOW);
     const V3 L_ext = mk(SD(F_LDIST), SD(F_LDIST + 1), SD(F_LDIST + 2));
-    int64_t tick = SI(I_TICK);
+    const int64_t tick = SI(I_TICK);
     int mask = (int)SI(I_MASK);
     int thr_factor = (int)SI(I_THRFACTOR), thr_active = (int)SI(I_THRACTIVE), rw_sat = (int)SI(I_RWSAT);
-    int64_t nswitch = SI(I_SWITCH);
+    int nswitch = 0;
 
     // ---------------- mode switch (SIM:543-588); modeRequest = str(action) ----------------
     if (action == 0) mask = LEO_TASK_NADIR | LEO_TASK_MRP;
@@ -717,158 +902,127 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         for (int k = 0; k < LEO_NTHR; k++) SD(F_THRREM + k) = 0.0;
     }
 
-    V3 tau_u = mk(0., 0., 0.);
+    a.tau_u = mk(0., 0., 0.);
 #pragma unroll
-    for (int i = 0; i < NRW; i++) tau_u = tau_u + arr(P.gs[i]) * u[i];
+    for (int i = 0; i < NRW; i++) a.tau_u = a.tau_u + arr(P.gs[i]) * a.u[i];
+    a.Lx = L_ext; a.Fm = mk(0., 0., 0.);
+    // thrusters: the burning set is re-derived by an exact step before the constant-thrust path is trusted
+    double thr_t_next = -1.0;
 
-    // the Sun message in force at the start of the interval was written at the previous decision boundary
+    // ---------------- clock: all tick times are integers below 2^53 ns, held exactly in doubles ----------------
+    const bool first = tick < 0;                               // tick 0 (t = 0, h = 0) only runs right after a reset
     const int tpf = P.ticks_per_fsw;
-    const int64_t ticks_per_step = (int64_t)tpf * P.fsw_per_step;
-    int64_t n = tick + 1;                                       // next tick to execute
-    const int64_t n_end = (tick < 0 ? 0 : tick) + ticks_per_step;  // inclusive (ConfigureStopTime is inclusive)
-    int64_t sun_ns = (tick < 0 ? 0 : tick) * P.dyn_ns;
-    SunLatch sun = sun_latch(P, sun_ns);
+    const int ticks = tpf * P.fsw_per_step;
+    const int64_t n_base = (first ? 0 : tick) + 1;             // loop index j executes tick n = n_base + j
+    const int64_t n_end = n_base - 1 + ticks;                  // inclusive (ConfigureStopTime is inclusive)
+    const double dyn_d = (double)P.dyn_ns;
+    double sun_d = (double)((n_base - 1) * P.dyn_ns);          // write time of the Sun message in force
+    SunLatch sun = sun_latch(P, (int64_t)sun_d);
     V3 A_prev = mk(0., 0., 0.);          // Sun indirect term at the end of the previous tick (= start of this one)
     bool A_ok = false;
+    int phase = (int)((n_base - 1) % tpf);                     // (n mod ticks_per_fsw) of the tick about to run
+    double now_d = (double)((n_base - 1) * P.dyn_ns);          // exact: n * dyn_ns
+    int desat_ran = 0;
 
-    while (n <= n_end) {
-        int desat_ran = 0;
+#pragma unroll 1
+    for (int j = -1; j < ticks; j++, now_d += dyn_d, phase = (phase + 1 == tpf) ? 0 : phase + 1) {
+        if (j < 0 && !first) continue;                         // keeps the lanes of a warp on the same FSW phase
         // ================= flight software every ticks_per_fsw-th tick =================
-        if (n % tpf == 0) {
-            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, mask, n, n * P.dyn_ns, x, sun.et);
+        if (phase == 0) {
+            const int64_t n = n_base + j;
+            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, mask, n, n * P.dyn_ns, x, (int64_t)sun_d);
             rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
             // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule)
-            if (n > 0 && n == n_end) { sun_ns = n * P.dyn_ns; sun = sun_latch(P, sun_ns); A_ok = false; }
+            if (n > 0 && n == n_end) { sun_d = now_d; sun = sun_latch(P, n * P.dyn_ns); A_ok = false; }
         }
-        int64_t m = (n / tpf + 1) * tpf - 1;                  // last tick before the next FSW pass
-        if (m > n_end) m = n_end;
+        // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
+        const double prev_d = j < 0 ? 0.0 : now_d - dyn_d;     // tick 0 integrates over an empty interval
+        const double newTime = t_mul(now_d, 1e-9);             // CurrentSimNanos * NANO2SEC
+        const double prevTime = t_mul(prev_d, 1e-9);
+        const double h = t_sub(newTime, prevTime);
+        const double tBefore = t_sub(newTime, h);
+        a.h = h;
+        // Sun position is Euler-stepped from the latch: dt = (systemClock - WriteClockNanos) * 1e-9
+        const bool wrapped = sun_d > prev_d;
+        double dts0 = t_mul(prev_d - sun_d, 1e-9), dtsm = dts0 + 0.5 * h, dts1 = dts0 + h;
+        if (wrapped) {
+            SunDt w = sun_dt_wrapped(prev_d, sun_d, tBefore, prevTime, h);
+            dts0 = w.d0; dtsm = w.dm; dts1 = w.d1;
+            A_ok = false;
+        }
+        // Sun indirect term: exact at both ends of the tick, linear in between
+        const V3 sr1 = sun.r + sun.v * dts1;
+        const V3 A0 = A_ok ? A_prev : sun_indirect(P, sun.r + sun.v * dts0);
+        const V3 A1 = sun_indirect(P, sr1);
+        A_prev = A1; A_ok = !wrapped;
 
-#pragma unroll 1
-        for (; n <= m; n++) {
-            const int64_t now_ns = n * P.dyn_ns;
-            const int64_t prev_ns = n > 0 ? now_ns - P.dyn_ns : 0;
-            // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
-            const double newTime = ns2sec(now_ns);
-            const double prevTime = ns2sec(prev_ns);
-            const double h = t_sub(newTime, prevTime);
-            const double tBefore = t_sub(newTime, h);
-            const double hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
-            // Sun position is Euler-stepped from the latch: dt = (systemClock - WriteClockNanos) * 1e-9
-            double dts0, dts1, dtsm;
-            if (sun_ns > prev_ns) {
-                // quirk Q18: the Sun message is newer than the integration time; Basilisk's unsigned
-                // (systemClock - WriteClockNanos) wraps.  Replicated (last tick of every decision interval).
-                uint64_t s0 = (uint64_t)t_add((double)prev_ns, t_div(t_sub(tBefore, prevTime), 1e-9));
-                uint64_t sm = (uint64_t)t_add((double)prev_ns, t_div(t_sub(t_add(tBefore, t_mul(h, 0.5)), prevTime), 1e-9));
-                uint64_t s1 = (uint64_t)t_add((double)prev_ns, t_div(t_sub(t_add(tBefore, h), prevTime), 1e-9));
-                dts0 = t_mul((double)(s0 - (uint64_t)sun_ns), 1e-9);
-                dtsm = t_mul((double)(sm - (uint64_t)sun_ns), 1e-9);
-                dts1 = t_mul((double)(s1 - (uint64_t)sun_ns), 1e-9);
-                A_ok = false;
-            } else {
-                dts0 = t_mul((double)(prev_ns - sun_ns), 1e-9);
-                dtsm = dts0 + hh; dts1 = dts0 + h;
+        if (wrapped || (thr_active && !(newTime + LEO_THR_MARGIN <= thr_t_next))) {
+            // a thruster may switch within this step (exact per-stage evaluation, then refresh the held thrust), or
+            // the stage clocks of the Sun are not on a line (stage 4 may land exactly on the message time while
+            // stages 1-3 are 2^64 ns away): every stage gets its own Sun position and indirect term
+            SunStages ss;
+            ss.sr0 = sun.r + sun.v * dts0; ss.srm = sun.r + sun.v * dtsm; ss.sr1 = sr1;
+            ss.A0 = A0; ss.A1 = A1;
+            ss.Am = wrapped ? sun_indirect(P, ss.srm) : (A0 + A1) * 0.5;
+            double tauPrev = 0.0;          // time of the previous equationsOfMotion call = last stage of the previous tick
+            if (j >= 0) {
+                const double ppT = (n_base + j > 1) ? t_mul(prev_d - dyn_d, 1e-9) : 0.0;
+                const double ph = t_sub(prevTime, ppT);
+                tauPrev = t_add(t_sub(prevTime, ph), ph);
             }
-            // Sun indirect term: exact at both ends of the tick, mean at the two midpoint stages (|rs| changes by
-            // 1e-8 relative over a tick: the curvature left out is ~1e-16 relative)
-            V3 A0 = A_ok ? A_prev : sun_indirect(P, sun.r + sun.v * dts0);
-            V3 A1 = sun_indirect(P, sun.r + sun.v * dts1);
-            V3 Am = (A0 + A1) * 0.5;
-            // in the wrapped tick the stage clocks are not on a line (stage 4 may land exactly on the message
-            // time while stages 1-3 are 2^64 ns away): evaluate the midpoint exactly there
-            if (sun_ns > prev_ns) Am = sun_indirect(P, sun.r + sun.v * dtsm);
-            A_prev = A1; A_ok = !(sun_ns > prev_ns);
-            {
-                Dyn<NRW> xs = x, xo = x, k;
-                double tauPrev = 0.0;
-                if (thr_active) { // time of the previous equationsOfMotion call = last stage of the previous tick
-                    if (n > 0) {
-                        const double pT = prevTime, ppT = n > 1 ? ns2sec(now_ns - 2 * P.dyn_ns) : 0.0;
-                        const double ph = t_sub(pT, ppT);
-                        tauPrev = t_add(t_sub(pT, ph), ph);
-                    }
-                }
-#if LEO_UNROLL_STAGES
+            ThrEventOut<NRW> o = rk4_general<NRW, J2, DIAG>(P, S, stride, e, a, ss, L_ext, tBefore, tauPrev, thr_factor, thr_active);
+            x = o.x; thr_factor = o.factor; thr_active = o.active;
+            ThrHold th = thr_hold(P, S, stride, e, thr_active ? thr_factor : 0);
+            a.Fm = th.F * P.inv_mass; a.Lx = L_ext + th.L; thr_t_next = th.t_next;
+        } else {
+            x = rk4_step<NRW, J2, DIAG>(P, a, sun.r, sun.v, dts0, A0, A1 - A0, thr_active != 0);
+        }
+        // HubEffector::modifyStates -- MRP shadow-set switch (|sigma| > 1)
+        {
+            double s2 = dot(x.s, x.s);
+            if (s2 > 1. && sqrt(s2) > 1.) { x.s = x.s * (-1. / s2); nswitch++; }
+        }
+        // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
+        const double r2 = dot(x.r, x.r);
+        // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
+        a.rho = P.rho0 * exp(-(r2 * rsq(r2) - P.Rp_atmo) * P.inv_H);
+        // reactionWheelStateEffector.UpdateState: re-latch only when the command is new or a speed limit is in play
+        {
+            int lim = 0;
 #pragma unroll
-#else
-#pragma unroll 1
-#endif
-                for (int st = 0; st < 4; st++) {
-                    const double dts = (st == 0) ? dts0 : (st == 3 ? dts1 : dtsm);
-                    const V3 a_ind = (st == 0) ? A0 : (st == 3 ? A1 : Am);
-                    V3 F_thr = mk(0., 0., 0.), L_tot = L_ext;
-                    const bool thr_on = thr_active != 0;
-                    if (thr_on) {
-                        const double tau = t_add(tBefore, (st == 0) ? 0.0 : (st == 3 ? h : t_mul(h, 0.5)));
-                        ThrOut to = thr_stage(P, S, stride, e, tau, t_sub(tau, tauPrev), thr_factor);
-                        thr_factor = to.factor; thr_active = to.active;
-                        F_thr = to.F; L_tot = L_tot + to.L;
-                        tauPrev = tau;
-                    }
-                    eom<NRW, J2, DIAG>(P, xs, k, sun.r + sun.v * dts, a_ind, rho, tau_u, u, L_tot, thr_on, F_thr);
-                    const double wo = (st == 0 || st == 3) ? h6 : h3;
-                    const double cn = (st == 2) ? h : hh;
-                    xo.r = xo.r + k.r * wo; xo.v = xo.v + k.v * wo; xo.s = xo.s + k.s * wo; xo.w = xo.w + k.w * wo;
+            for (int i = 0; i < NRW; i++) lim |= (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
+            if (rw_sat | lim) {
+                RwLatch<NRW> l = rw_latch<NRW>(P, S, stride, e, x);
 #pragma unroll
-                    for (int i = 0; i < NRW; i++) xo.W[i] = xo.W[i] + k.W[i] * wo;
-                    if (st < 3) {
-                        xs.r = x.r + k.r * cn; xs.v = x.v + k.v * cn; xs.s = x.s + k.s * cn; xs.w = x.w + k.w * cn;
-#pragma unroll
-                        for (int i = 0; i < NRW; i++) xs.W[i] = x.W[i] + k.W[i] * cn;
-                    }
-                }
-                x = xo;
+                for (int i = 0; i < NRW; i++) a.u[i] = l.u[i];
+                a.tau_u = l.tau_u;
+                rw_sat = lim;
             }
-            // HubEffector::modifyStates -- MRP shadow-set switch (|sigma| > 1)
-            {
-                double s2 = dot(x.s, x.s);
-                if (s2 > 1. && sqrt(s2) > 1.) { x.s = x.s * (-1. / s2); nswitch++; }
-            }
-            // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
-            const double r2 = dot(x.r, x.r);
-            // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
-            rho = P.rho0 * exp(-(sqrt(r2) - P.Rp_atmo) * P.inv_H);
-            // reactionWheelStateEffector.UpdateState: re-latch only when the command is new or a speed limit is in play
-            {
-                int lim = 0;
-#pragma unroll
-                for (int i = 0; i < NRW; i++) lim |= (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
-                if (rw_sat | lim) {
-                    tau_u = mk(0., 0., 0.);
-#pragma unroll
-                    for (int i = 0; i < NRW; i++) {
-                        double uc = SD(F_RWCMD + i);
-                        if (P.u_max[i] > 0.) { if (uc > P.u_max[i]) uc = P.u_max[i]; else if (uc < -P.u_max[i]) uc = -P.u_max[i]; }
-                        if (fabs(uc) < P.u_min[i]) uc = 0.0;
-                        if (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && x.W[i] * uc >= 0.0) uc = 0.0;
-                        u[i] = uc;
-                        tau_u = tau_u + arr(P.gs[i]) * uc;
-                    }
-                    rw_sat = lim;
-                }
-            }
-            // thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters
-            if (desat_ran) { thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor); desat_ran = 0; }
+        }
+        // thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters
+        if (desat_ran) {
+            thr_active = thr_latch(P, S, I, stride, e, (int64_t)now_d, thr_factor);
+            thr_t_next = -1.0;             // the burning set must be re-derived by an exact step
+            desat_ran = 0;
+        }
 
-            // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
-            shadow = eclipse_factor(P, sun, x.r, r2);
-            {
-                V3 r_SB = sun.r - x.r;
-                double d2 = dot(r_SB, r_SB), id = rsq(d2);
-                MrpRot R = mrp_rot(x.s);
-                V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
-                double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
-                if (proj < 0.) proj = 0.;
-                double panel = P.panel_coef * proj * (id * id) * shadow;
-                if (n > 0) {                                       // quirk Q2: the sink message does not exist at tick 0
-                    E = E + (panel + P.sink_power) * h;
-                    if (E > P.capacity) E = P.capacity;
-                    if (E < 0.) E = 0.;
-                }
+        // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
+        {
+            const V3 r_SB = sun.r - x.r;                       // spacecraft -> Sun
+            const double d2 = dot(r_SB, r_SB), id = rsq(d2);
+            shadow = eclipse_factor(P, sun, x.r, r2, r_SB, d2);
+            MrpRot R = mrp_rot(x.s);
+            V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
+            double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
+            if (proj < 0.) proj = 0.;
+            double panel = P.panel_coef * proj * (id * id) * shadow;
+            if (j >= 0) {                                      // quirk Q2: the sink message does not exist at tick 0
+                E = E + (panel + P.sink_power) * h;
+                if (E > P.capacity) E = P.capacity;
+                if (E < 0.) E = 0.;
             }
         }
     }
-    tick = n_end;
 
     // ---------------- observation sampling (SIM:598-642) + gym bookkeeping (ENV:98-145) ----------------
     double ob0 = norm(mk(SD(F_GUID), SD(F_GUID + 1), SD(F_GUID + 2)));
@@ -899,9 +1053,9 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     SD(F_SIG) = x.s.x; SD(F_SIG + 1) = x.s.y; SD(F_SIG + 2) = x.s.z;
     SD(F_OMG) = x.w.x; SD(F_OMG + 1) = x.w.y; SD(F_OMG + 2) = x.w.z;
 #pragma unroll
-    for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = x.W[i]; SD(F_UCUR + i) = u[i]; }
-    SD(F_RHO) = rho; SD(F_E) = E; SD(F_SHADOW) = shadow; SD(F_EPRET) = ret;
-    SI(I_TICK) = tick; SI(I_STEP) = curr_step + 1; SI(I_MASK) = mask; SI(I_SWITCH) = nswitch;
+    for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = x.W[i]; SD(F_UCUR + i) = a.u[i]; }
+    SD(F_RHO) = a.rho; SD(F_E) = E; SD(F_SHADOW) = shadow; SD(F_EPRET) = ret;
+    SI(I_TICK) = n_end; SI(I_STEP) = curr_step + 1; SI(I_MASK) = mask; SI(I_SWITCH) = SI(I_SWITCH) + nswitch;
     SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_OVER) = over; SI(I_RWSAT) = rw_sat;
 #undef SD
 #undef SI

@@ -61,7 +61,6 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
     memcpy(p.I_fsw, p.I, sizeof(p.I));                           // same inertia in FSW (SIM:392-403)
     // gravity (SIM:227-232): Earth central + Sun third body; NO J2 in the reference
     p.mu_c = 0.3986004415e15; p.mu_sun = 1.32712440018e20;       // [BSK: simIncludeGravBody]
-    p.use_sun3 = 1;
     p.j2k = 1.5 * 1.08262668355e-3 * p.mu_c * (6378136.6 * 6378136.6);
     p.hill_cel_pun = c.hill_cel_pun;
     // three orthogonal Honeywell HR16 at 50 Nms (AP:20-37, [BSK: simIncludeRW.Honeywell_HR16])
@@ -100,10 +99,18 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
         const int axis[8] = {0, 0, 1, 1, 2, 2, 1, 1}, sign[8] = {0, 1, 0, 1, 0, 1, 0, 1};   // 0:+ 1:-
         const double Lc[8][3] = {{0.05, 0, 0}, {0.05, 0, 0}, {0, 0.15, 0}, {0, -0.15, 0}, {0, 0, 0.1}, {0, 0, -0.1}, {0, 2., 0}, {0, 2., 0}};
         const double Cd = 2.2;
+        double K[3][2] = {{0}}, M[3][2][3] = {{{0}}};
         for (int f = 0; f < 8; f++) {
             double k = 0.5 * Cd * A[f];
-            p.dragK[axis[f]][sign[f]] += k;
-            for (int j = 0; j < 3; j++) p.dragM[axis[f]][sign[f]][j] += k * Lc[f][j];
+            K[axis[f]][sign[f]] += k;
+            for (int j = 0; j < 3; j++) M[axis[f]][sign[f]][j] += k * Lc[f][j];
+        }
+        for (int ax = 0; ax < 3; ax++) {
+            p.dragKa[ax] = 0.5 * (K[ax][0] + K[ax][1]); p.dragKd[ax] = 0.5 * (K[ax][0] - K[ax][1]);
+            for (int j = 0; j < 3; j++) {
+                p.dragMa[ax][j] = 0.5 * (M[ax][0][j] + M[ax][1][j]); p.dragMd[ax][j] = 0.5 * (M[ax][0][j] - M[ax][1][j]);
+                if (ax != j && (p.dragMa[ax][j] != 0.0 || p.dragMd[ax][j] != 0.0)) p.diag = 0;
+            }
         }
     }
     p.dist_mag = c.disturbance_magnitude;

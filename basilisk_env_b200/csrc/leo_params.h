@@ -23,16 +23,20 @@ struct LeoParams {
     // ---- gravity ----
     double mu_c, mu_sun;
     double j2k;           // 1.5 * J2 * mu * Req^2 (only when the J2 template flag is on)
-    int32_t use_sun3, hill_cel_pun;
-    int32_t diag, pad1;    // 1: diagonal hub inertia + three wheels along the body axes (the reference set-up): fast EOM path
+    int32_t pad2, hill_cel_pun;
+    int32_t diag, pad1;    // 1: diagonal hub inertia, three wheels along the body axes, drag facets on their normal axis
+                           //    (the reference set-up): fast EOM path
     // ---- reaction wheels ----
     int32_t nrw, pad0;
     double gs[LEO_MAX_RW][3], Js[LEO_MAX_RW], invJs[LEO_MAX_RW];
     double u_max[LEO_MAX_RW], u_min[LEO_MAX_RW], Om_max[LEO_MAX_RW];
     double Umap[LEO_MAX_RW][3];   // rwMotorTorque: us = Umap * (-Lr) = CGs^T (CGs CGs^T)^-1 C (-Lr)
     // ---- facet drag, facets with axis-aligned normals collapsed per axis and sign ----
-    double dragK[3][2];           // sum of 0.5*Cd*A over facets with normal (+/-) e_axis
-    double dragM[3][2][3];        // sum of 0.5*Cd*A*r_facet over the same facets
+    // K(+/-) = sum of 0.5*Cd*A over the facets with normal (+/-) e_axis, M(+/-) = sum of 0.5*Cd*A*r_facet over the
+    // same facets; a facet acts when v_B has a positive component along its normal, so the selected sums times
+    // |v_axis| are  Ka |v| + Kd v  with  Ka = (K+ + K-)/2,  Kd = (K+ - K-)/2  (no table look-up, no branch)
+    double dragKa[3], dragKd[3];
+    double dragMa[3][3], dragMd[3][3];   // [axis][component]
     double dist_mag;              // disturbance_magnitude (2e-4)
     // ---- exponential atmosphere ----
     double rho0, inv_H, Rp_atmo;

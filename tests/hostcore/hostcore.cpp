@@ -75,7 +75,8 @@ void hc_eclipse(HC *h, int64_t msg_ns, const double *r, int64_t n, double *out, 
     leo::SunLatch sun = leo::sun_latch(h->P, msg_ns);
     for (int64_t i = 0; i < n; i++) {
         leo::V3 p = leo::mk(r[3 * i], r[3 * i + 1], r[3 * i + 2]);
-        out[i] = leo::eclipse_factor(h->P, sun, p, leo::dot(p, p));
+        leo::V3 hb = sun.r - p;
+        out[i] = leo::eclipse_factor(h->P, sun, p, leo::dot(p, p), hb, leo::dot(hb, hb));
     }
     sun_r[0] = sun.r.x; sun_r[1] = sun.r.y; sun_r[2] = sun.r.z;
 }
