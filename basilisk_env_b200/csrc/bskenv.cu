@@ -20,12 +20,10 @@
 #include "leo_core.cuh"
 #include "leo_host.h"
 
-#ifndef LEO_BLOCK
-#define LEO_BLOCK 128
-#endif
 #ifndef LEO_MIN_BLOCKS
 #define LEO_MIN_BLOCKS 1
 #endif
+#define LEO_BUS_BYTES ((size_t)leo::LEO_NM * LEO_BLOCK * sizeof(double))   // shared-memory message bus of one block
 
 namespace {
 
@@ -45,13 +43,17 @@ leo_step_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int
                 double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
                 double *__restrict__ term_obs, double *__restrict__ stats)
 {
+    extern __shared__ double bus_smem[];          // [LEO_NM][LEO_BLOCK]: per-thread message bus (leo_core.cuh: MBus)
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = e < n;
     leo::StepOut o;
     o.done = 0; o.reason = 0; o.reward = 0.;
     double ep_ret = 0., ep_len = 0.;
     if (valid) {
-        leo::leo_step_env<NRW, J2, DIAG>(P, S, I, stride, e, actions[e], o);
+        leo::MBus bus;
+        bus.p = nullptr;
+        bus.a = (uint32_t)__cvta_generic_to_shared(bus_smem) + threadIdx.x * (uint32_t)sizeof(double);
+        leo::leo_step_env<NRW, J2, DIAG>(P, S, I, stride, e, bus, actions[e], o);
         reward[e] = o.reward;
         done[e] = (uint8_t)o.done;
         reason[e] = (uint8_t)o.reason;
@@ -184,8 +186,15 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
 {
     const int grid = (int)((h->n + LEO_BLOCK - 1) / LEO_BLOCK);
 #define LEO_LAUNCH(J2, DIAG)                                                                                   \
-    leo_step_kernel<3, J2, DIAG><<<grid, LEO_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, \
-                                                             reason, term_obs, h->stats)
+    do {                                                                                                       \
+        static bool attr_set[64] = {false};      /* opt in to > 48 KB of dynamic shared memory once per device */  \
+        if (!attr_set[h->device & 63]) {                                                                       \
+            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<3, J2, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEO_BUS_BYTES)); \
+            attr_set[h->device & 63] = true;                                                                   \
+        }                                                                                                      \
+        leo_step_kernel<3, J2, DIAG><<<grid, LEO_BLOCK, LEO_BUS_BYTES, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
+                                                                              rew, done, reason, term_obs, h->stats); \
+    } while (0)
     if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(true, true); else LEO_LAUNCH(true, false); }
     else               { if (h->P.diag) LEO_LAUNCH(false, true); else LEO_LAUNCH(false, false); }
 #undef LEO_LAUNCH

@@ -136,40 +136,38 @@ LEO_HD M3 mrp_to_BN(V3 q)
     return C;
 }
 LEO_HD V3 dcm_to_mrp(const M3 &C)
-{ // C2MRP via Sheppard's method (C2EP) with the non-negative scalar part
+{ // C2MRP via Sheppard's method (C2EP) with the non-negative scalar part.  The largest of the four squared
+  // Euler parameters is >= 1/4, so its reciprocal square root needs no guard.
     double tr = C.a.x + C.b.y + C.c.z;
-    double b2_0 = (1. + tr) / 4., b2_1 = (1. + 2. * C.a.x - tr) / 4., b2_2 = (1. + 2. * C.b.y - tr) / 4., b2_3 = (1. + 2. * C.c.z - tr) / 4.;
+    double b2_0 = (1. + tr) * 0.25, b2_1 = (1. + 2. * C.a.x - tr) * 0.25, b2_2 = (1. + 2. * C.b.y - tr) * 0.25, b2_3 = (1. + 2. * C.c.z - tr) * 0.25;
     int i = 0;
     double mx = b2_0;
     if (b2_1 > mx) { i = 1; mx = b2_1; }
     if (b2_2 > mx) { i = 2; mx = b2_2; }
     if (b2_3 > mx) { i = 3; mx = b2_3; }
+    const double irt = rsq(mx), rt = mx * irt, q = 0.25 * irt;     // sqrt(mx), 1 / (4 sqrt(mx))
     double b0, b1, b2, b3;
     if (i == 0) {
-        b0 = sqrt(b2_0);
-        b1 = (C.b.z - C.c.y) / 4. / b0; b2 = (C.c.x - C.a.z) / 4. / b0; b3 = (C.a.y - C.b.x) / 4. / b0;
+        b0 = rt;
+        b1 = (C.b.z - C.c.y) * q; b2 = (C.c.x - C.a.z) * q; b3 = (C.a.y - C.b.x) * q;
     } else if (i == 1) {
-        b1 = sqrt(b2_1);
-        b0 = (C.b.z - C.c.y) / 4. / b1;
-        if (b0 < 0.) { b1 = -b1; b0 = -b0; }
-        b2 = (C.a.y + C.b.x) / 4. / b1; b3 = (C.c.x + C.a.z) / 4. / b1;
+        b1 = rt; b0 = (C.b.z - C.c.y) * q; b2 = (C.a.y + C.b.x) * q; b3 = (C.c.x + C.a.z) * q;
     } else if (i == 2) {
-        b2 = sqrt(b2_2);
-        b0 = (C.c.x - C.a.z) / 4. / b2;
-        if (b0 < 0.) { b2 = -b2; b0 = -b0; }
-        b1 = (C.a.y + C.b.x) / 4. / b2; b3 = (C.b.z + C.c.y) / 4. / b2;
+        b2 = rt; b0 = (C.c.x - C.a.z) * q; b1 = (C.a.y + C.b.x) * q; b3 = (C.b.z + C.c.y) * q;
     } else {
-        b3 = sqrt(b2_3);
-        b0 = (C.a.y - C.b.x) / 4. / b3;
-        if (b0 < 0.) { b3 = -b3; b0 = -b0; }
-        b1 = (C.c.x + C.a.z) / 4. / b3; b2 = (C.b.z + C.c.y) / 4. / b3;
+        b3 = rt; b0 = (C.a.y - C.b.x) * q; b1 = (C.c.x + C.a.z) * q; b2 = (C.b.z + C.c.y) * q;
     }
-    return mk(b1 / (1. + b0), b2 / (1. + b0), b3 / (1. + b0));
+    // a negative scalar part flips the pivot before the other two components are divided by it (C2EP):
+    // the whole Euler-parameter set changes sign
+    if (i != 0 && b0 < 0.) { b0 = -b0; b1 = -b1; b2 = -b2; b3 = -b3; }
+    const double inv = frcp(1. + b0);
+    return mk(b1 * inv, b2 * inv, b3 * inv);
 }
 LEO_HD V3 mrp_inner(V3 q)
 {
     double m = dot(q, q);
-    return m > 1.0 ? q * (-1. / m) : q;
+    double f = -frcp(m);                    // discarded (possibly non-finite) when m <= 1
+    return m > 1.0 ? q * f : q;
 }
 LEO_HD V3 mrp_sub(V3 q1, V3 q2)
 { // sigma(q1 relative to q2) with the shadow-set guard near the singular denominator, mapped to |s|<=1
@@ -181,7 +179,7 @@ LEO_HD V3 mrp_sub(V3 q1, V3 q2)
     }
     V3 v1 = cross(s1, q2) * 2.;
     V3 res = s1 * (1. - dot(q2, q2)) - q2 * (1. - dot(s1, s1)) + v1;
-    return mrp_inner(res * (1. / det));
+    return mrp_inner(res * frcp(det));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -286,77 +284,6 @@ LEO_HD V3 sun_indirect(const LeoParams &P, V3 rs)
     return rs * (-P.mu_sun * (is * is * is));
 }
 
-// One evaluation of SpacecraftPlus::equationsOfMotion for the scenario's effector set.
-//   rs     Sun position at the stage time (Euler-stepped from the latch), a_ind = sun_indirect(rs)
-//   Lx     external body torque held over the step: extForceTorque (+ thrusters)
-//   Fm     thruster force in the body frame divided by the mass (only read when thr_on)
-//   DIAG   fast path of the reference configuration: diagonal hub inertia, three wheels along the body axes
-//          (AP:20-37) and drag facets located on their own normal axis (SIM:274-281) -- the same arithmetic
-//          with the structural zeros dropped
-template <int NRW, bool J2, bool DIAG>
-LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, V3 rs, V3 a_ind, double rho,
-                V3 tau_u, const double (&u)[NRW], V3 Lx, bool thr_on, V3 Fm)
-{
-    // gravity: central point mass (+J2) + Sun third body (gravityEffector)
-    V3 g;
-    {
-        double ir = rsq(dot(x.r, x.r));
-        double ir3 = ir * ir * ir;
-        V3 d = x.r - rs;
-        double id = rsq(dot(d, d));
-        g = a_ind + d * (-P.mu_sun * (id * id * id)) + x.r * (-P.mu_c * ir3);
-        if (J2) {
-            double ir2 = ir * ir, z2 = 5. * x.r.z * x.r.z * ir2, kk = -P.j2k * ir3 * ir2;
-            g = g + mk(kk * x.r.x * (1. - z2), kk * x.r.y * (1. - z2), kk * x.r.z * (3. - z2));
-        }
-    }
-    // facet drag with axis-aligned facets: F_B = -rho * S' * v_B (parallel to v_B, so [NB] F_B = -rho S' v_N),
-    // L_B = -rho * (M' x v_B).  A facet contributes when its normal has a positive component along v_B:
-    // K(sign v) |v| = Ka |v| + Kd v with Ka/Kd the half sum / half difference of the +/- facets.
-    MrpRot R = mrp_rot(x.s);
-    V3 vB = rot_BN(R, x.s, x.v);
-    V3 Mp;
-    double Sp;
-    {
-        double ax = fabs(vB.x), ay = fabs(vB.y), az = fabs(vB.z);
-        Sp = P.dragKa[0] * ax + P.dragKa[1] * ay + P.dragKa[2] * az + P.dragKd[0] * vB.x + P.dragKd[1] * vB.y + P.dragKd[2] * vB.z;
-        if (DIAG) {
-            Mp = mk(P.dragMa[0][0] * ax + P.dragMd[0][0] * vB.x, P.dragMa[1][1] * ay + P.dragMd[1][1] * vB.y,
-                    P.dragMa[2][2] * az + P.dragMd[2][2] * vB.z);
-        } else {
-            Mp = arr(P.dragMa[0]) * ax + arr(P.dragMa[1]) * ay + arr(P.dragMa[2]) * az
-               + arr(P.dragMd[0]) * vB.x + arr(P.dragMd[1]) * vB.y + arr(P.dragMd[2]) * vB.z;
-        }
-    }
-    const double mrho = -rho;
-    k.v = g + x.v * (mrho * Sp * P.inv_mass);
-    if (thr_on) k.v = k.v + rot_NB(R, x.s, Fm);
-    k.r = x.v;
-    // rotational EOM with balanced wheels (back-substitution, D constant):
-    //   [I - sum Js g g^T] wdot = -w x (I w + sum Js W g) - sum g u + L
-    V3 rot = (Lx - tau_u) + cross(Mp, vB) * mrho;
-    if (DIAG) {
-        V3 h = mk(P.I[0] * x.w.x + P.Js[0] * x.W[0], P.I[4] * x.w.y + P.Js[1] * x.W[1], P.I[8] * x.w.z + P.Js[2] * x.W[2]);
-        rot = rot - cross(x.w, h);
-        k.w = mk(rot.x * P.Dinv[0], rot.y * P.Dinv[4], rot.z * P.Dinv[8]);
-        k.W[0] = u[0] * P.invJs[0] - k.w.x;
-        k.W[1] = u[1] * P.invJs[1] - k.w.y;
-        k.W[2] = u[2] * P.invJs[2] - k.w.z;
-    } else {
-        V3 h = mv9(P.I, x.w);
-#pragma unroll
-        for (int i = 0; i < NRW; i++) h = h + arr(P.gs[i]) * (P.Js[i] * x.W[i]);
-        rot = rot - cross(x.w, h);
-        k.w = mv9(P.Dinv, rot);
-#pragma unroll
-        for (int i = 0; i < NRW; i++) k.W[i] = u[i] * P.invJs[i] - dot(arr(P.gs[i]), k.w);
-    }
-    { // sigma_dot = 1/4 [B(sigma)] omega
-        double sw = dot(x.s, x.w);
-        k.s = x.w * (0.25 * R.oms2) + cross(x.s, x.w) * 0.5 + x.s * (0.5 * sw);
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // flight software, one pass per fswRate
 // ------------------------------------------------------------------------------------------------
@@ -364,22 +291,28 @@ struct AttRef { V3 sigma_RN, omega_RN_N, domega_RN_N; };
 struct AttGuid { V3 sigma_BR, omega_BR_B, omega_RN_B, domega_RN_B; };
 
 LEO_HD AttRef hill_point(V3 r, V3 v, V3 cel_r, V3 cel_v)
-{ // hillPoint.computeHillPointingReference
+{ // hillPoint.computeHillPointingReference (v3Normalize: zero vector below a norm of 1e-30)
     V3 rel_r = r - cel_r, rel_v = v - cel_v;
-    M3 RN;
-    RN.a = unit_or_zero(rel_r);
+    const double r2 = dot(rel_r, rel_r);
+    double ir = rsq(r2);
+    ir = r2 > 1e-60 ? ir : 0.0;
     V3 h = cross(rel_r, rel_v);
-    RN.c = unit_or_zero(h);
+    const double h2 = dot(h, h);
+    double ih = rsq(h2);
+    ih = h2 > 1e-60 ? ih : 0.0;
+    M3 RN;
+    RN.a = rel_r * ir;
+    RN.c = h * ih;
     RN.b = cross(RN.c, RN.a);
     AttRef o;
     o.sigma_RN = dcm_to_mrp(RN);
-    double rm = norm(rel_r), hm = norm(h), dfdt = 0., ddfdt2 = 0.;
+    double rm = r2 * ir, hm = h2 * ih, dfdt = 0., ddfdt2 = 0.;
     if (rm > 1.) {
-        dfdt = hm / (rm * rm);
-        ddfdt2 = -2.0 * dot(rel_v, RN.a) / rm * dfdt;
+        dfdt = hm * ir * ir;
+        ddfdt2 = -2.0 * dot(rel_v, RN.a) * ir * dfdt;
     }
-    o.omega_RN_N = mtv(RN, mk(0., 0., dfdt));
-    o.domega_RN_N = mtv(RN, mk(0., 0., ddfdt2));
+    o.omega_RN_N = RN.c * dfdt;            // [RN]^T (0, 0, dfdt)
+    o.domega_RN_N = RN.c * ddfdt2;
     return o;
 }
 LEO_HD AttGuid att_tracking_error(V3 sigma_BN, V3 omega_BN_B, const AttRef &ref)
@@ -387,10 +320,10 @@ LEO_HD AttGuid att_tracking_error(V3 sigma_BN, V3 omega_BN_B, const AttRef &ref)
     AttGuid g;
     V3 sigma_RN = mrp_inner(ref.sigma_RN);
     g.sigma_BR = mrp_sub(sigma_BN, sigma_RN);
-    M3 BN = mrp_to_BN(sigma_BN);
-    g.omega_RN_B = mv(BN, ref.omega_RN_N);
+    MrpRot BN = mrp_rot(sigma_BN);
+    g.omega_RN_B = rot_BN(BN, sigma_BN, ref.omega_RN_N);
     g.omega_BR_B = omega_BN_B - g.omega_RN_B;
-    g.domega_RN_B = mv(BN, ref.domega_RN_N);
+    g.domega_RN_B = rot_BN(BN, sigma_BN, ref.domega_RN_N);
     return g;
 }
 LEO_HD V3 mrp_feedback(const LeoParams &P, const AttGuid &g)
@@ -539,20 +472,26 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP, d
 // The cone tests and the apparent-disk tests of computePercentShadow describe the same geometry (tangent
 // cones of two spheres), so outside the band both give exactly 0.0 or 1.0 (tests/test_hostcore_eclipse.py).
 #define ECL_BAND 1e-7
-LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r, double s2 /* = r.r */, V3 r_HB /* = sun.r - r */,
-                             double hb2 /* = r_HB.r_HB */)
+LEO_HD double eclipse_core(const LeoParams &P, const double (&ec)[6], V3 sun_r, V3 r, double s2 /* = r.r */,
+                           V3 r_HB /* = sun_r - r */, double hb2 /* = r_HB.r_HB */)
 {
-    const double s0 = -dot(r, sun.r) * sun.inv_hp;
-    const double c1 = s0 + sun.c1off, c2 = s0 - sun.c2off;
+    const double hp2 = ec[0], inv_hp = ec[1], c1off = ec[2], c2off = ec[3], tan1 = ec[4], tan2 = ec[5];
+    const double s0 = -dot(r, sun_r) * inv_hp;
+    const double c1 = s0 + c1off, c2 = s0 - c2off;
     const double l2sq = s2 - s0 * s0;                       // l^2
-    const double l1 = c1 * sun.tan1, l2 = c2 * sun.tan2;
+    const double l1 = c1 * tan1, l2 = c2 * tan2;
     const double p2 = l1 * l1, u2 = l2 * l2;                // squared penumbra / umbra cone radii at this depth
-    const bool lit = (hb2 < sun.hp2)                        // spacecraft on the sunny side of the planet
+    const bool lit = (hb2 < hp2)                            // spacecraft on the sunny side of the planet
                      || (l2sq > p2 * (1. + ECL_BAND) && l2sq > u2 * (1. + ECL_BAND));       // outside both cones
     const bool dark = l2sq < u2 * (1. - ECL_BAND) && c2 < 0. && P.R_sun > P.R_planet;      // inside the umbra, before its apex
     double f = lit ? 1.0 : 0.0;
     if (!lit && !dark) f = penumbra_fraction(P, r_HB, r, l2sq, p2, u2);
     return f;
+}
+LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r, double s2, V3 r_HB, double hb2)
+{
+    const double ec[6] = {sun.hp2, sun.inv_hp, sun.c1off, sun.c2off, sun.tan1, sun.tan2};
+    return eclipse_core(P, ec, sun.r, r, s2, r_HB, hb2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -648,14 +587,65 @@ LEO_HD void leo_reset_env(const LeoParams &P, double *S, int64_t *I, int64_t str
 // ------------------------------------------------------------------------------------------------
 struct StepOut { double ob[5]; double reward; int done; int reason; };
 
+// Per-thread "message bus": the flight-software messages, the Sun latch and the data of the rare paths live in
+// SHARED memory for the duration of the launch ([field][thread], conflict-free, immediate-offset LDS/STS), so
+// that none of it occupies registers in the tick loop and none of it costs address arithmetic.  Fields M_GUID..
+// M_RWCMD+3 mirror the persistent state fields F_GUID..F_RWCMD+3 (loaded at entry, written back at exit); the
+// rest is scratch.  On the host (tests/hostcore) the bus is a plain array.
+enum LeoMField : int {
+    M_GUID = 0,      // att_guidance (12)
+    M_REF = 12,      // att_reference (9)
+    M_LR = 21,       // commandedControlTorque (3)
+    M_RWCMD = 24,    // rwTorqueCommand (4)
+    M_SUNR = 28,     // Sun latch: position (3), velocity (3)
+    M_SUNV = 31,
+    M_ECL = 34,      // eclipse constants of the latch: |s_HP|^2, 1/|s_HP|, R_p/sin f1, R_p/sin f2, tan f1, tan f2
+    M_LEXT = 40,     // extForceTorque torque (3)
+    M_FM = 43,       // held thruster force / mass, body frame (3)
+    M_U = 46,        // latched wheel motor torques u_current (4)
+    LEO_NM = 50
+};
+#define LEO_M_MIRROR 28          // number of leading bus fields that mirror state fields starting at F_GUID
+struct MBus {
+    uint32_t a;      // device: shared-window byte address of this thread's column
+    double *p;       // host (tests/hostcore): plain array of LEO_NM doubles
+};
+LEO_HD double mld(MBus m, int f)
+{
+#ifdef __CUDA_ARCH__
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(m.a + (uint32_t)f * (uint32_t)(LEO_BLOCK * 8)) : "memory");
+    return v;
+#else
+    return m.p[f];
+#endif
+}
+LEO_HD void mst(MBus m, int f, double v)
+{
+#ifdef __CUDA_ARCH__
+    asm volatile("st.shared.f64 [%0], %1;" : : "r"(m.a + (uint32_t)f * (uint32_t)(LEO_BLOCK * 8)), "d"(v) : "memory");
+#else
+    m.p[f] = v;
+#endif
+}
+LEO_HD V3 mld3(MBus m, int f) { return mk(mld(m, f), mld(m, f + 1), mld(m, f + 2)); }
+LEO_HD void mst3(MBus m, int f, V3 v) { mst(m, f, v.x); mst(m, f + 1, v.y); mst(m, f + 2, v.z); }
+
+LEO_HD_NOINLINE void sun_latch_to_bus(const LeoParams &P, MBus m, int64_t msg_ns)
+{
+    SunLatch s = sun_latch(P, msg_ns);
+    mst3(m, M_SUNR, s.r); mst3(m, M_SUNV, s.v);
+    mst(m, M_ECL, s.hp2); mst(m, M_ECL + 1, s.inv_hp); mst(m, M_ECL + 2, s.c1off);
+    mst(m, M_ECL + 3, s.c2off); mst(m, M_ECL + 4, s.tan1); mst(m, M_ECL + 5, s.tan2);
+}
+
 // One flight-software pass at time now_ns (the priority 100/50 tasks run before DynTask at equal times).
 // nav = state written by the previous dynamics tick (zeros before tick 0: messages never written).
 // Out of line: it runs once per ticks_per_fsw dynamics ticks and must not bloat the hot tick loop.
 template <int NRW>
-LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int mask,
+LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m, int mask,
                              int64_t n, int64_t now_ns, Dyn<NRW> x, int64_t sun_ns)
 {
-#define SD(f) S[(int64_t)(f) * stride + e]
     V3 nr = x.r, nv = x.v, ns = x.s, nw = x.w;
     double ws[NRW];
 #pragma unroll
@@ -666,23 +656,19 @@ LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t 
         for (int i = 0; i < NRW; i++) ws[i] = 0.0;
     }
     AttRef ref;
-    ref.sigma_RN = mk(SD(F_REF), SD(F_REF + 1), SD(F_REF + 2));
-    ref.omega_RN_N = mk(SD(F_REF + 3), SD(F_REF + 4), SD(F_REF + 5));
-    ref.domega_RN_N = mk(SD(F_REF + 6), SD(F_REF + 7), SD(F_REF + 8));
-    if (mask & LEO_TASK_SUN) {                       // inertial3D
-        ref.sigma_RN = arr(P.sigma_R0N);
-        ref.omega_RN_N = mk(0., 0., 0.); ref.domega_RN_N = mk(0., 0., 0.);
-    }
     if (mask & LEO_TASK_NADIR) {                     // hillPoint
         V3 cr = mk(0., 0., 0.), cv = mk(0., 0., 0.);
         // r_BdyZero_N aliases {J2000Current, 0, 0} of the Sun message in force
         if (P.hill_cel_pun) cr.x = P.epoch_days * 86400.0 + ns2sec(sun_ns);
         ref = hill_point(nr, nv, cr, cv);
+    } else if (mask & LEO_TASK_SUN) {                // inertial3D
+        ref.sigma_RN = arr(P.sigma_R0N);
+        ref.omega_RN_N = mk(0., 0., 0.); ref.domega_RN_N = mk(0., 0., 0.);
+    } else {                                         // no guidance task enabled: the last message stays in force
+        ref.sigma_RN = mld3(m, M_REF); ref.omega_RN_N = mld3(m, M_REF + 3); ref.domega_RN_N = mld3(m, M_REF + 6);
     }
     if (mask & (LEO_TASK_SUN | LEO_TASK_NADIR)) {
-        SD(F_REF) = ref.sigma_RN.x; SD(F_REF + 1) = ref.sigma_RN.y; SD(F_REF + 2) = ref.sigma_RN.z;
-        SD(F_REF + 3) = ref.omega_RN_N.x; SD(F_REF + 4) = ref.omega_RN_N.y; SD(F_REF + 5) = ref.omega_RN_N.z;
-        SD(F_REF + 6) = ref.domega_RN_N.x; SD(F_REF + 7) = ref.domega_RN_N.y; SD(F_REF + 8) = ref.domega_RN_N.z;
+        mst3(m, M_REF, ref.sigma_RN); mst3(m, M_REF + 3, ref.omega_RN_N); mst3(m, M_REF + 6, ref.domega_RN_N);
     }
     int desat_ran = 0;
     if (mask & LEO_TASK_DESAT) {
@@ -692,34 +678,96 @@ LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t 
     if (mask & LEO_TASK_MRP) {
         // quirk Q1: MRP_Feedback runs BEFORE attTrackingError -> uses last pass's att_guidance
         AttGuid g;
-        g.sigma_BR = mk(SD(F_GUID), SD(F_GUID + 1), SD(F_GUID + 2));
-        g.omega_BR_B = mk(SD(F_GUID + 3), SD(F_GUID + 4), SD(F_GUID + 5));
-        g.omega_RN_B = mk(SD(F_GUID + 6), SD(F_GUID + 7), SD(F_GUID + 8));
-        g.domega_RN_B = mk(SD(F_GUID + 9), SD(F_GUID + 10), SD(F_GUID + 11));
+        g.sigma_BR = mld3(m, M_GUID); g.omega_BR_B = mld3(m, M_GUID + 3);
+        g.omega_RN_B = mld3(m, M_GUID + 6); g.domega_RN_B = mld3(m, M_GUID + 9);
         V3 Lr = mrp_feedback(P, g);
-        SD(F_LR) = Lr.x; SD(F_LR + 1) = Lr.y; SD(F_LR + 2) = Lr.z;
+        mst3(m, M_LR, Lr);
         g = att_tracking_error(ns, nw, ref);
-        SD(F_GUID) = g.sigma_BR.x; SD(F_GUID + 1) = g.sigma_BR.y; SD(F_GUID + 2) = g.sigma_BR.z;
-        SD(F_GUID + 3) = g.omega_BR_B.x; SD(F_GUID + 4) = g.omega_BR_B.y; SD(F_GUID + 5) = g.omega_BR_B.z;
-        SD(F_GUID + 6) = g.omega_RN_B.x; SD(F_GUID + 7) = g.omega_RN_B.y; SD(F_GUID + 8) = g.omega_RN_B.z;
-        SD(F_GUID + 9) = g.domega_RN_B.x; SD(F_GUID + 10) = g.domega_RN_B.y; SD(F_GUID + 11) = g.domega_RN_B.z;
+        mst3(m, M_GUID, g.sigma_BR); mst3(m, M_GUID + 3, g.omega_BR_B);
+        mst3(m, M_GUID + 6, g.omega_RN_B); mst3(m, M_GUID + 9, g.domega_RN_B);
         // rwMotorTorque: us = Umap (-Lr)
         V3 mLr = -Lr;
 #pragma unroll
-        for (int i = 0; i < NRW; i++) SD(F_RWCMD + i) = P.Umap[i][0] * mLr.x + P.Umap[i][1] * mLr.y + P.Umap[i][2] * mLr.z;
+        for (int i = 0; i < NRW; i++) mst(m, M_RWCMD + i, P.Umap[i][0] * mLr.x + P.Umap[i][1] * mLr.y + P.Umap[i][2] * mLr.z);
     }
     return desat_ran;
-#undef SD
 }
 
-// Everything one RK4 step needs besides the parameter block.
+// What one RK4 step needs besides the parameter block and the integrated state.
 template <int NRW>
 struct StageIn {
-    Dyn<NRW> x;
-    double u[NRW];
-    V3 tau_u, Lx, Fm;              // wheel motor torque on the hub, held external torque, thrust / mass (body frame)
+    double uJ[NRW];                // latched wheel motor torque / Js
+    V3 Lc;                         // held body torque: extForceTorque (+ thrusters) - wheel motor torque on the hub
+    V3 rs, A;                      // Sun position and Sun indirect term -mu_sun rs/|rs|^3, frozen at the step's mid time
     double rho, h;
 };
+
+// One evaluation of SpacecraftPlus::equationsOfMotion for the scenario's effector set.
+//   DIAG   fast path of the reference configuration: diagonal hub inertia, three wheels along the body axes
+//          (AP:20-37) and drag facets located on their own normal axis (SIM:274-281) -- the same arithmetic
+//          with the structural zeros dropped
+template <int NRW, bool J2, bool DIAG>
+LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, const StageIn<NRW> &a, bool thr_on, MBus m)
+{
+    // gravity: central point mass (+J2) + Sun third body (gravityEffector)
+    V3 g;
+    {
+        double ir = rsq(dot(x.r, x.r));
+        double ir3 = ir * ir * ir;
+        V3 d = x.r - a.rs;
+        double id = rsq(dot(d, d));
+        g = a.A + d * (-P.mu_sun * (id * id * id)) + x.r * (-P.mu_c * ir3);
+        if (J2) {
+            double ir2 = ir * ir, z2 = 5. * x.r.z * x.r.z * ir2, kk = -P.j2k * ir3 * ir2;
+            g = g + mk(kk * x.r.x * (1. - z2), kk * x.r.y * (1. - z2), kk * x.r.z * (3. - z2));
+        }
+    }
+    // facet drag with axis-aligned facets: F_B = -rho * S' * v_B (parallel to v_B, so [NB] F_B = -rho S' v_N),
+    // L_B = -rho * (M' x v_B).  A facet contributes when its normal has a positive component along v_B:
+    // K(sign v) |v| = Ka |v| + Kd v with Ka/Kd the half sum / half difference of the +/- facets.
+    MrpRot R = mrp_rot(x.s);
+    V3 vB = rot_BN(R, x.s, x.v);
+    V3 Mp;
+    double Sp;
+    {
+        double ax = fabs(vB.x), ay = fabs(vB.y), az = fabs(vB.z);
+        Sp = P.dragKa[0] * ax + P.dragKa[1] * ay + P.dragKa[2] * az + P.dragKd[0] * vB.x + P.dragKd[1] * vB.y + P.dragKd[2] * vB.z;
+        if (DIAG) {
+            Mp = mk(P.dragMa[0][0] * ax + P.dragMd[0][0] * vB.x, P.dragMa[1][1] * ay + P.dragMd[1][1] * vB.y,
+                    P.dragMa[2][2] * az + P.dragMd[2][2] * vB.z);
+        } else {
+            Mp = arr(P.dragMa[0]) * ax + arr(P.dragMa[1]) * ay + arr(P.dragMa[2]) * az
+               + arr(P.dragMd[0]) * vB.x + arr(P.dragMd[1]) * vB.y + arr(P.dragMd[2]) * vB.z;
+        }
+    }
+    const double mrho = -a.rho;
+    k.v = g + x.v * (mrho * Sp);                    // dragKa/Kd carry the 1/mass
+    if (thr_on) k.v = k.v + rot_NB(R, x.s, mld3(m, M_FM));
+    k.r = x.v;
+    // rotational EOM with balanced wheels (back-substitution, D constant):
+    //   [I - sum Js g g^T] wdot = -w x (I w + sum Js W g) - sum g u + L
+    V3 rot = a.Lc + cross(Mp, vB) * mrho;
+    if (DIAG) {
+        V3 h = mk(P.I[0] * x.w.x + P.Js[0] * x.W[0], P.I[4] * x.w.y + P.Js[1] * x.W[1], P.I[8] * x.w.z + P.Js[2] * x.W[2]);
+        rot = rot - cross(x.w, h);
+        k.w = mk(rot.x * P.Dinv[0], rot.y * P.Dinv[4], rot.z * P.Dinv[8]);
+        k.W[0] = a.uJ[0] - k.w.x;
+        k.W[1] = a.uJ[1] - k.w.y;
+        k.W[2] = a.uJ[2] - k.w.z;
+    } else {
+        V3 h = mv9(P.I, x.w);
+#pragma unroll
+        for (int i = 0; i < NRW; i++) h = h + arr(P.gs[i]) * (P.Js[i] * x.W[i]);
+        rot = rot - cross(x.w, h);
+        k.w = mv9(P.Dinv, rot);
+#pragma unroll
+        for (int i = 0; i < NRW; i++) k.W[i] = a.uJ[i] - dot(arr(P.gs[i]), k.w);
+    }
+    { // sigma_dot = 1/4 [B(sigma)] omega
+        double sw = dot(x.s, x.w);
+        k.s = x.w * (0.25 * R.oms2) + cross(x.s, x.w) * 0.5 + x.s * (0.5 * sw);
+    }
+}
 
 // Classical RK4 over one dynamics tick.  The four stages run as ONE rolled loop whose body is a single block of
 // FP64 arithmetic small enough to stay resident in the SM sub-partition's L0 instruction cache (a fully
@@ -727,15 +775,13 @@ struct StageIn {
 // stall_no_instruction, profiles/).  No register copies cross the back edge: the stage input is rebuilt from
 // the tick-start state and the previous slope (xs = x + c k, with k = 0 before the first stage), and the
 // weighted slopes are summed separately and added once.
-//   Sun position at stage time: sun_r + sun_v * (dts0 + theta h); Sun indirect term: A0 + theta (A1 - A0)
-//   (theta = 0, 1/2, 1/2, 1; |r_sun| changes by 1e-8 relative over a tick: the curvature left out is ~1e-16).
-// The thrust is constant over the step here; steps in which a thruster may switch, and the step whose Sun
-// clock wraps, go through rk4_general() below.
+// The Sun is frozen at the step's mid time for both third-body terms (its motion over a 0.1 s step changes the
+// tidal acceleration by ~1e-8 relative, i.e. ~5e-15 m/s^2); the thrust is constant over the step.  Steps in
+// which a thruster may switch, and the step whose Sun clock wraps, go through rk4_general() below.
 template <int NRW, bool J2, bool DIAG>
-LEO_HD Dyn<NRW> rk4_step(const LeoParams &P, const StageIn<NRW> &a, V3 sun_r, V3 sun_v, double dts0, V3 A0, V3 dA, bool thr_on)
+LEO_HD Dyn<NRW> rk4_step(const LeoParams &P, const Dyn<NRW> &x, const StageIn<NRW> &a, bool thr_on, MBus m)
 {
     const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
-    const Dyn<NRW> &x = a.x;
     Dyn<NRW> k, acc;
     k.r = k.v = k.s = k.w = acc.r = acc.v = acc.s = acc.w = mk(0., 0., 0.);
 #pragma unroll
@@ -747,9 +793,7 @@ LEO_HD Dyn<NRW> rk4_step(const LeoParams &P, const StageIn<NRW> &a, V3 sun_r, V3
         xs.r = x.r + k.r * c; xs.v = x.v + k.v * c; xs.s = x.s + k.s * c; xs.w = x.w + k.w * c;
 #pragma unroll
         for (int i = 0; i < NRW; i++) xs.W[i] = x.W[i] + k.W[i] * c;
-        const double theta = (st == 0) ? 0.0 : (st == 3 ? 1.0 : 0.5);
-        const double dts = dts0 + h * theta;
-        eom<NRW, J2, DIAG>(P, xs, k, sun_r + sun_v * dts, A0 + dA * theta, a.rho, a.tau_u, a.u, a.Lx, thr_on, a.Fm);
+        eom<NRW, J2, DIAG>(P, xs, k, a, thr_on, m);
         const double wo = (st == 0 || st == 3) ? h6 : h3;
         acc.r = acc.r + k.r * wo; acc.v = acc.v + k.v * wo; acc.s = acc.s + k.s * wo; acc.w = acc.w + k.w * wo;
 #pragma unroll
@@ -763,26 +807,29 @@ LEO_HD Dyn<NRW> rk4_step(const LeoParams &P, const StageIn<NRW> &a, V3 sun_r, V3
     return xo;
 }
 
-// Explicit stage data of the general step
-struct SunStages { V3 sr0, srm, sr1, A0, Am, A1; };
-
-// The same RK4 step with explicit per-stage Sun data and thrusterDynamicEffector::computeForceTorque evaluated at
-// every stage time: used for the steps in which a thruster may start or stop burning (a new on-time command was
-// just latched, or a commanded burn expires within the step) and for the step whose Sun clock wraps (quirk Q18).
-// Out of line; classical accumulation order.
+// The same RK4 step with the Sun evaluated at every stage time and thrusterDynamicEffector::computeForceTorque
+// evaluated at every stage time: used for the steps in which a thruster may start or stop burning (a new
+// on-time command was just latched, or a commanded burn expires within the step) and for the step whose Sun
+// clock wraps (quirk Q18: the stage clocks are not on a line, stage 4 may land exactly on the message time
+// while stages 1-3 are 2^64 ns away).  Out of line; classical accumulation order.
+struct SunDt { double d0, dm, d1; };
 template <int NRW>
 struct ThrEventOut { Dyn<NRW> x; int factor, active; };
 template <int NRW, bool J2, bool DIAG>
-LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S, int64_t stride, int64_t e, StageIn<NRW> a,
-                                             SunStages ss, V3 L_ext, double tBefore, double tauPrev, int thr_factor, int thr_active)
+LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S, int64_t stride, int64_t e, MBus m, Dyn<NRW> x,
+                                             StageIn<NRW> a, SunDt dts, double tBefore, double tauPrev, int thr_factor, int thr_active)
 {
     const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
-    const Dyn<NRW> x = a.x;
+    const V3 sun_r = mld3(m, M_SUNR), sun_v = mld3(m, M_SUNV), L_ext = mld3(m, M_LEXT);
+    V3 tau_u = mk(0., 0., 0.);
+#pragma unroll
+    for (int i = 0; i < NRW; i++) tau_u = tau_u + arr(P.gs[i]) * mld(m, M_U + i);
     Dyn<NRW> xs = x, xo = x, k;
 #pragma unroll 1
     for (int st = 0; st < 4; st++) {
-        const V3 rs = (st == 0) ? ss.sr0 : (st == 3 ? ss.sr1 : ss.srm);
-        const V3 a_ind = (st == 0) ? ss.A0 : (st == 3 ? ss.A1 : ss.Am);
+        const double dt = (st == 0) ? dts.d0 : (st == 3 ? dts.d1 : dts.dm);
+        a.rs = sun_r + sun_v * dt;
+        a.A = sun_indirect(P, a.rs);
         V3 Fm = mk(0., 0., 0.), Lx = L_ext;
         const bool thr_on = thr_active != 0;
         if (thr_on) {
@@ -792,7 +839,9 @@ LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S
             Fm = to.F * P.inv_mass; Lx = Lx + to.L;
             tauPrev = tau;
         }
-        eom<NRW, J2, DIAG>(P, xs, k, rs, a_ind, a.rho, a.tau_u, a.u, Lx, thr_on, Fm);
+        a.Lc = Lx - tau_u;
+        mst3(m, M_FM, Fm);
+        eom<NRW, J2, DIAG>(P, xs, k, a, thr_on, m);
         const double wo = (st == 0 || st == 3) ? h6 : h3;
         const double cn = (st == 2) ? h : hh;
         xo.r = xo.r + k.r * wo; xo.v = xo.v + k.v * wo; xo.s = xo.s + k.s * wo; xo.w = xo.w + k.w * wo;
@@ -811,27 +860,34 @@ LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S
 
 // Force / torque of the thrusters that are burning (bit mask `factor`) and the earliest time at which one of
 // them stops: until then computeForceTorque returns the same sums at every stage (expiry is monotone in
-// time and the commanded on-times only change at the next command latch).
-struct ThrHold { V3 F, L; double t_next; };
-LEO_HD_NOINLINE ThrHold thr_hold(const LeoParams &P, const double *S, int64_t stride, int64_t e, int factor)
+// time and the commanded on-times only change at the next command latch).  Publishes the held thrust on the
+// bus and rebuilds the held body torque.
+struct ThrRefresh { V3 Lc, L_thr; double t_next; };
+template <int NRW>
+LEO_HD_NOINLINE ThrRefresh thr_refresh(const LeoParams &P, const double *S, int64_t stride, int64_t e, MBus m, int factor)
 {
-    ThrHold o;
-    o.F = mk(0., 0., 0.); o.L = mk(0., 0., 0.); o.t_next = 1e300;
+    ThrRefresh o;
+    V3 F = mk(0., 0., 0.);
+    o.L_thr = mk(0., 0., 0.); o.t_next = 1e300;
     double start = S[(int64_t)F_THRSTART * stride + e];
     for (int k = 0; k < LEO_NTHR; k++) {
         if (!((factor >> k) & 1)) continue;
         V3 f = arr(P.thr_dir[k]) * (P.thr_Fmax * 1.0);
-        o.F = f + o.F;
-        o.L = cross(arr(P.thr_loc[k]), f) + o.L;
+        F = f + F;
+        o.L_thr = cross(arr(P.thr_loc[k]), f) + o.L_thr;
         double t_off = t_add(S[(int64_t)(F_THRON + k) * stride + e], start);
         if (t_off < o.t_next) o.t_next = t_off;
     }
+    mst3(m, M_FM, F * P.inv_mass);
+    V3 tau_u = mk(0., 0., 0.);
+#pragma unroll
+    for (int i = 0; i < NRW; i++) tau_u = tau_u + arr(P.gs[i]) * mld(m, M_U + i);
+    o.Lc = (mld3(m, M_LEXT) + o.L_thr) - tau_u;
     return o;
 }
 
 // Stage clocks of the step whose Sun message is newer than the integration time (quirk Q18): Basilisk's
 // unsigned (systemClock - WriteClockNanos) wraps.  Replicated (last tick of every decision interval).
-struct SunDt { double d0, dm, d1; };
 LEO_HD_NOINLINE SunDt sun_dt_wrapped(double prev_ns_d, double sun_ns_d, double tBefore, double prevTime, double h)
 {
     SunDt o;
@@ -845,23 +901,32 @@ LEO_HD_NOINLINE SunDt sun_dt_wrapped(double prev_ns_d, double sun_ns_d, double t
     return o;
 }
 
-// reactionWheelStateEffector.UpdateState: latch the motor torque command (torque and speed saturation)
+// The rare events after a dynamics tick, in task order:
+//  * reactionWheelStateEffector.UpdateState: latch the motor torque command (torque and speed saturation) when
+//    the command is new or a speed limit is in play;
+//  * thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters.
+// Rebuilds the held body torque.  Returns the new thr_active (or -1 when no thruster message arrived).
 template <int NRW>
-struct RwLatch { double u[NRW]; V3 tau_u; };
+struct PostOut { double uJ[NRW]; V3 Lc; int thr_active; };
 template <int NRW>
-LEO_HD_NOINLINE RwLatch<NRW> rw_latch(const LeoParams &P, const double *S, int64_t stride, int64_t e, Dyn<NRW> x)
+LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m,
+                                              Dyn<NRW> x, V3 L_thr, int desat_ran, int64_t now_ns, int thr_factor)
 {
-    RwLatch<NRW> o;
-    o.tau_u = mk(0., 0., 0.);
+    PostOut<NRW> o;
+    V3 tau_u = mk(0., 0., 0.);
 #pragma unroll
     for (int i = 0; i < NRW; i++) {
-        double uc = S[(int64_t)(F_RWCMD + i) * stride + e];
+        double uc = mld(m, M_RWCMD + i);
         if (P.u_max[i] > 0.) { if (uc > P.u_max[i]) uc = P.u_max[i]; else if (uc < -P.u_max[i]) uc = -P.u_max[i]; }
         if (fabs(uc) < P.u_min[i]) uc = 0.0;
         if (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && x.W[i] * uc >= 0.0) uc = 0.0;
-        o.u[i] = uc;
-        o.tau_u = o.tau_u + arr(P.gs[i]) * uc;
+        mst(m, M_U + i, uc);
+        o.uJ[i] = uc * P.invJs[i];
+        tau_u = tau_u + arr(P.gs[i]) * uc;
     }
+    o.Lc = (mld3(m, M_LEXT) + L_thr) - tau_u;
+    o.thr_active = -1;
+    if (desat_ran) o.thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor);
     return o;
 }
 
@@ -871,22 +936,35 @@ LEO_HD_NOINLINE RwLatch<NRW> rw_latch(const LeoParams &P, const double *S, int64
 
 template <int NRW, bool J2, bool DIAG>
 LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
-                         int action, StepOut &out)
+                         MBus m, int action, StepOut &out)
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
     // ---------------- load ----------------
+    Dyn<NRW> x;
     StageIn<NRW> a;
-    Dyn<NRW> &x = a.x;
     x.r = mk(SD(F_R), SD(F_R + 1), SD(F_R + 2));
     x.v = mk(SD(F_V), SD(F_V + 1), SD(F_V + 2));
     x.s = mk(SD(F_SIG), SD(F_SIG + 1), SD(F_SIG + 2));
     x.w = mk(SD(F_OMG), SD(F_OMG + 1), SD(F_OMG + 2));
+    V3 tau_u = mk(0., 0., 0.);
 #pragma unroll
-    for (int i = 0; i < NRW; i++) { x.W[i] = SD(F_WHL + i); a.u[i] = SD(F_UCUR + i); }
+    for (int i = 0; i < NRW; i++) {
+        x.W[i] = SD(F_WHL + i);
+        const double u = SD(F_UCUR + i);
+        mst(m, M_U + i, u);
+        a.uJ[i] = u * P.invJs[i];
+        tau_u = tau_u + arr(P.gs[i]) * u;
+    }
+    for (int f = 0; f < LEO_M_MIRROR; f++) mst(m, f, SD(F_GUID + f));
     a.rho = SD(F_RHO);
     double E = SD(F_E), shadow = SD(F_SHADOW);
-    const V3 L_ext = mk(SD(F_LDIST), SD(F_LDIST + 1), SD(F_LDIST + 2));
+    {
+        const V3 L_ext = mk(SD(F_LDIST), SD(F_LDIST + 1), SD(F_LDIST + 2));
+        mst3(m, M_LEXT, L_ext); mst3(m, M_FM, mk(0., 0., 0.));
+        a.Lc = L_ext - tau_u;
+    }
+    V3 L_thr = mk(0., 0., 0.);                                  // held thruster torque (zero outside burns)
     const int64_t tick = SI(I_TICK);
     int mask = (int)SI(I_MASK);
     int thr_factor = (int)SI(I_THRFACTOR), thr_active = (int)SI(I_THRACTIVE), rw_sat = (int)SI(I_RWSAT);
@@ -901,11 +979,6 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         SI(I_DUMPPRIOR) = 0; SI(I_DUMPCNT) = 0; SI(I_LASTDH) = 0;   // thrDumpWrap.Reset (SIM:581)
         for (int k = 0; k < LEO_NTHR; k++) SD(F_THRREM + k) = 0.0;
     }
-
-    a.tau_u = mk(0., 0., 0.);
-#pragma unroll
-    for (int i = 0; i < NRW; i++) a.tau_u = a.tau_u + arr(P.gs[i]) * a.u[i];
-    a.Lx = L_ext; a.Fm = mk(0., 0., 0.);
     // thrusters: the burning set is re-derived by an exact step before the constant-thrust path is trusted
     double thr_t_next = -1.0;
 
@@ -917,100 +990,86 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     const int64_t n_end = n_base - 1 + ticks;                  // inclusive (ConfigureStopTime is inclusive)
     const double dyn_d = (double)P.dyn_ns;
     double sun_d = (double)((n_base - 1) * P.dyn_ns);          // write time of the Sun message in force
-    SunLatch sun = sun_latch(P, (int64_t)sun_d);
-    V3 A_prev = mk(0., 0., 0.);          // Sun indirect term at the end of the previous tick (= start of this one)
-    bool A_ok = false;
+    sun_latch_to_bus(P, m, (n_base - 1) * P.dyn_ns);
     int phase = (int)((n_base - 1) % tpf);                     // (n mod ticks_per_fsw) of the tick about to run
-    double now_d = (double)((n_base - 1) * P.dyn_ns);          // exact: n * dyn_ns
+    double now_d = sun_d;                                      // exact: n * dyn_ns
     int desat_ran = 0;
 
 #pragma unroll 1
     for (int j = -1; j < ticks; j++, now_d += dyn_d, phase = (phase + 1 == tpf) ? 0 : phase + 1) {
         if (j < 0 && !first) continue;                         // keeps the lanes of a warp on the same FSW phase
+        bool wrapped = false;
         // ================= flight software every ticks_per_fsw-th tick =================
         if (phase == 0) {
             const int64_t n = n_base + j;
-            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, mask, n, n * P.dyn_ns, x, (int64_t)sun_d);
+            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, (int64_t)sun_d);
             rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
-            // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule)
-            if (n > 0 && n == n_end) { sun_d = now_d; sun = sun_latch(P, n * P.dyn_ns); A_ok = false; }
+            // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule); the
+            // message is then newer than the start of this integration step (quirk Q18)
+            if (n > 0 && n == n_end) { sun_d = now_d; sun_latch_to_bus(P, m, n * P.dyn_ns); wrapped = true; }
         }
         // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
         const double prev_d = j < 0 ? 0.0 : now_d - dyn_d;     // tick 0 integrates over an empty interval
         const double newTime = t_mul(now_d, 1e-9);             // CurrentSimNanos * NANO2SEC
         const double prevTime = t_mul(prev_d, 1e-9);
         const double h = t_sub(newTime, prevTime);
-        const double tBefore = t_sub(newTime, h);
         a.h = h;
-        // Sun position is Euler-stepped from the latch: dt = (systemClock - WriteClockNanos) * 1e-9
-        const bool wrapped = sun_d > prev_d;
-        double dts0 = t_mul(prev_d - sun_d, 1e-9), dtsm = dts0 + 0.5 * h, dts1 = dts0 + h;
-        if (wrapped) {
-            SunDt w = sun_dt_wrapped(prev_d, sun_d, tBefore, prevTime, h);
-            dts0 = w.d0; dtsm = w.dm; dts1 = w.d1;
-            A_ok = false;
-        }
-        // Sun indirect term: exact at both ends of the tick, linear in between
-        const V3 sr1 = sun.r + sun.v * dts1;
-        const V3 A0 = A_ok ? A_prev : sun_indirect(P, sun.r + sun.v * dts0);
-        const V3 A1 = sun_indirect(P, sr1);
-        A_prev = A1; A_ok = !wrapped;
-
         if (wrapped || (thr_active && !(newTime + LEO_THR_MARGIN <= thr_t_next))) {
-            // a thruster may switch within this step (exact per-stage evaluation, then refresh the held thrust), or
-            // the stage clocks of the Sun are not on a line (stage 4 may land exactly on the message time while
-            // stages 1-3 are 2^64 ns away): every stage gets its own Sun position and indirect term
-            SunStages ss;
-            ss.sr0 = sun.r + sun.v * dts0; ss.srm = sun.r + sun.v * dtsm; ss.sr1 = sr1;
-            ss.A0 = A0; ss.A1 = A1;
-            ss.Am = wrapped ? sun_indirect(P, ss.srm) : (A0 + A1) * 0.5;
+            // a thruster may switch within this step (exact per-stage evaluation, then refresh the held thrust),
+            // or the Sun clock wraps: every stage gets its own Sun position
+            const double tBefore = t_sub(newTime, h);
+            SunDt dts;
+            dts.d0 = t_mul(prev_d - sun_d, 1e-9); dts.dm = dts.d0 + 0.5 * h; dts.d1 = dts.d0 + h;
+            if (wrapped) dts = sun_dt_wrapped(prev_d, sun_d, tBefore, prevTime, h);
             double tauPrev = 0.0;          // time of the previous equationsOfMotion call = last stage of the previous tick
             if (j >= 0) {
                 const double ppT = (n_base + j > 1) ? t_mul(prev_d - dyn_d, 1e-9) : 0.0;
                 const double ph = t_sub(prevTime, ppT);
                 tauPrev = t_add(t_sub(prevTime, ph), ph);
             }
-            ThrEventOut<NRW> o = rk4_general<NRW, J2, DIAG>(P, S, stride, e, a, ss, L_ext, tBefore, tauPrev, thr_factor, thr_active);
+            ThrEventOut<NRW> o = rk4_general<NRW, J2, DIAG>(P, S, stride, e, m, x, a, dts, tBefore, tauPrev, thr_factor, thr_active);
             x = o.x; thr_factor = o.factor; thr_active = o.active;
-            ThrHold th = thr_hold(P, S, stride, e, thr_active ? thr_factor : 0);
-            a.Fm = th.F * P.inv_mass; a.Lx = L_ext + th.L; thr_t_next = th.t_next;
+            ThrRefresh th = thr_refresh<NRW>(P, S, stride, e, m, thr_active ? thr_factor : 0);
+            a.Lc = th.Lc; L_thr = th.L_thr; thr_t_next = th.t_next;
         } else {
-            x = rk4_step<NRW, J2, DIAG>(P, a, sun.r, sun.v, dts0, A0, A1 - A0, thr_active != 0);
+            // Sun frozen at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
+            const double dtsm = t_mul(prev_d - sun_d, 1e-9) + 0.5 * h;
+            a.rs = mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm;
+            a.A = sun_indirect(P, a.rs);
+            x = rk4_step<NRW, J2, DIAG>(P, x, a, thr_active != 0, m);
         }
-        // HubEffector::modifyStates -- MRP shadow-set switch (|sigma| > 1)
+        // HubEffector::modifyStates -- MRP shadow-set switch: |sigma| > 1 with the correctly rounded norm, i.e.
+        // sigma.sigma > 1 + 2^-52 (sqrt(1 + 2^-52) rounds to 1)
         {
-            double s2 = dot(x.s, x.s);
-            if (s2 > 1. && sqrt(s2) > 1.) { x.s = x.s * (-1. / s2); nswitch++; }
+            const double s2 = dot(x.s, x.s);
+            if (s2 > 1.0000000000000002) { x.s = x.s * (-1. / s2); nswitch++; }
         }
         // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
         const double r2 = dot(x.r, x.r);
         // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
         a.rho = P.rho0 * exp(-(r2 * rsq(r2) - P.Rp_atmo) * P.inv_H);
-        // reactionWheelStateEffector.UpdateState: re-latch only when the command is new or a speed limit is in play
+        // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
         {
             int lim = 0;
 #pragma unroll
             for (int i = 0; i < NRW; i++) lim |= (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
-            if (rw_sat | lim) {
-                RwLatch<NRW> l = rw_latch<NRW>(P, S, stride, e, x);
+            if (rw_sat | lim | desat_ran) {
+                PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, x, L_thr, desat_ran, (int64_t)now_d, thr_factor);
 #pragma unroll
-                for (int i = 0; i < NRW; i++) a.u[i] = l.u[i];
-                a.tau_u = l.tau_u;
+                for (int i = 0; i < NRW; i++) a.uJ[i] = po.uJ[i];
+                a.Lc = po.Lc;
                 rw_sat = lim;
+                if (po.thr_active >= 0) { thr_active = po.thr_active; thr_t_next = -1.0; }   // burning set: re-derive exactly
+                desat_ran = 0;
             }
         }
-        // thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters
-        if (desat_ran) {
-            thr_active = thr_latch(P, S, I, stride, e, (int64_t)now_d, thr_factor);
-            thr_t_next = -1.0;             // the burning set must be re-derived by an exact step
-            desat_ran = 0;
-        }
-
         // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
         {
-            const V3 r_SB = sun.r - x.r;                       // spacecraft -> Sun
+            const V3 sun_r = mld3(m, M_SUNR);
+            const V3 r_SB = sun_r - x.r;                       // spacecraft -> Sun
             const double d2 = dot(r_SB, r_SB), id = rsq(d2);
-            shadow = eclipse_factor(P, sun, x.r, r2, r_SB, d2);
+            const double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
+            shadow = eclipse_core(P, ec, sun_r, x.r, r2, r_SB, d2);
             MrpRot R = mrp_rot(x.s);
             V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
             double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
@@ -1025,7 +1084,8 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     }
 
     // ---------------- observation sampling (SIM:598-642) + gym bookkeeping (ENV:98-145) ----------------
-    double ob0 = norm(mk(SD(F_GUID), SD(F_GUID + 1), SD(F_GUID + 2)));
+    for (int f = 0; f < LEO_M_MIRROR; f++) SD(F_GUID + f) = mld(m, f);
+    double ob0 = norm(mld3(m, M_GUID));
     double ob1 = norm(x.w);
     double wn = 0.;
 #pragma unroll
@@ -1053,7 +1113,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     SD(F_SIG) = x.s.x; SD(F_SIG + 1) = x.s.y; SD(F_SIG + 2) = x.s.z;
     SD(F_OMG) = x.w.x; SD(F_OMG + 1) = x.w.y; SD(F_OMG + 2) = x.w.z;
 #pragma unroll
-    for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = x.W[i]; SD(F_UCUR + i) = a.u[i]; }
+    for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = x.W[i]; SD(F_UCUR + i) = mld(m, M_U + i); }
     SD(F_RHO) = a.rho; SD(F_E) = E; SD(F_SHADOW) = shadow; SD(F_EPRET) = ret;
     SI(I_TICK) = n_end; SI(I_STEP) = curr_step + 1; SI(I_MASK) = mask; SI(I_SWITCH) = SI(I_SWITCH) + nswitch;
     SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_OVER) = over; SI(I_RWSAT) = rw_sat;

@@ -106,7 +106,7 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
             for (int j = 0; j < 3; j++) M[axis[f]][sign[f]][j] += k * Lc[f][j];
         }
         for (int ax = 0; ax < 3; ax++) {
-            p.dragKa[ax] = 0.5 * (K[ax][0] + K[ax][1]); p.dragKd[ax] = 0.5 * (K[ax][0] - K[ax][1]);
+            p.dragKa[ax] = 0.5 * (K[ax][0] + K[ax][1]) * p.inv_mass; p.dragKd[ax] = 0.5 * (K[ax][0] - K[ax][1]) * p.inv_mass;
             for (int j = 0; j < 3; j++) {
                 p.dragMa[ax][j] = 0.5 * (M[ax][0][j] + M[ax][1][j]); p.dragMd[ax][j] = 0.5 * (M[ax][0][j] - M[ax][1][j]);
                 if (ax != j && (p.dragMa[ax][j] != 0.0 || p.dragMd[ax][j] != 0.0)) p.diag = 0;

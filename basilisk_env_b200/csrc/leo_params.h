@@ -11,6 +11,9 @@
 
 #define LEO_MAX_RW 4
 #define LEO_NTHR 8
+#ifndef LEO_BLOCK
+#define LEO_BLOCK 128          // threads per block of the step kernel = stride of the shared-memory message bus
+#endif
 
 struct LeoParams {
     // ---- task rates as integer nanoseconds (Basilisk sec2nano) and derived loop counts ----
@@ -34,7 +37,8 @@ struct LeoParams {
     // ---- facet drag, facets with axis-aligned normals collapsed per axis and sign ----
     // K(+/-) = sum of 0.5*Cd*A over the facets with normal (+/-) e_axis, M(+/-) = sum of 0.5*Cd*A*r_facet over the
     // same facets; a facet acts when v_B has a positive component along its normal, so the selected sums times
-    // |v_axis| are  Ka |v| + Kd v  with  Ka = (K+ + K-)/2,  Kd = (K+ - K-)/2  (no table look-up, no branch)
+    // |v_axis| are  Ka |v| + Kd v  with  Ka = (K+ + K-)/2,  Kd = (K+ - K-)/2  (no table look-up, no branch).
+    // dragKa / dragKd are pre-divided by the spacecraft mass.
     double dragKa[3], dragKd[3];
     double dragMa[3][3], dragMd[3][3];   // [axis][component]
     double dist_mag;              // disturbance_magnitude (2e-4)

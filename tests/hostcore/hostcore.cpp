@@ -53,12 +53,14 @@ void hc_reset_seeded(HC *h, uint64_t seed, int64_t first_env, double *ics_out, d
 }
 void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t *done, uint8_t *reason)
 {
+    double bus[leo::LEO_NM];
+    leo::MBus m; m.a = 0; m.p = bus;
     for (int64_t e = 0; e < h->n; e++) {
         leo::StepOut o;
         if (h->P.diag && !h->force_general)
-            leo::leo_step_env<3, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o);
+            leo::leo_step_env<3, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
         else
-            leo::leo_step_env<3, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o);
+            leo::leo_step_env<3, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
         for (int k = 0; k < 5; k++) obs[5 * e + k] = o.ob[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
     }
