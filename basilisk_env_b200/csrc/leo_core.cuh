@@ -227,8 +227,13 @@ LEO_HD_NOINLINE SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
 // ------------------------------------------------------------------------------------------------
 // integrated state and equations of motion
 // ------------------------------------------------------------------------------------------------
-template <int NRW>
-struct Dyn { V3 r, v, s, w; double W[NRW]; };
+// Integrated hub state.  The wheel speeds are NOT integrated: with balanced wheels the wheel equation
+// Omega_i' = u_i/Js_i - g_i.omega' is linear, so  Omega_i + g_i.omega = C_i + (u_i/Js_i) (t - t0)  holds exactly for the
+// continuous solution AND for every Runge-Kutta stage and step value (linear invariants are preserved by RK
+// methods).  The wheel momentum seen by the hub at stage time t0 + ct is then
+//   sum_i g_i Js_i Omega_i = HB + ct tau_u - (sum_i Js_i g_i g_i^T) omega,   HB = sum_i g_i Js_i C_i, tau_u = sum_i g_i u_i,
+// i.e. h = I omega + (wheel momentum) = D omega + HB + ct tau_u with the back-substitution matrix D.
+struct Dyn { V3 r, v, s, w; };
 
 // Thruster force/torque at one RK stage (thrusterDynamicEffector::computeForceTorque without ramps).
 // Rare path (only while a desat pulse may still burn): state stays in global memory.
@@ -644,12 +649,12 @@ LEO_HD_NOINLINE void sun_latch_to_bus(const LeoParams &P, MBus m, int64_t msg_ns
 // Out of line: it runs once per ticks_per_fsw dynamics ticks and must not bloat the hot tick loop.
 template <int NRW>
 LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m, int mask,
-                             int64_t n, int64_t now_ns, Dyn<NRW> x, int64_t sun_ns)
+                             int64_t n, int64_t now_ns, Dyn x, const double (&W)[NRW], int64_t sun_ns)
 {
     V3 nr = x.r, nv = x.v, ns = x.s, nw = x.w;
     double ws[NRW];
 #pragma unroll
-    for (int i = 0; i < NRW; i++) ws[i] = x.W[i];
+    for (int i = 0; i < NRW; i++) ws[i] = W[i];
     if (n == 0) {
         nr = nv = ns = nw = mk(0., 0., 0.);
 #pragma unroll
@@ -693,30 +698,54 @@ LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t 
     return desat_ran;
 }
 
+// Fused multiply-add: a true FMA on the device; plain arithmetic on the host (tests/hostcore is built with
+// -ffp-contract=off and must not depend on a libm fma()).
+LEO_HD double fmad(double p, double q, double r)
+{
+#ifdef __CUDA_ARCH__
+    return fma(p, q, r);
+#else
+    return p * q + r;
+#endif
+}
+LEO_HD V3 add_cross(V3 p, V3 u, V3 v)     // p + u x v, six fused operations
+{
+    return mk(fmad(u.y, v.z, fmad(-u.z, v.y, p.x)), fmad(u.z, v.x, fmad(-u.x, v.z, p.y)), fmad(u.x, v.y, fmad(-u.y, v.x, p.z)));
+}
+LEO_HD V3 sub_cross(V3 p, V3 u, V3 v)     // p - u x v
+{
+    return mk(fmad(-u.y, v.z, fmad(u.z, v.y, p.x)), fmad(-u.z, v.x, fmad(u.x, v.z, p.y)), fmad(-u.x, v.y, fmad(u.y, v.x, p.z)));
+}
+
+// Sun third-body acceleration of the gravityEffector (direct + indirect term) at spacecraft position r, Sun at rs
+LEO_HD V3 sun_accel(const LeoParams &P, V3 rs, V3 r)
+{
+    V3 d = r - rs;
+    double is = rsq(dot(rs, rs)), id = rsq(dot(d, d));
+    return rs * (-P.mu_sun * (is * is * is)) + d * (-P.mu_sun * (id * id * id));
+}
+
 // What one RK4 step needs besides the parameter block and the integrated state.
-template <int NRW>
 struct StageIn {
-    double uJ[NRW];                // latched wheel motor torque / Js
     V3 Lc;                         // held body torque: extForceTorque (+ thrusters) - wheel motor torque on the hub
-    V3 rs, A;                      // Sun position and Sun indirect term -mu_sun rs/|rs|^3, frozen at the step's mid time
+    V3 gsun;                       // Sun third-body acceleration
+    V3 HB, tau_u;                  // wheel momentum invariant at the start of the step and motor torque sum_i g_i u_i (see Dyn)
     double rho, h;
 };
 
-// One evaluation of SpacecraftPlus::equationsOfMotion for the scenario's effector set.
+// One evaluation of SpacecraftPlus::equationsOfMotion for the scenario's effector set at stage time t0 + ct.
 //   DIAG   fast path of the reference configuration: diagonal hub inertia, three wheels along the body axes
 //          (AP:20-37) and drag facets located on their own normal axis (SIM:274-281) -- the same arithmetic
 //          with the structural zeros dropped
-template <int NRW, bool J2, bool DIAG>
-LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, const StageIn<NRW> &a, bool thr_on, MBus m)
+template <bool J2, bool DIAG>
+LEO_HD void eom(const LeoParams &P, const Dyn &x, Dyn &k, const StageIn &a, double ct, bool thr_on, MBus m)
 {
     // gravity: central point mass (+J2) + Sun third body (gravityEffector)
     V3 g;
     {
         double ir = rsq(dot(x.r, x.r));
         double ir3 = ir * ir * ir;
-        V3 d = x.r - a.rs;
-        double id = rsq(dot(d, d));
-        g = a.A + d * (-P.mu_sun * (id * id * id)) + x.r * (-P.mu_c * ir3);
+        g = a.gsun + x.r * (-P.mu_c * ir3);
         if (J2) {
             double ir2 = ir * ir, z2 = 5. * x.r.z * x.r.z * ir2, kk = -P.j2k * ir3 * ir2;
             g = g + mk(kk * x.r.x * (1. - z2), kk * x.r.y * (1. - z2), kk * x.r.z * (3. - z2));
@@ -744,24 +773,18 @@ LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, const StageI
     k.v = g + x.v * (mrho * Sp);                    // dragKa/Kd carry the 1/mass
     if (thr_on) k.v = k.v + rot_NB(R, x.s, mld3(m, M_FM));
     k.r = x.v;
-    // rotational EOM with balanced wheels (back-substitution, D constant):
-    //   [I - sum Js g g^T] wdot = -w x (I w + sum Js W g) - sum g u + L
-    V3 rot = a.Lc + cross(Mp, vB) * mrho;
+    // rotational EOM with balanced wheels (back-substitution, D constant; wheel momentum from the invariant):
+    //   D wdot = -w x (D w + HB + ct tau_u) - sum g u + L
+    V3 rot = add_cross(a.Lc, Mp * mrho, vB);
+    const V3 hw = a.HB + a.tau_u * ct;
     if (DIAG) {
-        V3 h = mk(P.I[0] * x.w.x + P.Js[0] * x.W[0], P.I[4] * x.w.y + P.Js[1] * x.W[1], P.I[8] * x.w.z + P.Js[2] * x.W[2]);
-        rot = rot - cross(x.w, h);
+        V3 h = mk(fmad(P.D[0], x.w.x, hw.x), fmad(P.D[4], x.w.y, hw.y), fmad(P.D[8], x.w.z, hw.z));
+        rot = sub_cross(rot, x.w, h);
         k.w = mk(rot.x * P.Dinv[0], rot.y * P.Dinv[4], rot.z * P.Dinv[8]);
-        k.W[0] = a.uJ[0] - k.w.x;
-        k.W[1] = a.uJ[1] - k.w.y;
-        k.W[2] = a.uJ[2] - k.w.z;
     } else {
-        V3 h = mv9(P.I, x.w);
-#pragma unroll
-        for (int i = 0; i < NRW; i++) h = h + arr(P.gs[i]) * (P.Js[i] * x.W[i]);
-        rot = rot - cross(x.w, h);
+        V3 h = mv9(P.D, x.w) + hw;
+        rot = sub_cross(rot, x.w, h);
         k.w = mv9(P.Dinv, rot);
-#pragma unroll
-        for (int i = 0; i < NRW; i++) k.W[i] = a.uJ[i] - dot(arr(P.gs[i]), k.w);
     }
     { // sigma_dot = 1/4 [B(sigma)] omega
         double sw = dot(x.s, x.w);
@@ -775,61 +798,52 @@ LEO_HD void eom(const LeoParams &P, const Dyn<NRW> &x, Dyn<NRW> &k, const StageI
 // stall_no_instruction, profiles/).  No register copies cross the back edge: the stage input is rebuilt from
 // the tick-start state and the previous slope (xs = x + c k, with k = 0 before the first stage), and the
 // weighted slopes are summed separately and added once.
-// The Sun is frozen at the step's mid time for both third-body terms (its motion over a 0.1 s step changes the
-// tidal acceleration by ~1e-8 relative, i.e. ~5e-15 m/s^2); the thrust is constant over the step.  Steps in
-// which a thruster may switch, and the step whose Sun clock wraps, go through rk4_general() below.
-template <int NRW, bool J2, bool DIAG>
-LEO_HD Dyn<NRW> rk4_step(const LeoParams &P, const Dyn<NRW> &x, const StageIn<NRW> &a, bool thr_on, MBus m)
+// The Sun's third-body acceleration is held over the step (evaluated by the caller at the step's mid time and
+// the predicted mid position r + v h/2): its gradient is 2 mu_sun/d^3 = 8e-14 s^-2, the stage positions are
+// within 0.4 km of that point and the deviations of the first and last stage cancel in the RK4 weights -- the
+// net effect is < 1e-10 m of position per decision interval (1e-17 relative); the thrust is constant over the
+// step.  Steps in which a thruster may switch, and the step whose Sun clock wraps, go through rk4_general().
+template <bool J2, bool DIAG>
+LEO_HD Dyn rk4_step(const LeoParams &P, const Dyn &x, const StageIn &a, bool thr_on, MBus m)
 {
     const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
-    Dyn<NRW> k, acc;
+    Dyn k, acc;
     k.r = k.v = k.s = k.w = acc.r = acc.v = acc.s = acc.w = mk(0., 0., 0.);
-#pragma unroll
-    for (int i = 0; i < NRW; i++) k.W[i] = acc.W[i] = 0.;
     double c = 0.;
 #pragma unroll 1
     for (int st = 0; st < 4; st++) {
-        Dyn<NRW> xs;
+        Dyn xs;
         xs.r = x.r + k.r * c; xs.v = x.v + k.v * c; xs.s = x.s + k.s * c; xs.w = x.w + k.w * c;
-#pragma unroll
-        for (int i = 0; i < NRW; i++) xs.W[i] = x.W[i] + k.W[i] * c;
-        eom<NRW, J2, DIAG>(P, xs, k, a, thr_on, m);
+        eom<J2, DIAG>(P, xs, k, a, c, thr_on, m);
         const double wo = (st == 0 || st == 3) ? h6 : h3;
         acc.r = acc.r + k.r * wo; acc.v = acc.v + k.v * wo; acc.s = acc.s + k.s * wo; acc.w = acc.w + k.w * wo;
-#pragma unroll
-        for (int i = 0; i < NRW; i++) acc.W[i] = acc.W[i] + k.W[i] * wo;
         c = (st == 2) ? h : hh;
     }
-    Dyn<NRW> xo;
+    Dyn xo;
     xo.r = x.r + acc.r; xo.v = x.v + acc.v; xo.s = x.s + acc.s; xo.w = x.w + acc.w;
-#pragma unroll
-    for (int i = 0; i < NRW; i++) xo.W[i] = x.W[i] + acc.W[i];
     return xo;
 }
 
-// The same RK4 step with the Sun evaluated at every stage time and thrusterDynamicEffector::computeForceTorque
-// evaluated at every stage time: used for the steps in which a thruster may start or stop burning (a new
-// on-time command was just latched, or a commanded burn expires within the step) and for the step whose Sun
-// clock wraps (quirk Q18: the stage clocks are not on a line, stage 4 may land exactly on the message time
-// while stages 1-3 are 2^64 ns away).  Out of line; classical accumulation order.
+// The same RK4 step with the Sun evaluated at every stage time and position, and with
+// thrusterDynamicEffector::computeForceTorque evaluated at every stage time: used for the steps in which a
+// thruster may start or stop burning (a new on-time command was just latched, or a commanded burn expires
+// within the step) and for the step whose Sun clock wraps (quirk Q18: the stage clocks are not on a line,
+// stage 4 may land exactly on the message time while stages 1-3 are 2^64 ns away).  Out of line; classical
+// accumulation order.
 struct SunDt { double d0, dm, d1; };
-template <int NRW>
-struct ThrEventOut { Dyn<NRW> x; int factor, active; };
-template <int NRW, bool J2, bool DIAG>
-LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S, int64_t stride, int64_t e, MBus m, Dyn<NRW> x,
-                                             StageIn<NRW> a, SunDt dts, double tBefore, double tauPrev, int thr_factor, int thr_active)
+struct ThrEventOut { Dyn x; int factor, active; };
+template <bool J2, bool DIAG>
+LEO_HD_NOINLINE ThrEventOut rk4_general(const LeoParams &P, const double *S, int64_t stride, int64_t e, MBus m, Dyn x,
+                                        StageIn a, SunDt dts, double tBefore, double tauPrev, int thr_factor, int thr_active)
 {
     const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
     const V3 sun_r = mld3(m, M_SUNR), sun_v = mld3(m, M_SUNV), L_ext = mld3(m, M_LEXT);
-    V3 tau_u = mk(0., 0., 0.);
-#pragma unroll
-    for (int i = 0; i < NRW; i++) tau_u = tau_u + arr(P.gs[i]) * mld(m, M_U + i);
-    Dyn<NRW> xs = x, xo = x, k;
+    Dyn xs = x, xo = x, k;
 #pragma unroll 1
     for (int st = 0; st < 4; st++) {
         const double dt = (st == 0) ? dts.d0 : (st == 3 ? dts.d1 : dts.dm);
-        a.rs = sun_r + sun_v * dt;
-        a.A = sun_indirect(P, a.rs);
+        const double ct = (st == 0) ? 0.0 : (st == 3 ? h : hh);
+        a.gsun = sun_accel(P, sun_r + sun_v * dt, xs.r);
         V3 Fm = mk(0., 0., 0.), Lx = L_ext;
         const bool thr_on = thr_active != 0;
         if (thr_on) {
@@ -839,21 +853,15 @@ LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S
             Fm = to.F * P.inv_mass; Lx = Lx + to.L;
             tauPrev = tau;
         }
-        a.Lc = Lx - tau_u;
+        a.Lc = Lx - a.tau_u;
         mst3(m, M_FM, Fm);
-        eom<NRW, J2, DIAG>(P, xs, k, a, thr_on, m);
+        eom<J2, DIAG>(P, xs, k, a, ct, thr_on, m);
         const double wo = (st == 0 || st == 3) ? h6 : h3;
         const double cn = (st == 2) ? h : hh;
         xo.r = xo.r + k.r * wo; xo.v = xo.v + k.v * wo; xo.s = xo.s + k.s * wo; xo.w = xo.w + k.w * wo;
-#pragma unroll
-        for (int i = 0; i < NRW; i++) xo.W[i] = xo.W[i] + k.W[i] * wo;
-        if (st < 3) {
-            xs.r = x.r + k.r * cn; xs.v = x.v + k.v * cn; xs.s = x.s + k.s * cn; xs.w = x.w + k.w * cn;
-#pragma unroll
-            for (int i = 0; i < NRW; i++) xs.W[i] = x.W[i] + k.W[i] * cn;
-        }
+        if (st < 3) { xs.r = x.r + k.r * cn; xs.v = x.v + k.v * cn; xs.s = x.s + k.s * cn; xs.w = x.w + k.w * cn; }
     }
-    ThrEventOut<NRW> o;
+    ThrEventOut o;
     o.x = xo; o.factor = thr_factor; o.active = thr_active;
     return o;
 }
@@ -863,8 +871,7 @@ LEO_HD_NOINLINE ThrEventOut<NRW> rk4_general(const LeoParams &P, const double *S
 // time and the commanded on-times only change at the next command latch).  Publishes the held thrust on the
 // bus and rebuilds the held body torque.
 struct ThrRefresh { V3 Lc, L_thr; double t_next; };
-template <int NRW>
-LEO_HD_NOINLINE ThrRefresh thr_refresh(const LeoParams &P, const double *S, int64_t stride, int64_t e, MBus m, int factor)
+LEO_HD_NOINLINE ThrRefresh thr_refresh(const LeoParams &P, const double *S, int64_t stride, int64_t e, MBus m, int factor, V3 tau_u)
 {
     ThrRefresh o;
     V3 F = mk(0., 0., 0.);
@@ -879,9 +886,6 @@ LEO_HD_NOINLINE ThrRefresh thr_refresh(const LeoParams &P, const double *S, int6
         if (t_off < o.t_next) o.t_next = t_off;
     }
     mst3(m, M_FM, F * P.inv_mass);
-    V3 tau_u = mk(0., 0., 0.);
-#pragma unroll
-    for (int i = 0; i < NRW; i++) tau_u = tau_u + arr(P.gs[i]) * mld(m, M_U + i);
     o.Lc = (mld3(m, M_LEXT) + o.L_thr) - tau_u;
     return o;
 }
@@ -907,10 +911,10 @@ LEO_HD_NOINLINE SunDt sun_dt_wrapped(double prev_ns_d, double sun_ns_d, double t
 //  * thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters.
 // Rebuilds the held body torque.  Returns the new thr_active (or -1 when no thruster message arrived).
 template <int NRW>
-struct PostOut { double uJ[NRW]; V3 Lc; int thr_active; };
+struct PostOut { double uJ[NRW]; V3 Lc, tau_u; int thr_active; };
 template <int NRW>
 LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m,
-                                              Dyn<NRW> x, V3 L_thr, int desat_ran, int64_t now_ns, int thr_factor)
+                                              const double (&W)[NRW], V3 L_thr, int desat_ran, int64_t now_ns, int thr_factor)
 {
     PostOut<NRW> o;
     V3 tau_u = mk(0., 0., 0.);
@@ -919,11 +923,12 @@ LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int
         double uc = mld(m, M_RWCMD + i);
         if (P.u_max[i] > 0.) { if (uc > P.u_max[i]) uc = P.u_max[i]; else if (uc < -P.u_max[i]) uc = -P.u_max[i]; }
         if (fabs(uc) < P.u_min[i]) uc = 0.0;
-        if (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && x.W[i] * uc >= 0.0) uc = 0.0;
+        if (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && W[i] * uc >= 0.0) uc = 0.0;
         mst(m, M_U + i, uc);
         o.uJ[i] = uc * P.invJs[i];
         tau_u = tau_u + arr(P.gs[i]) * uc;
     }
+    o.tau_u = tau_u;
     o.Lc = (mld3(m, M_LEXT) + L_thr) - tau_u;
     o.thr_active = -1;
     if (desat_ran) o.thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor);
@@ -934,6 +939,42 @@ LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int
 // constant-thrust path (the exact test has a tolerance of 1e-9 * stage spacing around the expiry time).
 #define LEO_THR_MARGIN 1e-6
 
+// Wheel speeds from the momentum invariant (see Dyn): Omega_i = C_i - g_i.omega
+template <int NRW, bool DIAG>
+LEO_HD void wheel_speeds(const LeoParams &P, V3 HB, const double (&C)[NRW], V3 w, double (&W)[NRW])
+{
+    if (DIAG) {
+        W[0] = fmad(HB.x, P.invJs[0], -w.x); W[1] = fmad(HB.y, P.invJs[1], -w.y); W[2] = fmad(HB.z, P.invJs[2], -w.z);
+    } else {
+#pragma unroll
+        for (int i = 0; i < NRW; i++) W[i] = C[i] - dot(arr(P.gs[i]), w);
+    }
+}
+
+// exp(x) for |x| <= 700 without special-operand handling (the atmosphere's argument): Cody-Waite reduction by
+// ln 2, degree-13 Taylor polynomial on |r| <= ln2/2 in Estrin form (truncation 4e-18), exponent patched in.
+LEO_HD double exp_bounded(double x)
+{
+#ifdef __CUDA_ARCH__
+    x = fmin(fmax(x, -700.0), 700.0);
+    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const int kk = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, x);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = fma(r, 1.0, 1.0), a1 = fma(r, 1. / 6., 0.5), a2 = fma(r, 1. / 120., 1. / 24.), a3 = fma(r, 1. / 5040., 1. / 720.);
+    const double a4 = fma(r, 1. / 362880., 1. / 40320.), a5 = fma(r, 1. / 39916800., 1. / 3628800.);
+    const double a6 = fma(r, 1. / 6227020800., 1. / 479001600.);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
+    const double p = fma(d1, r8, d0);
+    return __hiloint2double(__double2hiint(p) + (kk << 20), __double2loint(p));
+#else
+    return exp(x);
+#endif
+}
+
 template <int NRW, bool J2, bool DIAG>
 LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
                          MBus m, int action, StepOut &out)
@@ -941,20 +982,22 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
     // ---------------- load ----------------
-    Dyn<NRW> x;
-    StageIn<NRW> a;
+    Dyn x;
+    StageIn a;
     x.r = mk(SD(F_R), SD(F_R + 1), SD(F_R + 2));
     x.v = mk(SD(F_V), SD(F_V + 1), SD(F_V + 2));
     x.s = mk(SD(F_SIG), SD(F_SIG + 1), SD(F_SIG + 2));
     x.w = mk(SD(F_OMG), SD(F_OMG + 1), SD(F_OMG + 2));
-    V3 tau_u = mk(0., 0., 0.);
+    double C[NRW], uJ[NRW];                                     // wheel invariants / motor torque over Js (general path)
+    a.tau_u = mk(0., 0., 0.); a.HB = mk(0., 0., 0.);
 #pragma unroll
     for (int i = 0; i < NRW; i++) {
-        x.W[i] = SD(F_WHL + i);
         const double u = SD(F_UCUR + i);
         mst(m, M_U + i, u);
-        a.uJ[i] = u * P.invJs[i];
-        tau_u = tau_u + arr(P.gs[i]) * u;
+        uJ[i] = u * P.invJs[i];
+        C[i] = SD(F_WHL + i) + dot(arr(P.gs[i]), x.w);
+        a.tau_u = a.tau_u + arr(P.gs[i]) * u;
+        a.HB = a.HB + arr(P.gs[i]) * (P.Js[i] * C[i]);
     }
     for (int f = 0; f < LEO_M_MIRROR; f++) mst(m, f, SD(F_GUID + f));
     a.rho = SD(F_RHO);
@@ -962,7 +1005,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     {
         const V3 L_ext = mk(SD(F_LDIST), SD(F_LDIST + 1), SD(F_LDIST + 2));
         mst3(m, M_LEXT, L_ext); mst3(m, M_FM, mk(0., 0., 0.));
-        a.Lc = L_ext - tau_u;
+        a.Lc = L_ext - a.tau_u;
     }
     V3 L_thr = mk(0., 0., 0.);                                  // held thruster torque (zero outside burns)
     const int64_t tick = SI(I_TICK);
@@ -1002,7 +1045,9 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         // ================= flight software every ticks_per_fsw-th tick =================
         if (phase == 0) {
             const int64_t n = n_base + j;
-            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, (int64_t)sun_d);
+            double W[NRW];
+            wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
+            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, W, (int64_t)sun_d);
             rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
             // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule); the
             // message is then newer than the start of this integration step (quirk Q18)
@@ -1027,37 +1072,44 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
                 const double ph = t_sub(prevTime, ppT);
                 tauPrev = t_add(t_sub(prevTime, ph), ph);
             }
-            ThrEventOut<NRW> o = rk4_general<NRW, J2, DIAG>(P, S, stride, e, m, x, a, dts, tBefore, tauPrev, thr_factor, thr_active);
+            ThrEventOut o = rk4_general<J2, DIAG>(P, S, stride, e, m, x, a, dts, tBefore, tauPrev, thr_factor, thr_active);
             x = o.x; thr_factor = o.factor; thr_active = o.active;
-            ThrRefresh th = thr_refresh<NRW>(P, S, stride, e, m, thr_active ? thr_factor : 0);
+            ThrRefresh th = thr_refresh(P, S, stride, e, m, thr_active ? thr_factor : 0, a.tau_u);
             a.Lc = th.Lc; L_thr = th.L_thr; thr_t_next = th.t_next;
         } else {
-            // Sun frozen at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
+            // Sun at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
             const double dtsm = t_mul(prev_d - sun_d, 1e-9) + 0.5 * h;
-            a.rs = mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm;
-            a.A = sun_indirect(P, a.rs);
-            x = rk4_step<NRW, J2, DIAG>(P, x, a, thr_active != 0, m);
+            a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+            x = rk4_step<J2, DIAG>(P, x, a, thr_active != 0, m);
+        }
+        // the wheel invariant advances with the motor torque held over the step
+        a.HB = a.HB + a.tau_u * h;
+        if (!DIAG) {
+#pragma unroll
+            for (int i = 0; i < NRW; i++) C[i] = fmad(uJ[i], h, C[i]);
         }
         // HubEffector::modifyStates -- MRP shadow-set switch: |sigma| > 1 with the correctly rounded norm, i.e.
         // sigma.sigma > 1 + 2^-52 (sqrt(1 + 2^-52) rounds to 1)
         {
             const double s2 = dot(x.s, x.s);
-            if (s2 > 1.0000000000000002) { x.s = x.s * (-1. / s2); nswitch++; }
+            if (s2 > 1.0000000000000002) { x.s = x.s * (-frcp(s2)); nswitch++; }
         }
         // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
         const double r2 = dot(x.r, x.r);
         // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
-        a.rho = P.rho0 * exp(-(r2 * rsq(r2) - P.Rp_atmo) * P.inv_H);
+        a.rho = P.rho0 * exp_bounded(-(r2 * rsq(r2) - P.Rp_atmo) * P.inv_H);
         // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
         {
+            double W[NRW];
+            wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
             int lim = 0;
 #pragma unroll
-            for (int i = 0; i < NRW; i++) lim |= (fabs(x.W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
+            for (int i = 0; i < NRW; i++) lim |= (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
             if (rw_sat | lim | desat_ran) {
-                PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, x, L_thr, desat_ran, (int64_t)now_d, thr_factor);
+                PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, W, L_thr, desat_ran, (int64_t)now_d, thr_factor);
 #pragma unroll
-                for (int i = 0; i < NRW; i++) a.uJ[i] = po.uJ[i];
-                a.Lc = po.Lc;
+                for (int i = 0; i < NRW; i++) uJ[i] = po.uJ[i];
+                a.Lc = po.Lc; a.tau_u = po.tau_u;
                 rw_sat = lim;
                 if (po.thr_active >= 0) { thr_active = po.thr_active; thr_t_next = -1.0; }   // burning set: re-derive exactly
                 desat_ran = 0;
@@ -1085,11 +1137,13 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
 
     // ---------------- observation sampling (SIM:598-642) + gym bookkeeping (ENV:98-145) ----------------
     for (int f = 0; f < LEO_M_MIRROR; f++) SD(F_GUID + f) = mld(m, f);
+    double W[NRW];
+    wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
     double ob0 = norm(mld3(m, M_GUID));
     double ob1 = norm(x.w);
     double wn = 0.;
 #pragma unroll
-    for (int i = 0; i < NRW; i++) wn += x.W[i] * x.W[i];
+    for (int i = 0; i < NRW; i++) wn += W[i] * W[i];
     double ob2 = sqrt(wn), ob3 = E / 3600., ob4 = shadow;
     int sim_over = norm(x.r) < P.decay_radius;
     int64_t curr_step = SI(I_STEP);
@@ -1113,7 +1167,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     SD(F_SIG) = x.s.x; SD(F_SIG + 1) = x.s.y; SD(F_SIG + 2) = x.s.z;
     SD(F_OMG) = x.w.x; SD(F_OMG + 1) = x.w.y; SD(F_OMG + 2) = x.w.z;
 #pragma unroll
-    for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = x.W[i]; SD(F_UCUR + i) = mld(m, M_U + i); }
+    for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = W[i]; SD(F_UCUR + i) = mld(m, M_U + i); }
     SD(F_RHO) = a.rho; SD(F_E) = E; SD(F_SHADOW) = shadow; SD(F_EPRET) = ret;
     SI(I_TICK) = n_end; SI(I_STEP) = curr_step + 1; SI(I_MASK) = mask; SI(I_SWITCH) = SI(I_SWITCH) + nswitch;
     SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_OVER) = over; SI(I_RWSAT) = rw_sat;

@@ -75,6 +75,7 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
     for (int i = 0; i < p.nrw; i++)
         for (int a = 0; a < 3; a++)
             for (int b = 0; b < 3; b++) D[3 * a + b] -= p.Js[i] * p.gs[i][a] * p.gs[i][b];
+    memcpy(p.D, D, sizeof(D));
     if (!inv3(D, p.Dinv)) return "singular back-substitution matrix";
     { // structural fast path: diagonal inertia and wheel i along body axis i
         bool diag = p.nrw == 3;

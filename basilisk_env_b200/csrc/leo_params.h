@@ -22,7 +22,8 @@ struct LeoParams {
     // ---- hub ----
     double inv_mass;
     double I[9];          // IHubPntBc_B (= ISCPntB_B: balanced wheels carry no mass properties)
-    double Dinv[9];       // inverse of  I - sum_i Js_i g_i g_i^T   (constant back-substitution matrix)
+    double D[9];          // I - sum_i Js_i g_i g_i^T   (constant back-substitution matrix of the balanced wheels)
+    double Dinv[9];       // its inverse
     // ---- gravity ----
     double mu_c, mu_sun;
     double j2k;           // 1.5 * J2 * mu * Req^2 (only when the J2 template flag is on)

@@ -39,15 +39,17 @@ def test_fast_path_equals_reference_formula(orc, hostcore):
 
 
 def test_general_eom_path_equals_fast_path(hostcore, orc):
-    """DIAG fast path (structural zeros dropped) == general 3x3 path, bit for bit on the host."""
+    """DIAG fast path (structural zeros dropped, wheel speeds from the per-axis momentum invariant) == general
+    3x3 path (per-wheel invariants) up to rounding: discrete outputs exact, continuous ones to 1e-10."""
     from tests import parity
     rows = parity.sample_rows(orc, 4, seed=77)
     a = hostcore.HostCore(4); b = hostcore.HostCore(4); b.force_general()
     a.reset_ics(rows); b.reset_ics(rows)
     for acts in ([0, 1, 2, 0], [2, 2, 1, 0], [1, 0, 2, 2]):
         oa = a.step(acts); ob = b.step(acts)
-        for x, y in zip(oa, ob):
-            np.testing.assert_array_equal(x, y)
+        np.testing.assert_allclose(oa[0], ob[0], rtol=1e-10, atol=1e-13)
+        np.testing.assert_allclose(oa[1], ob[1], rtol=0, atol=1e-12)
+        np.testing.assert_array_equal(oa[2], ob[2]); np.testing.assert_array_equal(oa[3], ob[3])
     Sa, Ia = a.state(); Sb, Ib = b.state()
-    np.testing.assert_allclose(Sa, Sb, rtol=1e-13, atol=1e-18)
+    np.testing.assert_allclose(Sa, Sb, rtol=1e-10, atol=1e-13)
     np.testing.assert_array_equal(Ia, Ib)
