@@ -84,6 +84,16 @@ LEO_HD double frcp(double x)
     return 1.0 / x;
 #endif
 }
+// Fused multiply-add: a true FMA on the device; plain arithmetic on the host (tests/hostcore is built with
+// -ffp-contract=off and must not depend on a libm fma()).
+LEO_HD double fmad(double p, double q, double r)
+{
+#ifdef __CUDA_ARCH__
+    return fma(p, q, r);
+#else
+    return p * q + r;
+#endif
+}
 LEO_HD double clamp_asin(double x) { return x > 1. ? asin(1.) : (x < -1. ? asin(-1.) : asin(x)); }
 LEO_HD double clamp_acos(double x) { return x > 1. ? acos(1.) : (x < -1. ? acos(-1.) : acos(x)); }
 
@@ -450,12 +460,10 @@ LEO_HD_NOINLINE int thr_latch(const LeoParams &P, double *S, int64_t *I, int64_t
 // ------------------------------------------------------------------------------------------------
 // eclipse (conical shadow model) and solar panel, per environment tick
 // ------------------------------------------------------------------------------------------------
-LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP, double l2sq, double p2, double u2)
-{ // eclipse.cpp: `if (fabs(l) < fabs(l_2) || fabs(l) < fabs(l_1))` gate, then computePercentShadow
-    if (!(sqrt(l2sq) < sqrt(u2) || sqrt(l2sq) < sqrt(p2))) return 1.0;
-    double nH = norm(r_HB), nB = norm(s_BP);
-    double a = clamp_asin(P.R_sun / nH), b = clamp_asin(P.R_planet / nB);
-    double c = clamp_acos((-dot(s_BP, r_HB)) / (nB * nH));
+// eclipse.cpp computePercentShadow, literal form (apparent radii a, b and separation c as angles).  Cold path:
+// only used when the small-Sun expansion of penumbra_fraction() below does not apply.
+LEO_HD_NOINLINE double percent_shadow_general(double a, double b, double c)
+{
     const double PI = 3.14159265358979323846;
     double shadow = 1.0;
     if (c < b - a) {
@@ -471,14 +479,53 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, V3 r_HB, V3 s_BP, d
     }
     return shadow;
 }
+// asin(t) for |t| <= 0.1 (Maclaurin series through t^13: truncation < 1e-17 relative)
+LEO_HD double asin_small(double t)
+{
+    const double t2 = t * t;
+    double p = fmad(t2, 231. / 13312., 63. / 2816.);
+    p = fmad(p, t2, 35. / 1152.); p = fmad(p, t2, 5. / 112.); p = fmad(p, t2, 3. / 40.); p = fmad(p, t2, 1. / 6.);
+    return fmad(t * t2, p, t);
+}
+// Fraction of the solar disk left visible inside the penumbra (eclipse.cpp computePercentShadow: overlap of two
+// disks of apparent radii a = asin(R_sun/|r_HB|), b = asin(R_p/|s_BP|) whose centres are c apart).
+// The Sun's disk is small (a = 4.65e-3 rad) and c is within a of b, so the reference's five inverse
+// trigonometric calls reduce to two: a and the offset delta = c - b come from their sines (series; sin(delta)
+// = sin c cos b - cos c sin b is formed algebraically, which also avoids the cancellation in c - b), and the
+// planet's circular segment b^2 (phi - sin phi cos phi), sin phi = y/b <= a/b, is a short series.  The same
+// lens-area formula, regrouped as (Sun segment) + (planet segment); agreement with the literal form is ~1e-13.
+//   ir = 1/|s_BP|, id = 1/|r_HB|, rdh = s_BP . r_HB
+LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double id, double rdh)
+{
+    const double PI = 3.14159265358979323846;
+    const double ta = P.R_sun * id, tb = P.R_planet * ir;             // sin a, sin b
+    const double cc = -rdh * ir * id;                                  // cos c
+    const double sc2 = 1. - cc * cc, cb2 = 1. - tb * tb;
+    const double sd = (sc2 > 0. && cb2 > 0.) ? sqrt(sc2) * sqrt(cb2) - cc * tb : 2.0;   // sin(c - b)
+    if (!(ta <= 0.05 && fabs(sd) <= 0.1 && tb >= 20. * ta && tb < 1.))                  // not a small Sun next to a big limb
+        return percent_shadow_general(clamp_asin(ta), clamp_asin(tb), clamp_acos(cc));
+    const double a = asin_small(ta), d = asin_small(sd), b = asin(tb);
+    if (d < -a) return 0.0;                                            // c < b - a: total
+    if (!(d < a)) return 1.0;                                          // c >= a + b: clear   (c < a - b cannot occur: b > a)
+    const double c = b + d;
+    const double x = (a * a + d * (2. * b + d)) / (2. * c);
+    double y2 = a * a - x * x;
+    if (y2 < 0.) y2 = 0.;
+    const double y = sqrt(y2);
+    const double u = y / b, u2 = u * u;
+    double seg = fmad(u2, 5. / 72., 3. / 28.);
+    seg = fmad(seg, u2, 1. / 5.); seg = fmad(seg, u2, 2. / 3.);
+    const double area = a * a * clamp_acos(x / a) - x * y + (b * b) * (u * u2) * seg;
+    return 1. - area / (PI * a * a);
+}
 // Shadow factor of the planet at the origin (zeroBase earth), eclipse.UpdateState + computePercentShadow.
 // Full sun / umbra are decided on squared cone radii (no sqrt, no transcendentals); a relative guard band of
-// ECL_BAND around both cone surfaces, and the penumbra itself, go through the reference formula.
+// ECL_BAND around both cone surfaces, and the penumbra itself, go through the disk-overlap formula.
 // The cone tests and the apparent-disk tests of computePercentShadow describe the same geometry (tangent
 // cones of two spheres), so outside the band both give exactly 0.0 or 1.0 (tests/test_hostcore_eclipse.py).
+//   s2 = r.r, ir = 1/|r|, r_HB = sun_r - r, hb2 = r_HB.r_HB, id = 1/|r_HB|
 #define ECL_BAND 1e-7
-LEO_HD double eclipse_core(const LeoParams &P, const double (&ec)[6], V3 sun_r, V3 r, double s2 /* = r.r */,
-                           V3 r_HB /* = sun_r - r */, double hb2 /* = r_HB.r_HB */)
+LEO_HD double eclipse_core(const LeoParams &P, const double (&ec)[6], V3 sun_r, V3 r, double s2, double ir, V3 r_HB, double hb2, double id)
 {
     const double hp2 = ec[0], inv_hp = ec[1], c1off = ec[2], c2off = ec[3], tan1 = ec[4], tan2 = ec[5];
     const double s0 = -dot(r, sun_r) * inv_hp;
@@ -490,13 +537,14 @@ LEO_HD double eclipse_core(const LeoParams &P, const double (&ec)[6], V3 sun_r, 
                      || (l2sq > p2 * (1. + ECL_BAND) && l2sq > u2 * (1. + ECL_BAND));       // outside both cones
     const bool dark = l2sq < u2 * (1. - ECL_BAND) && c2 < 0. && P.R_sun > P.R_planet;      // inside the umbra, before its apex
     double f = lit ? 1.0 : 0.0;
-    if (!lit && !dark) f = penumbra_fraction(P, r_HB, r, l2sq, p2, u2);
+    // eclipse.cpp gate `fabs(l) < fabs(l_2) || fabs(l) < fabs(l_1)`, on the squares
+    if (!lit && !dark) f = (l2sq < u2 || l2sq < p2) ? penumbra_fraction(P, ir, id, dot(r, r_HB)) : 1.0;
     return f;
 }
 LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r, double s2, V3 r_HB, double hb2)
 {
     const double ec[6] = {sun.hp2, sun.inv_hp, sun.c1off, sun.c2off, sun.tan1, sun.tan2};
-    return eclipse_core(P, ec, sun.r, r, s2, r_HB, hb2);
+    return eclipse_core(P, ec, sun.r, r, s2, rsq(s2), r_HB, hb2, rsq(hb2));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -698,16 +746,6 @@ LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t 
     return desat_ran;
 }
 
-// Fused multiply-add: a true FMA on the device; plain arithmetic on the host (tests/hostcore is built with
-// -ffp-contract=off and must not depend on a libm fma()).
-LEO_HD double fmad(double p, double q, double r)
-{
-#ifdef __CUDA_ARCH__
-    return fma(p, q, r);
-#else
-    return p * q + r;
-#endif
-}
 LEO_HD V3 add_cross(V3 p, V3 u, V3 v)     // p + u x v, six fused operations
 {
     return mk(fmad(u.y, v.z, fmad(-u.z, v.y, p.x)), fmad(u.z, v.x, fmad(-u.x, v.z, p.y)), fmad(u.x, v.y, fmad(-u.y, v.x, p.z)));
@@ -1095,9 +1133,9 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             if (s2 > 1.0000000000000002) { x.s = x.s * (-frcp(s2)); nswitch++; }
         }
         // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
-        const double r2 = dot(x.r, x.r);
+        const double r2 = dot(x.r, x.r), ir = rsq(r2);
         // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
-        a.rho = P.rho0 * exp_bounded(-(r2 * rsq(r2) - P.Rp_atmo) * P.inv_H);
+        a.rho = P.rho0 * exp_bounded(-(r2 * ir - P.Rp_atmo) * P.inv_H);
         // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
         {
             double W[NRW];
@@ -1121,7 +1159,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             const V3 r_SB = sun_r - x.r;                       // spacecraft -> Sun
             const double d2 = dot(r_SB, r_SB), id = rsq(d2);
             const double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
-            shadow = eclipse_core(P, ec, sun_r, x.r, r2, r_SB, d2);
+            shadow = eclipse_core(P, ec, sun_r, x.r, r2, ir, r_SB, d2, id);
             MrpRot R = mrp_rot(x.s);
             V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
             double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B

@@ -21,11 +21,18 @@ W, T = 4096.0, 1800.0
 
 txt = subprocess.run(["nvdisasm", "--print-line-info-inline", cubin], capture_output=True, text=True).stdout
 chains, cur, on = {}, [], False
+sub, subs = "kernel", {}
 for line in txt.splitlines():
     if line.startswith(".text."):
         on = kern in line
         continue
     if not on:
+        continue
+    m = re.match(r"^\$\S*\$(\S+):\s*$", line)          # out-of-line device function / libdevice slow path
+    if m:
+        nm = m.group(1)
+        mm = re.search(r"3leo(\d+)", nm)
+        sub = nm[mm.end():mm.end() + int(mm.group(1))] if mm else nm.strip("_$")[:40]
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', line)
     if m:
@@ -37,6 +44,7 @@ for line in txt.splitlines():
         if cur:
             chains["last"] = cur
         chains[a] = chains.get("last", [])
+        subs[a] = sub
         cur = []
 
 rows = list(csv.reader(open(src)))
@@ -44,6 +52,7 @@ hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 base = None
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+sagg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 tot = 0
 for r in rows[2:]:
     if len(r) < len(hdr):
@@ -60,6 +69,10 @@ for r in rows[2:]:
     n = int(r[ix["# Samples"]] or 0)
     ex = int(r[ix["Instructions Executed"]] or 0) / W / T
     op = [o for o in r[ix["Source"]].split() if not o.startswith("@")][0].split(".")[0]
+    sname = subs.get(a - base, "?")
+    sagg[sname][0] += n; sagg[sname][1] += ex
+    if op in ("DFMA", "DMUL", "DADD", "DSETP"):
+        sagg[sname][2] += ex
     agg[key][0] += n
     agg[key][1] += ex
     if op in ("DFMA", "DMUL", "DADD", "DSETP"):
@@ -70,7 +83,33 @@ try:
     lines = dict(enumerate(open("/root/repo/basilisk_env_b200/csrc/leo_core.cuh").read().splitlines(), 1))
 except OSError:
     pass
+# per-function totals (function = the last definition that starts at or before the line)
+fstarts = []
+for ln, text in sorted(lines.items()):
+    m = re.match(r"^(?:LEO_HD_NOINLINE|LEO_HD)\s+.*?(\w+)\(", text)
+    if m and not text.startswith(" "):
+        fstarts.append((ln, m.group(1)))
+def func_of(key):
+    if key[0] != "leo_core.cuh":
+        return key[0]
+    name = "?"
+    for ln, n in fstarts:
+        if ln <= key[1]:
+            name = n
+    return name
+fagg = collections.defaultdict(lambda: [0, 0.0, 0.0])
+for key, (n, ex, fp) in agg.items():
+    f = func_of(key)
+    fagg[f][0] += n; fagg[f][1] += ex; fagg[f][2] += fp
+print(f"{'code section':>28s} {'time%':>6s} {'instr/tick':>10s} {'fp64/tick':>9s}")
+for f, (n, ex, fp) in sorted(sagg.items(), key=lambda kv: -kv[1][0])[:25]:
+    print(f"{f:>28s} {100 * n / tot:6.2f} {ex:10.1f} {fp:9.1f}")
+print()
+print(f"{'function':>28s} {'time%':>6s} {'instr/tick':>10s} {'fp64/tick':>9s}")
+for f, (n, ex, fp) in sorted(fagg.items(), key=lambda kv: -kv[1][0])[:25]:
+    print(f"{f:>28s} {100 * n / tot:6.2f} {ex:10.1f} {fp:9.1f}")
+print()
 print(f"{'line':>16s} {'time%':>6s} {'instr/tick':>10s} {'fp64/tick':>9s}")
-for key, (n, ex, fp) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:100000]:
+for key, (n, ex, fp) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[5]) if len(sys.argv) > 5 else 60]:
     text = lines.get(key[1], "").strip()[:90] if key[0] == "leo_core.cuh" else ""
     print(f"{key[0][:10]:>10s}:{key[1]:<5d} {100 * n / tot:6.2f} {ex:10.1f} {fp:9.1f}  {text}")
