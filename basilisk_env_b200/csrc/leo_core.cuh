@@ -384,9 +384,12 @@ LEO_HD_NOINLINE void thr_force_mapping(const LeoParams &P, V3 Lr, double (&F)[LE
 
 // rwDesatTask = thrMomentumManagement -> thrForceMapping -> thrMomentumDumping (SIM:488-490).
 // wheel speeds = the RWSpeed message of the previous dynamics tick (zeros before the first tick).
+// Returns 1 when the dumping block ran and left nothing to do: no on-time remaining on any thruster and a zero
+// command (the chain is then "quiet": until the next Reset every pass only advances the rest counter and the
+// time tag, see fsw_pass).
 template <int NRW>
-LEO_HD_NOINLINE void fsw_desat(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int64_t now_ns,
-                               const double (&ws)[NRW])
+LEO_HD_NOINLINE int fsw_desat(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int64_t now_ns,
+                              const double (&ws)[NRW])
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
@@ -432,7 +435,12 @@ LEO_HD_NOINLINE void fsw_desat(const LeoParams &P, double *S, int64_t *I, int64_
         }
     }
     SI(I_DUMPPRIOR) = now_ns;
-    for (int k = 0; k < LEO_NTHR; k++) SD(F_THRCMD + k) = tOn[k];
+    int quiet = prior != 0;
+    for (int k = 0; k < LEO_NTHR; k++) {
+        SD(F_THRCMD + k) = tOn[k];
+        if (tOn[k] != 0.0 || SD(F_THRREM + k) != 0.0) quiet = 0;
+    }
+    return quiet;
 #undef SD
 #undef SI
 }
@@ -695,9 +703,12 @@ LEO_HD_NOINLINE void sun_latch_to_bus(const LeoParams &P, MBus m, int64_t msg_ns
 // One flight-software pass at time now_ns (the priority 100/50 tasks run before DynTask at equal times).
 // nav = state written by the previous dynamics tick (zeros before tick 0: messages never written).
 // Out of line: it runs once per ticks_per_fsw dynamics ticks and must not bloat the hot tick loop.
+// Returns the state of the desat chain: 0 did not run; 1 full pass; 3 full pass that left the chain quiet (to be
+// confirmed by the thruster latch); 4 quiet pass (all on-times and commands are zero and stay zero: only
+// thrMomentumDumping's rest counter and time tag advance).
 template <int NRW>
 LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m, int mask,
-                             int64_t n, int64_t now_ns, Dyn x, const double (&W)[NRW], int64_t sun_ns)
+                             int64_t n, int64_t now_ns, Dyn x, const double (&W)[NRW], int64_t sun_ns, int desat_quiet)
 {
     V3 nr = x.r, nv = x.v, ns = x.s, nw = x.w;
     double ws[NRW];
@@ -725,8 +736,14 @@ LEO_HD_NOINLINE int fsw_pass(const LeoParams &P, double *S, int64_t *I, int64_t 
     }
     int desat_ran = 0;
     if (mask & LEO_TASK_DESAT) {
-        fsw_desat<NRW>(P, S, I, stride, e, now_ns, ws);
-        desat_ran = 1;
+        if (desat_quiet) {
+            const int64_t cnt = I[(int64_t)I_DUMPCNT * stride + e];
+            I[(int64_t)I_DUMPCNT * stride + e] = cnt <= 0 ? (int64_t)P.maxCounterValue : cnt - 1;
+            I[(int64_t)I_DUMPPRIOR * stride + e] = now_ns;
+            desat_ran = 4;
+        } else {
+            desat_ran = 1 | (fsw_desat<NRW>(P, S, I, stride, e, now_ns, ws) << 1);
+        }
     }
     if (mask & LEO_TASK_MRP) {
         // quirk Q1: MRP_Feedback runs BEFORE attTrackingError -> uses last pass's att_guidance
@@ -949,7 +966,7 @@ LEO_HD_NOINLINE SunDt sun_dt_wrapped(double prev_ns_d, double sun_ns_d, double t
 //  * thrusterDynamicEffector.UpdateState: only a NEW on-time message re-configures the thrusters.
 // Rebuilds the held body torque.  Returns the new thr_active (or -1 when no thruster message arrived).
 template <int NRW>
-struct PostOut { double uJ[NRW]; V3 Lc, tau_u; int thr_active; };
+struct PostOut { double uJ[NRW]; V3 Lc, tau_u; int thr_active, quiet; };
 template <int NRW>
 LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m,
                                               const double (&W)[NRW], V3 L_thr, int desat_ran, int64_t now_ns, int thr_factor)
@@ -968,8 +985,14 @@ LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int
     }
     o.tau_u = tau_u;
     o.Lc = (mld3(m, M_LEXT) + L_thr) - tau_u;
-    o.thr_active = -1;
-    if (desat_ran) o.thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor);
+    o.thr_active = -1; o.quiet = 0;
+    if (desat_ran & 1) {
+        o.thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor);
+        o.quiet = (desat_ran & 2) && o.thr_active == 0;          // nothing commanded, nothing burning
+    } else if (desat_ran & 4) {                                 // quiet: the latch would rewrite zeros; keep the time tag
+        S[(int64_t)F_THRSTART * stride + e] = t_mul((double)now_ns, 1.0E-9);
+        o.quiet = 1;
+    }
     return o;
 }
 
@@ -1074,7 +1097,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     sun_latch_to_bus(P, m, (n_base - 1) * P.dyn_ns);
     int phase = (int)((n_base - 1) % tpf);                     // (n mod ticks_per_fsw) of the tick about to run
     double now_d = sun_d;                                      // exact: n * dyn_ns
-    int desat_ran = 0;
+    int desat_ran = 0, desat_quiet = 0;                        // the chain's quiet state is re-established once per launch
 
 #pragma unroll 1
     for (int j = -1; j < ticks; j++, now_d += dyn_d, phase = (phase + 1 == tpf) ? 0 : phase + 1) {
@@ -1085,7 +1108,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             const int64_t n = n_base + j;
             double W[NRW];
             wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
-            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, W, (int64_t)sun_d);
+            desat_ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, W, (int64_t)sun_d, desat_quiet);
             rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
             // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule); the
             // message is then newer than the start of this integration step (quirk Q18)
@@ -1150,6 +1173,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
                 a.Lc = po.Lc; a.tau_u = po.tau_u;
                 rw_sat = lim;
                 if (po.thr_active >= 0) { thr_active = po.thr_active; thr_t_next = -1.0; }   // burning set: re-derive exactly
+                if (desat_ran) desat_quiet = po.quiet;
                 desat_ran = 0;
             }
         }

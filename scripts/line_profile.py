@@ -18,6 +18,8 @@ cubin, src = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else "leo_step_kernelILi3ELb0ELb1"
 depth = int(sys.argv[4]) if len(sys.argv) > 4 else -1
 W, T = 4096.0, 1800.0
+import os
+only = os.environ.get("SECTION")     # restrict the per-line table to one out-of-line function
 
 txt = subprocess.run(["nvdisasm", "--print-line-info-inline", cubin], capture_output=True, text=True).stdout
 chains, cur, on = {}, [], False
@@ -70,6 +72,9 @@ for r in rows[2:]:
     ex = int(r[ix["Instructions Executed"]] or 0) / W / T
     op = [o for o in r[ix["Source"]].split() if not o.startswith("@")][0].split(".")[0]
     sname = subs.get(a - base, "?")
+    if only and sname != only:
+        tot += int(r[ix["# Samples"]] or 0)
+        continue
     sagg[sname][0] += n; sagg[sname][1] += ex
     if op in ("DFMA", "DMUL", "DADD", "DSETP"):
         sagg[sname][2] += ex
