@@ -12,6 +12,7 @@
 // There is no CPU path in this library.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -21,7 +22,7 @@
 #include "leo_host.h"
 
 #ifndef LEO_MIN_BLOCKS
-#define LEO_MIN_BLOCKS 1
+#define LEO_MIN_BLOCKS 3        // resident blocks per SM: 3 x 128 threads x 168 registers
 #endif
 #define LEO_BUS_BYTES ((size_t)leo::LEO_NM * LEO_BLOCK * sizeof(double))   // shared-memory message bus of one block
 
@@ -36,64 +37,91 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+#ifdef LEO_MAXNREG
+#define LEO_STEP_BOUNDS __maxnreg__(LEO_MAXNREG)       // tuning builds: explicit register cap instead of an occupancy target
+#else
+#define LEO_STEP_BOUNDS __launch_bounds__(LEO_BLOCK, LEO_MIN_BLOCKS)
+#endif
+
+// Work distribution.  One warp steps one group of 32 consecutive envs through the whole decision interval and
+// every group costs the same.  When there are more groups than resident warps (12 per SM: three 128-thread
+// blocks of 168 registers), the grid is exactly one resident set of blocks and the warps pull groups from an
+// atomic queue until it is empty: no block-granular waves, no warp waits for the slowest warp of its block, and
+// the tail is spread over all SMs (131072 envs on 148 SMs: 16.15 ms with one block per 128 envs, 15.7 ms with
+// the queue; an early-retiring third block per SM was measured as well and does not help).
+//   sched[0] = queue head (zeroed before the launch)
+struct LeoSched { int *sched; int n_groups; int dynamic; };
+
 template <int NRW, bool J2, bool DIAG>
-__global__ void __launch_bounds__(LEO_BLOCK, LEO_MIN_BLOCKS)
+__global__ void LEO_STEP_BOUNDS
 leo_step_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                 int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                 double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
-                double *__restrict__ term_obs, double *__restrict__ stats)
+                double *__restrict__ term_obs, double *__restrict__ stats, const LeoSched sc)
 {
     extern __shared__ double bus_smem[];          // [LEO_NM][LEO_BLOCK]: per-thread message bus (leo_core.cuh: MBus)
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = e < n;
-    leo::StepOut o;
-    o.done = 0; o.reason = 0; o.reward = 0.;
-    double ep_ret = 0., ep_len = 0.;
-    if (valid) {
-        leo::MBus bus;
-        bus.p = nullptr;
-        bus.a = (uint32_t)__cvta_generic_to_shared(bus_smem) + threadIdx.x * (uint32_t)sizeof(double);
-        leo::leo_step_env<NRW, J2, DIAG>(P, S, I, stride, e, bus, actions[e], o);
-        reward[e] = o.reward;
-        done[e] = (uint8_t)o.done;
-        reason[e] = (uint8_t)o.reason;
-        if (o.done) {
-            ep_ret = S[(int64_t)F_EPRET * stride + e];
-            ep_len = (double)I[(int64_t)I_STEP * stride + e];
-            if (term_obs)
-                for (int k = 0; k < 5; k++) term_obs[e * 5 + k] = o.ob[k];
-            if (P.auto_reset) {
-                // SB-VecEnv convention: the returned observation is the first one of the next episode
-                int64_t ep = I[(int64_t)I_EPISODE * stride + e] + 1;
-                I[(int64_t)I_EPISODE * stride + e] = ep;
-                double ic[19];
-                leo::sample_ic(P, P.first_env_index + e, ep, ic);
-                for (int k = 0; k < 19; k++) ics[(int64_t)k * stride + e] = ic[k];
-                leo::leo_reset_env(P, S, I, stride, e, ic, o.ob);
-            }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    leo::MBus bus;
+    bus.p = nullptr;
+    bus.a = (uint32_t)__cvta_generic_to_shared(bus_smem) + threadIdx.x * (uint32_t)sizeof(double);
+    for (bool more = true; more; more = sc.dynamic != 0) {
+        int g;
+        if (sc.dynamic) {
+            g = 0;
+            if (lane == 0) g = atomicAdd(&sc.sched[0], 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= sc.n_groups) break;
+        } else {
+            g = blockIdx.x * (LEO_BLOCK / 32) + warp;
         }
-        for (int k = 0; k < 5; k++) obs[e * 5 + k] = o.ob[k];
-    }
-    // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
-    if (stats) {
-        const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
-        const int lane = threadIdx.x & 31;
-        if (any_done) {
-            double v_ret = warp_sum(o.done ? ep_ret : 0.), v_len = warp_sum(o.done ? ep_len : 0.);
-            int c_all = __popc(any_done);
-            int c_w = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
-            int c_p = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 4)));
-            int c_d = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 8)));
-            int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
-            if (lane == 0) {
-                atomicAdd(&stats[ST_RET], v_ret); atomicAdd(&stats[ST_LEN], v_len);
-                atomicAdd(&stats[ST_COUNT], (double)c_all); atomicAdd(&stats[ST_WHEEL], (double)c_w);
-                atomicAdd(&stats[ST_POWER], (double)c_p); atomicAdd(&stats[ST_DECAY], (double)c_d);
-                atomicAdd(&stats[ST_MAXLEN], (double)c_m);
+        const int64_t e = (int64_t)g * 32 + lane;
+        const bool valid = e < n;
+        leo::StepOut o;
+        o.done = 0; o.reason = 0; o.reward = 0.;
+        double ep_ret = 0., ep_len = 0.;
+        if (valid) {
+            leo::leo_step_env<NRW, J2, DIAG>(P, S, I, stride, e, bus, actions[e], o);
+            reward[e] = o.reward;
+            done[e] = (uint8_t)o.done;
+            reason[e] = (uint8_t)o.reason;
+            if (o.done) {
+                ep_ret = S[(int64_t)F_EPRET * stride + e];
+                ep_len = (double)I[(int64_t)I_STEP * stride + e];
+                if (term_obs)
+                    for (int k = 0; k < 5; k++) term_obs[e * 5 + k] = o.ob[k];
+                if (P.auto_reset) {
+                    // SB-VecEnv convention: the returned observation is the first one of the next episode
+                    int64_t ep = I[(int64_t)I_EPISODE * stride + e] + 1;
+                    I[(int64_t)I_EPISODE * stride + e] = ep;
+                    double ic[19];
+                    leo::sample_ic(P, P.first_env_index + e, ep, ic);
+                    for (int k = 0; k < 19; k++) ics[(int64_t)k * stride + e] = ic[k];
+                    leo::leo_reset_env(P, S, I, stride, e, ic, o.ob);
+                }
             }
+            for (int k = 0; k < 5; k++) obs[e * 5 + k] = o.ob[k];
         }
-        const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
-        if (lane == 0 && c_valid) atomicAdd(&stats[ST_STEPS], (double)c_valid);
+        // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
+        if (stats) {
+            const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
+            if (any_done) {
+                double v_ret = warp_sum(o.done ? ep_ret : 0.), v_len = warp_sum(o.done ? ep_len : 0.);
+                int c_all = __popc(any_done);
+                int c_w = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
+                int c_p = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 4)));
+                int c_d = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 8)));
+                int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
+                if (lane == 0) {
+                    atomicAdd(&stats[ST_RET], v_ret); atomicAdd(&stats[ST_LEN], v_len);
+                    atomicAdd(&stats[ST_COUNT], (double)c_all); atomicAdd(&stats[ST_WHEEL], (double)c_w);
+                    atomicAdd(&stats[ST_POWER], (double)c_p); atomicAdd(&stats[ST_DECAY], (double)c_d);
+                    atomicAdd(&stats[ST_MAXLEN], (double)c_m);
+                }
+            }
+            const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
+            if (lane == 0 && c_valid) atomicAdd(&stats[ST_STEPS], (double)c_valid);
+        }
+        __syncwarp();
     }
 }
 
@@ -164,6 +192,8 @@ struct bskenv_handle {
     int64_t n, stride;
     double *S, *ics, *stats;
     int64_t *I;
+    int *sched;                 // work queue head of the step kernel
+    int sm_count;
     // staging for the host-buffer entry point
     int32_t *d_act; double *d_obs, *d_rew; uint8_t *d_done, *d_reason;
     int32_t *h_act; double *h_obs, *h_rew; uint8_t *h_done, *h_reason;
@@ -184,7 +214,17 @@ struct bskenv_handle {
 static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double *rew, uint8_t *done, uint8_t *reason,
                        double *term_obs, cudaStream_t st)
 {
-    const int grid = (int)((h->n + LEO_BLOCK - 1) / LEO_BLOCK);
+    const int wpb = LEO_BLOCK / 32;
+    const int64_t groups = (h->n + 31) / 32;
+    const int resident = h->sm_count * LEO_MIN_BLOCKS;          // blocks of one full resident set
+    int grid = (int)((groups + wpb - 1) / wpb);
+    LeoSched sc;
+    sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
+    if (grid > resident) {
+        sc.dynamic = 1;
+        grid = resident;
+        CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
+    }
 #define LEO_LAUNCH(J2, DIAG)                                                                                   \
     do {                                                                                                       \
         static bool attr_set[64] = {false};      /* opt in to > 48 KB of dynamic shared memory once per device */  \
@@ -193,7 +233,7 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
             attr_set[h->device & 63] = true;                                                                   \
         }                                                                                                      \
         leo_step_kernel<3, J2, DIAG><<<grid, LEO_BLOCK, LEO_BUS_BYTES, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
-                                                                              rew, done, reason, term_obs, h->stats); \
+                                                                              rew, done, reason, term_obs, h->stats, sc); \
     } while (0)
     if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(true, true); else LEO_LAUNCH(true, false); }
     else               { if (h->P.diag) LEO_LAUNCH(false, true); else LEO_LAUNCH(false, false); }
@@ -228,10 +268,12 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     if (!perr.empty()) { g_create_error = "bskenv_create: " + perr; delete h; return BSKENV_EINVAL; }
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
-    h->S = h->ics = h->stats = nullptr; h->I = nullptr;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;
     h->d_act = nullptr; h->d_obs = h->d_rew = nullptr; h->d_done = h->d_reason = nullptr;
     h->h_act = nullptr; h->h_obs = h->h_rew = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * 4);
     if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * LEO_ND * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * LEO_NI * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * 19 * h->stride);
@@ -253,7 +295,7 @@ int bskenv_destroy(bskenv_handle *h)
 {
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_reason);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done); cudaFreeHost(h->h_reason);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);

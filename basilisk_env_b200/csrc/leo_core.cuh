@@ -664,7 +664,11 @@ enum LeoMField : int {
     M_LEXT = 40,     // extForceTorque torque (3)
     M_FM = 43,       // held thruster force / mass, body frame (3)
     M_U = 46,        // latched wheel motor torques u_current (4)
-    LEO_NM = 50
+    M_LTHR = 50,     // held thruster torque (3), zero outside burns
+    M_TNEXT = 53,    // earliest expiry of a burning thruster
+    M_CHARGE = 54,        // storedCharge
+    M_SHADOW = 55,   // shadowFactor of the last environment tick
+    LEO_NM = 56
 };
 #define LEO_M_MIRROR 28          // number of leading bus fields that mirror state fields starting at F_GUID
 struct MBus {
@@ -1062,13 +1066,13 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     }
     for (int f = 0; f < LEO_M_MIRROR; f++) mst(m, f, SD(F_GUID + f));
     a.rho = SD(F_RHO);
-    double E = SD(F_E), shadow = SD(F_SHADOW);
+    mst(m, M_CHARGE, SD(F_E)); mst(m, M_SHADOW, SD(F_SHADOW));
     {
         const V3 L_ext = mk(SD(F_LDIST), SD(F_LDIST + 1), SD(F_LDIST + 2));
         mst3(m, M_LEXT, L_ext); mst3(m, M_FM, mk(0., 0., 0.));
         a.Lc = L_ext - a.tau_u;
     }
-    V3 L_thr = mk(0., 0., 0.);                                  // held thruster torque (zero outside burns)
+    mst3(m, M_LTHR, mk(0., 0., 0.));                            // held thruster torque (zero outside burns)
     const int64_t tick = SI(I_TICK);
     int mask = (int)SI(I_MASK);
     int thr_factor = (int)SI(I_THRFACTOR), thr_active = (int)SI(I_THRACTIVE), rw_sat = (int)SI(I_RWSAT);
@@ -1084,7 +1088,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         for (int k = 0; k < LEO_NTHR; k++) SD(F_THRREM + k) = 0.0;
     }
     // thrusters: the burning set is re-derived by an exact step before the constant-thrust path is trusted
-    double thr_t_next = -1.0;
+    mst(m, M_TNEXT, -1.0);
 
     // ---------------- clock: all tick times are integers below 2^53 ns, held exactly in doubles ----------------
     const bool first = tick < 0;                               // tick 0 (t = 0, h = 0) only runs right after a reset
@@ -1120,7 +1124,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         const double prevTime = t_mul(prev_d, 1e-9);
         const double h = t_sub(newTime, prevTime);
         a.h = h;
-        if (wrapped || (thr_active && !(newTime + LEO_THR_MARGIN <= thr_t_next))) {
+        if (wrapped || (thr_active && !(newTime + LEO_THR_MARGIN <= mld(m, M_TNEXT)))) {
             // a thruster may switch within this step (exact per-stage evaluation, then refresh the held thrust),
             // or the Sun clock wraps: every stage gets its own Sun position
             const double tBefore = t_sub(newTime, h);
@@ -1136,7 +1140,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             ThrEventOut o = rk4_general<J2, DIAG>(P, S, stride, e, m, x, a, dts, tBefore, tauPrev, thr_factor, thr_active);
             x = o.x; thr_factor = o.factor; thr_active = o.active;
             ThrRefresh th = thr_refresh(P, S, stride, e, m, thr_active ? thr_factor : 0, a.tau_u);
-            a.Lc = th.Lc; L_thr = th.L_thr; thr_t_next = th.t_next;
+            a.Lc = th.Lc; mst3(m, M_LTHR, th.L_thr); mst(m, M_TNEXT, th.t_next);
         } else {
             // Sun at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
             const double dtsm = t_mul(prev_d - sun_d, 1e-9) + 0.5 * h;
@@ -1167,12 +1171,12 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
 #pragma unroll
             for (int i = 0; i < NRW; i++) lim |= (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
             if (rw_sat | lim | desat_ran) {
-                PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, W, L_thr, desat_ran, (int64_t)now_d, thr_factor);
+                PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, W, mld3(m, M_LTHR), desat_ran, (int64_t)now_d, thr_factor);
 #pragma unroll
                 for (int i = 0; i < NRW; i++) uJ[i] = po.uJ[i];
                 a.Lc = po.Lc; a.tau_u = po.tau_u;
                 rw_sat = lim;
-                if (po.thr_active >= 0) { thr_active = po.thr_active; thr_t_next = -1.0; }   // burning set: re-derive exactly
+                if (po.thr_active >= 0) { thr_active = po.thr_active; mst(m, M_TNEXT, -1.0); }   // burning set: re-derive exactly
                 if (desat_ran) desat_quiet = po.quiet;
                 desat_ran = 0;
             }
@@ -1183,16 +1187,18 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             const V3 r_SB = sun_r - x.r;                       // spacecraft -> Sun
             const double d2 = dot(r_SB, r_SB), id = rsq(d2);
             const double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
-            shadow = eclipse_core(P, ec, sun_r, x.r, r2, ir, r_SB, d2, id);
+            const double shadow = eclipse_core(P, ec, sun_r, x.r, r2, ir, r_SB, d2, id);
+            mst(m, M_SHADOW, shadow);
             MrpRot R = mrp_rot(x.s);
             V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
             double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
             if (proj < 0.) proj = 0.;
             double panel = P.panel_coef * proj * (id * id) * shadow;
             if (j >= 0) {                                      // quirk Q2: the sink message does not exist at tick 0
-                E = E + (panel + P.sink_power) * h;
+                double E = mld(m, M_CHARGE) + (panel + P.sink_power) * h;
                 if (E > P.capacity) E = P.capacity;
                 if (E < 0.) E = 0.;
+                mst(m, M_CHARGE, E);
             }
         }
     }
@@ -1206,6 +1212,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     double wn = 0.;
 #pragma unroll
     for (int i = 0; i < NRW; i++) wn += W[i] * W[i];
+    const double E = mld(m, M_CHARGE), shadow = mld(m, M_SHADOW);
     double ob2 = sqrt(wn), ob3 = E / 3600., ob4 = shadow;
     int sim_over = norm(x.r) < P.decay_radius;
     int64_t curr_step = SI(I_STEP);
