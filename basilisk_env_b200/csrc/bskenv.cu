@@ -225,18 +225,19 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
         grid = resident;
         CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
     }
-#define LEO_LAUNCH(J2, DIAG)                                                                                   \
+#define LEO_LAUNCH(NRW, J2, DIAG)                                                                              \
     do {                                                                                                       \
         static bool attr_set[64] = {false};      /* opt in to > 48 KB of dynamic shared memory once per device */  \
         if (!attr_set[h->device & 63]) {                                                                       \
-            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<3, J2, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEO_BUS_BYTES)); \
+            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEO_BUS_BYTES)); \
             attr_set[h->device & 63] = true;                                                                   \
         }                                                                                                      \
-        leo_step_kernel<3, J2, DIAG><<<grid, LEO_BLOCK, LEO_BUS_BYTES, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
-                                                                              rew, done, reason, term_obs, h->stats, sc); \
+        leo_step_kernel<NRW, J2, DIAG><<<grid, LEO_BLOCK, LEO_BUS_BYTES, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
+                                                                                rew, done, reason, term_obs, h->stats, sc); \
     } while (0)
-    if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(true, true); else LEO_LAUNCH(true, false); }
-    else               { if (h->P.diag) LEO_LAUNCH(false, true); else LEO_LAUNCH(false, false); }
+    if (h->P.nrw == 4) { if (h->cfg.use_j2) LEO_LAUNCH(4, true, false); else LEO_LAUNCH(4, false, false); }
+    else if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(3, true, true); else LEO_LAUNCH(3, true, false); }
+    else                    { if (h->P.diag) LEO_LAUNCH(3, false, true); else LEO_LAUNCH(3, false, false); }
 #undef LEO_LAUNCH
     CU_TRY(h, cudaGetLastError());
     h->launches++;

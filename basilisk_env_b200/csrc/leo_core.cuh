@@ -628,6 +628,8 @@ LEO_HD void leo_reset_env(const LeoParams &P, double *S, int64_t *I, int64_t str
     for (int k = 0; k < 12; k++) SD(F_R + k) = ic[k];
     for (int k = 0; k < 3; k++) SD(F_LDIST + k) = P.dist_mag * ic[12 + k];             // SIM:295 (quirk Q4: raw vector)
     for (int k = 0; k < 3; k++) SD(F_WHL + k) = ic[15 + k] * P.wheel_rpm2rad;       // SIM:303-305
+    const double w4 = (ic[15] + ic[16] + ic[17]) / 3.0;                              // rw_set 1: fourth wheel at the mean speed
+    if (P.nrw == 4) SD(F_WHL + 3) = w4 * P.wheel_rpm2rad;
     SD(F_E) = ic[18];
     SI(I_TICK) = -1;
     SI(I_MASK) = LEO_TASK_ALL;       // every task starts enabled
@@ -635,7 +637,7 @@ LEO_HD void leo_reset_env(const LeoParams &P, double *S, int64_t *I, int64_t str
     if (obs) { // SIM:347-351 (wheel speeds in RPM, un-converted: SIM:306) then ENV:189-190
         obs[0] = sqrt(ic[6] * ic[6] + ic[7] * ic[7] + ic[8] * ic[8]);
         obs[1] = sqrt(ic[9] * ic[9] + ic[10] * ic[10] + ic[11] * ic[11]);
-        obs[2] = sqrt(ic[15] * ic[15] + ic[16] * ic[16] + ic[17] * ic[17]) / P.wheel_limit;
+        obs[2] = sqrt(ic[15] * ic[15] + ic[16] * ic[16] + ic[17] * ic[17] + (P.nrw == 4 ? w4 * w4 : 0.0)) / P.wheel_limit;
         obs[3] = ic[18] / 3600.0 / P.power_max;
         obs[4] = 0.0;
     }

@@ -62,11 +62,19 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
     // gravity (SIM:227-232): Earth central + Sun third body; NO J2 in the reference
     p.mu_c = 0.3986004415e15; p.mu_sun = 1.32712440018e20;       // [BSK: simIncludeGravBody]
     p.j2k = 1.5 * 1.08262668355e-3 * p.mu_c * (6378136.6 * 6378136.6);
-    p.hill_cel_pun = c.hill_cel_pun;
-    // three orthogonal Honeywell HR16 at 50 Nms (AP:20-37, [BSK: simIncludeRW.Honeywell_HR16])
-    p.nrw = 3;
-    for (int i = 0; i < 3; i++) {
-        p.gs[i][i] = 1.0;
+    p.hill_cel_pun = c.hill_cel_pun; p.use_j2 = c.use_j2 ? 1 : 0;
+    // Honeywell HR16 at 50 Nms ([BSK: simIncludeRW.Honeywell_HR16]): three along the body axes (AP:20-37), or the
+    // four-wheel pyramid of the opNav spacecraft (opNav_models/BSK_OpNavDynamics.py:269-293:
+    // gsHat = M3(-az) M2(el) e_x = (cos el cos az, cos el sin az, sin el))
+    if (c.rw_set != 0 && c.rw_set != 1) return "rw_set must be 0 (triad) or 1 (four-wheel pyramid)";
+    p.nrw = c.rw_set == 1 ? 4 : 3;
+    for (int i = 0; i < p.nrw; i++) {
+        if (c.rw_set == 1) {
+            const double D2R = 3.14159265358979323846 / 180.0, el = 40.0 * D2R, az = (45.0 + 90.0 * i) * D2R;
+            p.gs[i][0] = cos(el) * cos(az); p.gs[i][1] = cos(el) * sin(az); p.gs[i][2] = sin(el);
+        } else {
+            p.gs[i][i] = 1.0;
+        }
         p.Om_max[i] = 6000.0 * RPM; p.u_max[i] = 0.200; p.u_min[i] = 0.0;
         p.Js[i] = 50. / p.Om_max[i]; p.invJs[i] = 1.0 / p.Js[i];
     }

@@ -27,7 +27,7 @@ struct LeoParams {
     // ---- gravity ----
     double mu_c, mu_sun;
     double j2k;           // 1.5 * J2 * mu * Req^2 (only when the J2 template flag is on)
-    int32_t pad2, hill_cel_pun;
+    int32_t use_j2, hill_cel_pun;
     int32_t diag, pad1;    // 1: diagonal hub inertia, three wheels along the body axes, drag facets on their normal axis
                            //    (the reference set-up): fast EOM path
     // ---- reaction wheels ----

@@ -70,7 +70,11 @@ typedef struct bskenv_config {
     /* documented deviations / switches: all 0 reproduces the reference wiring */
     int32_t use_j2;              /* reference has no J2; 1 only for the stress config */
     int32_t hill_cel_pun;        /* 1 = hillPoint reads the SPICE message as an ephemeris message */
-    int32_t reserved[8];
+    int32_t rw_set;              /* 0: three HR16 along the body axes (reference LEO env, actuatorPrimatives.py:20-37);
+                                    1: four HR16 in the opNav pyramid, elevation 40 deg, azimuth 45/135/225/315 deg
+                                    (opNav_models/BSK_OpNavDynamics.py:269-293): BASELINE stress config.  The fourth
+                                    wheel starts at the mean of the three sampled speeds. */
+    int32_t reserved[7];
 } bskenv_config;
 
 typedef struct bskenv_handle bskenv_handle;

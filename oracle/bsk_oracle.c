@@ -251,6 +251,39 @@ void orc_sun_ephemeris(double t, double r[3], double v[3], double *j2000_et)
     if (j2000_et) *j2000_et = EPOCH_DAYS_TT_FROM_J2000 * 86400.0 + t;
 }
 
+/* Sun relative to the Mars barycentre, J2000 equatorial axes: analytic stand-in for SPICE de430 with
+ * zeroBase = "mars barycenter" (opNav_models/BSK_OpNavDynamics.py:396-401).  Keplerian elements of Mars and their
+ * rates from E. M. Standish, "Keplerian Elements for Approximate Positions of the Major Planets" (JPL, valid
+ * 1800-2050); epoch '2019 DECEMBER 12 18:00:00.0' UTC (:396).  Documented deviation, as for the LEO Sun. */
+void orc_sun_from_mars(double t, double r[3], double v[3], double *j2000_et)
+{
+    const double D2R = PI_D / 180.0, AUm = 149597870700.0;
+    double days = 7285.25 + 69.184 / 86400.0 + t / 86400.0;       /* TT days from J2000 */
+    double T = days / 36525.0;
+    double a = (1.52371034 + 0.00001847 * T) * AUm, e = 0.09339410 + 0.00007882 * T;
+    double I = (1.84969142 - 0.00813131 * T) * D2R, L = (-4.55343205 + 19140.30268499 * T) * D2R;
+    double wbar = (-23.94362959 + 0.44441088 * T) * D2R, Om = (49.55953891 - 0.29257343 * T) * D2R;
+    double w = wbar - Om, M = L - wbar;
+    double n = (19140.30268499 - 0.44441088) * D2R / (36525.0 * 86400.0);   /* dM/dt [rad/s] */
+    M = fmod(M, 2.0 * PI_D);
+    double E = M + e * sin(M);
+    for (int it = 0; it < 8; it++) E = E - (E - e * sin(E) - M) / (1.0 - e * cos(E));
+    double b = a * sqrt(1.0 - e * e);
+    double xp = a * (cos(E) - e), yp = b * sin(E);
+    double Edot = n / (1.0 - e * cos(E));
+    double xd = -a * sin(E) * Edot, yd = b * cos(E) * Edot;
+    double cw = cos(w), sw = sin(w), cO = cos(Om), sO = sin(Om), cI = cos(I), sI = sin(I);
+    double P1[3] = {cw * cO - sw * sO * cI, cw * sO + sw * cO * cI, sw * sI};
+    double P2[3] = {-sw * cO - cw * sO * cI, -sw * sO + cw * cO * cI, cw * sI};
+    double eps = 23.43928 * D2R, ce = cos(eps), se = sin(eps);
+    double re[3], ve[3];
+    for (int k = 0; k < 3; k++) { re[k] = P1[k] * xp + P2[k] * yp; ve[k] = P1[k] * xd + P2[k] * yd; }
+    /* ecliptic -> equatorial, heliocentric Mars -> Mars-centred Sun */
+    r[0] = -re[0]; r[1] = -(ce * re[1] - se * re[2]); r[2] = -(se * re[1] + ce * re[2]);
+    v[0] = -ve[0]; v[1] = -(ce * ve[1] - se * ve[2]); v[2] = -(se * ve[1] + ce * ve[2]);
+    if (j2000_et) *j2000_et = days * 86400.0;
+}
+
 /* ================================ message bus ================================================= */
 typedef struct { uint64_t write_ns; uint64_t count; } MsgHdr;
 static void msg_stamp(MsgHdr *h, uint64_t now) { h->write_ns = now; h->count++; }
@@ -299,7 +332,8 @@ typedef struct { /* messageLogger entry */
     int have;
 } LogEntry;
 
-enum { T_DYN, T_SPICE, T_ENV, T_SUNPOINT, T_NADIRPOINT, T_MRPCONTROL, T_RWDESAT, N_TASKS };
+enum { T_DYN, T_SPICE, T_ENV, T_SUNPOINT, T_NADIRPOINT, T_MRPCONTROL, T_RWDESAT,
+       T_OPNAVPOINT, T_SUNSAFE, T_MRPRW /* opNav scenario only */, N_TASKS };
 
 struct orc_leo_sim {
     orc_leo_cfg cfg;
@@ -358,6 +392,13 @@ struct orc_leo_sim {
     int thrForceSign; double tfm_epsilon, tfm_angErrThresh; int tfm_use2ndLoop; double outTorqAngErr;
     int maxCounterValue, thrDumpingCounter; double thrMinFireTime;
     double thrOnTimeRemaining[MAX_THR]; uint64_t dumpPriorTime, lastDeltaHInMsgTime;
+    /* ---- opNav scenario (dynamics half of simulators/opNavSimulator.py + opNav_models/) ---- */
+    int scenario;                      /* 0 LEO power/attitude, 1 opNav dynamics */
+    double mu_central;
+    double sigma_R0R[3];               /* attTrackingError.sigma_R0R (camera frame offset in the opNav scenario) */
+    double sHatBdyCmd[3];              /* sunSafePoint */
+    NavAttMsg sunPointData;            /* "sun_point_data": cssWlsEst output (truth sun heading substitute) */
+    int modeCounter, numModes;
     /* ---- logging ---- */
     LogEntry logs[8]; int n_logs;
     double obs[5];
@@ -434,6 +475,8 @@ static void log_all_messages(orc_leo_sim *s)
 static void spice_update(orc_leo_sim *s, uint64_t now)
 { /* zeroBase = "earth" (SIM:225): Earth at the origin, Sun relative to Earth */
     double et;
+    if (s->scenario == 1) orc_sun_from_mars(now * NANO2SEC, s->sunMsg.PositionVector, s->sunMsg.VelocityVector, &et);
+    else
     orc_sun_ephemeris(now * NANO2SEC, s->sunMsg.PositionVector, s->sunMsg.VelocityVector, &et);
     s->sunMsg.J2000Current = et;
     s->earthMsg.J2000Current = et;
@@ -491,7 +534,7 @@ static void gravity_compute(orc_leo_sim *s, const double r_cF_N[3])
     grav_point_mass(MU_SUN, r_cP_N, tmp); v3Add(acc, tmp, acc);
     grav_body_position(&s->gravEarth, s->sysTimeNanos, r_PN_N);
     v3Subtract(r_cN_N, r_PN_N, r_cP_N);
-    grav_point_mass(MU_EARTH, r_cP_N, tmp);
+    grav_point_mass(s->mu_central, r_cP_N, tmp);
     if (s->cfg.use_j2) { double j[3]; grav_j2(r_cP_N, j); v3Add(tmp, j, tmp); }
     v3Add(acc, tmp, acc);
     v3Copy(acc, s->g_N);
@@ -835,8 +878,8 @@ static void attTrackingError_update(orc_leo_sim *s, uint64_t now)
     memset(&ref, 0, sizeof(ref)); memset(&nav, 0, sizeof(nav));
     if (msg_written(&s->attRef.h)) ref = s->attRef;
     if (msg_written(&s->navAtt.h)) nav = s->navAtt;
-    double sigma_R0R[3] = {0, 0, 0}, sigma_RR0[3], sigma_RN[3], dcm_BN[3][3];
-    v3Scale(-1.0, sigma_R0R, sigma_RR0);
+    double sigma_RR0[3], sigma_RN[3], dcm_BN[3][3];
+    v3Scale(-1.0, s->sigma_R0R, sigma_RR0);         /* zero in the LEO scenario */
     orc_addMRP(ref.sigma_RN, sigma_RR0, sigma_RN);
     orc_subMRP(nav.sigma_BN, sigma_RN, s->attGuid.sigma_BR);
     orc_MRP2C(nav.sigma_BN, dcm_BN);
@@ -1086,6 +1129,7 @@ orc_leo_sim *orc_leo_create(const orc_leo_ic *ic, const orc_leo_cfg *cfg)
 {
     orc_leo_sim *s = (orc_leo_sim *)calloc(1, sizeof(orc_leo_sim));
     s->cfg = *cfg; s->ic = *ic;
+    s->scenario = 0; s->mu_central = MU_EARTH;
     /* tasks, in creation order with their priorities (SIM:101-103, 383-386) */
     sched_add_task(s, T_DYN, cfg->dynRate, -1);
     sched_add_task(s, T_SPICE, cfg->step_duration, -1);
@@ -1110,15 +1154,23 @@ orc_leo_sim *orc_leo_create(const orc_leo_ic *ic, const orc_leo_cfg *cfg)
         for (int i = 0; i < 8; i++) { s->facetArea[i] = A[i]; s->facetCd[i] = 2.2; v3Copy(N[i], s->facetN[i]); v3Copy(Lc[i], s->facetLoc[i]); }
     }
     v3Scale(2e-4, ic->disturbance_vector, s->extTorquePntB_B);           /* SIM:295 */
-    { /* balancedHR16Triad AP:20-37 + [BSK: simIncludeRW.py Honeywell_HR16, maxMomentum=50] */
-        const double gs[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-        s->nRW = 3;
-        for (int i = 0; i < 3; i++) {
+    { /* balancedHR16Triad AP:20-37 + [BSK: simIncludeRW.py Honeywell_HR16, maxMomentum=50]; or the opNav pyramid
+         (BSK_OpNavDynamics.py:269-293): gsHat = Mi(-az,3) Mi(el,2) [1,0,0] */
+        const double gs3[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        s->nRW = cfg->rw_set == 1 ? 4 : 3;
+        for (int i = 0; i < s->nRW; i++) {
             RWheel *w = &s->rw[i];
-            v3Copy(gs[i], w->gsHat_B);
+            if (cfg->rw_set == 1) {
+                double el = 40.0 * PI_D / 180.0, az = (45.0 + 90.0 * i) * PI_D / 180.0;
+                w->gsHat_B[0] = cos(el) * cos(az); w->gsHat_B[1] = cos(el) * sin(az); w->gsHat_B[2] = sin(el);
+            } else {
+                v3Copy(gs3[i], w->gsHat_B);
+            }
             w->Omega_max = 6000.0 * RPM; w->u_max = 0.200; w->u_min = 0.0;  /* useMinTorque False */
             w->Js = 50. / w->Omega_max;
-            w->Omega = ic->wheelSpeeds_rpm[i] * RPM;                      /* SIM:303-305 */
+            double rpm = i < 3 ? ic->wheelSpeeds_rpm[i]
+                               : (ic->wheelSpeeds_rpm[0] + ic->wheelSpeeds_rpm[1] + ic->wheelSpeeds_rpm[2]) / 3.0;
+            w->Omega = rpm * RPM;                                         /* SIM:303-305 */
         }
     }
     s->nThr = 8;
@@ -1131,7 +1183,9 @@ orc_leo_sim *orc_leo_create(const orc_leo_ic *ic, const orc_leo_cfg *cfg)
     s->storageCapacity = 20.0 * 3600.; s->storedCharge = ic->storedCharge_Init;
     /* initial obs SIM:347-351 */
     s->obs[0] = v3Norm(ic->sigma_init); s->obs[1] = v3Norm(ic->omega_init);
-    { double w[3]; for (int i = 0; i < 3; i++) w[i] = ic->wheelSpeeds_rpm[i]; s->obs[2] = v3Norm(w); } /* RPM, un-converted (SIM:306,350) */
+    { double w[3], w4 = 0.0; for (int i = 0; i < 3; i++) w[i] = ic->wheelSpeeds_rpm[i];
+      if (s->nRW == 4) w4 = (w[0] + w[1] + w[2]) / 3.0;
+      s->obs[2] = sqrt(v3Dot(w, w) + w4 * w4); } /* RPM, un-converted (SIM:306,350) */
     s->obs[3] = ic->storedCharge_Init / 3600.0; s->obs[4] = 0.0;
     /* model -> task assignment, in AddModelToTask order (SIM:356-366) */
     task_add_model(s, T_DYN, sc_update);
@@ -1211,7 +1265,7 @@ int orc_leo_run_sim(orc_leo_sim *s, int action, double obs[5])
     const double *eclRec = (const double *)s->logs[6].last;
     s->obs[0] = v3Norm(guidRec);
     s->obs[1] = v3Norm(navRec + 3);
-    s->obs[2] = v3Norm(rwRec);
+    { double w2 = 0.0; for (int i = 0; i < s->nRW; i++) w2 += rwRec[i] * rwRec[i]; s->obs[2] = sqrt(w2); } /* wheelSpeeds[0:3] (SIM:636); all four in the stress config */
     s->obs[3] = batRec[1] / 3600.;
     s->obs[4] = eclRec[0];
     if (v3Norm(scRec) < (REQ_EARTH_KM / 1000.)) sim_over = 1;           /* quirk Q6 */

@@ -37,7 +37,10 @@ typedef struct {
     double step_duration;    /* 180. */
     int    use_j2;           /* 0: reference has no J2; 1: stress config */
     int    hill_cel_pun;     /* 0: planet at origin (intended); 1: type-punned SPICE msg */
-    int    reserved[6];
+    int    rw_set;           /* 0: balancedHR16Triad (actuatorPrimatives.py:20-37); 1: the four-wheel HR16 pyramid of
+                                opNav_models/BSK_OpNavDynamics.py:269-293 (stress config); fourth wheel starts at the
+                                mean of the three sampled speeds */
+    int    reserved[5];
 } orc_leo_cfg;
 
 /* Everything a parity test wants to see at a decision boundary. */

@@ -23,7 +23,7 @@ class LeoIC(C.Structure):
 
 class LeoCfg(C.Structure):
     _fields_ = [("dynRate", C.c_double), ("fswRate", C.c_double), ("step_duration", C.c_double),
-                ("use_j2", C.c_int), ("hill_cel_pun", C.c_int), ("reserved", C.c_int * 6)]
+                ("use_j2", C.c_int), ("hill_cel_pun", C.c_int), ("rw_set", C.c_int), ("reserved", C.c_int * 5)]
 
 
 class LeoState(C.Structure):

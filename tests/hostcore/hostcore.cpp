@@ -57,10 +57,17 @@ void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t
     leo::MBus m; m.a = 0; m.p = bus;
     for (int64_t e = 0; e < h->n; e++) {
         leo::StepOut o;
-        if (h->P.diag && !h->force_general)
-            leo::leo_step_env<3, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
-        else
-            leo::leo_step_env<3, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+        const bool diag = h->P.diag && !h->force_general;
+        if (h->P.nrw == 4) {
+            if (h->P.use_j2) leo::leo_step_env<4, true, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            else leo::leo_step_env<4, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+        } else if (h->P.use_j2) {
+            if (diag) leo::leo_step_env<3, true, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            else leo::leo_step_env<3, true, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+        } else {
+            if (diag) leo::leo_step_env<3, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            else leo::leo_step_env<3, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+        }
         for (int k = 0; k < 5; k++) obs[5 * e + k] = o.ob[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
     }

@@ -47,11 +47,11 @@ def compare_state(st, S, I, where=""):
     errs["sigma"] = vec_err(S[F("sigma_BN"):F("sigma_BN") + 3], st.sigma_BN[:], floor=1.0)
     w_o = np.array(st.omega_BN_B[:]); w_k = S[F("omega_BN_B"):F("omega_BN_B") + 3]
     errs["omega"] = float(np.linalg.norm(w_k - w_o) / (np.linalg.norm(w_o) + OMEGA_ATOL / RTOL))
-    errs["Omega"] = vec_err(S[F("Omega"):F("Omega") + 3], st.Omega[:3], floor=1.0)
+    errs["Omega"] = vec_err(S[F("Omega"):F("Omega") + 4], st.Omega[:4], floor=1.0)
     errs["charge"] = abs(S[F("storedCharge")] - st.storedCharge) / max(abs(st.storedCharge), 1.0)
     errs["shadow"] = abs(S[F("shadowFactor")] - st.shadowFactor)
     errs["sigma_BR"] = vec_err(S[F("att_guidance"):F("att_guidance") + 3], st.sigma_BR[:], floor=1.0)
-    errs["u"] = vec_err(S[F("u_current"):F("u_current") + 3], st.u_current[:3], floor=1e-3)
+    errs["u"] = vec_err(S[F("u_current"):F("u_current") + 4], st.u_current[:4], floor=1e-3)
     for k, v in errs.items():
         tol = SHADOW_ATOL if k == "shadow" else RTOL
         assert v <= tol, f"{where}: {k} differs by {v:.3e} (> {tol})"

@@ -29,7 +29,7 @@ def _state_np(env):
 def _run_against_oracle(bsk, orc, rows, action_seq, host_path=False, **cfg):
     n = len(rows)
     env = _vec(bsk, n, **cfg)
-    ocfg = orc.default_cfg(**{k: v for k, v in cfg.items() if k in ("dynRate", "fswRate", "step_duration", "use_j2", "hill_cel_pun")})
+    ocfg = orc.default_cfg(**{k: v for k, v in cfg.items() if k in ("dynRate", "fswRate", "step_duration", "use_j2", "hill_cel_pun", "rw_set")})
     batch = orc.LeoEnvBatch(rows, ocfg)
     ob0 = env.reset_ics(rows).cpu().numpy()
     np.testing.assert_allclose(ob0, batch.obs0, rtol=1e-14, atol=0)   # reset obs: norms, FMA-contracted on the GPU
@@ -73,6 +73,15 @@ def test_unknown_actions_and_short_interval(bsk, orc):
     rows = parity.sample_rows(orc, 5, seed=7)
     acts = np.array([[0, 1, 2, -1, 9], [-1, -1, -1, 0, 1], [2, 0, 1, 5, 2]])
     _run_against_oracle(bsk, orc, rows, acts, step_duration=60.0)
+
+
+def test_stress_config_j2_four_wheels(bsk, orc):
+    """BASELINE configs[4] (FP64 leg): J2 + drag + eclipse + four wheels in the opNav pyramid with momentum dumping."""
+    rows = parity.sample_rows(orc, 40, seed=12)
+    rows[:8, 15:18] = np.random.RandomState(13).uniform(1500, 2900, size=(8, 3)) * np.array([1, -1, 1])
+    acts = np.random.RandomState(14).randint(0, 3, size=(5, 40))
+    acts[:2, :8] = 2
+    _run_against_oracle(bsk, orc, rows, acts, use_j2=1, rw_set=1)
 
 
 def test_single_env(bsk, orc):

@@ -10,7 +10,7 @@ from tests import parity
 def run_pair(orc, hostcore, rows, action_seq, **cfg):
     n = len(rows)
     hc = hostcore.HostCore(n, **cfg)
-    ocfg = orc.default_cfg(**{k: v for k, v in cfg.items() if k in ("dynRate", "fswRate", "step_duration", "use_j2", "hill_cel_pun")})
+    ocfg = orc.default_cfg(**{k: v for k, v in cfg.items() if k in ("dynRate", "fswRate", "step_duration", "use_j2", "hill_cel_pun", "rw_set")})
     envs = [orc.LeoEnv(ocfg) for _ in range(n)]
     ob_h = hc.reset_ics(rows)
     ob_o = np.stack([e.reset(r) for e, r in zip(envs, rows)])
@@ -71,8 +71,21 @@ def test_unknown_action_keeps_mode(orc, hostcore):
 def test_short_step_duration_and_j2(orc, hostcore):
     rows = parity.sample_rows(orc, 2, seed=21)
     run_pair(orc, hostcore, rows, np.array([[0, 2], [1, 0], [2, 1]]), step_duration=60.0)
-    hc = hostcore.HostCore(2, use_j2=1)      # host core is instantiated without J2: config only checks plumbing
-    assert hc.cfg.use_j2 == 1
+    run_pair(orc, hostcore, rows, np.array([[0, 2], [1, 0]]), use_j2=1)
+
+
+def test_stress_config_j2_four_wheel_pyramid(orc, hostcore):
+    """BASELINE configs[4]: J2 on, four reaction wheels in the opNav pyramid, momentum dumping; general EOM path."""
+    rows = parity.sample_rows(orc, 5, seed=55)
+    rows[0, 15:18] = [2800., -2600., 2900.]          # enough momentum for the thrusters to fire in mode 2
+    acts = np.array([[2, 0, 1, 2, 0], [2, 1, 0, 2, 1], [0, 2, 2, 1, 0], [1, 0, 2, 0, 2]])
+    worst = run_pair(orc, hostcore, rows, acts, use_j2=1, rw_set=1)
+    assert max(worst.values()) <= parity.RTOL
+    hc = hostcore.HostCore(5, use_j2=1, rw_set=1); hc.reset_ics(rows)
+    hc.step([2] * 5); hc.step([2] * 5)
+    S, I = hc.state()
+    assert I[parity.F("fireCounter"):parity.F("fireCounter") + 8, 0].sum() > 0
+    assert np.all(S[parity.F("Omega") + 3] != 0.0)    # the fourth wheel is alive
 
 
 def test_hill_cel_pun_switch(orc, hostcore):
