@@ -7,6 +7,6 @@ timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/pytest_gpu_${TAG}.l
 bash scripts/bench_variants.sh
 if [ -n "$PROF" ]; then
   export BSKENV_LIB=$PWD/variants/libbskenv_${PROF}.so
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:leo_step -s 3 -c 1 -f -o gpurun_out/prof_${TAG} \
+  timeout 900 ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.sum --clock-control none --import-source on -k regex:leo_step -s 3 -c 1 -f -o gpurun_out/prof_${TAG} \
       python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline > gpurun_out/ncu_full_${TAG}.log 2>&1; echo "ncu full exit $?"
 fi
