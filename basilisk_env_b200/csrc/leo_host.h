@@ -173,11 +173,25 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
     return "";
 }
 
-// ALGORITHMIC FP64 flop per env-decision-step (DESIGN.md "Flop model"): FMA = 2, add/mul = 1,
-// div/sqrt/rsqrt/transcendental = 1.  Counted from the operation list of leo_core.cuh for modes 0/1.
+// FP64 flop per env-decision-step of the step kernel AS BUILT (DESIGN.md "Flop model"): FMA = 2, add/mul = 1,
+// one per MUFU seed; counted from the operation list of leo_core.cuh for modes 0/1 and cross-checked against the
+// executed instruction counters of ncu (2 DFMA + DMUL + DADD thread instructions per env: 2.074e6 for the
+// reference configuration, profiles/ncu_r01c.md; this formula gives 2.0736e6).  It is the work the kernel performs,
+// not the larger count of the un-fused Basilisk formulation (4.29e6), so the roofline fraction built
+// on it is the fraction of the FP64 pipe's flop rate actually delivered.
+//   per RK stage   gravity 22, MRP rotation set-up 17, [BN] v 30, collapsed drag 27, torque/gyro/inverse inertia 42,
+//                  MRP kinematics 31                                                               = 169 (diagonal path)
+//   RK4 per tick   stage inputs 96, weighted slope sums 96, final update 12                          = 204
+//   per tick       Sun third body 55, invariant/switch/|r| 30, atmosphere 40, wheel test 6, eclipse + panel + battery 105 = 236
+//   FSW pass       hillPoint 130, attTrackingError 146, MRP_Feedback 69, rwMotorTorque 15           = 360
 static inline double flops_per_step(const LeoParams &p)
 {
-    const double F_eom = 403.0, F_rk4 = 15 * 2 * 7.0, F_tick = 172.0, F_fsw = 390.0;
+    double F_eom = 169.0;
+    const double F_rk4 = 204.0, F_tick = 236.0;
+    double F_fsw = 360.0;
+    if (!p.diag) F_eom += 36.0 + 8.0 * (p.nrw - 3);        // full 3x3 D / Dinv / drag moment arms, wheel invariants
+    if (p.use_j2) F_eom += 14.0;
+    if (p.nrw == 4) F_fsw += 5.0;
     double ticks = (double)p.ticks_per_fsw * p.fsw_per_step;
     return ticks * (4 * F_eom + F_rk4 + F_tick) + p.fsw_per_step * F_fsw;
 }

@@ -243,7 +243,10 @@ def main():
                        "parallelism": f"env-sharded x{world}, no collective on the step path"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                         "kernel": "leo_step_kernel<3,false>", "kernel_ms": kern_ms, "flop_per_env_step": flops,
+                         "kernel": "leo_step_kernel<3,false,true>", "kernel_ms": kern_ms, "flop_per_env_step": flops,
+                         "flop_source": "operation list of the kernel as built (bskenv_flops_per_step), equal to the executed "
+                                        "2*DFMA+DMUL+DADD count of ncu (profiles/ncu_r01c.md: 2.074e6 per env-step); the un-fused "
+                                        "Basilisk formulation of SURVEY 8(d) would be 4.29e6",
                          "peak_source": "DFMA-chain microbenchmark run in this process (bskenv_fp64_peak); MEASURED_PEAKS.json "
                                         "has no FP64 figure; nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s",
                          "hbm": {"achieved": alg_bytes / (kern_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
