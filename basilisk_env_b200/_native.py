@@ -27,6 +27,22 @@ class Config(C.Structure):
                 ("use_j2", C.c_int32), ("hill_cel_pun", C.c_int32), ("rw_set", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
+class OpNavConfig(C.Structure):
+    """Mirror of `bskenv_opnav_config` (include/bskenv.h)."""
+    _fields_ = [("abi_version", C.c_int32), ("reserved0", C.c_int32),
+                ("dynRate", C.c_double), ("fswRate", C.c_double), ("step_duration_min", C.c_double),
+                ("max_length", C.c_int32), ("numModes", C.c_int32), ("auto_reset", C.c_int32), ("nav_noise", C.c_int32),
+                ("camera_reenable", C.c_int32), ("sample_orbit", C.c_int32),
+                ("pixel_noise_std", C.c_double), ("circle_unc", C.c_double), ("reward_mult", C.c_double),
+                ("noise_seed", C.c_uint64), ("reserved", C.c_int32 * 8)]
+
+
+OPNAV_EXPORTS = ["bskenv_opnav_default_config", "bskenv_opnav_create", "bskenv_opnav_destroy", "bskenv_opnav_last_error",
+                 "bskenv_opnav_num_envs", "bskenv_opnav_reset_seeded", "bskenv_opnav_reset_ics", "bskenv_opnav_reset_init",
+                 "bskenv_opnav_get_ics", "bskenv_opnav_step", "bskenv_opnav_step_host", "bskenv_opnav_state_dims",
+                 "bskenv_opnav_get_state", "bskenv_opnav_set_state", "bskenv_opnav_state_field",
+                 "bskenv_opnav_episode_stats", "bskenv_opnav_launch_count", "bskenv_opnav_flops_per_step"]
+
 EXPORTS = ["bskenv_abi_version", "bskenv_default_config", "bskenv_create", "bskenv_destroy", "bskenv_last_error",
            "bskenv_num_envs", "bskenv_reset_seeded", "bskenv_reset_ics", "bskenv_reset_init", "bskenv_get_ics",
            "bskenv_step", "bskenv_step_host", "bskenv_state_dims", "bskenv_get_state", "bskenv_set_state",
@@ -72,6 +88,28 @@ def lib():
     L.bskenv_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double)]
     L.bskenv_flops_per_step.restype = C.c_double
     L.bskenv_flops_per_step.argtypes = [vp]
+    L.bskenv_opnav_default_config.argtypes = [C.POINTER(OpNavConfig)]
+    L.bskenv_opnav_create.argtypes = [C.POINTER(OpNavConfig), C.c_int, i64, i64, C.POINTER(vp)]
+    L.bskenv_opnav_destroy.argtypes = [vp]
+    L.bskenv_opnav_last_error.restype = C.c_char_p
+    L.bskenv_opnav_last_error.argtypes = [vp]
+    L.bskenv_opnav_num_envs.restype = i64
+    L.bskenv_opnav_num_envs.argtypes = [vp]
+    L.bskenv_opnav_reset_seeded.argtypes = [vp, u64, vp, vp, vp]
+    L.bskenv_opnav_reset_ics.argtypes = [vp, vp, vp, vp, vp]
+    L.bskenv_opnav_reset_init.argtypes = [vp, vp, vp, vp]
+    L.bskenv_opnav_get_ics.argtypes = [vp, vp, vp]
+    L.bskenv_opnav_step.argtypes = [vp] * 9
+    L.bskenv_opnav_step_host.argtypes = [vp] * 7
+    L.bskenv_opnav_state_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.bskenv_opnav_get_state.argtypes = [vp, vp, vp, vp]
+    L.bskenv_opnav_set_state.argtypes = [vp, vp, vp, vp]
+    L.bskenv_opnav_state_field.argtypes = [C.c_char_p, C.POINTER(i32)]
+    L.bskenv_opnav_episode_stats.argtypes = [vp, vp]
+    L.bskenv_opnav_launch_count.restype = i64
+    L.bskenv_opnav_launch_count.argtypes = [vp]
+    L.bskenv_opnav_flops_per_step.restype = C.c_double
+    L.bskenv_opnav_flops_per_step.argtypes = [vp]
     if L.bskenv_abi_version() != 1:
         raise RuntimeError("libbskenv.so ABI version mismatch")
     _LIB = L
@@ -93,6 +131,24 @@ def default_config(**overrides):
 def state_field(name):
     is_int = C.c_int32(0)
     idx = lib().bskenv_state_field(name.encode(), C.byref(is_int))
+    if idx < 0:
+        raise KeyError(name)
+    return idx, bool(is_int.value)
+
+
+def opnav_default_config(**overrides):
+    cfg = OpNavConfig()
+    lib().bskenv_opnav_default_config(C.byref(cfg))
+    for k, v in overrides.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(f"bskenv_opnav_config has no field {k!r}")
+        setattr(cfg, k, v)
+    return cfg
+
+
+def opnav_state_field(name):
+    is_int = C.c_int32(0)
+    idx = lib().bskenv_opnav_state_field(name.encode(), C.byref(is_int))
     if idx < 0:
         raise KeyError(name)
     return idx, bool(is_int.value)

@@ -1,0 +1,392 @@
+// opnav.cu -- sm_100a kernels and the C ABI (include/bskenv.h, bskenv_opnav_*) of the batched opNav environment step.
+//
+// Kernels:
+//   opnav_step_kernel   one thread = one spacecraft; ONE launch = one 50-minute decision interval (3000 ticks) for all
+//                       envs (replaces Basilisk ExecuteSimulation(), reference simulators/opNavSimulator.py:256-261,
+//                       and the gym bookkeeping of envs/opNavEnvironment.py:55-125); warp-shuffle reduction of the
+//                       episode statistics; optional in-kernel auto-reset.
+//   opnav_reset_kernel  simulator construction + initial observation from explicit, stored or device-sampled ICs.
+// There is no CPU path in this library.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+
+#include "../../include/bskenv.h"
+#include "opnav_core.cuh"
+#include "opnav_host.h"
+
+#ifndef ON_MIN_BLOCKS
+#define ON_MIN_BLOCKS 2
+#endif
+
+namespace {
+
+enum { OST_RET = 0, OST_LEN, OST_COUNT, OST_MAXLEN, OST_MODES, OST_STEPS, OST_MEAS, OST_BAD, OST_N };
+
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One warp steps a group of 32 consecutive envs; when there are more groups than resident warps the grid is one
+// resident set and the warps pull groups from an atomic queue (same scheme as the LEO step kernel).
+struct OnSched { int *sched; int n_groups; int dynamic; };
+
+__global__ void __launch_bounds__(ON_BLOCK, ON_MIN_BLOCKS)
+opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+                  int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
+                  double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
+                  double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (bool more = true; more; more = sc.dynamic != 0) {
+        int g;
+        if (sc.dynamic) {
+            g = 0;
+            if (lane == 0) g = atomicAdd(&sc.sched[0], 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
+            if (g >= sc.n_groups) break;
+        } else {
+            g = blockIdx.x * (ON_BLOCK / 32) + warp;
+        }
+        const int64_t e = (int64_t)g * 32 + lane;
+        const bool valid = e < n;
+        opnav::StepOut o;
+        o.done = 0; o.reason = 0; o.reward = 0.;
+        double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
+        if (valid) {
+            const int64_t m0 = I[(int64_t)OI_NMEAS * stride + e], b0 = I[(int64_t)OI_NBAD * stride + e];
+            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o);
+            d_meas = (double)(I[(int64_t)OI_NMEAS * stride + e] - m0); d_bad = (double)(I[(int64_t)OI_NBAD * stride + e] - b0);
+            reward[e] = o.reward;
+            done[e] = (uint8_t)o.done;
+            reason[e] = (uint8_t)o.reason;
+            if (debug)
+                for (int k = 0; k < 12; k++) debug[e * 12 + k] = o.debug[k];
+            if (o.done) {
+                ep_ret = S[(int64_t)OF_EPRET * stride + e];
+                ep_len = (double)I[(int64_t)OI_STEP * stride + e];
+                if (term_obs)
+                    for (int k = 0; k < 4; k++) term_obs[e * 4 + k] = o.ob[k];
+                if (P.auto_reset) {
+                    int64_t ep = I[(int64_t)OI_EPISODE * stride + e] + 1;
+                    I[(int64_t)OI_EPISODE * stride + e] = ep;
+                    double ic[OPNAV_IC_DIM];
+                    opnav::sample_ic(P, P.first_env_index + e, ep, ic);
+                    for (int k = 0; k < OPNAV_IC_DIM; k++) ics[(int64_t)k * stride + e] = ic[k];
+                    opnav::opnav_reset_env(P, S, I, stride, e, ic, o.ob);
+                }
+            }
+            for (int k = 0; k < 4; k++) obs[e * 4 + k] = o.ob[k];
+        }
+        if (stats) {
+            const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
+            if (any_done) {
+                double v_ret = warp_sum_d(o.done ? ep_ret : 0.), v_len = warp_sum_d(o.done ? ep_len : 0.);
+                int c_all = __popc(any_done);
+                int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
+                int c_s = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
+                if (lane == 0) {
+                    atomicAdd(&stats[OST_RET], v_ret); atomicAdd(&stats[OST_LEN], v_len);
+                    atomicAdd(&stats[OST_COUNT], (double)c_all); atomicAdd(&stats[OST_MAXLEN], (double)c_m);
+                    atomicAdd(&stats[OST_MODES], (double)c_s);
+                }
+            }
+            const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
+            double v_meas = warp_sum_d(d_meas), v_bad = warp_sum_d(d_bad);
+            if (lane == 0 && c_valid) {
+                atomicAdd(&stats[OST_STEPS], (double)c_valid);
+                atomicAdd(&stats[OST_MEAS], v_meas);
+                if (v_bad != 0.0) atomicAdd(&stats[OST_BAD], v_bad);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// mode 0: explicit ICs (row-major [n][12]); 1: stored ICs; 2: device-sampled ICs
+__global__ void __launch_bounds__(256)
+opnav_reset_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+                   int64_t stride, int64_t n, int mode, const double *__restrict__ ics_in, const uint8_t *__restrict__ mask,
+                   double *__restrict__ obs)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    if (mask && !mask[e]) return;
+    double ic[OPNAV_IC_DIM];
+    if (mode == 0) {
+        for (int k = 0; k < OPNAV_IC_DIM; k++) ic[k] = ics_in[e * OPNAV_IC_DIM + k];
+    } else if (mode == 1) {
+        for (int k = 0; k < OPNAV_IC_DIM; k++) ic[k] = ics[(int64_t)k * stride + e];
+    } else {
+        int64_t ep = I[(int64_t)OI_EPISODE * stride + e] + 1;
+        I[(int64_t)OI_EPISODE * stride + e] = ep;
+        opnav::sample_ic(P, P.first_env_index + e, ep, ic);
+    }
+    for (int k = 0; k < OPNAV_IC_DIM; k++) ics[(int64_t)k * stride + e] = ic[k];
+    double ob[4];
+    opnav::opnav_reset_env(P, S, I, stride, e, ic, ob);
+    if (obs)
+        for (int k = 0; k < 4; k++) obs[e * 4 + k] = ob[k];
+}
+__global__ void opnav_gather_ics_kernel(const double *__restrict__ ics, int64_t stride, int64_t n, double *__restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    for (int k = 0; k < OPNAV_IC_DIM; k++) out[e * OPNAV_IC_DIM + k] = ics[(int64_t)k * stride + e];
+}
+template <typename T>
+__global__ void opnav_copy_fields_kernel(const T *__restrict__ src, int64_t src_stride, T *__restrict__ dst, int64_t dst_stride,
+                                         int64_t n, int fields)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    for (int f = 0; f < fields; f++) dst[(int64_t)f * dst_stride + e] = src[(int64_t)f * src_stride + e];
+}
+
+thread_local std::string g_opnav_create_error;
+
+}  // namespace
+
+struct bskenv_opnav_handle {
+    bskenv_opnav_config cfg;
+    OpNavParams P;
+    int device;
+    int64_t n, stride;
+    double *S, *ics, *stats;
+    int64_t *I;
+    int *sched;
+    int sm_count;
+    int32_t *d_act; double *d_obs, *d_rew, *d_dbg; uint8_t *d_done, *d_reason;
+    int32_t *h_act; double *h_obs, *h_rew, *h_dbg; uint8_t *h_done, *h_reason;
+    cudaStream_t own_stream;
+    int64_t launches;
+    std::string err;
+};
+
+#define ON_TRY(h, call)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess) {                                                                     \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(_e);                            \
+            return BSKENV_ECUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double *obs, double *rew, uint8_t *done,
+                             uint8_t *reason, double *debug, double *term_obs, cudaStream_t st)
+{
+    const int wpb = ON_BLOCK / 32;
+    const int64_t groups = (h->n + 31) / 32;
+    const int resident = h->sm_count * ON_MIN_BLOCKS;
+    int grid = (int)((groups + wpb - 1) / wpb);
+    OnSched sc;
+    sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
+    if (grid > resident) {
+        sc.dynamic = 1;
+        grid = resident;
+        ON_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
+    }
+    opnav_step_kernel<<<grid, ON_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
+                                                 term_obs, h->stats, sc);
+    ON_TRY(h, cudaGetLastError());
+    h->launches++;
+    return BSKENV_OK;
+}
+
+extern "C" {
+
+void bskenv_opnav_default_config(bskenv_opnav_config *cfg) { opnav_host::default_config(cfg); }
+const char *bskenv_opnav_last_error(const bskenv_opnav_handle *h) { return h ? h->err.c_str() : g_opnav_create_error.c_str(); }
+int64_t bskenv_opnav_num_envs(const bskenv_opnav_handle *h) { return h ? h->n : 0; }
+int64_t bskenv_opnav_launch_count(const bskenv_opnav_handle *h) { return h ? h->launches : 0; }
+double bskenv_opnav_flops_per_step(const bskenv_opnav_handle *h) { return h ? opnav_host::flops_per_step(h->P) : 0.0; }
+
+int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_envs, int64_t first_env_index,
+                        bskenv_opnav_handle **out)
+{
+    if (!cfg || !out || n_envs <= 0) { g_opnav_create_error = "bskenv_opnav_create: bad arguments"; return BSKENV_EINVAL; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        g_opnav_create_error = "bskenv_opnav_create: no CUDA device (this library has no CPU path)";
+        return BSKENV_ENODEV;
+    }
+    if (device < 0 || device >= ndev) { g_opnav_create_error = "bskenv_opnav_create: device index out of range"; return BSKENV_EINVAL; }
+    bskenv_opnav_handle *h = new bskenv_opnav_handle();
+    h->cfg = *cfg;
+    std::string perr = opnav_host::build_params(*cfg, h->P);
+    if (!perr.empty()) { g_opnav_create_error = "bskenv_opnav_create: " + perr; delete h; return BSKENV_EINVAL; }
+    h->P.first_env_index = first_env_index;
+    h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;
+    h->d_act = nullptr; h->d_obs = h->d_rew = h->d_dbg = nullptr; h->d_done = h->d_reason = nullptr;
+    h->h_act = nullptr; h->h_obs = h->h_rew = h->h_dbg = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * OPNAV_ND * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * OPNAV_NI * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * OPNAV_IC_DIM * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->stats, sizeof(double) * OST_N);
+    if (e == cudaSuccess) e = cudaMemset(h->S, 0, sizeof(double) * OPNAV_ND * h->stride);
+    if (e == cudaSuccess) e = cudaMemset(h->I, 0, sizeof(int64_t) * OPNAV_NI * h->stride);
+    if (e == cudaSuccess) e = cudaMemset(h->ics, 0, sizeof(double) * OPNAV_IC_DIM * h->stride);
+    if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(double) * OST_N);
+    if (e != cudaSuccess) {
+        g_opnav_create_error = std::string("bskenv_opnav_create: ") + cudaGetErrorString(e);
+        bskenv_opnav_destroy(h);
+        return BSKENV_ECUDA;
+    }
+    *out = h;
+    return BSKENV_OK;
+}
+
+int bskenv_opnav_destroy(bskenv_opnav_handle *h)
+{
+    if (!h) return BSKENV_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched);
+    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_dbg); cudaFree(h->d_done); cudaFree(h->d_reason);
+    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_dbg); cudaFreeHost(h->h_done);
+    cudaFreeHost(h->h_reason);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return BSKENV_OK;
+}
+
+static int opnav_do_reset(bskenv_opnav_handle *h, int mode, const double *ics_in, const uint8_t *mask, double *obs, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    ON_TRY(h, cudaSetDevice(h->device));
+    const int grid = (int)((h->n + 255) / 256);
+    opnav_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, mode, ics_in, mask, obs);
+    ON_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+int bskenv_opnav_reset_seeded(bskenv_opnav_handle *h, uint64_t seed, const uint8_t *mask_dev, double *obs_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    h->P.seed = seed;             // the IC stream and the sensor-noise streams share the key from here on
+    return opnav_do_reset(h, 2, nullptr, mask_dev, obs_dev, stream);
+}
+int bskenv_opnav_reset_ics(bskenv_opnav_handle *h, const double *ics_dev, const uint8_t *mask_dev, double *obs_dev, void *stream)
+{
+    if (!h || !ics_dev) { if (h) h->err = "bskenv_opnav_reset_ics: null ics"; return BSKENV_EINVAL; }
+    return opnav_do_reset(h, 0, ics_dev, mask_dev, obs_dev, stream);
+}
+int bskenv_opnav_reset_init(bskenv_opnav_handle *h, const uint8_t *mask_dev, double *obs_dev, void *stream)
+{
+    return opnav_do_reset(h, 1, nullptr, mask_dev, obs_dev, stream);
+}
+int bskenv_opnav_get_ics(bskenv_opnav_handle *h, double *ics_dev, void *stream)
+{
+    if (!h || !ics_dev) return BSKENV_EINVAL;
+    ON_TRY(h, cudaSetDevice(h->device));
+    opnav_gather_ics_kernel<<<(int)((h->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h->ics, h->stride, h->n, ics_dev);
+    ON_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+
+int bskenv_opnav_step(bskenv_opnav_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev,
+                      uint8_t *done_reason_dev, double *debug_dev, double *term_obs_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev || !done_reason_dev) { h->err = "bskenv_opnav_step: null buffer"; return BSKENV_EINVAL; }
+    ON_TRY(h, cudaSetDevice(h->device));
+    return opnav_launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, done_reason_dev, debug_dev, term_obs_dev, (cudaStream_t)stream);
+}
+
+int bskenv_opnav_step_host(bskenv_opnav_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done,
+                           uint8_t *done_reason, double *debug)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!actions || !obs || !reward || !done || !done_reason) { h->err = "bskenv_opnav_step_host: null buffer"; return BSKENV_EINVAL; }
+    ON_TRY(h, cudaSetDevice(h->device));
+    const int64_t n = h->n;
+    if (!h->own_stream) {
+        ON_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        ON_TRY(h, cudaMalloc(&h->d_act, n * sizeof(int32_t))); ON_TRY(h, cudaMalloc(&h->d_obs, n * 4 * sizeof(double)));
+        ON_TRY(h, cudaMalloc(&h->d_rew, n * sizeof(double))); ON_TRY(h, cudaMalloc(&h->d_dbg, n * 12 * sizeof(double)));
+        ON_TRY(h, cudaMalloc(&h->d_done, n)); ON_TRY(h, cudaMalloc(&h->d_reason, n));
+        ON_TRY(h, cudaMallocHost(&h->h_act, n * sizeof(int32_t))); ON_TRY(h, cudaMallocHost(&h->h_obs, n * 4 * sizeof(double)));
+        ON_TRY(h, cudaMallocHost(&h->h_rew, n * sizeof(double))); ON_TRY(h, cudaMallocHost(&h->h_dbg, n * 12 * sizeof(double)));
+        ON_TRY(h, cudaMallocHost(&h->h_done, n)); ON_TRY(h, cudaMallocHost(&h->h_reason, n));
+    }
+    cudaStream_t st = h->own_stream;
+    memcpy(h->h_act, actions, n * sizeof(int32_t));
+    ON_TRY(h, cudaMemcpyAsync(h->d_act, h->h_act, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    int rc = opnav_launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_reason, debug ? h->d_dbg : nullptr, nullptr, st);
+    if (rc) return rc;
+    ON_TRY(h, cudaMemcpyAsync(h->h_obs, h->d_obs, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ON_TRY(h, cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (debug) ON_TRY(h, cudaMemcpyAsync(h->h_dbg, h->d_dbg, n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    ON_TRY(h, cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
+    ON_TRY(h, cudaMemcpyAsync(h->h_reason, h->d_reason, n, cudaMemcpyDeviceToHost, st));
+    ON_TRY(h, cudaStreamSynchronize(st));
+    memcpy(obs, h->h_obs, n * 4 * sizeof(double)); memcpy(reward, h->h_rew, n * sizeof(double));
+    if (debug) memcpy(debug, h->h_dbg, n * 12 * sizeof(double));
+    memcpy(done, h->h_done, n); memcpy(done_reason, h->h_reason, n);
+    return BSKENV_OK;
+}
+
+int bskenv_opnav_state_dims(const bskenv_opnav_handle *h, int32_t *nd, int32_t *ni)
+{
+    (void)h;
+    if (nd) *nd = OPNAV_ND;
+    if (ni) *ni = OPNAV_NI;
+    return BSKENV_OK;
+}
+int bskenv_opnav_get_state(bskenv_opnav_handle *h, double *dstate_dev, int64_t *istate_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    ON_TRY(h, cudaSetDevice(h->device));
+    const int grid = (int)((h->n + 255) / 256);
+    if (dstate_dev) opnav_copy_fields_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(h->S, h->stride, dstate_dev, h->n, h->n, OPNAV_ND);
+    if (istate_dev) opnav_copy_fields_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(h->I, h->stride, istate_dev, h->n, h->n, OPNAV_NI);
+    ON_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+int bskenv_opnav_set_state(bskenv_opnav_handle *h, const double *dstate_dev, const int64_t *istate_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    ON_TRY(h, cudaSetDevice(h->device));
+    const int grid = (int)((h->n + 255) / 256);
+    if (dstate_dev) opnav_copy_fields_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(dstate_dev, h->n, h->S, h->stride, h->n, OPNAV_ND);
+    if (istate_dev) opnav_copy_fields_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(istate_dev, h->n, h->I, h->stride, h->n, OPNAV_NI);
+    ON_TRY(h, cudaGetLastError());
+    return BSKENV_OK;
+}
+int bskenv_opnav_state_field(const char *name, int32_t *is_int)
+{
+    struct Ent { const char *n; int idx; int is_int; };
+    static const Ent tab[] = {
+        {"r_BN_N", OF_R, 0}, {"v_BN_N", OF_V, 0}, {"sigma_BN", OF_SIG, 0}, {"omega_BN_B", OF_OMG, 0}, {"Omega", OF_WHL, 0},
+        {"reactionwheel_cmds", OF_RWCMD, 0}, {"navErrors", OF_NAVERR, 0}, {"sun_point_data", OF_SUNPT, 0},
+        {"shadowFactor", OF_SHADOW, 0}, {"filter_state", OF_FSTATE, 0}, {"filter_sBar", OF_FS, 0},
+        {"reward_total", OF_EPRET, 0}, {"sim_obs", OF_OBS, 0}, {"sim_states", OF_DEBUG, 0},
+        {"tick", OI_TICK, 1}, {"curr_step", OI_STEP, 1}, {"mode", OI_MODE, 1}, {"cameraIsOn", OI_CAMERA, 1},
+        {"modeCounter", OI_MODECNT, 1}, {"first_run", OI_FIRST, 1}, {"MRPSwitchCount", OI_SWITCH, 1}, {"episode", OI_EPISODE, 1},
+        {"episode_over", OI_OVER, 1}, {"n_meas", OI_NMEAS, 1}, {"n_bad", OI_NBAD, 1}, {"filter_tick", OI_FTICK, 1},
+        {"sun_point_written", OI_SUNPT_W, 1}, {"n_images", OI_NIMG, 1}};
+    if (!name) return -1;
+    for (const Ent &t : tab)
+        if (!strcmp(t.n, name)) { if (is_int) *is_int = t.is_int; return t.idx; }
+    return -1;
+}
+
+int bskenv_opnav_episode_stats(bskenv_opnav_handle *h, double *stats_host)
+{
+    if (!h || !stats_host) return BSKENV_EINVAL;
+    ON_TRY(h, cudaSetDevice(h->device));
+    ON_TRY(h, cudaDeviceSynchronize());
+    ON_TRY(h, cudaMemcpy(stats_host, h->stats, sizeof(double) * OST_N, cudaMemcpyDeviceToHost));
+    ON_TRY(h, cudaMemset(h->stats, 0, sizeof(double) * OST_N));
+    return BSKENV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,674 @@
+// opnav_core.cuh -- per-environment body of the fused opNav decision step.
+//
+// One call of opnav_step_env() replaces one `scenario_OpNav.run_sim(action)`
+// (/root/reference/basilisk_env/simulators/opNavSimulator.py:225-299, cited ONS:line) plus the bookkeeping of
+// `opNavEnv.step` (/root/reference/basilisk_env/envs/opNavEnvironment.py:55-125, ONE:line) for ONE spacecraft:
+// 3000 ticks of  [wheel latch -> CSS -> eclipse -> RK4 hub + 4 wheels -> Sun -> simple_nav -> camera]  (dynamics
+// process, opNav_models/BSK_OpNavDynamics.py:100-110, OND:line) followed by  [guidance -> MRP feedback ->
+// wheel torque map -> circle -> pixelLine -> relative-OD filter]  (FSW process, opNav_models/BSK_OpNavFsw.py,
+// ONF:line).  The Vizard / OpenCV image path is replaced by a pinhole projection of the Mars disc.
+//
+// The filter is the square-root unscented Kalman filter of relativeODuKF restated for a streaming register
+// implementation.  With d_i = Y_i - Y_0 the propagated deviations from the central sigma point and
+// m = sum_i w d_i, the SR-UKF covariance  sum_i wC_i (Y_i - xBar)(Y_i - xBar)^T + Q  equals
+//     Q + sum_{i>=1} w d_i d_i^T + (2 - alpha^2) m m^T
+// (all terms positive: no down-date, no stored sigma points), built here by Givens rank-one sweeps on the
+// lower-triangular factor.  The measurement is linear (y = r), so Pxy and Pyy are blocks of the a-priori
+// covariance and the update is three hyperbolic rank-one sweeps.  The oracle keeps Basilisk's formulation
+// (Householder QR + Gill-Murray down-dates); the two agree to rounding (tests/test_opnav_*).
+//
+// Everything is __host__ __device__ (tests/hostcore compiles it with g++); the product only runs it on the GPU.
+#pragma once
+#include "leo_core.cuh"
+#include "opnav_params.h"
+
+namespace opnav {
+using namespace leo;
+
+#define ON_HD LEO_HD
+#define ON_HD_NOINLINE LEO_HD_NOINLINE
+
+struct Truth { V3 r, v, s, w; double Om[ON_NRW]; };
+
+ON_HD void sincos_hd(double x, double &s, double &c)
+{
+#ifdef __CUDA_ARCH__
+    sincos(x, &s, &c);
+#else
+    s = sin(x); c = cos(x);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// noise streams: Philox4x32-10, counter (env_lo, env_hi, tick, stream<<16 | block), key (seed_lo, seed_hi ^ episode)
+// ------------------------------------------------------------------------------------------------
+ON_HD void normals4(const OpNavParams &P, int64_t env, int64_t episode, uint32_t tick, uint32_t stream, uint32_t block,
+                    double (&out)[4])
+{
+    uint32_t x[4];
+    philox4x32((uint32_t)(uint64_t)env, (uint32_t)((uint64_t)env >> 32), tick, (stream << 16) | block, (uint32_t)P.seed,
+               (uint32_t)(P.seed >> 32) ^ (uint32_t)episode, x);
+    const double TWO_PI = 2.0 * 3.14159265358979323846;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        double u1 = ((double)x[2 * p] + 1.0) * (1.0 / 4294967296.0);
+        double u2 = (double)x[2 * p + 1] * (1.0 / 4294967296.0);
+        double rr = sqrt(-2.0 * log(u1)), s, c;
+        sincos_hd(TWO_PI * u2, s, c);
+        out[2 * p] = rr * c;
+        out[2 * p + 1] = rr * s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sun relative to the Mars barycentre (analytic stand-in for SPICE, zeroBase "mars barycenter", OND:396-401):
+// evaluated exactly at the two ends of a decision interval, cubic Hermite in between (error < 1e-5 m).
+// ------------------------------------------------------------------------------------------------
+struct SunState { V3 r, v; };
+ON_HD_NOINLINE SunState sun_from_mars(const OpNavParams &P, double t)
+{
+    const double PI = 3.14159265358979323846, D2R = PI / 180.0, AUm = 149597870700.0;
+    double days = P.epoch_days + t / 86400.0;
+    double T = days / 36525.0;
+    double a = (1.52371034 + 0.00001847 * T) * AUm, e = 0.09339410 + 0.00007882 * T;
+    double I = (1.84969142 - 0.00813131 * T) * D2R, L = (-4.55343205 + 19140.30268499 * T) * D2R;
+    double wbar = (-23.94362959 + 0.44441088 * T) * D2R, Om = (49.55953891 - 0.29257343 * T) * D2R;
+    double w = wbar - Om, M = L - wbar;
+    double n = (19140.30268499 - 0.44441088) * D2R / (36525.0 * 86400.0);
+    M = fmod(M, 2.0 * PI);
+    double E = M + e * sin(M);
+    for (int it = 0; it < 8; it++) E = E - (E - e * sin(E) - M) / (1.0 - e * cos(E));
+    double b = a * sqrt(1.0 - e * e);
+    double xp = a * (cos(E) - e), yp = b * sin(E);
+    double Edot = n / (1.0 - e * cos(E));
+    double xd = -a * sin(E) * Edot, yd = b * cos(E) * Edot;
+    double cw = cos(w), sw = sin(w), cO = cos(Om), sO = sin(Om), cI = cos(I), sI = sin(I);
+    V3 P1 = mk(cw * cO - sw * sO * cI, cw * sO + sw * cO * cI, sw * sI);
+    V3 P2 = mk(-sw * cO - cw * sO * cI, -sw * sO + cw * cO * cI, cw * sI);
+    double eps = 23.43928 * D2R, ce = cos(eps), se = sin(eps);
+    V3 re = P1 * xp + P2 * yp, ve = P1 * xd + P2 * yd;
+    SunState o;
+    o.r = mk(-re.x, -(ce * re.y - se * re.z), -(se * re.y + ce * re.z));
+    o.v = mk(-ve.x, -(ce * ve.y - se * ve.z), -(se * ve.y + ce * ve.z));
+    return o;
+}
+struct SunSpan { V3 r0, v0, r1, v1; double t0, T; };      // v0, v1 pre-multiplied by T
+ON_HD V3 sun_at(const SunSpan &s, double t)
+{
+    double u = (t - s.t0) / s.T, u2 = u * u, u3 = u2 * u;
+    double h00 = 2 * u3 - 3 * u2 + 1, h10 = u3 - 2 * u2 + u, h01 = -2 * u3 + 3 * u2, h11 = u3 - u2;
+    return s.r0 * h00 + s.v0 * h10 + s.r1 * h01 + s.v1 * h11;
+}
+
+// ------------------------------------------------------------------------------------------------
+// truth dynamics: hub + four balanced wheels, Mars point mass (OND:382-391); thrusters never commanded,
+// extForceTorque zero
+// ------------------------------------------------------------------------------------------------
+ON_HD void eom(const OpNavParams &P, const Truth &x, const double (&u)[ON_NRW], Truth &k)
+{
+    double r2 = dot(x.r, x.r), ir = rsq(r2);
+    k.r = x.v;
+    k.v = x.r * (-P.mu_dyn * (ir * ir * ir));
+    V3 hw = mk(0., 0., 0.), gu = mk(0., 0., 0.);
+#pragma unroll
+    for (int i = 0; i < ON_NRW; i++) {
+        V3 g = arr(P.gs[i]);
+        hw = hw + g * (P.Js * x.Om[i]);
+        gu = gu + g * u[i];
+    }
+    V3 tau = -gu - cross(x.w, mv9(P.I, x.w) + hw);
+    V3 wd = mv9(P.Dinv, tau);
+    k.w = wd;
+    double s2 = dot(x.s, x.s), sw = dot(x.s, x.w);
+    k.s = (x.w * (1. - s2) + cross(x.s, x.w) * 2. + x.s * (2. * sw)) * 0.25;
+#pragma unroll
+    for (int i = 0; i < ON_NRW; i++) k.Om[i] = u[i] * P.invJs - dot(arr(P.gs[i]), wd);
+}
+ON_HD Truth axpy(const Truth &x, double a, const Truth &k)
+{
+    Truth o;
+    o.r = x.r + k.r * a; o.v = x.v + k.v * a; o.s = x.s + k.s * a; o.w = x.w + k.w * a;
+#pragma unroll
+    for (int i = 0; i < ON_NRW; i++) o.Om[i] = x.Om[i] + k.Om[i] * a;
+    return o;
+}
+ON_HD Truth rk4(const OpNavParams &P, const Truth &x0, const double (&u)[ON_NRW], double h)
+{
+    Truth k, xo, x;
+    eom(P, x0, u, k);
+    xo = axpy(x0, h / 6.0, k); x = axpy(x0, 0.5 * h, k);
+    eom(P, x, u, k);
+    xo = axpy(xo, h / 3.0, k); x = axpy(x0, 0.5 * h, k);
+    eom(P, x, u, k);
+    xo = axpy(xo, h / 3.0, k); x = axpy(x0, h, k);
+    eom(P, x, u, k);
+    return axpy(xo, h / 6.0, k);
+}
+
+// ------------------------------------------------------------------------------------------------
+// eclipse (conical model, one planet at the origin), coarse sun sensors, cssWlsEst, sunSafePoint
+// ------------------------------------------------------------------------------------------------
+ON_HD_NOINLINE double eclipse_mars(const OpNavParams &P, V3 sun, V3 r)
+{
+    V3 s_HP = sun, r_HB = sun - r, s_BP = r;
+    double hb = norm(r_HB), hp = norm(s_HP);
+    if (hb < hp) return 1.0;
+    double sn = norm(s_BP), RS = P.R_sun, Rp = P.R_planet;
+    double f_1 = asin((RS + Rp) / hp), f_2 = asin((RS - Rp) / hp);
+    double s_0 = (-dot(s_BP, s_HP)) / hp;
+    double c_1 = s_0 + Rp / sin(f_1), c_2 = s_0 - Rp / sin(f_2);
+    double l = sqrt(sn * sn - s_0 * s_0), l_1 = c_1 * tan(f_1), l_2 = c_2 * tan(f_2);
+    double shadow = 1.0;
+    if (fabs(l) < fabs(l_2) || fabs(l) < fabs(l_1)) {
+        const double PI = 3.14159265358979323846;
+        double a = clamp_asin(RS / hb), b = clamp_asin(Rp / sn);
+        double c = clamp_acos((-dot(s_BP, r_HB)) / (sn * hb));
+        if (c < b - a) shadow = 0.0;
+        else if (c < a - b) shadow = 1 - (PI * a * a - PI * b * b) / (PI * a * a);
+        else if (c < a + b) {
+            double x = (c * c + a * a - b * b) / (2 * c), y = sqrt(a * a - x * x);
+            double area = a * a * clamp_acos(x / a) + b * b * clamp_acos((c - x) / b) - c * y;
+            shadow = 1 - area / (PI * a * a);
+        }
+    }
+    return shadow;
+}
+ON_HD V3 mrp_add(V3 q1, V3 q2)
+{ // RigidBodyKinematics addMRP: [FN(out)] = [FB(q2)][BN(q1)], shadow-set guard, inner-set map
+    V3 s1 = q1;
+    double det = 1. + dot(s1, s1) * dot(q2, q2) - 2. * dot(s1, q2);
+    if (fabs(det) < 0.1) {
+        s1 = s1 * (-1.0 / dot(s1, s1));
+        det = 1. + dot(s1, s1) * dot(q2, q2) - 2. * dot(s1, q2);
+    }
+    V3 res = s1 * (1. - dot(q2, q2)) + q2 * (1. - dot(s1, s1)) + cross(s1, q2) * 2.;
+    return mrp_inner(res * frcp(det));
+}
+// CSS (prio 299) + cssWlsEst: returns the estimated sun heading (zero when no sensor sees the Sun)
+ON_HD_NOINLINE V3 css_wls(const OpNavParams &P, V3 sHat_B, double shadow)
+{
+    double HtH[6] = {0, 0, 0, 0, 0, 0}, Hty[3] = {0, 0, 0};
+    int n = 0;
+    V3 H0 = mk(0, 0, 0), H1 = mk(0, 0, 0);
+    double y0 = 0, y1 = 0;
+    for (int i = 0; i < ON_NCSS; i++) {
+        V3 nh = arr(P.cssN[i]);
+        double d = dot(nh, sHat_B);
+        double y = (d >= P.css_cos_fov ? d : 0.0) * shadow * P.css_scale;
+        if (y > 0.0) {
+            if (n == 0) { H0 = nh; y0 = y; } else if (n == 1) { H1 = nh; y1 = y; }
+            n++;
+            HtH[0] += nh.x * nh.x; HtH[1] += nh.x * nh.y; HtH[2] += nh.x * nh.z;
+            HtH[3] += nh.y * nh.y; HtH[4] += nh.y * nh.z; HtH[5] += nh.z * nh.z;
+            Hty[0] += nh.x * y; Hty[1] += nh.y * y; Hty[2] += nh.z * y;
+        }
+    }
+    V3 d = mk(0, 0, 0);
+    if (n >= 3) {
+        double m00 = HtH[0], m01 = HtH[1], m02 = HtH[2], m11 = HtH[3], m12 = HtH[4], m22 = HtH[5];
+        double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+        double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+        double det = m00 * c00 + m01 * c01 + m02 * c02, id = 1.0 / det;
+        d = mk((c00 * Hty[0] + c01 * Hty[1] + c02 * Hty[2]) * id, (c01 * Hty[0] + c11 * Hty[1] + c12 * Hty[2]) * id,
+               (c02 * Hty[0] + c12 * Hty[1] + c22 * Hty[2]) * id);
+    } else if (n == 2) {
+        double a = dot(H0, H0), b = dot(H0, H1), c = dot(H1, H1), det = a * c - b * b;
+        double l0 = (c * y0 - b * y1) / det, l1 = (a * y1 - b * y0) / det;
+        d = H0 * l0 + H1 * l1;
+    } else if (n == 1) {
+        d = H0 * (y0 / dot(H0, H0));
+    }
+    return n > 0 ? unit_or_zero(d) : mk(0, 0, 0);
+}
+ON_HD_NOINLINE AttGuid sun_safe_point(V3 sHat, V3 omega_BN_B)
+{ // sunSafePoint with sHatBdyCmd = (0,0,1), minUnitMag = smallAngle = sunAxisSpinRate = 0 (ONF:290-295)
+    AttGuid g;
+    g.omega_RN_B = mk(0, 0, 0); g.domega_RN_B = mk(0, 0, 0); g.sigma_BR = mk(0, 0, 0);
+    double sNorm = norm(sHat);
+    if (sNorm > 0.0) {
+        double ct = sHat.z / sNorm;
+        ct = fabs(ct) > 1.0 ? ct / fabs(ct) : ct;
+        double err = acos(ct);
+        V3 e_hat = unit_or_zero(cross(sHat, mk(0, 0, 1)));
+        g.sigma_BR = mrp_inner(e_hat * tan(err * 0.25));
+    }
+    g.omega_BR_B = omega_BN_B;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------------
+// relative-OD square-root UKF (see the header comment).  S: lower triangle, row-major, S(i,j) = S[i(i+1)/2+j].
+// ------------------------------------------------------------------------------------------------
+#define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+ON_HD void two_body_rk4(double (&x)[6], double mu, double dt)
+{
+    double k[6], s[6], acc[6];
+#pragma unroll
+    for (int st = 0; st < 4; st++) {
+        const double cin = st == 0 ? 0.0 : (st == 3 ? dt : 0.5 * dt);
+        const double cw = (st == 0 || st == 3) ? dt / 6.0 : dt / 3.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++) s[i] = st == 0 ? x[i] : x[i] + cin * k[i];
+        double r2 = s[0] * s[0] + s[1] * s[1] + s[2] * s[2], ir = rsq(r2), g = -mu * (ir * ir * ir);
+        k[0] = s[3]; k[1] = s[4]; k[2] = s[5]; k[3] = g * s[0]; k[4] = g * s[1]; k[5] = g * s[2];
+#pragma unroll
+        for (int i = 0; i < 6; i++) acc[i] = st == 0 ? cw * k[i] : acc[i] + cw * k[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] += acc[i];
+}
+// L L^T += x x^T (Givens sweep); x is destroyed
+ON_HD void chol_update6(double (&L)[21], double (&x)[6])
+{
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double Lkk = L[TRI(k, k)], t = Lkk * Lkk + x[k] * x[k];
+        if (t > 0.0) {
+            double ir = rsq(t), c = Lkk * ir, s = x[k] * ir;
+            L[TRI(k, k)] = t * ir;
+#pragma unroll
+            for (int j = k + 1; j < 6; j++) {
+                double Ljk = L[TRI(j, k)];
+                L[TRI(j, k)] = c * Ljk + s * x[j];
+                x[j] = c * x[j] - s * Ljk;
+            }
+        }
+    }
+}
+// L L^T -= x x^T (hyperbolic sweep); returns false when the result is not positive definite
+ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
+{
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double Lkk = L[TRI(k, k)], t = Lkk * Lkk - x[k] * x[k];
+        if (!(t > 0.0)) { ok = false; t = 1.0; }
+        double ir = rsq(t), c = Lkk * ir, s = x[k] * ir;
+        L[TRI(k, k)] = t * ir;
+#pragma unroll
+        for (int j = k + 1; j < 6; j++) {
+            double Ljk = L[TRI(j, k)];
+            L[TRI(j, k)] = c * Ljk - s * x[j];
+            x[j] = c * x[j] - s * Ljk;
+        }
+    }
+    return ok;
+}
+struct Ukf { double x[6]; double S[21]; double m[6]; };
+// relODuKFTimeUpdate over dt
+ON_HD_NOINLINE void ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
+{
+    double Y0[6], L[21], m[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { Y0[i] = f.x[i]; m[i] = 0.0; }
+    two_body_rk4(Y0, P.mu_fsw, dt);
+#pragma unroll
+    for (int i = 0; i < 21; i++) L[i] = 0.0;
+    const double qp = P.ukf_sq_pos * (dt * dt / 2), qv = P.ukf_sq_vel * dt;
+    L[TRI(0, 0)] = qp; L[TRI(1, 1)] = qp; L[TRI(2, 2)] = qp; L[TRI(3, 3)] = qv; L[TRI(4, 4)] = qv; L[TRI(5, 5)] = qv;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int idx = 0; idx < 12; idx++) {
+        const int i = idx >> 1;
+        const double g = (idx & 1) ? -P.ukf_gamma : P.ukf_gamma;
+        double Y[6];
+        // column i of S (rows >= i); the switch keeps S in registers
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            double col = 0.0;
+#pragma unroll
+            for (int c = 0; c < 6; c++) if (c <= r) col = (c == i) ? f.S[TRI(r, c)] : col;
+            Y[r] = f.x[r] + g * col;
+        }
+        two_body_rk4(Y, P.mu_fsw, dt);
+        double d[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) { double dd = Y[r] - Y0[r]; m[r] += P.ukf_w * dd; d[r] = P.ukf_sqrt_w * dd; }
+        chol_update6(L, d);
+    }
+    double d[6];
+#pragma unroll
+    for (int r = 0; r < 6; r++) d[r] = P.ukf_sqrt_cm * m[r];
+    chol_update6(L, d);
+#pragma unroll
+    for (int i = 0; i < 21; i++) f.S[i] = L[i];
+#pragma unroll
+    for (int i = 0; i < 6; i++) { f.x[i] = Y0[i]; f.m[i] = m[i]; }
+}
+// relODuKFMeasUpdate for y = r_BN_N with noise covariance R (symmetric, m^2, already scaled by noiseSF);
+// `dt` is the span of the time update that has just run (its process noise is not part of Pxy / Pyy)
+ON_HD_NOINLINE bool ukf_meas_update(const OpNavParams &P, Ukf &f, double dt, const double (&obs)[3], const double (&R)[6])
+{
+    const double qp = P.ukf_sq_pos * (dt * dt / 2), qp2 = qp * qp;
+    double Pxy[6][3];
+    for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 3; b++) {
+            double s = 0.0;
+            const int kmax = a < b ? a : b;
+            for (int k = 0; k <= kmax; k++) s += f.S[TRI(a, k)] * f.S[TRI(b, k)];
+            Pxy[a][b] = (a == b) ? s - qp2 : s;
+        }
+    // Sy = chol(Pyy), Pyy = Pxy[0:3][0:3] + R
+    double A00 = Pxy[0][0] + R[0], A10 = Pxy[1][0] + R[1], A20 = Pxy[2][0] + R[2], A11 = Pxy[1][1] + R[3],
+           A21 = Pxy[2][1] + R[4], A22 = Pxy[2][2] + R[5];
+    if (!(A00 > 0.0)) return false;
+    double l00 = sqrt(A00), l10 = A10 / l00, l20 = A20 / l00;
+    double t11 = A11 - l10 * l10;
+    if (!(t11 > 0.0)) return false;
+    double l11 = sqrt(t11), l21 = (A21 - l20 * l10) / l11;
+    double t22 = A22 - l20 * l20 - l21 * l21;
+    if (!(t22 > 0.0)) return false;
+    double l22 = sqrt(t22);
+    double innov[3] = {obs[0] - (f.x[0] + f.m[0]), obs[1] - (f.x[1] + f.m[1]), obs[2] - (f.x[2] + f.m[2])};
+    double xn[6], U[3][6];
+    for (int a = 0; a < 6; a++) {
+        // K[a] = (Sy Sy^T)^-1 Pxy[a]: forward then backward substitution
+        double t0 = Pxy[a][0] / l00, t1 = (Pxy[a][1] - l10 * t0) / l11, t2 = (Pxy[a][2] - l20 * t0 - l21 * t1) / l22;
+        double k2 = t2 / l22, k1 = (t1 - l21 * k2) / l11, k0 = (t0 - l10 * k1 - l20 * k2) / l00;
+        xn[a] = f.x[a] + k0 * innov[0] + k1 * innov[1] + k2 * innov[2];
+        U[0][a] = k0 * l00 + k1 * l10 + k2 * l20; U[1][a] = k1 * l11 + k2 * l21; U[2][a] = k2 * l22;   // U = K Sy
+    }
+    double L[21];
+    for (int i = 0; i < 21; i++) L[i] = f.S[i];
+    bool ok = true;
+    for (int c = 0; c < 3; c++) {
+        double x[6];
+        for (int a = 0; a < 6; a++) x[a] = U[c][a];
+        ok = chol_downdate6(L, x) && ok;
+    }
+    if (!ok) return false;
+    for (int i = 0; i < 21; i++) f.S[i] = L[i];
+    for (int a = 0; a < 6; a++) f.x[a] = xn[a];
+    return true;
+}
+
+// synthetic camera + circle finder: pinhole image of the Mars disc from the TRUE state (what the renderer shows);
+// returns validity (disc centre inside the frame, radius >= houghMinRadius)
+ON_HD bool project_circle(const OpNavParams &P, V3 r_C, double (&c)[3])
+{
+    double d2 = dot(r_C, r_C), Rm = P.planet_radius_km * 1000.0;
+    c[0] = c[1] = c[2] = 0.0;
+    if (!(r_C.z > 0.0) || !(d2 > Rm * Rm)) return false;
+    c[0] = (r_C.x / r_C.z + P.cam_half) / P.cam_X;
+    c[1] = (r_C.y / r_C.z + P.cam_half) / P.cam_X;
+    c[2] = Rm / sqrt(d2 - Rm * Rm) / P.cam_X;
+    return !(c[0] < 0.0 || c[0] >= P.cam_res || c[1] < 0.0 || c[1] >= P.cam_res || c[2] < P.hough_min_radius);
+}
+// pixelLineConverter (planetTarget = Mars): circle -> r_BN_N [m] and covariance [m^2] (xx, yx, zx, yy, zy, zz) * noiseSF
+ON_HD_NOINLINE void pixel_line(const OpNavParams &P, const double (&c)[3], V3 sigma_nav, double (&r_BN_N)[3], double (&R)[6])
+{
+    const double X = P.cam_X;
+    V3 rt = mk(X * c[0] - P.cam_half, X * c[1] - P.cam_half, 1.0);
+    V3 rh_C = unit_or_zero(rt) * (-1.0);
+    MrpRot CN = mrp_rot(sigma_nav);
+    V3 rh_N = rot_NB(CN, sigma_nav, rh_C);
+    const double z = X * c[2], q = sqrt(1.0 + z * z);
+    const double denom = z / q;                         // sin(atan(z))
+    const double rNorm = P.planet_radius_km / denom;    // km
+    r_BN_N[0] = rNorm * 1E3 * rh_N.x; r_BN_N[1] = rNorm * 1E3 * rh_N.y; r_BN_N[2] = rNorm * 1E3 * rh_N.z;
+    const double x_map = rNorm * X, rho_map = P.planet_radius_km * (X / q - q / (X * c[2] * c[2]));
+    const double dxy = x_map * x_map * P.circle_unc, dz = rho_map * rho_map * P.circle_unc;
+    // covar_N = [NC] diag(dxy, dxy, dz) [NC]^T = dxy I + (dz - dxy) n n^T with n = [NC] e_z
+    V3 nz = rot_NB(CN, sigma_nav, mk(0, 0, 1));
+    const double sc = 1E6 * P.ukf_noiseSF, a = dxy * sc, b = (dz - dxy) * sc;
+    R[0] = a + b * nz.x * nz.x; R[1] = b * nz.y * nz.x; R[2] = b * nz.z * nz.x;
+    R[3] = a + b * nz.y * nz.y; R[4] = b * nz.z * nz.y; R[5] = a + b * nz.z * nz.z;
+}
+
+// ------------------------------------------------------------------------------------------------
+// initial conditions (ONS:163-202) and reset (scenario_OpNav.__init__, ONE:153-168)
+// ------------------------------------------------------------------------------------------------
+ON_HD_NOINLINE void sample_ic(const OpNavParams &P, int64_t global_env, int64_t episode, double (&ic)[OPNAV_IC_DIM])
+{
+    IcRng g; g.seed = P.seed; g.env = (uint64_t)global_env; g.episode = (uint32_t)episode; g.block = 0; g.have = 0;
+    const double PI = 3.14159265358979323846, D2R = PI / 180.0;
+    if (P.sample_orbit) { // the commented-out draws of ONS:166-171
+        double a = g.uniform(17000 * 1E3, 22000 * 1E3), ecc = g.uniform(0, 0.6), inc = g.uniform(-20 * D2R, 20 * D2R);
+        double Om = g.uniform(0 * D2R, 360 * D2R), om = g.uniform(0 * D2R, 360 * D2R), f = g.uniform(0 * D2R, 360 * D2R);
+        double mu = P.mu_dyn, p = a * (1.0 - ecc * ecc), r = p / (1.0 + ecc * cos(f)), th = om + f, h = sqrt(mu * p);
+        ic[0] = r * (cos(th) * cos(Om) - cos(inc) * sin(th) * sin(Om));
+        ic[1] = r * (cos(th) * sin(Om) + cos(inc) * sin(th) * cos(Om));
+        ic[2] = r * (sin(th) * sin(inc));
+        ic[3] = -mu / h * (cos(Om) * (ecc * sin(om) + sin(th)) + cos(inc) * (ecc * cos(om) + cos(th)) * sin(Om));
+        ic[4] = -mu / h * (sin(Om) * (ecc * sin(om) + sin(th)) - cos(inc) * (ecc * cos(om) + cos(th)) * cos(Om));
+        ic[5] = mu / h * (ecc * cos(om) + cos(th)) * sin(inc);
+    } else {
+        for (int k = 0; k < 3; k++) { ic[k] = P.rN0[k]; ic[3 + k] = P.vN0[k]; }
+    }
+    for (int k = 0; k < 3; k++) ic[6 + k] = g.uniform(100000, -100000);     // ONS:187
+    for (int k = 0; k < 3; k++) ic[9 + k] = g.uniform(1000, -1000);         // ONS:188
+}
+ON_HD void opnav_reset_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e,
+                           const double (&ic)[OPNAV_IC_DIM], double *obs /* 4, may be null */)
+{
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+    for (int f = 0; f < OPNAV_ND; f++) SD(f) = 0.0;
+    int64_t episode = SI(OI_EPISODE);
+    for (int f = 0; f < OPNAV_NI; f++) SI(f) = 0;
+    SI(OI_EPISODE) = episode;
+    for (int k = 0; k < 6; k++) SD(OF_R + k) = ic[k];                        // sigma = omega = Omega = 0 (ONS:189-194)
+    for (int k = 0; k < 6; k++) SD(OF_FSTATE + k) = ic[k] + ic[6 + k];       // stateInit (ONS:189)
+    for (int k = 0; k < 3; k++) { SD(OF_FS + TRI(k, k)) = P.ukf_P0_pos; SD(OF_FS + TRI(k + 3, k + 3)) = P.ukf_P0_vel; }
+    SD(OF_SHADOW) = 1.0;
+    SI(OI_TICK) = -1;
+    SI(OI_CAMERA) = 1;                                                       // OND:130
+    SI(OI_FIRST) = 1;
+    if (obs) for (int k = 0; k < 4; k++) obs[k] = 0.0;                       // ONS:152
+#undef SD
+#undef SI
+}
+
+// ------------------------------------------------------------------------------------------------
+// one decision interval of one environment
+// ------------------------------------------------------------------------------------------------
+struct StepOut { double ob[4]; double debug[12]; double reward; int done; int reason; };
+
+ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out)
+{
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+    const int64_t genv = P.first_env_index + e, episode = SI(OI_EPISODE);
+    // ---- opNavEnv.step prologue (ONE:94-95) and run_sim mode switching (ONS:237-254) ----
+    int over = (int)SI(OI_OVER), reason = 0;
+    const int64_t curr_step = SI(OI_STEP);
+    if (curr_step >= P.max_length) { over = 1; reason |= 1; }
+    int mode = (int)SI(OI_MODE), camera = (int)SI(OI_CAMERA);
+    const int modeCounter = (int)SI(OI_MODECNT) + 1;
+    if (action == 0) { mode = 0; if (P.camera_reenable) camera = 1; }
+    else if (action == 1) { mode = 1; camera = 0; }
+    if (SI(OI_FIRST)) mode = 0;          // pending 'OpNavOD' event fires at the first ExecuteSimulation (ONS:157, ONF:219-224)
+    // ---- load the persistent state ----
+    Truth x;
+    x.r = mk(SD(OF_R), SD(OF_R + 1), SD(OF_R + 2)); x.v = mk(SD(OF_V), SD(OF_V + 1), SD(OF_V + 2));
+    x.s = mk(SD(OF_SIG), SD(OF_SIG + 1), SD(OF_SIG + 2)); x.w = mk(SD(OF_OMG), SD(OF_OMG + 1), SD(OF_OMG + 2));
+    double rwcmd[ON_NRW], nerr[15];
+    for (int i = 0; i < ON_NRW; i++) { x.Om[i] = SD(OF_WHL + i); rwcmd[i] = SD(OF_RWCMD + i); }
+    for (int i = 0; i < 15; i++) nerr[i] = SD(OF_NAVERR + i);
+    V3 sunpt = mk(SD(OF_SUNPT), SD(OF_SUNPT + 1), SD(OF_SUNPT + 2));
+    int sunpt_w = (int)SI(OI_SUNPT_W);
+    double shadow_msg = SD(OF_SHADOW);
+    Ukf f;
+    for (int i = 0; i < 6; i++) { f.x[i] = SD(OF_FSTATE + i); f.m[i] = 0.0; }
+    for (int i = 0; i < 21; i++) f.S[i] = SD(OF_FS + i);
+    int64_t ftick = SI(OI_FTICK), n_meas = SI(OI_NMEAS), n_bad = SI(OI_NBAD), n_img = SI(OI_NIMG), n_switch = SI(OI_SWITCH);
+    const int64_t tick0 = SI(OI_TICK);
+    const int64_t k_first = tick0 + 1, k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;   // stop time inclusive
+    // ---- Sun over this interval ----
+    SunSpan sun;
+    sun.t0 = (double)(tick0 < 0 ? 0 : tick0) * P.dt; sun.T = (double)P.ticks_per_step * P.dt;
+    { SunState a = sun_from_mars(P, sun.t0), b = sun_from_mars(P, sun.t0 + sun.T);
+      sun.r0 = a.r; sun.v0 = a.v * sun.T; sun.r1 = b.r; sun.v1 = b.v * sun.T; }
+    V3 sun_prev = sun_at(sun, (double)(k_first > 0 ? k_first - 1 : 0) * P.dt);     // SPICE message of the previous tick
+    V3 nav_sun_B = mk(0, 0, 1);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int64_t k = k_first; k <= k_last; k++) {
+        const double t = (double)k * P.dt;
+        // ================= DynamicsTask =================
+        // ReactionWheelStateEffector (prio 301): latch last pass's motor torques; publish Omega before the integration
+        double u[ON_NRW], Om_msg[ON_NRW];
+#pragma unroll
+        for (int i = 0; i < ON_NRW; i++) {
+            double ui = rwcmd[i];
+            ui = ui > P.u_max ? P.u_max : (ui < -P.u_max ? -P.u_max : ui);
+            if (fabs(x.Om[i]) >= P.Om_max && x.Om[i] * ui >= 0.0) ui = 0.0;
+            u[i] = ui; Om_msg[i] = x.Om[i];
+        }
+        // CSSConstellation (prio 299) then Eclipse (prio 204): both see the spacecraft / Sun messages of the previous
+        // tick; the CSS see the eclipse message of the previous tick.  Only the sun-safe pass consumes the CSS.
+        V3 css_sun = mk(0, 0, 0);
+        if (mode == 1) {
+            if (k > 0) {
+                MrpRot BN = mrp_rot(x.s);
+                css_sun = css_wls(P, rot_BN(BN, x.s, unit_or_zero(sun_prev - x.r)), shadow_msg);
+            }
+        }
+        if (mode == 1 || k == k_last) shadow_msg = k > 0 ? eclipse_mars(P, sun_prev, x.r) : 1.0;
+        // SpacecraftPlus (prio 201)
+        if (k > 0) {
+            x = rk4(P, x, u, P.dt);
+            double s2 = dot(x.s, x.s);
+            if (s2 > 1.0) { x.s = x.s * (-1.0 / s2); n_switch++; }      // |sigma| > 1
+        }
+        // SpiceInterface (prio 200)
+        const bool need_sun = (mode == 1) || (k >= k_last - 1);
+        V3 sun_now = need_sun ? sun_at(sun, t) : sun_prev;
+        // SimpleNav (prio 109)
+        if (P.nav_noise) {
+            double ran[16];
+#pragma unroll
+            for (int b = 0; b < 4; b++) {
+                double n4[4];
+                normals4(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
+                ran[4 * b] = n4[0]; ran[4 * b + 1] = n4[1]; ran[4 * b + 2] = n4[2]; ran[4 * b + 3] = n4[3];
+            }
+            const double ndt = k > 0 ? P.dt : 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; i++) nerr[i] += ndt * nerr[3 + i];
+#pragma unroll
+            for (int i = 0; i < 15; i++) {
+                const double xs = nerr[i], bound = P.navBound[i];
+                double rn = ran[i];
+                double sc = fabs(xs) > bound * 1E-10 ? fabs(xs) : bound;
+                double bc = (bound * 2.0 - sc) / sc;
+                bc = bc > bound * 1E-10 ? bc : bound * 1E-10;
+                if (bc < 7.2) {                                       // beyond: 1/exp(bc^3) squared underflows to zero
+                    double b3 = bc * bc * bc;
+                    double ex = b3 < 1e-17 ? 1.0 : 1.0 / exp(b3);
+                    rn += ex * copysign(ex, -xs);
+                }
+                nerr[i] = xs + P.navP[i] * rn;
+            }
+        }
+        const V3 nav_r = x.r + mk(nerr[0], nerr[1], nerr[2]), nav_v = x.v + mk(nerr[3], nerr[4], nerr[5]);
+        const V3 nav_s = P.nav_noise ? mrp_add(x.s, mk(nerr[6], nerr[7], nerr[8])) : mrp_inner(x.s);
+        const V3 nav_w = x.w + mk(nerr[9], nerr[10], nerr[11]);
+        if (k == k_last) {
+            MrpRot BN = mrp_rot(x.s);
+            V3 sb = rot_BN(BN, x.s, unit_or_zero(sun_now - x.r));
+            V3 se = mk(nerr[12], nerr[13], nerr[14]);
+            MrpRot OT = mrp_rot(se);
+            nav_sun_B = rot_BN(OT, se, sb);
+        }
+        // CameraTask (prio 999, every cam_ticks): the frame shows the true state of this tick
+        const bool frame = camera && (k % P.cam_ticks == 0);
+        if (frame) n_img++;
+        // ================= FSW process =================
+        AttGuid g;
+        if (mode == 0) { // opNavPointTaskCheat: hillPoint + attTrackingError(sigma_R0R)
+            AttRef ref = hill_point(nav_r, nav_v, mk(0, 0, 0), mk(0, 0, 0));
+            ref.sigma_RN = mrp_add(ref.sigma_RN, arr(P.sigma_RR0));
+            g.sigma_BR = mrp_sub(nav_s, ref.sigma_RN);
+            MrpRot BN = mrp_rot(nav_s);
+            g.omega_RN_B = rot_BN(BN, nav_s, ref.omega_RN_N);
+            g.omega_BR_B = nav_w - g.omega_RN_B;
+            g.domega_RN_B = rot_BN(BN, nav_s, ref.domega_RN_N);
+        } else {         // sunSafePointTask: sunSafePoint (last pass's heading) then cssWlsEst
+            g = sun_safe_point(sunpt_w ? sunpt : mk(0, 0, 0), nav_w);
+            sunpt = css_sun; sunpt_w = 1;
+        }
+        { // mrpFeedbackRWsTask: MRP_Feedback with wheel momentum, rwMotorTorque
+            V3 w = g.omega_BR_B + g.omega_RN_B;
+            V3 Lr = g.omega_BR_B * P.Pgain + g.sigma_BR * P.K;
+            V3 hI = mv9(P.I, w);
+#pragma unroll
+            for (int i = 0; i < ON_NRW; i++) {
+                V3 gi = arr(P.gs[i]);
+                hI = hI + gi * (P.Js * (dot(w, gi) + Om_msg[i]));
+            }
+            Lr = Lr - cross(g.omega_RN_B, hI);
+            Lr = Lr - mv9(P.I, g.domega_RN_B - cross(w, g.omega_RN_B));
+            // commanded torque = -Lr; rwMotorTorque maps -(commanded) = Lr
+#pragma unroll
+            for (int i = 0; i < ON_NRW; i++) rwcmd[i] = dot(arr(P.Umap[i]), Lr);
+        }
+        { // relativeODuKF (opNavODTask: after imageProcessing + pixelLine; sunSafePointTask: time update only)
+            bool meas = false;
+            double c[3], obs[3], R[6];
+            if (mode == 0 && frame) {
+                MrpRot BN = mrp_rot(x.s);
+                meas = project_circle(P, rot_BN(BN, x.s, -x.r), c);
+                if (meas) {
+                    if (P.pixel_noise_std > 0.0) {
+                        double n4[4];
+                        normals4(P, genv, episode, (uint32_t)k, 2u, 0u, n4);
+                        c[0] += P.pixel_noise_std * n4[0]; c[1] += P.pixel_noise_std * n4[1]; c[2] += P.pixel_noise_std * n4[2];
+                    }
+                    pixel_line(P, c, nav_s, obs, R);
+                }
+            }
+            const double fdt = (double)(k - ftick) * P.dt;
+            if (meas || k > ftick) { ukf_time_update(P, f, fdt); ftick = k; }
+            if (meas) {
+                if (ukf_meas_update(P, f, fdt, obs, R)) n_meas++; else n_bad++;
+            }
+        }
+        sun_prev = sun_now;
+    }
+    // ---- observation (ONS:263-293) ----
+    const double nr2 = f.x[0] * f.x[0] + f.x[1] * f.x[1] + f.x[2] * f.x[2], inr = 1.0 / sqrt(nr2);
+    {
+        MrpRot BN = mrp_rot(x.s);
+        V3 pos_B = -rot_BN(BN, x.s, mk(f.x[0], f.x[1], f.x[2]) * inr);
+        V3 sh = nav_sun_B * (1.0 / norm(nav_sun_B));
+        out.ob[0] = dot(pos_B, sh);
+        double p00 = f.S[TRI(0, 0)] * f.S[TRI(0, 0)];
+        double p11 = f.S[TRI(1, 0)] * f.S[TRI(1, 0)] + f.S[TRI(1, 1)] * f.S[TRI(1, 1)];
+        double p22 = f.S[TRI(2, 0)] * f.S[TRI(2, 0)] + f.S[TRI(2, 1)] * f.S[TRI(2, 1)] + f.S[TRI(2, 2)] * f.S[TRI(2, 2)];
+        out.ob[1] = sqrt(p00) * inr; out.ob[2] = sqrt(p11) * inr; out.ob[3] = sqrt(p22) * inr;
+    }
+    out.debug[0] = f.x[0]; out.debug[1] = f.x[1]; out.debug[2] = f.x[2];
+    out.debug[3] = x.r.x; out.debug[4] = x.r.y; out.debug[5] = x.r.z;
+    out.debug[6] = x.v.x; out.debug[7] = x.v.y; out.debug[8] = x.v.z;
+    out.debug[9] = x.s.x; out.debug[10] = x.s.y; out.debug[11] = x.s.z;
+    // ---- opNavEnv.step epilogue (ONE:100-125, :139-152) ----
+    double reward = 0.0;
+    if (action == 1) {
+        V3 real = x.r, nav = (mk(f.x[0], f.x[1], f.x[2]) - real) * (1.0 / norm(real));
+        reward = fabs(P.reward_mult / (1.0 + dot(nav, nav)));
+    }
+    if (modeCounter >= P.numModes) { over = 1; reason |= 2; }
+    out.reward = reward; out.done = over; out.reason = reason;
+    // ---- store ----
+    SD(OF_R) = x.r.x; SD(OF_R + 1) = x.r.y; SD(OF_R + 2) = x.r.z; SD(OF_V) = x.v.x; SD(OF_V + 1) = x.v.y; SD(OF_V + 2) = x.v.z;
+    SD(OF_SIG) = x.s.x; SD(OF_SIG + 1) = x.s.y; SD(OF_SIG + 2) = x.s.z; SD(OF_OMG) = x.w.x; SD(OF_OMG + 1) = x.w.y; SD(OF_OMG + 2) = x.w.z;
+    for (int i = 0; i < ON_NRW; i++) { SD(OF_WHL + i) = x.Om[i]; SD(OF_RWCMD + i) = rwcmd[i]; }
+    for (int i = 0; i < 15; i++) SD(OF_NAVERR + i) = nerr[i];
+    SD(OF_SUNPT) = sunpt.x; SD(OF_SUNPT + 1) = sunpt.y; SD(OF_SUNPT + 2) = sunpt.z;
+    SD(OF_SHADOW) = shadow_msg;
+    for (int i = 0; i < 6; i++) SD(OF_FSTATE + i) = f.x[i];
+    for (int i = 0; i < 21; i++) SD(OF_FS + i) = f.S[i];
+    SD(OF_EPRET) = SD(OF_EPRET) + reward;
+    for (int i = 0; i < 4; i++) SD(OF_OBS + i) = out.ob[i];
+    for (int i = 0; i < 12; i++) SD(OF_DEBUG + i) = out.debug[i];
+    SI(OI_TICK) = k_last; SI(OI_STEP) = curr_step + 1; SI(OI_MODE) = mode; SI(OI_CAMERA) = camera; SI(OI_MODECNT) = modeCounter;
+    SI(OI_FIRST) = 0; SI(OI_SWITCH) = n_switch; SI(OI_OVER) = over; SI(OI_NMEAS) = n_meas; SI(OI_NBAD) = n_bad;
+    SI(OI_FTICK) = ftick; SI(OI_SUNPT_W) = sunpt_w; SI(OI_NIMG) = n_img;
+#undef SD
+#undef SI
+}
+
+}  // namespace opnav

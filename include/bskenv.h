@@ -140,6 +140,76 @@ int bskenv_fp64_peak(int device, double seconds, double *tflops);
 /* ALGORITHMIC FP64 flop per env-decision-step for this configuration (DESIGN.md derivation). */
 double bskenv_flops_per_step(const bskenv_handle *h);
 
+/* =====================================================================================================
+ * opNav environment (dynamics half + synthetic nav measurement + relative-OD filter, no rendering).
+ *
+ * Replaces everything below `scenario_OpNav.run_sim(action)` (reference: basilisk_env/simulators/
+ * opNavSimulator.py:225-299: the Basilisk ExecuteSimulation() at :261 and the message sampling at :263-293) plus the
+ * bookkeeping of `opNavEnv.step` / `reset` (basilisk_env/envs/opNavEnvironment.py:55-125, :153-168), vectorised over
+ * N independent environments.  One launch = one decision interval of 50 min = 3000 ticks of 1 s: truth RK4 (hub +
+ * four-wheel pyramid, Mars point mass), simple_nav error model, hillPoint / sunSafePoint guidance, MRP feedback,
+ * wheel torque map, a pinhole circle measurement every 60 s, pixelLineConverter and the six-state SR-UKF.
+ * ===================================================================================================== */
+#define BSKENV_OPNAV_OBS_DIM 4    /* [cos(sun-Mars angle in body), sqrt(diag P_rr)/|r_nav| (3)]  (opNavSimulator.py:284-293) */
+#define BSKENV_OPNAV_DEBUG_DIM 12 /* nav r(3), true r(3), true v(3), sigma_BN(3)                 (opNavSimulator.py:292) */
+#define BSKENV_OPNAV_IC_DIM 12    /* rN(3) vN(3) rError(3) vError(3)                             (opNavSimulator.py:181-189) */
+#define BSKENV_OPNAV_DONE_MAXLEN 1 /* curr_step >= max_length (opNavEnvironment.py:94-95) */
+#define BSKENV_OPNAV_DONE_MODES 2  /* modeCounter >= numModes (opNavSimulator.py:296-297) */
+
+typedef struct bskenv_opnav_config {
+    int32_t abi_version;         /* BSKENV_ABI_VERSION */
+    int32_t reserved0;
+    double dynRate, fswRate;     /* 1.0, 1.0 s: scenario_OpNav(1., 1., step_duration) (opNavEnvironment.py:86) */
+    double step_duration_min;    /* 50. minutes (opNavEnvironment.py:31, opNavSimulator.py:256-257) */
+    int32_t max_length;          /* 40 (opNavEnvironment.py:23) */
+    int32_t numModes;            /* 50 (opNavSimulator.py:149) */
+    int32_t auto_reset;          /* 0: gym single-env semantics; 1: re-sample ICs in-kernel when done */
+    int32_t nav_noise;           /* 1: simple_nav Gauss-Markov errors (BSK_OpNavDynamics.py:236-258); 0: truth */
+    int32_t camera_reenable;     /* 0: reference behaviour (action 1 switches the camera off for the rest of the episode,
+                                    opNavSimulator.py:239 is commented out); 1: action 0 switches it back on */
+    int32_t sample_orbit;        /* 0: the fixed reference orbit (opNavSimulator.py:173-178); 1: the commented-out random
+                                    element ranges (:166-171) for the device-side sampler */
+    double pixel_noise_std;      /* synthetic circle finder: 1-sigma noise on centre / radius [px] */
+    double circle_unc;           /* synthetic circle finder: CirclesOpNavMsg.uncertainty diagonal [px^2] */
+    double reward_mult;          /* 1.0 (opNavEnvironment.py:32) */
+    uint64_t noise_seed;         /* key of the per-env sensor-noise streams (counter-based; keyed by global env index
+                                    and episode as well, so results do not depend on the sharding) */
+    int32_t reserved[8];
+} bskenv_opnav_config;
+
+typedef struct bskenv_opnav_handle bskenv_opnav_handle;
+
+void bskenv_opnav_default_config(bskenv_opnav_config *cfg);
+int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_envs, int64_t first_env_index,
+                        bskenv_opnav_handle **out);
+int bskenv_opnav_destroy(bskenv_opnav_handle *h);
+const char *bskenv_opnav_last_error(const bskenv_opnav_handle *h);
+int64_t bskenv_opnav_num_envs(const bskenv_opnav_handle *h);
+/* reset(): device-sampled ICs (filter initial error U(+-1e5 m), U(+-1e3 m/s), opNavSimulator.py:187-188; orbit fixed or
+ * sampled); `obs_dev` (double[n*4], may be NULL) receives the initial observation (zeros, opNavSimulator.py:152). */
+int bskenv_opnav_reset_seeded(bskenv_opnav_handle *h, uint64_t seed, const uint8_t *mask_dev, double *obs_dev, void *stream);
+int bskenv_opnav_reset_ics(bskenv_opnav_handle *h, const double *ics_dev /* [n*12] */, const uint8_t *mask_dev,
+                           double *obs_dev, void *stream);
+int bskenv_opnav_reset_init(bskenv_opnav_handle *h, const uint8_t *mask_dev, double *obs_dev, void *stream);
+int bskenv_opnav_get_ics(bskenv_opnav_handle *h, double *ics_dev, void *stream);
+/* step(): ONE launch = one decision interval for every env.  Caller-owned device buffers:
+ *   actions int32[n]; obs double[n*4]; reward double[n]; done uint8[n]; done_reason uint8[n];
+ *   debug double[n*12] (may be NULL: info['full_states']); term_obs double[n*4] (may be NULL; auto_reset only). */
+int bskenv_opnav_step(bskenv_opnav_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
+                      uint8_t *done_dev, uint8_t *done_reason_dev, double *debug_dev, double *term_obs_dev, void *stream);
+/* same with HOST buffers (pinned staging inside the handle, synchronous): what bench.py times as e2e */
+int bskenv_opnav_step_host(bskenv_opnav_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done,
+                           uint8_t *done_reason, double *debug);
+int bskenv_opnav_state_dims(const bskenv_opnav_handle *h, int32_t *n_double_fields, int32_t *n_int_fields);
+int bskenv_opnav_get_state(bskenv_opnav_handle *h, double *dstate_dev, int64_t *istate_dev, void *stream);
+int bskenv_opnav_set_state(bskenv_opnav_handle *h, const double *dstate_dev, const int64_t *istate_dev, void *stream);
+int bskenv_opnav_state_field(const char *name, int32_t *is_int);
+/* [sum of returns, sum of lengths, episodes finished, by max_length, by numModes, env-steps, measurement updates,
+ *  rejected filter updates] since the last call */
+int bskenv_opnav_episode_stats(bskenv_opnav_handle *h, double *stats_host);
+int64_t bskenv_opnav_launch_count(const bskenv_opnav_handle *h);
+double bskenv_opnav_flops_per_step(const bskenv_opnav_handle *h);
+
 #ifdef __cplusplus
 }
 #endif

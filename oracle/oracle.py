@@ -44,8 +44,8 @@ class EnvOut(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "libbsk_oracle.so")
-    src = os.path.join(_HERE, "bsk_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("bsk_oracle.c", "bsk_oracle.h", "opnav_oracle.c", "opnav_oracle.h", "Makefile")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"])
     return so
 
