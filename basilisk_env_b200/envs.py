@@ -201,3 +201,4 @@ class leoPowerAttEnv:
             self.simulator.close()
             self.simulator = None
             self.simulator_init = 0
+from .opnav_env import opNavEnv, scenario_OpNav  # noqa: E402,F401  (reference: envs/__init__.py:2)

@@ -10,6 +10,7 @@ import numpy as np
 from . import oracle as _o
 
 MU_MARS = 4.2828371901284001E+13
+MU_MARS_FSW = 42828.314 * 1E9    # the filter's gravitational parameter ([BSK astroConstants MU_MARS] * 1e9)
 IC_DIM = 12          # rN(3) vN(3) rError(3) vError(3): the C-ABI's opNav IC row
 
 

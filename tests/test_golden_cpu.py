@@ -58,3 +58,45 @@ def test_hostcore_replays_constant_zero_episode(hostcore):
 def test_hostcore_replays_random_full_episode(hostcore):
     g = _replay(hostcore, "leo_episode_random.npz")
     assert len(g["obs"]) == 541 and g["reason"][-1] == 1     # quirk Q9: the 541st call ends the episode
+
+
+# --------------------------------------------------------------------------------------------------
+# opNav fixture (tests/golden/opnav_batch8.npz, generator make_golden_opnav.py)
+# --------------------------------------------------------------------------------------------------
+def test_opnav_oracle_reproduces_its_fixture():
+    from oracle import opnav as on
+    g = np.load(os.path.join(GOLDEN, "opnav_batch8.npz"))
+    assert list(g["actions"][:, 0]) == [1, 1, 0, 0, 1, 1, 1, 0, 0, 1]      # the reference's recorded actHist (ONS:327)
+    rN, vN = on.reference_orbit()
+    np.testing.assert_array_equal(g["ics"][0, :6], np.concatenate([rN, vN]))
+    for tag, kw in (("ref", dict()), ("cam", dict(camera_reenable=1))):
+        batch = on.OpNavEnvBatch(g["ics"], on.default_cfg(seed=int(g["seed"]), **kw), first_env_index=int(g["first_env"]))
+        for t in range(len(g["actions"])):
+            o, r, d, w, dbg = batch.step(g["actions"][t], nthreads=2)
+            np.testing.assert_allclose(o, g[f"{tag}_obs"][t], rtol=1e-12, atol=1e-15)
+            np.testing.assert_allclose(r, g[f"{tag}_reward"][t], rtol=1e-12)
+            np.testing.assert_array_equal(d, g[f"{tag}_done"][t]); np.testing.assert_array_equal(w, g[f"{tag}_reason"][t])
+            np.testing.assert_array_equal([s.n_meas for s in batch.states()], g[f"{tag}_n_meas"][t])
+    # reference semantics: the camera never comes back after the first action 1 -> env 0 never measures
+    assert g["ref_n_meas"][-1, 0] == 0 and g["cam_n_meas"][-1, 0] > 100
+
+
+def test_opnav_hostcore_replays_fixture():
+    from tests import opnav_parity as par
+    from tests.hostcore_binding import HostCoreOpNav
+    g = np.load(os.path.join(GOLDEN, "opnav_batch8.npz"))
+    n = len(g["ics"])
+    for tag, kw in (("ref", dict()), ("cam", dict(camera_reenable=1))):
+        hc = HostCoreOpNav(n, first_env=int(g["first_env"]), noise_seed=int(g["seed"]), **kw)
+        hc.reset_ics(g["ics"])
+        for t in range(len(g["actions"])):
+            obs, rew, done, reason, dbg = hc.step(g["actions"][t])
+            for e in range(n):
+                par.compare_obs(obs[e], g[f"{tag}_obs"][t, e], f"{tag} step {t} env {e}")
+                par.compare_debug(dbg[e], g[f"{tag}_debug"][t, e], f"{tag} step {t} env {e}")
+            np.testing.assert_allclose(rew, g[f"{tag}_reward"][t], rtol=1e-12, atol=1e-14)
+            np.testing.assert_array_equal(done, g[f"{tag}_done"][t])
+            S, I = hc.state()
+            np.testing.assert_array_equal(I[par.F("n_meas")], g[f"{tag}_n_meas"][t])
+        np.testing.assert_allclose(S[par.F("filter_state"):par.F("filter_state") + 3].T, g[f"{tag}_filt_state"][:, :3], rtol=1e-9)
+        np.testing.assert_allclose(S[par.F("Omega"):par.F("Omega") + 4].T, g[f"{tag}_Omega"], rtol=1e-9, atol=1e-9)

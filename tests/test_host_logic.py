@@ -16,6 +16,28 @@ def test_registry_and_spaces():
     assert all(0 <= d.sample() < 3 for _ in range(20))
 
 
+def test_opnav_env_attributes_without_gpu():
+    """opNavEnv mirrors opNavEnvironment.py:17-49 and is importable from the package and from `envs` (envs/__init__.py:2)."""
+    import basilisk_env_b200 as b
+    from basilisk_env_b200.envs import opNavEnv
+    from basilisk_env_b200.opnav_env import configure_initial_conditions, elem2rv, MU_MARS
+    from basilisk_env_b200.vec_env import BskEnvError
+    assert b.opNavEnv is opNavEnv
+    env = opNavEnv()
+    assert env.max_length == 40 and env.step_duration == 50. and env.reward_mult == 1.
+    assert env.observation_space.shape == (4, 1) and env.action_space.n == 2 and env.obs.shape == (4,)
+    with pytest.raises(BskEnvError):
+        env.step(0)
+    np.random.seed(3)
+    row = configure_initial_conditions()
+    np.random.seed(3)
+    np.testing.assert_array_equal(row[6:9], np.random.uniform(100000, -100000, 3))
+    np.testing.assert_array_equal(row[9:12], np.random.uniform(1000, -1000, 3))
+    from oracle import opnav as on
+    rN, vN = on.reference_orbit()
+    np.testing.assert_allclose(row[:3], rN, rtol=1e-15); np.testing.assert_allclose(row[3:6], vN, rtol=1e-15)
+
+
 def test_env_attributes_without_gpu():
     from basilisk_env_b200.envs import leoPowerAttEnv, _decode_action
     from basilisk_env_b200.vec_env import BskEnvError

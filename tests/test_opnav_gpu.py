@@ -1,0 +1,175 @@
+"""GPU suite (`-m gpu`) of the opNav path: the CUDA kernel, called through the C ABI (bskenv_opnav_*), against the
+opNav oracle on the same seeded inputs, against the committed golden fixture, and -- at BASELINE's batch sizes --
+through size-independent properties (sharding invariance, checkpoint round trip, filter consistency).
+
+"Oracle" = the in-repo FP64 restatement of the Basilisk 1.x algorithms (PARITY UNPINNED).  Tolerances:
+tests/opnav_parity.py."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import opnav_parity as par
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ORC_KEYS = ("dynRate", "fswRate", "step_duration_min", "nav_noise", "camera_reenable", "pixel_noise_std", "circle_unc", "numModes")
+
+
+def _vec(n, **kw):
+    from basilisk_env_b200.opnav_env import OpNavVecEnv
+    return OpNavVecEnv(n, device=0, **kw)
+
+
+def _state_np(env):
+    d, i = env.get_state()
+    return d.cpu().numpy(), i.cpu().numpy()
+
+
+def _run_against_oracle(bsk, rows, action_seq, host_path=False, first_env=0, seed=77, **cfg):
+    from oracle import opnav as on
+    n = len(rows)
+    env = _vec(n, first_env_index=first_env, noise_seed=seed, **cfg)
+    batch = on.OpNavEnvBatch(rows, on.default_cfg(seed=seed, **{k: v for k, v in cfg.items() if k in ORC_KEYS}), first_env_index=first_env)
+    ob0 = env.reset_ics(rows).cpu().numpy()
+    np.testing.assert_array_equal(ob0, np.zeros((n, 4)))
+    for t, acts in enumerate(action_seq):
+        if host_path:
+            obs, rew, done, reason, dbg = env.step_host(np.asarray(acts, np.int32))
+        else:
+            o, r, d, info = env.step(acts)
+            obs, rew, done, reason = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), info["done_reason"].cpu().numpy()
+            dbg = info["full_states"].cpu().numpy()
+        S, I = _state_np(env)
+        o_ob, o_rew, o_done, o_reason, o_dbg = batch.step(acts)
+        for e, st in enumerate(batch.states()):
+            where = f"step {t} env {e} action {acts[e]}"
+            par.compare_obs(obs[e], o_ob[e], where)
+            par.compare_debug(dbg[e], o_dbg[e], where)
+            assert bool(done[e]) == bool(o_done[e]) and int(reason[e]) == int(o_reason[e]), where
+            assert abs(rew[e] - o_rew[e]) <= 1e-12, where
+            par.compare_state(st, S[:, e], I[:, e], where)
+    assert env.launch_count() == len(action_seq)
+    env.close()
+
+
+def test_opnav_random_actions_64_envs(bsk):
+    from oracle import opnav as on
+    rows = par.sample_rows(on, 64, seed=1)
+    acts = np.random.RandomState(2).randint(0, 2, size=(4, 64))
+    _run_against_oracle(bsk, rows, acts, first_env=1000, camera_reenable=1)
+
+
+def test_opnav_reference_semantics_and_host_entry_point(bsk):
+    """Reference camera behaviour (never re-enabled), ragged batch, host-buffer entry point."""
+    from oracle import opnav as on
+    rows = par.sample_rows(on, 33, seed=3)
+    acts = np.random.RandomState(4).randint(0, 2, size=(3, 33))
+    acts[0, :16] = 0
+    _run_against_oracle(bsk, rows, acts, host_path=True)
+
+
+def test_opnav_noise_free_and_unknown_actions(bsk):
+    from oracle import opnav as on
+    rows = par.sample_rows(on, 6, seed=5)
+    acts = np.array([[0, 1, 0, 0, 1, 7], [-1, 1, 1, 0, 0, 0], [1, 0, 5, 1, 0, 1]])
+    _run_against_oracle(bsk, rows, acts, nav_noise=0, pixel_noise_std=0.0, camera_reenable=1)
+
+
+def test_opnav_golden_fixture(bsk):
+    g = np.load(os.path.join(GOLDEN, "opnav_batch8.npz"))
+    n = len(g["ics"])
+    for tag, kw in (("ref", dict()), ("cam", dict(camera_reenable=1))):
+        env = _vec(n, first_env_index=int(g["first_env"]), noise_seed=int(g["seed"]), **kw)
+        env.reset_ics(g["ics"])
+        for t in range(len(g["actions"])):
+            o, r, d, info = env.step(g["actions"][t])
+            obs, rew, done, dbg = o.cpu().numpy(), r.cpu().numpy(), d.cpu().numpy(), info["full_states"].cpu().numpy()
+            for e in range(n):
+                par.compare_obs(obs[e], g[f"{tag}_obs"][t, e], f"{tag} step {t} env {e}")
+                par.compare_debug(dbg[e], g[f"{tag}_debug"][t, e], f"{tag} step {t} env {e}")
+            np.testing.assert_allclose(rew, g[f"{tag}_reward"][t], rtol=1e-12, atol=1e-14)
+            np.testing.assert_array_equal(done.astype(bool), g[f"{tag}_done"][t])
+            np.testing.assert_array_equal(env.field("n_meas")[0].cpu().numpy(), g[f"{tag}_n_meas"][t])
+        env.close()
+
+
+def test_opnav_full_episode_bookkeeping(bsk):
+    """41 calls end the episode (40-step limit checked before the action); short interval to keep the oracle quick."""
+    from oracle import opnav as on
+    rows = par.sample_rows(on, 4, seed=6)
+    acts = np.random.RandomState(1).randint(0, 2, size=(42, 4))
+    _run_against_oracle(bsk, rows, acts, step_duration_min=1.0, camera_reenable=1)
+
+
+def test_opnav_sharding_checkpoint_and_auto_reset_at_4096(bsk):
+    """BASELINE batch size: (i) 4096 envs in one handle == two handles of 2048 (streams keyed by the global index);
+    (ii) get_state -> set_state into a fresh handle continues bit-identically; (iii) the filter stays consistent over
+    the batch (normalised position error of order one); (iv) auto-reset re-samples finished envs and the episode
+    statistics add up."""
+    import torch
+    n = 4096
+    kw = dict(noise_seed=9, sample_orbit=1, camera_reenable=1, step_duration_min=10.0)
+    whole = _vec(n, first_env_index=0, **kw)
+    halves = [_vec(n // 2, first_env_index=0, **kw), _vec(n // 2, first_env_index=n // 2, **kw)]
+    whole.reset(seed=9)
+    for h in halves:
+        h.reset(seed=9)
+    torch.manual_seed(0)
+    for t in range(3):
+        a = torch.randint(0, 2, (n,), dtype=torch.int32, device="cuda")
+        ow = [x.clone() for x in whole.step(a)[:3]]
+        oh = [h.step(a[k * n // 2:(k + 1) * n // 2])[:3] for k, h in enumerate(halves)]
+        for j in range(3):
+            assert torch.equal(ow[j], torch.cat([o[j] for o in oh])), f"step {t} output {j}"
+    d, i = whole.get_state()
+    clone = _vec(n, first_env_index=0, **kw)
+    clone.set_state(d, i)
+    a = torch.randint(0, 2, (n,), dtype=torch.int32, device="cuda")
+    o1 = [x.clone() for x in whole.step(a)[:3]]
+    o2 = clone.step(a)[:3]
+    for j in range(3):
+        assert torch.equal(o1[j], o2[j])
+    # filter consistency: |r_nav - r_true| against the filter's own sigma, envs that have measured at least 20 times
+    d, i = whole.get_state()
+    F = par.F
+    meas = i[F("n_meas")] >= 20
+    assert int(meas.sum()) > n // 4
+    err = (d[F("filter_state"):F("filter_state") + 3] - d[F("r_BN_N"):F("r_BN_N") + 3])[:, meas]
+    S = d[F("filter_sBar"):F("filter_sBar") + 21][:, meas]
+    sig = torch.stack([S[0].abs(), torch.sqrt(S[1] ** 2 + S[2] ** 2), torch.sqrt(S[3] ** 2 + S[4] ** 2 + S[5] ** 2)])
+    z = (err / sig).abs()
+    assert float(z.median()) < 3.0 and int(i[F("n_bad")].sum()) == 0
+    for e in (whole, clone, *halves):
+        e.close()
+    # auto-reset
+    env = _vec(256, auto_reset=True, max_length=2, step_duration_min=1.0, noise_seed=3)
+    env.reset(seed=3)
+    zeros = torch.zeros(256, dtype=torch.int32, device="cuda")
+    dones = []
+    for t in range(6):
+        obs, rew, done, info = env.step(zeros + (t % 2))
+        dones.append(int(done.sum()))
+    assert dones == [0, 0, 256, 0, 0, 256]
+    st = env.episode_stats()
+    assert st["episodes"] == 512 and st["length_sum"] == 512 * 3 and st["max_length_ends"] == 512 and st["env_steps"] == 6 * 256
+    assert torch.equal(obs, torch.zeros_like(obs))                  # first observation of the new episodes
+    assert int(env.field("episode")[0].min()) == 3
+    env.close()
+
+
+def test_opnav_gym_surface(bsk):
+    """`opNavEnv` / `scenario_OpNav` keep the reference's shapes, keys and step semantics."""
+    import basilisk_env_b200 as b
+    env = b.opNavEnv()
+    assert env.observation_space.shape == (4, 1) and env.action_space.n == 2 and env.max_length == 40
+    ob = env.reset()
+    assert ob.shape == (4, 1) and not ob.any()
+    ob, reward, over, info = env.step(1)
+    assert ob.shape == (4, 1) and set(info) == {"full_states", "obs"} and info["full_states"].shape == (12, 1)
+    assert 0 < reward <= 1 and not over
+    ob, reward, over, info = env.step(0)
+    assert reward == 0
+    sim = env.simulator
+    assert sim.modeCounter == 2 and sim.simTime == 100.0
+    env.close()

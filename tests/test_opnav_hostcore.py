@@ -1,0 +1,137 @@
+"""CPU suite: the opNav device core (basilisk_env_b200/csrc/opnav_core.cuh) compiled for the host against the
+independent oracle -- fused schedule, noise streams, streaming square-root filter, gym bookkeeping."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import opnav as on
+from tests import opnav_parity as par
+from tests.hostcore_binding import HostCoreOpNav
+
+
+def _run(rows, acts, first_env=0, **kw):
+    cfg = on.default_cfg(seed=77, **kw)
+    hc = HostCoreOpNav(len(rows), first_env=first_env, noise_seed=77, **kw)
+    ob0 = hc.reset_ics(rows)
+    np.testing.assert_array_equal(ob0, np.zeros_like(ob0))
+    batch = on.OpNavEnvBatch(rows, cfg, first_env_index=first_env)
+    for t in range(len(acts)):
+        obs, rew, done, reason, dbg = hc.step(acts[t])
+        o_ob, o_rew, o_done, o_reason, o_dbg = batch.step(acts[t])
+        S, I = hc.state()
+        for e, st in enumerate(batch.states()):
+            where = f"{kw} step {t} env {e}"
+            par.compare_state(st, S[:, e], I[:, e], where)
+            par.compare_obs(obs[e], o_ob[e], where)
+            par.compare_debug(dbg[e], o_dbg[e], where)
+        np.testing.assert_array_equal(done, o_done)
+        np.testing.assert_array_equal(reason, o_reason)
+        np.testing.assert_allclose(rew, o_rew, rtol=1e-12, atol=1e-14)
+    return hc, batch
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(camera_reenable=1), dict(nav_noise=0, pixel_noise_std=0.0, camera_reenable=1)],
+                         ids=["reference", "camera_reenable", "noise_free"])
+def test_fused_schedule_matches_oracle(kw):
+    rows = par.sample_rows(on, 4, seed=3)
+    acts = np.array([[0, 0, 1, 1], [0, 1, 1, 0], [1, 1, 0, 0], [0, 0, 0, 1]])
+    _run(rows, acts, first_env=10, **kw)
+
+
+def test_invalid_action_keeps_the_task_set():
+    rows = par.sample_rows(on, 2, seed=4)
+    acts = np.array([[0, 1], [7, -1], [1, 0]])
+    _run(rows, acts, camera_reenable=1)
+
+
+def test_noise_streams_are_bit_identical_to_the_oracle():
+    """Same Philox counters and Box-Muller on both sides; libm vs libm here, so exactly equal on the CPU."""
+    hc = HostCoreOpNav(1, noise_seed=0x1234567890ABCDEF)
+    L = on.lib()
+    out = np.zeros(4)
+    for env, ep, tick, stream, block in ((0, 0, 0, 1, 0), (5, 2, 1234, 1, 3), (2**33 + 1, 7, 119999, 2, 0)):
+        L.orc_opnav_normals(0x1234567890ABCDEF, env, ep, tick, stream, block, on._p(out))
+        np.testing.assert_array_equal(hc.normals(env, ep, tick, stream, block), out)
+
+
+def test_sun_ephemeris_matches_oracle():
+    hc = HostCoreOpNav(1)
+    L = on.lib()
+    r, v, et = np.zeros(3), np.zeros(3), np.zeros(1)
+    for t in (0.0, 3000.0, 123456.0):
+        L.orc_sun_from_mars(t, on._p(r), on._p(v), on._p(et))
+        rk, vk = hc.sun(t)
+        np.testing.assert_allclose(rk, r, rtol=1e-15); np.testing.assert_allclose(vk, v, rtol=1e-15)
+
+
+def test_streaming_filter_matches_basilisk_form():
+    """Givens / hyperbolic sweeps (kernel) vs Householder QR + Gill-Murray down-dates (oracle): one time update and
+    one measurement update from a dense, correlated covariance."""
+    L = on.lib()
+    hc = HostCoreOpNav(1)
+    rN, vN = on.reference_orbit()
+    x0 = np.concatenate([rN, vN])
+    rng = np.random.RandomState(8)
+    M = rng.randn(6, 6) * np.array([3e3, 3e3, 3e3, 3., 3., 3.])[:, None]
+    P0 = M @ M.T + np.diag([1e6] * 3 + [1.0] * 3)
+    Q = np.diag([1e-6] * 3 + [1e-8] * 3)
+    f = on.Ukf()
+    L.orc_ukf_init(C.byref(f), on._p(x0), on._p(P0.ravel()), on._p(Q.ravel()), on.MU_MARS_FSW, 5.0)
+    S0 = np.linalg.cholesky(P0)
+    S21 = np.array([S0[i, j] for i in range(6) for j in range(i + 1)])
+    for dt in (1.0, 0.0, 60.0):
+        L.orc_ukf_time_update(C.byref(f), f.timeTag + dt)
+        x0k, S21, m = hc.ukf_time_update(x0, S21, dt)
+        np.testing.assert_allclose(x0k, np.array(f.state[:]), rtol=1e-15)
+        Lk = par.tri_to_full(S21)
+        P_o = np.array(f.covar[:]).reshape(6, 6)
+        sc = np.sqrt(np.outer(np.diag(P_o), np.diag(P_o)))
+        assert np.max(np.abs(Lk @ Lk.T - P_o) / sc) < 1e-9
+        np.testing.assert_allclose(x0k + m, np.array(f.xBar[:]), rtol=1e-11)   # the oracle sums with wM[0] = -2499
+        x0 = x0k
+    Rm = np.array([[4e7, 1e6, -2e6], [1e6, 9e7, 3e6], [-2e6, 3e6, 1e8]])
+    obs = x0[:3] + np.array([2e3, -1e3, 5e2])
+    L.orc_ukf_meas_update(C.byref(f), on._p(obs), on._p((Rm / 5.0).ravel()))
+    R6 = np.array([Rm[0, 0], Rm[1, 0], Rm[2, 0], Rm[1, 1], Rm[2, 1], Rm[2, 2]])
+    xk, S21, ok = hc.ukf_meas_update(x0, S21, m, 60.0, obs, R6)
+    assert ok and f.n_bad == 0
+    np.testing.assert_allclose(xk, np.array(f.state[:]), rtol=1e-11)
+    Lk = par.tri_to_full(S21)
+    P_o = np.array(f.covar[:]).reshape(6, 6)
+    sc = np.sqrt(np.outer(np.diag(P_o), np.diag(P_o)))
+    assert np.max(np.abs(Lk @ Lk.T - P_o) / sc) < 1e-9
+    assert np.all(np.diag(Lk) > 0)
+
+
+def test_device_sampler_ranges_and_sharding_invariance():
+    """Per-env streams are keyed by the GLOBAL env index: 6 envs in one batch == two shards of 3, bit for bit."""
+    whole = HostCoreOpNav(6, first_env=100, noise_seed=5, sample_orbit=1, camera_reenable=1)
+    ics, ob0 = whole.reset_seeded(42)
+    assert np.all(np.abs(ics[:, 6:9]) <= 1e5) and np.all(np.abs(ics[:, 9:12]) <= 1e3)
+    r = np.linalg.norm(ics[:, 0:3], axis=1); v = np.linalg.norm(ics[:, 3:6], axis=1)
+    a = 1.0 / (2.0 / r - v * v / on.MU_MARS)
+    assert np.all(a > 17000e3 * (1 - 1e-12)) and np.all(a < 22000e3 * (1 + 1e-12))
+    fixed = HostCoreOpNav(2, noise_seed=5)
+    ics_f, _ = fixed.reset_seeded(42)
+    rN, vN = on.reference_orbit()
+    np.testing.assert_allclose(ics_f[:, 0:3], np.tile(rN, (2, 1)), rtol=1e-15)
+    acts = np.array([0, 1, 0, 0, 1, 1])
+    shards = [HostCoreOpNav(3, first_env=100, noise_seed=5, sample_orbit=1, camera_reenable=1),
+              HostCoreOpNav(3, first_env=103, noise_seed=5, sample_orbit=1, camera_reenable=1)]
+    ics_s = np.concatenate([s.reset_seeded(42)[0] for s in shards])
+    np.testing.assert_array_equal(ics, ics_s)
+    for t in range(2):
+        ow = whole.step(acts)
+        os_ = [s.step(acts[3 * k:3 * k + 3]) for k, s in enumerate(shards)]
+        for j in range(5):
+            np.testing.assert_array_equal(ow[j], np.concatenate([o[j] for o in os_]))
+
+
+def test_episode_bookkeeping_matches_oracle_to_the_end():
+    """A full 41-call episode at a short decision interval: done / reason / reward sequence identical."""
+    rows = par.sample_rows(on, 2, seed=6)
+    acts = np.random.RandomState(1).randint(0, 2, size=(42, 2))
+    hc, batch = _run(rows, acts, step_duration_min=1.0, camera_reenable=1)
+    S, I = hc.state()
+    assert list(I[par.F("curr_step")]) == [42, 42] and list(I[par.F("episode_over")]) == [1, 1]
