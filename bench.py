@@ -41,7 +41,10 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env side measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env and opNav side measurements")
+    ap.add_argument("--workload", default="leo", choices=["leo", "opnav"],
+                    help="leo: the headline line (default); opnav: the same JSON line for BASELINE configs[3] (N=1 only)")
+    ap.add_argument("--opnav-envs", type=int, default=32768)
     return ap.parse_args()
 
 
@@ -164,7 +167,22 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
+        if args.workload == "opnav":
+            if rank == 0:
+                cb = opnav_cpu_arm(4, 0.0, fixed_steps=args.steps)
+                print(json.dumps({"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
+                                  "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
+                                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                                  "data": "synthetic", "config": {"workload": opnav_workload_name(args.opnav_envs)},
+                                  "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                                  "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                                  "gpu_launches": 0}), flush=True)
+            return
         run_reference(args, rank)
+        return
+    if args.workload == "opnav":
+        if rank == 0:
+            run_opnav(args)
         return
     import torch
     import torch.distributed as dist
@@ -259,6 +277,9 @@ def main():
         }
         if not args.no_extra:
             line["batch4096"] = side_batch(4096, torch, dev, flops, peak_tf)
+            if world == 1:
+                line["opnav"] = side_opnav(args.opnav_envs, torch, dev, peak_tf, steps=3, warmup=3,
+                                           cpu_seconds=0.0 if args.no_cpu_baseline else 4.0)
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_arm(envs_per_core_step=4, seconds=args.cpu_seconds, min_steps=2, warmup=1)
             line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -283,6 +304,104 @@ def side_batch(n, torch, dev, flops, peak_tf):
     tf = flops * n / (ms * 1e-3) / 1e12
     return {"envs": n, "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "fp64_tflops": tf,
             "frac": tf / peak_tf if peak_tf else None}
+
+
+# --------------------------------------------------------------------------------------------------
+# opNav env (BASELINE configs[3]): dynamics + nav measurement model + relative-OD filter, batched
+# --------------------------------------------------------------------------------------------------
+OPNAV_STATE_BYTES_PER_ENV = (83 + 14) * 8
+OPNAV_H2D_BYTES_PER_ENV = 4
+OPNAV_D2H_BYTES_PER_ENV = 4 * 8 + 8 + 1 + 1 + 12 * 8
+
+
+def opnav_workload_name(n):
+    return (f"opNav env, {n} envs on one GPU (BASELINE configs[3]): Mars orbits from the reference's element ranges, filter "
+            "initial error U(+-1e5 m, +-1e3 m/s), simple_nav noise on, one synthetic circle measurement per 60 s while imaging, "
+            "i.i.d. uniform actions {0,1}, camera re-enabled by action 0, auto-reset, FP64; one step = 50 min = 3000 ticks")
+
+
+def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None):
+    from oracle import opnav as on
+    from oracle import oracle as orc
+    from tests import opnav_parity as par
+    threads = threads or orc.max_threads()
+    n = envs_per_core * threads
+    rows = par.sample_rows(on, n, seed=7)
+    batch = on.OpNavEnvBatch(rows, on.default_cfg(seed=5, camera_reenable=1))
+    rng = np.random.RandomState(3)
+    batch.step(rng.randint(0, 2, n), nthreads=threads)
+    steps, t0 = 0, time.perf_counter()
+    while True:
+        batch.step(rng.randint(0, 2, n), nthreads=threads)
+        steps += 1
+        el = time.perf_counter() - t0
+        if (fixed_steps is not None and steps >= fixed_steps) or (fixed_steps is None and el >= seconds):
+            break
+    return {"value": n * steps / el, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": el / steps * 1e3,
+            "sample": f"{n} envs x {steps} decision steps (oracle/opnav_oracle.c, OpenMP over envs, {el:.1f} s)"}
+
+
+def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
+    from basilisk_env_b200.opnav_env import OpNavVecEnv
+    env = OpNavVecEnv(n, device=dev.index, seed=5, auto_reset=True, sample_orbit=1, camera_reenable=1)
+    env.reset()
+    acts = torch.randint(0, 2, (steps + warmup, n), dtype=torch.int32, device=dev)
+    acts_host = acts.cpu().numpy()
+    l0 = env.launch_count()
+    total_ms, per = time_device_steps(env, acts, steps, warmup, torch, None, 1)
+    outs = (np.empty((n, 4)), np.empty(n), np.empty(n, np.uint8), np.empty(n, np.uint8), np.empty((n, 12)))
+    env.step_host(acts_host[0], outs)
+    torch.cuda.synchronize()
+    e0 = time.perf_counter()
+    for t in range(steps):
+        env.step_host(acts_host[warmup + t], outs)
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / steps
+    launches = env.launch_count() - l0 - warmup - 1
+    stats = env.episode_stats()
+    flops = env.flops_per_step()
+    env.close()
+    ms = float(np.mean(per))
+    tf = flops * n / (ms * 1e-3) / 1e12
+    alg_bytes = (2 * OPNAV_STATE_BYTES_PER_ENV + OPNAV_H2D_BYTES_PER_ENV + OPNAV_D2H_BYTES_PER_ENV) * n
+    out = {"workload": opnav_workload_name(n), "envs": n, "value": n * steps / (total_ms * 1e-3), "unit": UNIT,
+           "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup, "ticks_per_step": 3000,
+           "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
+                        "kernel": "opnav_step_kernel", "kernel_ms": ms, "flop_per_env_step": flops,
+                        "flop_source": "operation list of opnav_core.cuh (bskenv_opnav_flops_per_step; DESIGN.md)",
+                        "algorithmic_bytes_per_launch": alg_bytes},
+           "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": OPNAV_H2D_BYTES_PER_ENV * n,
+                   "d2h_bytes_per_step": OPNAV_D2H_BYTES_PER_ENV * n, "api": "bskenv_opnav_step_host"},
+           "gpu_launches": int(launches), "episode_stats": stats, "checksum": float(outs[0].sum())}
+    if cpu_seconds > 0:
+        cb = opnav_cpu_arm(2, cpu_seconds)
+        out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    return out
+
+
+def run_opnav(args):
+    """The full JSON line for the opNav workload (N = 1)."""
+    import torch
+    from basilisk_env_b200.vec_env import fp64_peak_tflops
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the environment step has no CPU path)")
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    peak_tf = fp64_peak_tflops(0, 0.5)
+    sampler = ClockSampler(0)
+    t0 = time.perf_counter()
+    r = side_opnav(args.opnav_envs, torch, dev, peak_tf, steps=args.steps, warmup=max(args.warmup, 3),
+                   cpu_seconds=0.0 if args.no_cpu_baseline else args.cpu_seconds)
+    clocks = sampler.stop(t0, time.perf_counter())
+    n = args.opnav_envs
+    line = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": r["steps"], "warmup": r["warmup"],
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": r["workload"], "envs_per_gpu": n, "ticks_per_step": 3000,
+                       "l2": f"{(OPNAV_STATE_BYTES_PER_ENV + 12 * 8) * n / 2**20:.0f} MiB of per-env state, touched once per launch; "
+                             "the kernel is FP64-pipe / latency bound, not memory bound"},
+            "roofline": dict(r["roofline"], traffic=None), "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks,
+            "episode_stats": r["episode_stats"], "checksum": r["checksum"], "cpu_baseline": r.get("cpu_baseline")}
+    print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":

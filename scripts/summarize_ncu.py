@@ -73,7 +73,7 @@ def raw():
     if rd is not None and wr is not None:
         tb = rd * scale.get(d["dram__bytes_read.sum"][1], 1) + wr * scale.get(d["dram__bytes_write.sum"][1], 1)
         json.dump({"tag": tag, "dram_bytes_per_launch": tb, "kernel": d.get("Kernel Name", ("", ""))[0][:80]},
-                  open(os.path.join(ROOT, "profiles", "traffic.json"), "w"))
+                  open(os.path.join(ROOT, "profiles", "traffic_opnav.json" if tag.startswith("opnav") else "traffic.json"), "w"))
         out.append(f"DRAM traffic per launch: {tb / 1e6:.1f} MB (read {rd} + write {wr} {d['dram__bytes_read.sum'][1]})\n")
     return rep
 
