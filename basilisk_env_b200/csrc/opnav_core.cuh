@@ -12,10 +12,11 @@
 // implementation.  With d_i = Y_i - Y_0 the propagated deviations from the central sigma point and
 // m = sum_i w d_i, the SR-UKF covariance  sum_i wC_i (Y_i - xBar)(Y_i - xBar)^T + Q  equals
 //     Q + sum_{i>=1} w d_i d_i^T + (2 - alpha^2) m m^T
-// (all terms positive: no down-date, no stored sigma points), built here by Givens rank-one sweeps on the
-// lower-triangular factor.  The measurement is linear (y = r), so Pxy and Pyy are blocks of the a-priori
-// covariance and the update is three hyperbolic rank-one sweeps.  The oracle keeps Basilisk's formulation
-// (Householder QR + Gill-Murray down-dates); the two agree to rounding (tests/test_opnav_*).
+// (all terms positive: no down-date, no stored sigma points).  The 21 entries of that sum are independent FMA
+// chains over the sigma points; one 6 x 6 Cholesky per tick gives the factor the next sigma points need.  The
+// measurement is linear (y = r), so Pxy and Pyy are blocks of the a-priori covariance and the update is three
+// hyperbolic rank-one sweeps.  The oracle keeps Basilisk's formulation (Householder QR + Gill-Murray
+// down-dates); the two agree to rounding (tests/test_opnav_*).
 //
 // Everything is __host__ __device__ (tests/hostcore compiles it with g++); the product only runs it on the GPU.
 #pragma once
@@ -42,19 +43,25 @@ ON_HD void sincos_hd(double x, double &s, double &c)
 // ------------------------------------------------------------------------------------------------
 // noise streams: Philox4x32-10, counter (env_lo, env_hi, tick, stream<<16 | block), key (seed_lo, seed_hi ^ episode)
 // ------------------------------------------------------------------------------------------------
-ON_HD void normals4(const OpNavParams &P, int64_t env, int64_t episode, uint32_t tick, uint32_t stream, uint32_t block,
-                    double (&out)[4])
+ON_HD_NOINLINE void normals4(const OpNavParams &P, int64_t env, int64_t episode, uint32_t tick, uint32_t stream, uint32_t block,
+                             double (&out)[4])
 {
     uint32_t x[4];
     philox4x32((uint32_t)(uint64_t)env, (uint32_t)((uint64_t)env >> 32), tick, (stream << 16) | block, (uint32_t)P.seed,
                (uint32_t)(P.seed >> 32) ^ (uint32_t)episode, x);
-    const double TWO_PI = 2.0 * 3.14159265358979323846;
 #pragma unroll
     for (int p = 0; p < 2; p++) {
         double u1 = ((double)x[2 * p] + 1.0) * (1.0 / 4294967296.0);
         double u2 = (double)x[2 * p + 1] * (1.0 / 4294967296.0);
-        double rr = sqrt(-2.0 * log(u1)), s, c;
-        sincos_hd(TWO_PI * u2, s, c);
+        double s, c;
+#ifdef __CUDA_ARCH__
+        const double t = -2.0 * log(u1);
+        const double rr = t > 0.0 ? t * rsq(t) : 0.0;      // sqrt without the special-operand path
+        sincospi(2.0 * u2, &s, &c);                         // exact argument reduction of 2 pi u2
+#else
+        const double rr = sqrt(-2.0 * log(u1));
+        s = sin(2.0 * 3.14159265358979323846 * u2); c = cos(2.0 * 3.14159265358979323846 * u2);
+#endif
         out[2 * p] = rr * c;
         out[2 * p + 1] = rr * s;
     }
@@ -136,45 +143,97 @@ ON_HD Truth axpy(const Truth &x, double a, const Truth &k)
     return o;
 }
 ON_HD Truth rk4(const OpNavParams &P, const Truth &x0, const double (&u)[ON_NRW], double h)
+{ // svIntegratorRK4; the stage loop stays rolled so that the equations of motion exist once in the instruction stream
+    Truth k, xo = x0, x = x0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int st = 0; st < 4; st++) {
+        eom(P, x, u, k);
+        const double cw = (st == 0 || st == 3) ? h / 6.0 : h / 3.0;
+        const double cn = st == 2 ? h : 0.5 * h;
+        xo = axpy(xo, cw, k);
+        x = axpy(x0, cn, k);
+    }
+    return xo;
+}
+
+// One state of the bounded random walk of [BSK: utilities/gauss_markov.cpp] computeNextState (identity propagation):
+//   x += P * (n + push),  push = e * copysign(e, -x),  e = 1/exp(b^3),  b = max((2 bound - s)/s, 1e-10 bound),
+//   s = |x| if |x| > 1e-10 bound else bound.
+// For b >= 7.2 the push underflows to zero; for b^3 < 1e-17 it is exactly +-1 (the attitude states: bound 1e-18 deg).
+ON_HD double gm_step(double xs, double bound, double pm, double rn)
 {
-    Truth k, xo, x;
-    eom(P, x0, u, k);
-    xo = axpy(x0, h / 6.0, k); x = axpy(x0, 0.5 * h, k);
-    eom(P, x, u, k);
-    xo = axpy(xo, h / 3.0, k); x = axpy(x0, 0.5 * h, k);
-    eom(P, x, u, k);
-    xo = axpy(xo, h / 3.0, k); x = axpy(x0, h, k);
-    eom(P, x, u, k);
-    return axpy(xo, h / 6.0, k);
+    const double ax = fabs(xs);
+    const double sc = ax > bound * 1E-10 ? ax : bound;
+#ifdef __CUDA_ARCH__
+    double bc = fmad(bound * 2.0, frcp(sc), -1.0);
+#else
+    double bc = (bound * 2.0 - sc) / sc;
+#endif
+    bc = bc > bound * 1E-10 ? bc : bound * 1E-10;
+    if (bc < 7.2) {
+        const double b3 = bc * bc * bc;
+#ifdef __CUDA_ARCH__
+        const double ex = b3 < 1e-17 ? 1.0 : exp(-b3);
+#else
+        const double ex = b3 < 1e-17 ? 1.0 : 1.0 / exp(b3);
+#endif
+        rn += ex * copysign(ex, -xs);
+    }
+    return xs + pm * rn;
 }
 
 // ------------------------------------------------------------------------------------------------
 // eclipse (conical model, one planet at the origin), coarse sun sensors, cssWlsEst, sunSafePoint
 // ------------------------------------------------------------------------------------------------
-ON_HD_NOINLINE double eclipse_mars(const OpNavParams &P, V3 sun, V3 r)
+// Same geometry as leo::penumbra_fraction / leo::eclipse_core (tangent cones of two spheres; the disk-overlap formula of
+// eclipse.cpp computePercentShadow inside the guard band around the cone surfaces), for the planet of this scenario.
+ON_HD_NOINLINE double penumbra_fraction_on(const OpNavParams &P, double ir, double id, double rdh)
 {
-    V3 s_HP = sun, r_HB = sun - r, s_BP = r;
-    double hb = norm(r_HB), hp = norm(s_HP);
-    if (hb < hp) return 1.0;
-    double sn = norm(s_BP), RS = P.R_sun, Rp = P.R_planet;
-    double f_1 = asin((RS + Rp) / hp), f_2 = asin((RS - Rp) / hp);
-    double s_0 = (-dot(s_BP, s_HP)) / hp;
-    double c_1 = s_0 + Rp / sin(f_1), c_2 = s_0 - Rp / sin(f_2);
-    double l = sqrt(sn * sn - s_0 * s_0), l_1 = c_1 * tan(f_1), l_2 = c_2 * tan(f_2);
-    double shadow = 1.0;
-    if (fabs(l) < fabs(l_2) || fabs(l) < fabs(l_1)) {
-        const double PI = 3.14159265358979323846;
-        double a = clamp_asin(RS / hb), b = clamp_asin(Rp / sn);
-        double c = clamp_acos((-dot(s_BP, r_HB)) / (sn * hb));
-        if (c < b - a) shadow = 0.0;
-        else if (c < a - b) shadow = 1 - (PI * a * a - PI * b * b) / (PI * a * a);
-        else if (c < a + b) {
-            double x = (c * c + a * a - b * b) / (2 * c), y = sqrt(a * a - x * x);
-            double area = a * a * clamp_acos(x / a) + b * b * clamp_acos((c - x) / b) - c * y;
-            shadow = 1 - area / (PI * a * a);
-        }
-    }
-    return shadow;
+    const double PI = 3.14159265358979323846;
+    const double ta = P.R_sun * id, tb = P.R_planet * ir;             // sin a, sin b
+    const double cc = -rdh * ir * id;                                  // cos c
+    const double sc2 = 1. - cc * cc, cb2 = 1. - tb * tb;
+    const double sd = (sc2 > 0. && cb2 > 0.) ? sqrt(sc2) * sqrt(cb2) - cc * tb : 2.0;   // sin(c - b)
+    if (!(ta <= 0.05 && fabs(sd) <= 0.1 && tb >= 20. * ta && tb < 1.))
+        return percent_shadow_general(clamp_asin(ta), clamp_asin(tb), clamp_acos(cc));
+    const double a = asin_small(ta), d = asin_small(sd), b = asin(tb);
+    if (d < -a) return 0.0;
+    if (!(d < a)) return 1.0;
+    const double c = b + d;
+    const double x = (a * a + d * (2. * b + d)) / (2. * c);
+    double y2 = a * a - x * x;
+    if (y2 < 0.) y2 = 0.;
+    const double y = sqrt(y2);
+    const double u = y / b, u2 = u * u;
+    double seg = fmad(u2, 5. / 72., 3. / 28.);
+    seg = fmad(seg, u2, 1. / 5.); seg = fmad(seg, u2, 2. / 3.);
+    const double area = a * a * clamp_acos(x / a) - x * y + (b * b) * (u * u2) * seg;
+    return 1. - area / (PI * a * a);
+}
+// Eclipse::UpdateState for Mars at the origin.  The cone constants follow from |sun| algebraically:
+// sin f = (R_sun +- R_p)/|sun|, R_p/sin f = R_p |sun| / (R_sun +- R_p), tan f = sin f / sqrt(1 - sin^2 f).
+// Full sun / umbra are decided on squared cone radii; only the band around the cone surfaces evaluates the disk overlap.
+ON_HD double eclipse_mars(const OpNavParams &P, V3 sun, V3 r)
+{
+    const double hp2 = dot(sun, sun), inv_hp = rsq(hp2), hp = hp2 * inv_hp;
+    const double Rs = P.R_sun, Rp = P.R_planet;
+    const double s1 = (Rs + Rp) * inv_hp, s2f = (Rs - Rp) * inv_hp;
+    const double c1off = Rp * hp * P.inv_RsPlusRp, c2off = Rp * hp * P.inv_RsMinusRp;
+    const double tan1 = s1 * rsq(1. - s1 * s1), tan2 = s2f * rsq(1. - s2f * s2f);
+    const V3 r_HB = sun - r;
+    const double s2 = dot(r, r), hb2 = dot(r_HB, r_HB);
+    const double s0 = -dot(r, sun) * inv_hp;
+    const double c1 = s0 + c1off, c2 = s0 - c2off;
+    const double l2sq = s2 - s0 * s0;
+    const double l1 = c1 * tan1, l2 = c2 * tan2;
+    const double p2 = l1 * l1, u2 = l2 * l2;
+    const bool lit = (hb2 < hp2) || (l2sq > p2 * (1. + ECL_BAND) && l2sq > u2 * (1. + ECL_BAND));
+    const bool dark = l2sq < u2 * (1. - ECL_BAND) && c2 < 0. && Rs > Rp;
+    double f = lit ? 1.0 : 0.0;
+    if (!lit && !dark) f = (l2sq < u2 || l2sq < p2) ? penumbra_fraction_on(P, rsq(s2), rsq(hb2), dot(r, r_HB)) : 1.0;
+    return f;
 }
 ON_HD V3 mrp_add(V3 q1, V3 q2)
 { // RigidBodyKinematics addMRP: [FN(out)] = [FB(q2)][BN(q1)], shadow-set guard, inner-set map
@@ -260,24 +319,6 @@ ON_HD void two_body_rk4(double (&x)[6], double mu, double dt)
 #pragma unroll
     for (int i = 0; i < 6; i++) x[i] += acc[i];
 }
-// L L^T += x x^T (Givens sweep); x is destroyed
-ON_HD void chol_update6(double (&L)[21], double (&x)[6])
-{
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        double Lkk = L[TRI(k, k)], t = Lkk * Lkk + x[k] * x[k];
-        if (t > 0.0) {
-            double ir = rsq(t), c = Lkk * ir, s = x[k] * ir;
-            L[TRI(k, k)] = t * ir;
-#pragma unroll
-            for (int j = k + 1; j < 6; j++) {
-                double Ljk = L[TRI(j, k)];
-                L[TRI(j, k)] = c * Ljk + s * x[j];
-                x[j] = c * x[j] - s * Ljk;
-            }
-        }
-    }
-}
 // L L^T -= x x^T (hyperbolic sweep); returns false when the result is not positive definite
 ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
 {
@@ -298,46 +339,74 @@ ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
     return ok;
 }
 struct Ukf { double x[6]; double S[21]; double m[6]; };
-// relODuKFTimeUpdate over dt
-ON_HD_NOINLINE void ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
+// relODuKFTimeUpdate over dt.  The twelve deviations are accumulated into the 21 independent entries of the Gram
+// matrix (no serial dependence between sigma points: the +/- pair of a column is propagated side by side), then one
+// 6 x 6 Cholesky factorisation gives the new square-root factor.  FP64 Cholesky of this covariance loses
+// eps * cond(scaled P) ~ 1e-12, the same as the differencing of the sigma points themselves.
+// Returns false (filter left untouched) when the covariance is not positive definite.
+ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
 {
-    double Y0[6], L[21], m[6];
+    double Y0[6], A[21], ms[6], col[36];
 #pragma unroll
-    for (int i = 0; i < 6; i++) { Y0[i] = f.x[i]; m[i] = 0.0; }
+    for (int c = 0; c < 6; c++)
+#pragma unroll
+        for (int r = 0; r < 6; r++) col[c * 6 + r] = c <= r ? f.S[TRI(r, c)] : 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) { Y0[i] = f.x[i]; ms[i] = 0.0; }
     two_body_rk4(Y0, P.mu_fsw, dt);
 #pragma unroll
-    for (int i = 0; i < 21; i++) L[i] = 0.0;
-    const double qp = P.ukf_sq_pos * (dt * dt / 2), qv = P.ukf_sq_vel * dt;
-    L[TRI(0, 0)] = qp; L[TRI(1, 1)] = qp; L[TRI(2, 2)] = qp; L[TRI(3, 3)] = qv; L[TRI(4, 4)] = qv; L[TRI(5, 5)] = qv;
+    for (int i = 0; i < 21; i++) A[i] = 0.0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int idx = 0; idx < 12; idx++) {
-        const int i = idx >> 1;
-        const double g = (idx & 1) ? -P.ukf_gamma : P.ukf_gamma;
-        double Y[6];
-        // column i of S (rows >= i); the switch keeps S in registers
+    for (int i = 0; i < 6; i++) {
+        double Yp[6], Ym[6];
 #pragma unroll
-        for (int r = 0; r < 6; r++) {
-            double col = 0.0;
+        for (int r = 0; r < 6; r++) { const double c = P.ukf_gamma * col[i * 6 + r]; Yp[r] = f.x[r] + c; Ym[r] = f.x[r] - c; }
+        two_body_rk4(Yp, P.mu_fsw, dt);
+        two_body_rk4(Ym, P.mu_fsw, dt);
 #pragma unroll
-            for (int c = 0; c < 6; c++) if (c <= r) col = (c == i) ? f.S[TRI(r, c)] : col;
-            Y[r] = f.x[r] + g * col;
-        }
-        two_body_rk4(Y, P.mu_fsw, dt);
-        double d[6];
+        for (int r = 0; r < 6; r++) { Yp[r] -= Y0[r]; Ym[r] -= Y0[r]; ms[r] += Yp[r] + Ym[r]; }
 #pragma unroll
-        for (int r = 0; r < 6; r++) { double dd = Y[r] - Y0[r]; m[r] += P.ukf_w * dd; d[r] = P.ukf_sqrt_w * dd; }
-        chol_update6(L, d);
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) A[TRI(a, b)] = fmad(Yp[a], Yp[b], fmad(Ym[a], Ym[b], A[TRI(a, b)]));
     }
-    double d[6];
+    double m[6], L[21];
 #pragma unroll
-    for (int r = 0; r < 6; r++) d[r] = P.ukf_sqrt_cm * m[r];
-    chol_update6(L, d);
+    for (int r = 0; r < 6; r++) m[r] = P.ukf_w * ms[r];
+    const double qp = P.ukf_sq_pos * (dt * dt / 2), qv = P.ukf_sq_vel * dt;
+#pragma unroll
+    for (int a = 0; a < 6; a++)
+#pragma unroll
+        for (int b = 0; b <= a; b++) {
+            double v = P.ukf_w * A[TRI(a, b)] + P.ukf_cm * (m[a] * m[b]);
+            if (a == b) v += a < 3 ? qp * qp : qv * qv;
+            A[TRI(a, b)] = v;
+        }
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double t = A[TRI(j, j)];
+#pragma unroll
+        for (int k = 0; k < j; k++) t -= L[TRI(j, k)] * L[TRI(j, k)];
+        if (!(t > 0.0)) { ok = false; t = 1.0; }
+        const double ir = rsq(t);
+        L[TRI(j, j)] = t * ir;
+#pragma unroll
+        for (int i = j + 1; i < 6; i++) {
+            double v = A[TRI(i, j)];
+#pragma unroll
+            for (int k = 0; k < j; k++) v -= L[TRI(i, k)] * L[TRI(j, k)];
+            L[TRI(i, j)] = v * ir;
+        }
+    }
+    if (!ok) return false;
 #pragma unroll
     for (int i = 0; i < 21; i++) f.S[i] = L[i];
 #pragma unroll
     for (int i = 0; i < 6; i++) { f.x[i] = Y0[i]; f.m[i] = m[i]; }
+    return true;
 }
 // relODuKFMeasUpdate for y = r_BN_N with noise covariance R (symmetric, m^2, already scaled by noiseSF);
 // `dt` is the span of the time update that has just run (its process noise is not part of Pxy / Pyy)
@@ -541,29 +610,22 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
         V3 sun_now = need_sun ? sun_at(sun, t) : sun_prev;
         // SimpleNav (prio 109)
         if (P.nav_noise) {
-            double ran[16];
-#pragma unroll
-            for (int b = 0; b < 4; b++) {
-                double n4[4];
-                normals4(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
-                ran[4 * b] = n4[0]; ran[4 * b + 1] = n4[1]; ran[4 * b + 2] = n4[2]; ran[4 * b + 3] = n4[3];
-            }
             const double ndt = k > 0 ? P.dt : 0.0;
 #pragma unroll
             for (int i = 0; i < 3; i++) nerr[i] += ndt * nerr[3 + i];
-#pragma unroll
-            for (int i = 0; i < 15; i++) {
-                const double xs = nerr[i], bound = P.navBound[i];
-                double rn = ran[i];
-                double sc = fabs(xs) > bound * 1E-10 ? fabs(xs) : bound;
-                double bc = (bound * 2.0 - sc) / sc;
-                bc = bc > bound * 1E-10 ? bc : bound * 1E-10;
-                if (bc < 7.2) {                                       // beyond: 1/exp(bc^3) squared underflows to zero
-                    double b3 = bc * bc * bc;
-                    double ex = b3 < 1e-17 ? 1.0 : 1.0 / exp(b3);
-                    rn += ex * copysign(ex, -xs);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int b = 0; b < 4; b++) {                             // four normals per Philox block, 15 walk states
+                double n4[4];
+                normals4(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int j = 0; j < 4; j++) {
+                    const int i = 4 * b + j;
+                    if (i < 15) nerr[i] = gm_step(nerr[i], P.navBound[i], P.navP[i], n4[j]);
                 }
-                nerr[i] = xs + P.navP[i] * rn;
             }
         }
         const V3 nav_r = x.r + mk(nerr[0], nerr[1], nerr[2]), nav_v = x.v + mk(nerr[3], nerr[4], nerr[5]);
@@ -624,8 +686,12 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
                 }
             }
             const double fdt = (double)(k - ftick) * P.dt;
-            if (meas || k > ftick) { ukf_time_update(P, f, fdt); ftick = k; }
-            if (meas) {
+            bool tu_ok = true;
+            if (meas || k > ftick) {
+                tu_ok = ukf_time_update(P, f, fdt);
+                if (tu_ok) ftick = k; else n_bad++;          // relODuKFCleanUpdate: the filter keeps its previous state and time
+            }
+            if (meas && tu_ok) {
                 if (ukf_meas_update(P, f, fdt, obs, R)) n_meas++; else n_bad++;
             }
         }

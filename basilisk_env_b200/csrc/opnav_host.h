@@ -77,6 +77,7 @@ static inline std::string build_params(const bskenv_opnav_config &c, OpNavParams
       memcpy(p.cssN, n, sizeof(n)); }
     p.css_cos_fov = cos(80. * D2R); p.css_scale = 2.0;  // OND:337-338
     p.R_sun = 695000.0 * 1000; p.R_planet = 3396.19 * 1000;   // [BSK: astroConstants REQ_SUN, REQ_MARS]
+    p.inv_RsPlusRp = 1.0 / (p.R_sun + p.R_planet); p.inv_RsMinusRp = 1.0 / (p.R_sun - p.R_planet);
     { // simple_nav PMatrix diagonal and walk bounds (OND:238-253); the DV states are not used
         const double P[15] = {10.0, 10.0, 10.0, 0.001, 0.001, 0.001,
                               1.0 / 36000.0 * PI / 180.0, 1.0 / 36000.0 * PI / 180.0, 1.0 / 36000.0 * PI / 180.0,

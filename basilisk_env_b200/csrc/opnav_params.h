@@ -29,7 +29,7 @@ struct OpNavParams {
     double K, Pgain;
     double sigma_RR0[3];            // -sigma_R0R of trackingErrorCam
     double cssN[ON_NCSS][3], css_cos_fov, css_scale;
-    double R_sun, R_planet;
+    double R_sun, R_planet, inv_RsPlusRp, inv_RsMinusRp;
     // ---- simple_nav (OND:236-258) ----
     double navP[15], navBound[15];
     int32_t nav_noise, camera_reenable;

@@ -17,8 +17,9 @@ import sys
 cubin, src = sys.argv[1], sys.argv[2]
 kern = sys.argv[3] if len(sys.argv) > 3 else "leo_step_kernelILi3ELb0ELb1"
 depth = int(sys.argv[4]) if len(sys.argv) > 4 else -1
-W, T = 4096.0, 1800.0
 import os
+W, T = float(os.environ.get("WARPS", 4096.0)), float(os.environ.get("TICKS", 1800.0))
+CORE = os.environ.get("CORE", "leo_core.cuh")     # CORE=opnav_core.cuh WARPS=1024 TICKS=3000 for the opNav kernel
 only = os.environ.get("SECTION")     # restrict the per-line table to one out-of-line function
 
 txt = subprocess.run(["nvdisasm", "--print-line-info-inline", cubin], capture_output=True, text=True).stdout
@@ -33,7 +34,7 @@ for line in txt.splitlines():
     m = re.match(r"^\$\S*\$(\S+):\s*$", line)          # out-of-line device function / libdevice slow path
     if m:
         nm = m.group(1)
-        mm = re.search(r"3leo(\d+)", nm)
+        mm = re.search(r"(?:3leo|5opnav)(\d+)", nm)
         sub = nm[mm.end():mm.end() + int(mm.group(1))] if mm else nm.strip("_$")[:40]
         continue
     m = re.match(r'\s*//## File "([^"]+)", line (\d+)', line)
@@ -63,7 +64,7 @@ for r in rows[2:]:
     if base is None:
         base = a
     ch = chains.get(a - base, [])
-    core = [c for c in ch if c[0] == "leo_core.cuh"]
+    core = [c for c in ch if c[0] == CORE]
     if depth == -1:
         key = core[-1] if core else (ch[-1] if ch else ("?", 0))
     else:
@@ -85,17 +86,17 @@ for r in rows[2:]:
     tot += n
 lines = {}
 try:
-    lines = dict(enumerate(open("/root/repo/basilisk_env_b200/csrc/leo_core.cuh").read().splitlines(), 1))
+    lines = dict(enumerate(open("/root/repo/basilisk_env_b200/csrc/" + CORE).read().splitlines(), 1))
 except OSError:
     pass
 # per-function totals (function = the last definition that starts at or before the line)
 fstarts = []
 for ln, text in sorted(lines.items()):
-    m = re.match(r"^(?:LEO_HD_NOINLINE|LEO_HD)\s+.*?(\w+)\(", text)
+    m = re.match(r"^(?:LEO_HD_NOINLINE|LEO_HD|ON_HD_NOINLINE|ON_HD)\s+.*?(\w+)\(", text)
     if m and not text.startswith(" "):
         fstarts.append((ln, m.group(1)))
 def func_of(key):
-    if key[0] != "leo_core.cuh":
+    if key[0] != CORE:
         return key[0]
     name = "?"
     for ln, n in fstarts:
@@ -116,5 +117,5 @@ for f, (n, ex, fp) in sorted(fagg.items(), key=lambda kv: -kv[1][0])[:25]:
 print()
 print(f"{'line':>16s} {'time%':>6s} {'instr/tick':>10s} {'fp64/tick':>9s}")
 for key, (n, ex, fp) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:int(sys.argv[5]) if len(sys.argv) > 5 else 60]:
-    text = lines.get(key[1], "").strip()[:90] if key[0] == "leo_core.cuh" else ""
+    text = lines.get(key[1], "").strip()[:90] if key[0] == CORE else ""
     print(f"{key[0][:10]:>10s}:{key[1]:<5d} {100 * n / tot:6.2f} {ex:10.1f} {fp:9.1f}  {text}")

@@ -4,7 +4,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from basilisk_env_b200.opnav_env import OpNavVecEnv
 
-for n in (4096, 32768, 65536):
+import os
+for n in [int(v) for v in os.environ.get("OPNAV_N", "4096,32768,65536").split(",")]:
     env = OpNavVecEnv(n, device=0, auto_reset=True, sample_orbit=1, camera_reenable=1, noise_seed=1)
     env.reset(seed=1)
     torch.manual_seed(0)

@@ -78,13 +78,17 @@ void hco_sun(HCO *h, double t, double *r, double *v)
     opnav::SunState s = opnav::sun_from_mars(h->P, t);
     r[0] = s.r.x; r[1] = s.r.y; r[2] = s.r.z; v[0] = s.v.x; v[1] = s.v.y; v[2] = s.v.z;
 }
+double hco_eclipse(HCO *h, const double *sun, const double *r)
+{
+    return opnav::eclipse_mars(h->P, leo::mk(sun[0], sun[1], sun[2]), leo::mk(r[0], r[1], r[2]));
+}
 // streaming SR-UKF on caller data: x[6], S[21] lower triangle row-major
 void hco_ukf_time_update(HCO *h, double *x, double *S, double *m, double dt)
 {
     opnav::Ukf f;
     for (int i = 0; i < 6; i++) { f.x[i] = x[i]; f.m[i] = 0; }
     for (int i = 0; i < 21; i++) f.S[i] = S[i];
-    opnav::ukf_time_update(h->P, f, dt);
+    (void)opnav::ukf_time_update(h->P, f, dt);
     for (int i = 0; i < 6; i++) { x[i] = f.x[i]; m[i] = f.m[i]; }
     for (int i = 0; i < 21; i++) S[i] = f.S[i];
 }

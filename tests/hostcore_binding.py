@@ -146,6 +146,8 @@ def lib_opnav():
         L.hco_dims.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.hco_normals.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.hco_sun.argtypes = [vp, C.c_double, vp, vp]
+        L.hco_eclipse.restype = C.c_double
+        L.hco_eclipse.argtypes = [vp, vp, vp]
         L.hco_ukf_time_update.argtypes = [vp, vp, vp, vp, C.c_double]
         L.hco_ukf_meas_update.restype = C.c_int
         L.hco_ukf_meas_update.argtypes = [vp, vp, vp, vp, C.c_double, vp, vp]
@@ -206,6 +208,10 @@ class HostCoreOpNav:
         r = np.zeros(3); v = np.zeros(3)
         self.L.hco_sun(self.h, float(t), r.ctypes.data, v.ctypes.data)
         return r, v
+
+    def eclipse(self, sun, r):
+        sun = np.ascontiguousarray(sun, dtype=np.float64); r = np.ascontiguousarray(r, dtype=np.float64)
+        return float(self.L.hco_eclipse(self.h, sun.ctypes.data, r.ctypes.data))
 
     def ukf_time_update(self, x, S21, dt):
         x = np.array(x, dtype=np.float64); S21 = np.array(S21, dtype=np.float64); m = np.zeros(6)

@@ -65,6 +65,35 @@ def test_sun_ephemeris_matches_oracle():
         np.testing.assert_allclose(rk, r, rtol=1e-15); np.testing.assert_allclose(vk, v, rtol=1e-15)
 
 
+def test_mars_eclipse_fast_path_matches_conical_model():
+    """Squared-cone tests + regrouped penumbra form (kernel) vs the literal eclipse.cpp restatement (oracle): exactly 0 / 1
+    outside the penumbra, <= 1e-7 inside it (the literal form is ill-conditioned there: tests/parity.py)."""
+    from oracle import oracle as orc
+    hc = HostCoreOpNav(1)
+    L = on.lib()
+    sun, v, et = np.zeros(3), np.zeros(3), np.zeros(1)
+    L.orc_sun_from_mars(1000.0, on._p(sun), on._p(v), on._p(et))
+    s_hat = sun / np.linalg.norm(sun)
+    e1 = np.cross(s_hat, [0, 0, 1.0]); e1 /= np.linalg.norm(e1)
+    Rm = 3396.19e3
+    rng = np.random.RandomState(0)
+    zero = np.zeros(3)
+    seen = set()
+    for _ in range(4000):
+        depth = rng.uniform(-2e7, 3e7)                        # along the anti-sun line (negative: sunny side)
+        lat = Rm * (1 + rng.uniform(-0.02, 0.02)) if rng.rand() < 0.7 else rng.uniform(0.2 * Rm, 3 * Rm)
+        r = -s_hat * depth + e1 * lat
+        if np.linalg.norm(r) <= Rm:
+            continue
+        want = orc.lib().orc_eclipse_shadow(on._p(sun), on._p(zero), on._p(r), Rm)
+        got = hc.eclipse(sun, r)
+        if want in (0.0, 1.0) and abs(got - want) > 0:
+            assert min(got, 1 - got) < 1e-7
+        assert abs(got - want) <= 1e-7, (depth, lat, got, want)
+        seen.add("umbra" if want == 0.0 else ("sun" if want == 1.0 else "penumbra"))
+    assert seen == {"umbra", "sun", "penumbra"}
+
+
 def test_streaming_filter_matches_basilisk_form():
     """Givens / hyperbolic sweeps (kernel) vs Householder QR + Gill-Murray down-dates (oracle): one time update and
     one measurement update from a dense, correlated covariance."""
