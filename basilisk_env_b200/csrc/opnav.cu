@@ -36,7 +36,12 @@ __device__ __forceinline__ double warp_sum_d(double v)
 // resident set and the warps pull groups from an atomic queue (same scheme as the LEO step kernel).
 struct OnSched { int *sched; int n_groups; int dynamic; };
 
-__global__ void __launch_bounds__(ON_BLOCK, ON_MIN_BLOCKS)
+#ifdef ON_MAXNREG
+#define ON_STEP_BOUNDS __maxnreg__(ON_MAXNREG)          // tuning builds: explicit register cap instead of an occupancy target
+#else
+#define ON_STEP_BOUNDS __launch_bounds__(ON_BLOCK, ON_MIN_BLOCKS)
+#endif
+__global__ void ON_STEP_BOUNDS
 opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                   int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                   double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,

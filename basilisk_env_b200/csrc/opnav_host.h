@@ -115,16 +115,21 @@ static inline std::string build_params(const bskenv_opnav_config &c, OpNavParams
     return "";
 }
 
-// FP64 flop per env-decision-step of the opNav kernel (FMA = 2, add/mul = 1, one per MUFU seed), counted from
-// opnav_core.cuh for the OpNavOD mode with nav noise on:
-//   truth RK4        4 x eom (gravity 14, wheels 4 x 13, torque 33 + Dinv 15, MRP kinematics 26, wheel rates 4 x 7) = 4 x 168,
-//                    stage combinations 7 x 32                                                          ~  900
-//   simple_nav       16 Box-Muller normals (log 30 + sqrt 12 + sincos 70 per pair) + 15 walk states x 14 ~ 1100
-//   guidance + ctrl  hillPoint 130, tracking error 170, MRP feedback 110, torque map 24                  ~  430
-//   filter           13 x two-body RK4 (4 x 22 + 60) + 13 Givens sweeps (6 x 12 + 15 x 6) + deviations 13 x 24 ~ 4350
+// FP64 flop per env-decision-step of the opNav kernel AS BUILT (FMA = 2, add/mul = 1, one per MUFU seed), from the
+// operation list of opnav_core.cuh and matched to ncu's executed 2*DFMA + DMUL + DADD thread-instruction counters
+// (profiles/ncu_opnav_r01c.md: 5.853e11 per 32768-env launch = 5954 per tick and env with the 50/50 action mix):
+//   filter time update   13 two-body RK4 steps (4 x 44 + 6), sigma points and deviations 6 x 60, Gram matrix 6 x 84,
+//                        covariance assembly 100, 6 x 6 Cholesky 185                                        ~ 3400
+//   truth RK4            4 x eom (gravity 20, wheel momentum and torque 52, gyroscopics + inverse 45, MRP kinematics 40,
+//                        wheel rates 28) + stage combinations 4 x 64                                        ~  950
+//   simple_nav           16 Box-Muller normals (log, rsqrt, sincospi: ~100 per pair) and 15 bounded-walk states ~ 1150
+//   guidance + control   hillPoint / tracking error / MRP feedback / torque map (OpNav pointing) or eclipse / CSS /
+//                        cssWlsEst / sunSafePoint / MRP feedback (sun-safe)                                  ~  400
+//   nav message          MRP composition of the attitude error, position / velocity / rate sums             ~   55
+// The measurement update (once per 60 ticks while imaging) adds ~10 per tick on average.
 static inline double flops_per_step(const OpNavParams &p)
 {
-    const double per_tick = 900.0 + (p.nav_noise ? 1100.0 : 60.0) + 430.0 + 4350.0;
+    const double per_tick = 3400.0 + 950.0 + (p.nav_noise ? 1150.0 : 0.0) + 400.0 + 55.0;
     return per_tick * p.ticks_per_step;
 }
 
