@@ -47,6 +47,8 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
                   double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
                   double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc)
 {
+    extern __shared__ double on_smem[];            // per-thread filter scratch (opnav::Ukf), 49-double stride: conflict-free
+    opnav::Ukf &filt = *reinterpret_cast<opnav::Ukf *>(on_smem + (size_t)threadIdx.x * (sizeof(opnav::Ukf) / sizeof(double)));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (bool more = true; more; more = sc.dynamic != 0) {
         int g;
@@ -65,7 +67,7 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
         double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
         if (valid) {
             const int64_t m0 = I[(int64_t)OI_NMEAS * stride + e], b0 = I[(int64_t)OI_NBAD * stride + e];
-            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o);
+            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o, filt);
             d_meas = (double)(I[(int64_t)OI_NMEAS * stride + e] - m0); d_bad = (double)(I[(int64_t)OI_NBAD * stride + e] - b0);
             reward[e] = o.reward;
             done[e] = (uint8_t)o.done;
@@ -196,7 +198,13 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
         grid = resident;
         ON_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
     }
-    opnav_step_kernel<<<grid, ON_BLOCK, 0, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
+    const size_t smem = sizeof(opnav::Ukf) * ON_BLOCK;
+    static bool attr_set[64] = {false};             // opt in to > 48 KB of dynamic shared memory once per device
+    if (!attr_set[h->device & 63]) {
+        ON_TRY(h, cudaFuncSetAttribute(opnav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[h->device & 63] = true;
+    }
+    opnav_step_kernel<<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
                                                  term_obs, h->stats, sc);
     ON_TRY(h, cudaGetLastError());
     h->launches++;

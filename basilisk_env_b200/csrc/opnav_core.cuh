@@ -338,7 +338,11 @@ ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
     }
     return ok;
 }
-struct Ukf { double x[6]; double S[21]; double m[6]; };
+// Filter state as the kernel holds it during a launch: estimate, square-root covariance as a full column-major 6 x 6 (column c
+// at C[6c .. 6c+5], zeros above the diagonal: a sigma-point column is six consecutive words), mean shift of the last time
+// update.  49 doubles: an odd stride keeps the per-thread copies in shared memory free of bank conflicts.
+struct Ukf { double x[6]; double C[36]; double m[6]; double pad; };
+#define SC(r, c) C[(c) * 6 + (r)]
 // relODuKFTimeUpdate over dt.  The twelve deviations are accumulated into the 21 independent entries of the Gram
 // matrix (no serial dependence between sigma points: the +/- pair of a column is propagated side by side), then one
 // 6 x 6 Cholesky factorisation gives the new square-root factor.  FP64 Cholesky of this covariance loses
@@ -346,11 +350,7 @@ struct Ukf { double x[6]; double S[21]; double m[6]; };
 // Returns false (filter left untouched) when the covariance is not positive definite.
 ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
 {
-    double Y0[6], A[21], ms[6], col[36];
-#pragma unroll
-    for (int c = 0; c < 6; c++)
-#pragma unroll
-        for (int r = 0; r < 6; r++) col[c * 6 + r] = c <= r ? f.S[TRI(r, c)] : 0.0;
+    double Y0[6], A[21], ms[6];
 #pragma unroll
     for (int i = 0; i < 6; i++) { Y0[i] = f.x[i]; ms[i] = 0.0; }
     two_body_rk4(Y0, P.mu_fsw, dt);
@@ -362,7 +362,7 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
     for (int i = 0; i < 6; i++) {
         double Yp[6], Ym[6];
 #pragma unroll
-        for (int r = 0; r < 6; r++) { const double c = P.ukf_gamma * col[i * 6 + r]; Yp[r] = f.x[r] + c; Ym[r] = f.x[r] - c; }
+        for (int r = 0; r < 6; r++) { const double c = P.ukf_gamma * f.C[i * 6 + r]; Yp[r] = f.x[r] + c; Ym[r] = f.x[r] - c; }
         two_body_rk4(Yp, P.mu_fsw, dt);
         two_body_rk4(Ym, P.mu_fsw, dt);
 #pragma unroll
@@ -403,7 +403,9 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
     }
     if (!ok) return false;
 #pragma unroll
-    for (int i = 0; i < 21; i++) f.S[i] = L[i];
+    for (int c = 0; c < 6; c++)
+#pragma unroll
+        for (int r = c; r < 6; r++) f.SC(r, c) = L[TRI(r, c)];
 #pragma unroll
     for (int i = 0; i < 6; i++) { f.x[i] = Y0[i]; f.m[i] = m[i]; }
     return true;
@@ -418,7 +420,7 @@ ON_HD_NOINLINE bool ukf_meas_update(const OpNavParams &P, Ukf &f, double dt, con
         for (int b = 0; b < 3; b++) {
             double s = 0.0;
             const int kmax = a < b ? a : b;
-            for (int k = 0; k <= kmax; k++) s += f.S[TRI(a, k)] * f.S[TRI(b, k)];
+            for (int k = 0; k <= kmax; k++) s += f.SC(a, k) * f.SC(b, k);
             Pxy[a][b] = (a == b) ? s - qp2 : s;
         }
     // Sy = chol(Pyy), Pyy = Pxy[0:3][0:3] + R
@@ -442,7 +444,8 @@ ON_HD_NOINLINE bool ukf_meas_update(const OpNavParams &P, Ukf &f, double dt, con
         U[0][a] = k0 * l00 + k1 * l10 + k2 * l20; U[1][a] = k1 * l11 + k2 * l21; U[2][a] = k2 * l22;   // U = K Sy
     }
     double L[21];
-    for (int i = 0; i < 21; i++) L[i] = f.S[i];
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c <= r; c++) L[TRI(r, c)] = f.SC(r, c);
     bool ok = true;
     for (int c = 0; c < 3; c++) {
         double x[6];
@@ -450,7 +453,8 @@ ON_HD_NOINLINE bool ukf_meas_update(const OpNavParams &P, Ukf &f, double dt, con
         ok = chol_downdate6(L, x) && ok;
     }
     if (!ok) return false;
-    for (int i = 0; i < 21; i++) f.S[i] = L[i];
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c <= r; c++) f.SC(r, c) = L[TRI(r, c)];
     for (int a = 0; a < 6; a++) f.x[a] = xn[a];
     return true;
 }
@@ -537,7 +541,8 @@ ON_HD void opnav_reset_env(const OpNavParams &P, double *S, int64_t *I, int64_t 
 // ------------------------------------------------------------------------------------------------
 struct StepOut { double ob[4]; double debug[12]; double reward; int done; int reason; };
 
-ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out)
+// `f` is scratch storage for the filter during the call (per-thread shared memory on the device, a stack object on the host)
+ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out, Ukf &f)
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
@@ -561,9 +566,9 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
     V3 sunpt = mk(SD(OF_SUNPT), SD(OF_SUNPT + 1), SD(OF_SUNPT + 2));
     int sunpt_w = (int)SI(OI_SUNPT_W);
     double shadow_msg = SD(OF_SHADOW);
-    Ukf f;
     for (int i = 0; i < 6; i++) { f.x[i] = SD(OF_FSTATE + i); f.m[i] = 0.0; }
-    for (int i = 0; i < 21; i++) f.S[i] = SD(OF_FS + i);
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? SD(OF_FS + TRI(r, c)) : 0.0;
     int64_t ftick = SI(OI_FTICK), n_meas = SI(OI_NMEAS), n_bad = SI(OI_NBAD), n_img = SI(OI_NIMG), n_switch = SI(OI_SWITCH);
     const int64_t tick0 = SI(OI_TICK);
     const int64_t k_first = tick0 + 1, k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;   // stop time inclusive
@@ -704,9 +709,9 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
         V3 pos_B = -rot_BN(BN, x.s, mk(f.x[0], f.x[1], f.x[2]) * inr);
         V3 sh = nav_sun_B * (1.0 / norm(nav_sun_B));
         out.ob[0] = dot(pos_B, sh);
-        double p00 = f.S[TRI(0, 0)] * f.S[TRI(0, 0)];
-        double p11 = f.S[TRI(1, 0)] * f.S[TRI(1, 0)] + f.S[TRI(1, 1)] * f.S[TRI(1, 1)];
-        double p22 = f.S[TRI(2, 0)] * f.S[TRI(2, 0)] + f.S[TRI(2, 1)] * f.S[TRI(2, 1)] + f.S[TRI(2, 2)] * f.S[TRI(2, 2)];
+        double p00 = f.SC(0, 0) * f.SC(0, 0);
+        double p11 = f.SC(1, 0) * f.SC(1, 0) + f.SC(1, 1) * f.SC(1, 1);
+        double p22 = f.SC(2, 0) * f.SC(2, 0) + f.SC(2, 1) * f.SC(2, 1) + f.SC(2, 2) * f.SC(2, 2);
         out.ob[1] = sqrt(p00) * inr; out.ob[2] = sqrt(p11) * inr; out.ob[3] = sqrt(p22) * inr;
     }
     out.debug[0] = f.x[0]; out.debug[1] = f.x[1]; out.debug[2] = f.x[2];
@@ -729,7 +734,8 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
     SD(OF_SUNPT) = sunpt.x; SD(OF_SUNPT + 1) = sunpt.y; SD(OF_SUNPT + 2) = sunpt.z;
     SD(OF_SHADOW) = shadow_msg;
     for (int i = 0; i < 6; i++) SD(OF_FSTATE + i) = f.x[i];
-    for (int i = 0; i < 21; i++) SD(OF_FS + i) = f.S[i];
+    for (int r = 0; r < 6; r++)
+        for (int c = 0; c <= r; c++) SD(OF_FS + TRI(r, c)) = f.SC(r, c);
     SD(OF_EPRET) = SD(OF_EPRET) + reward;
     for (int i = 0; i < 4; i++) SD(OF_OBS + i) = out.ob[i];
     for (int i = 0; i < 12; i++) SD(OF_DEBUG + i) = out.debug[i];

@@ -55,7 +55,8 @@ void hco_step(HCO *h, const int32_t *actions, double *obs, double *reward, uint8
 {
     for (int64_t e = 0; e < h->n; e++) {
         opnav::StepOut o;
-        opnav::opnav_step_env(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o);
+        opnav::Ukf f;
+        opnav::opnav_step_env(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o, f);
         for (int k = 0; k < 4; k++) obs[4 * e + k] = o.ob[k];
         if (debug) for (int k = 0; k < 12; k++) debug[12 * e + k] = o.debug[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
@@ -87,21 +88,21 @@ void hco_ukf_time_update(HCO *h, double *x, double *S, double *m, double dt)
 {
     opnav::Ukf f;
     for (int i = 0; i < 6; i++) { f.x[i] = x[i]; f.m[i] = 0; }
-    for (int i = 0; i < 21; i++) f.S[i] = S[i];
+    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? S[k++] : 0.0;
     (void)opnav::ukf_time_update(h->P, f, dt);
     for (int i = 0; i < 6; i++) { x[i] = f.x[i]; m[i] = f.m[i]; }
-    for (int i = 0; i < 21; i++) S[i] = f.S[i];
+    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c <= r; c++) S[k++] = f.SC(r, c);
 }
 int hco_ukf_meas_update(HCO *h, double *x, double *S, const double *m, double dt, const double *obs, const double *R6)
 {
     opnav::Ukf f;
     for (int i = 0; i < 6; i++) { f.x[i] = x[i]; f.m[i] = m[i]; }
-    for (int i = 0; i < 21; i++) f.S[i] = S[i];
+    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? S[k++] : 0.0;
     double o[3] = {obs[0], obs[1], obs[2]}, R[6];
     for (int i = 0; i < 6; i++) R[i] = R6[i];
     bool ok = opnav::ukf_meas_update(h->P, f, dt, o, R);
     for (int i = 0; i < 6; i++) x[i] = f.x[i];
-    for (int i = 0; i < 21; i++) S[i] = f.S[i];
+    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c <= r; c++) S[k++] = f.SC(r, c);
     return ok ? 1 : 0;
 }
 }
