@@ -101,13 +101,12 @@ ON_HD_NOINLINE SunState sun_from_mars(const OpNavParams &P, double t)
 }
 // Four exact evaluations per decision interval (nodes at 0, 1/3, 2/3, 1 of the span), cubic Lagrange in between:
 // interpolation error < 1e-5 m on 2.3e11 m; only the Sun POSITION is used on this path.
-struct SunSpan { V3 p0, p1, p2, p3; double t0, T; };
-ON_HD V3 sun_at(const SunSpan &s, double t)
+ON_HD V3 sun_at(const volatile double *n, double t0, double T, double t)
 {
-    double q = 3.0 * ((t - s.t0) / s.T);
+    double q = 3.0 * ((t - t0) / T);
     double a = q - 1.0, b = q - 2.0, c = q - 3.0;
     double l0 = -(a * b * c) * (1.0 / 6.0), l1 = (q * b * c) * 0.5, l2 = -(q * a * c) * 0.5, l3 = (q * a * b) * (1.0 / 6.0);
-    return s.p0 * l0 + s.p1 * l1 + s.p2 * l2 + s.p3 * l3;
+    return mk(n[0], n[1], n[2]) * l0 + mk(n[3], n[4], n[5]) * l1 + mk(n[6], n[7], n[8]) * l2 + mk(n[9], n[10], n[11]) * l3;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -340,8 +339,11 @@ ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
 }
 // Filter state as the kernel holds it during a launch: estimate, square-root covariance as a full column-major 6 x 6 (column c
 // at C[6c .. 6c+5], zeros above the diagonal: a sigma-point column is six consecutive words), mean shift of the last time
-// update.  49 doubles: an odd stride keeps the per-thread copies in shared memory free of bank conflicts.
-struct Ukf { double x[6]; double C[36]; double m[6]; double pad; };
+// update; then the cold per-env data of the launch (four Sun nodes of the interval, Sun-heading / eclipse latches, nav Sun
+// heading).  An odd stride (67 doubles) keeps the per-thread copies in shared memory free of bank conflicts; the cold
+// fields are read through volatile accesses so that they are re-loaded at their (rare) points of use instead of being
+// carried in registers through the tick loop.
+struct Ukf { double x[6]; double C[36]; double m[6]; double sun[12]; double cold[7]; };   // + Sun nodes, cold per-env latches: 67 doubles
 #define SC(r, c) C[(c) * 6 + (r)]
 // relODuKFTimeUpdate over dt.  The twelve deviations are accumulated into the 21 independent entries of the Gram
 // matrix (no serial dependence between sigma points: the +/- pair of a column is propagated side by side), then one
@@ -359,7 +361,10 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int i = 0; i < 6; i++) {
+    for (int idx = 0; idx < 12; idx++) {
+#ifdef ON_UKF_PAIR
+        if (idx & 1) continue;
+        const int i = idx >> 1;
         double Yp[6], Ym[6];
 #pragma unroll
         for (int r = 0; r < 6; r++) { const double c = P.ukf_gamma * f.C[i * 6 + r]; Yp[r] = f.x[r] + c; Ym[r] = f.x[r] - c; }
@@ -371,6 +376,20 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
         for (int a = 0; a < 6; a++)
 #pragma unroll
             for (int b = 0; b <= a; b++) A[TRI(a, b)] = fmad(Yp[a], Yp[b], fmad(Ym[a], Ym[b], A[TRI(a, b)]));
+#else
+        const int i = idx >> 1;
+        const double g = (idx & 1) ? -P.ukf_gamma : P.ukf_gamma;
+        double Y[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) Y[r] = fmad(g, f.C[i * 6 + r], f.x[r]);
+        two_body_rk4(Y, P.mu_fsw, dt);
+#pragma unroll
+        for (int r = 0; r < 6; r++) { Y[r] -= Y0[r]; ms[r] += Y[r]; }
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b <= a; b++) A[TRI(a, b)] = fmad(Y[a], Y[b], A[TRI(a, b)]);
+#endif
     }
     double m[6], L[21];
 #pragma unroll
@@ -563,9 +582,11 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
     double rwcmd[ON_NRW], nerr[15];
     for (int i = 0; i < ON_NRW; i++) { x.Om[i] = SD(OF_WHL + i); rwcmd[i] = SD(OF_RWCMD + i); }
     for (int i = 0; i < 15; i++) nerr[i] = SD(OF_NAVERR + i);
-    V3 sunpt = mk(SD(OF_SUNPT), SD(OF_SUNPT + 1), SD(OF_SUNPT + 2));
+    volatile double *cold = f.cold;            // [0..2] sun_point_data, [3] eclipse message, [4..6] nav Sun heading
+    cold[0] = SD(OF_SUNPT); cold[1] = SD(OF_SUNPT + 1); cold[2] = SD(OF_SUNPT + 2);
     int sunpt_w = (int)SI(OI_SUNPT_W);
-    double shadow_msg = SD(OF_SHADOW);
+    cold[3] = SD(OF_SHADOW);
+    cold[4] = 0.0; cold[5] = 0.0; cold[6] = 1.0;
     for (int i = 0; i < 6; i++) { f.x[i] = SD(OF_FSTATE + i); f.m[i] = 0.0; }
     for (int r = 0; r < 6; r++)
         for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? SD(OF_FS + TRI(r, c)) : 0.0;
@@ -573,12 +594,12 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
     const int64_t tick0 = SI(OI_TICK);
     const int64_t k_first = tick0 + 1, k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;   // stop time inclusive
     // ---- Sun over this interval ----
-    SunSpan sun;
-    sun.t0 = (double)(tick0 < 0 ? 0 : tick0) * P.dt; sun.T = (double)P.ticks_per_step * P.dt;
-    sun.p0 = sun_from_mars(P, sun.t0).r; sun.p1 = sun_from_mars(P, sun.t0 + sun.T / 3.0).r;
-    sun.p2 = sun_from_mars(P, sun.t0 + 2.0 * sun.T / 3.0).r; sun.p3 = sun_from_mars(P, sun.t0 + sun.T).r;
-    V3 sun_prev = sun_at(sun, (double)(k_first > 0 ? k_first - 1 : 0) * P.dt);     // SPICE message of the previous tick
-    V3 nav_sun_B = mk(0, 0, 1);
+    const double sun_t0 = (double)(tick0 < 0 ? 0 : tick0) * P.dt, sun_T = (double)P.ticks_per_step * P.dt;
+    volatile double *sunn = f.sun;
+    for (int j = 0; j < 4; j++) {
+        V3 p = sun_from_mars(P, sun_t0 + (double)j * sun_T / 3.0).r;
+        sunn[3 * j] = p.x; sunn[3 * j + 1] = p.y; sunn[3 * j + 2] = p.z;
+    }
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -600,19 +621,18 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
         if (mode == 1) {
             if (k > 0) {
                 MrpRot BN = mrp_rot(x.s);
-                css_sun = css_wls(P, rot_BN(BN, x.s, unit_or_zero(sun_prev - x.r)), shadow_msg);
+                css_sun = css_wls(P, rot_BN(BN, x.s, unit_or_zero(sun_at(sunn, sun_t0, sun_T, t - P.dt) - x.r)), cold[3]);
             }
         }
-        if (mode == 1 || k == k_last) shadow_msg = k > 0 ? eclipse_mars(P, sun_prev, x.r) : 1.0;
+        if (mode == 1 || k == k_last) cold[3] = k > 0 ? eclipse_mars(P, sun_at(sunn, sun_t0, sun_T, t - P.dt), x.r) : 1.0;
         // SpacecraftPlus (prio 201)
         if (k > 0) {
             x = rk4(P, x, u, P.dt);
             double s2 = dot(x.s, x.s);
             if (s2 > 1.0) { x.s = x.s * (-1.0 / s2); n_switch++; }      // |sigma| > 1
         }
-        // SpiceInterface (prio 200)
-        const bool need_sun = (mode == 1) || (k >= k_last - 1);
-        V3 sun_now = need_sun ? sun_at(sun, t) : sun_prev;
+        // SpiceInterface (prio 200): the Sun message of this tick is evaluated where it is consumed (here at the last tick
+        // for the nav Sun heading, at the next tick by the CSS and the eclipse model)
         // SimpleNav (prio 109)
         if (P.nav_noise) {
             const double ndt = k > 0 ? P.dt : 0.0;
@@ -638,10 +658,11 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
         const V3 nav_w = x.w + mk(nerr[9], nerr[10], nerr[11]);
         if (k == k_last) {
             MrpRot BN = mrp_rot(x.s);
-            V3 sb = rot_BN(BN, x.s, unit_or_zero(sun_now - x.r));
+            V3 sb = rot_BN(BN, x.s, unit_or_zero(sun_at(sunn, sun_t0, sun_T, t) - x.r));
             V3 se = mk(nerr[12], nerr[13], nerr[14]);
             MrpRot OT = mrp_rot(se);
-            nav_sun_B = rot_BN(OT, se, sb);
+            V3 ns = rot_BN(OT, se, sb);
+            cold[4] = ns.x; cold[5] = ns.y; cold[6] = ns.z;
         }
         // CameraTask (prio 999, every cam_ticks): the frame shows the true state of this tick
         const bool frame = camera && (k % P.cam_ticks == 0);
@@ -657,8 +678,8 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
             g.omega_BR_B = nav_w - g.omega_RN_B;
             g.domega_RN_B = rot_BN(BN, nav_s, ref.domega_RN_N);
         } else {         // sunSafePointTask: sunSafePoint (last pass's heading) then cssWlsEst
-            g = sun_safe_point(sunpt_w ? sunpt : mk(0, 0, 0), nav_w);
-            sunpt = css_sun; sunpt_w = 1;
+            g = sun_safe_point(sunpt_w ? mk(cold[0], cold[1], cold[2]) : mk(0, 0, 0), nav_w);
+            cold[0] = css_sun.x; cold[1] = css_sun.y; cold[2] = css_sun.z; sunpt_w = 1;
         }
         { // mrpFeedbackRWsTask: MRP_Feedback with wheel momentum, rwMotorTorque
             V3 w = g.omega_BR_B + g.omega_RN_B;
@@ -700,13 +721,13 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
                 if (ukf_meas_update(P, f, fdt, obs, R)) n_meas++; else n_bad++;
             }
         }
-        sun_prev = sun_now;
     }
     // ---- observation (ONS:263-293) ----
     const double nr2 = f.x[0] * f.x[0] + f.x[1] * f.x[1] + f.x[2] * f.x[2], inr = 1.0 / sqrt(nr2);
     {
         MrpRot BN = mrp_rot(x.s);
         V3 pos_B = -rot_BN(BN, x.s, mk(f.x[0], f.x[1], f.x[2]) * inr);
+        V3 nav_sun_B = mk(cold[4], cold[5], cold[6]);
         V3 sh = nav_sun_B * (1.0 / norm(nav_sun_B));
         out.ob[0] = dot(pos_B, sh);
         double p00 = f.SC(0, 0) * f.SC(0, 0);
@@ -731,8 +752,8 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
     SD(OF_SIG) = x.s.x; SD(OF_SIG + 1) = x.s.y; SD(OF_SIG + 2) = x.s.z; SD(OF_OMG) = x.w.x; SD(OF_OMG + 1) = x.w.y; SD(OF_OMG + 2) = x.w.z;
     for (int i = 0; i < ON_NRW; i++) { SD(OF_WHL + i) = x.Om[i]; SD(OF_RWCMD + i) = rwcmd[i]; }
     for (int i = 0; i < 15; i++) SD(OF_NAVERR + i) = nerr[i];
-    SD(OF_SUNPT) = sunpt.x; SD(OF_SUNPT + 1) = sunpt.y; SD(OF_SUNPT + 2) = sunpt.z;
-    SD(OF_SHADOW) = shadow_msg;
+    SD(OF_SUNPT) = cold[0]; SD(OF_SUNPT + 1) = cold[1]; SD(OF_SUNPT + 2) = cold[2];
+    SD(OF_SHADOW) = cold[3];
     for (int i = 0; i < 6; i++) SD(OF_FSTATE + i) = f.x[i];
     for (int r = 0; r < 6; r++)
         for (int c = 0; c <= r; c++) SD(OF_FS + TRI(r, c)) = f.SC(r, c);
