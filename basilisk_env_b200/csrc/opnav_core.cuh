@@ -43,6 +43,47 @@ ON_HD void sincos_hd(double x, double &s, double &c)
 // ------------------------------------------------------------------------------------------------
 // noise streams: Philox4x32-10, counter (env_lo, env_hi, tick, stream<<16 | block), key (seed_lo, seed_hi ^ episode)
 // ------------------------------------------------------------------------------------------------
+#ifdef __CUDA_ARCH__
+// -2 ln((x + 1) / 2^32) for a 32-bit draw x: the argument is an integer times a power of two, so the exponent and a
+// mantissa in [1/sqrt2, sqrt2) come from integer operations and ln m = 2 atanh((m - 1)/(m + 1)) needs eleven odd terms
+// (|s| <= 0.1716: truncation 1e-18).  Agrees with libm's log to ~1e-16 relative.
+__device__ __forceinline__ double neg2_log_u32(uint32_t x)
+{
+    const uint32_t n = x + 1u;                               // 0 stands for 2^32, i.e. u = 1
+    if (n == 0u) return 0.0;
+    const int lz = __clz((int)n);
+    double m = (double)(n << lz) * (1.0 / 2147483648.0);     // [1, 2)
+    int e = -1 - lz;
+    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    const double sq = (m - 1.0) * frcp(m + 1.0), s2 = sq * sq;
+    double p = fma(s2, 1.0 / 21.0, 1.0 / 19.0);
+    p = fma(p, s2, 1.0 / 17.0); p = fma(p, s2, 1.0 / 15.0); p = fma(p, s2, 1.0 / 13.0); p = fma(p, s2, 1.0 / 11.0);
+    p = fma(p, s2, 1.0 / 9.0); p = fma(p, s2, 1.0 / 7.0); p = fma(p, s2, 1.0 / 5.0); p = fma(p, s2, 1.0 / 3.0);
+    const double lnm = fma(sq * s2, p, sq);                  // atanh(s)
+    return fma((double)e, -2.0 * 0.6931471805599453, -4.0 * lnm);
+}
+// sin and cos of 2 pi j / 2^32: the octant comes from the top three bits, the remainder (reflected in odd octants, exactly,
+// on the integer) is an angle in [0, pi/4] for two short Taylor polynomials (truncation < 1e-17).
+__device__ __forceinline__ void sincos_2pi_u32(uint32_t j, double &sn, double &cs)
+{
+    const uint32_t oct = j >> 29;
+    uint32_t fr = j & 0x1FFFFFFFu;
+    if (oct & 1u) fr = 0x20000000u - fr;
+    const double a = (double)fr * (0.78539816339744831 / 536870912.0), a2 = a * a;
+    double ps = fma(a2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
+    ps = fma(ps, a2, -1.0 / 39916800.0); ps = fma(ps, a2, 1.0 / 362880.0); ps = fma(ps, a2, -1.0 / 5040.0);
+    ps = fma(ps, a2, 1.0 / 120.0); ps = fma(ps, a2, -1.0 / 6.0);
+    const double si = fma(a * a2, ps, a);
+    double pc = fma(a2, 1.0 / 20922789888000.0, -1.0 / 87178291200.0);
+    pc = fma(pc, a2, 1.0 / 479001600.0); pc = fma(pc, a2, -1.0 / 3628800.0); pc = fma(pc, a2, 1.0 / 40320.0);
+    pc = fma(pc, a2, -1.0 / 720.0); pc = fma(pc, a2, 1.0 / 24.0); pc = fma(pc, a2, -0.5);
+    const double co = fma(a2, pc, 1.0);
+    const bool swap = ((oct + 1u) & 2u) != 0u;               // octants 1, 2, 5, 6
+    double s0 = swap ? co : si, c0 = swap ? si : co;
+    sn = (oct & 4u) ? -s0 : s0;                              // octants 4..7
+    cs = ((oct + 2u) & 4u) ? -c0 : c0;                       // octants 2..5
+}
+#endif
 ON_HD_NOINLINE void normals4(const OpNavParams &P, int64_t env, int64_t episode, uint32_t tick, uint32_t stream, uint32_t block,
                              double (&out)[4])
 {
@@ -51,14 +92,14 @@ ON_HD_NOINLINE void normals4(const OpNavParams &P, int64_t env, int64_t episode,
                (uint32_t)(P.seed >> 32) ^ (uint32_t)episode, x);
 #pragma unroll
     for (int p = 0; p < 2; p++) {
-        double u1 = ((double)x[2 * p] + 1.0) * (1.0 / 4294967296.0);
-        double u2 = (double)x[2 * p + 1] * (1.0 / 4294967296.0);
         double s, c;
 #ifdef __CUDA_ARCH__
-        const double t = -2.0 * log(u1);
+        const double t = neg2_log_u32(x[2 * p]);
         const double rr = t > 0.0 ? t * rsq(t) : 0.0;      // sqrt without the special-operand path
-        sincospi(2.0 * u2, &s, &c);                         // exact argument reduction of 2 pi u2
+        sincos_2pi_u32(x[2 * p + 1], s, c);
 #else
+        double u1 = ((double)x[2 * p] + 1.0) * (1.0 / 4294967296.0);
+        double u2 = (double)x[2 * p + 1] * (1.0 / 4294967296.0);
         const double rr = sqrt(-2.0 * log(u1));
         s = sin(2.0 * 3.14159265358979323846 * u2); c = cos(2.0 * 3.14159265358979323846 * u2);
 #endif
@@ -644,10 +685,8 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
             for (int b = 0; b < 4; b++) {                             // four normals per Philox block, 15 walk states
                 double n4[4];
                 normals4(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-                for (int j = 0; j < 4; j++) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {                         // four independent walk states side by side
                     const int i = 4 * b + j;
                     if (i < 15) nerr[i] = gm_step(nerr[i], P.navBound[i], P.navP[i], n4[j]);
                 }
