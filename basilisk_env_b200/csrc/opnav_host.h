@@ -117,19 +117,20 @@ static inline std::string build_params(const bskenv_opnav_config &c, OpNavParams
 
 // FP64 flop per env-decision-step of the opNav kernel AS BUILT (FMA = 2, add/mul = 1, one per MUFU seed), from the
 // operation list of opnav_core.cuh and matched to ncu's executed 2*DFMA + DMUL + DADD thread-instruction counters
-// (profiles/ncu_opnav_r01c.md: 5.853e11 per 32768-env launch = 5954 per tick and env with the 50/50 action mix):
+// (profiles/ncu_opnav_r01e.md: 5.765e11 per 32768-env launch = 5864 per tick and env with the 50/50 action mix):
 //   filter time update   13 two-body RK4 steps (4 x 44 + 6), sigma points and deviations 6 x 60, Gram matrix 6 x 84,
 //                        covariance assembly 100, 6 x 6 Cholesky 185                                        ~ 3400
 //   truth RK4            4 x eom (gravity 20, wheel momentum and torque 52, gyroscopics + inverse 45, MRP kinematics 40,
 //                        wheel rates 28) + stage combinations 4 x 64                                        ~  950
-//   simple_nav           16 Box-Muller normals (log, rsqrt, sincospi: ~100 per pair) and 15 bounded-walk states ~ 1150
+//   simple_nav           16 Box-Muller normals (atanh-series log, rsqrt, octant sincos: ~85 per pair) and 15 bounded-walk
+//                        states (reciprocal, exp)                                                           ~ 1060
 //   guidance + control   hillPoint / tracking error / MRP feedback / torque map (OpNav pointing) or eclipse / CSS /
 //                        cssWlsEst / sunSafePoint / MRP feedback (sun-safe)                                  ~  400
 //   nav message          MRP composition of the attitude error, position / velocity / rate sums             ~   55
 // The measurement update (once per 60 ticks while imaging) adds ~10 per tick on average.
 static inline double flops_per_step(const OpNavParams &p)
 {
-    const double per_tick = 3400.0 + 950.0 + (p.nav_noise ? 1150.0 : 0.0) + 400.0 + 55.0;
+    const double per_tick = 3400.0 + 950.0 + (p.nav_noise ? 1060.0 : 0.0) + 400.0 + 55.0;
     return per_tick * p.ticks_per_step;
 }
 

@@ -17,3 +17,4 @@ echo "== ncu full capture of the step kernel"
 timeout 1200 ncu --set full --metrics smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,sm__inst_executed_pipe_fp64.sum --clock-control none --import-source on -k regex:leo_step -s 3 -c 1 -f -o $OUT/prof_${TAG} \
     python bench.py --steps 2 --warmup 3 --no-extra --no-cpu-baseline > $OUT/ncu_full_${TAG}.log 2>&1; echo "ncu full exit $?"
 ls -la $OUT
+echo "== opNav path"; bash scripts/gpu_check_opnav.sh opnav_${TAG}
