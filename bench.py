@@ -91,12 +91,21 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads():
+    """All host threads this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm asks
+    OpenMP for an explicit thread count instead, so that it is the same under `python` and under `torchrun`."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_arm(envs_per_core_step, seconds, min_steps, warmup, threads=None, fixed_steps=None):
     """Times the oracle port (oracle/bsk_oracle.c, OpenMP over envs) on the host cores: the same
     workload definition (random initial orbits, i.i.d. uniform actions), bounded sample."""
     from oracle import oracle as orc
     from tests import parity
-    threads = threads or orc.max_threads()
+    threads = threads or host_threads()
     n = envs_per_core_step * threads
     rows = parity.sample_rows(orc, n, seed=7)
     batch = orc.LeoEnvBatch(rows)
@@ -121,7 +130,7 @@ def cpu_arm(envs_per_core_step, seconds, min_steps, warmup, threads=None, fixed_
 def run_reference(args, rank):
     if rank != 0:
         return
-    res = cpu_arm(envs_per_core_step=4, seconds=0.0, min_steps=1, warmup=args.warmup, fixed_steps=args.steps)
+    res = cpu_arm(envs_per_core_step=32, seconds=0.0, min_steps=1, warmup=args.warmup, fixed_steps=args.steps)
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -169,7 +178,7 @@ def main():
     if args.impl == "reference":
         if args.workload == "opnav":
             if rank == 0:
-                cb = opnav_cpu_arm(4, 0.0, fixed_steps=args.steps)
+                cb = opnav_cpu_arm(8, 0.0, fixed_steps=args.steps)
                 print(json.dumps({"metric": METRIC, "value": cb["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus,
                                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -324,7 +333,7 @@ def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None):
     from oracle import opnav as on
     from oracle import oracle as orc
     from tests import opnav_parity as par
-    threads = threads or orc.max_threads()
+    threads = threads or host_threads()
     n = envs_per_core * threads
     rows = par.sample_rows(on, n, seed=7)
     batch = on.OpNavEnvBatch(rows, on.default_cfg(seed=5, camera_reenable=1))
