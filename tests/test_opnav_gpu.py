@@ -60,6 +60,15 @@ def test_opnav_random_actions_64_envs(bsk):
     _run_against_oracle(bsk, rows, acts, first_env=1000, camera_reenable=1)
 
 
+def test_opnav_1024_envs_one_decision_step(bsk):
+    """BASELINE configs[3] at batch scale: 1024 envs (orbits over the reference's element ranges), two full 3000-tick decision
+    intervals (the first has 3001 ticks), every env against its own oracle run."""
+    from oracle import opnav as on
+    rows = par.sample_rows(on, 1024, seed=21)
+    acts = np.random.RandomState(22).randint(0, 2, size=(2, 1024))
+    _run_against_oracle(bsk, rows, acts, first_env=5000, seed=123, camera_reenable=1)
+
+
 def test_opnav_reference_semantics_and_host_entry_point(bsk):
     """Reference camera behaviour (never re-enabled), ragged batch, host-buffer entry point."""
     from oracle import opnav as on
