@@ -43,6 +43,22 @@ ON_HD void sincos_hd(double x, double &s, double &c)
 // ------------------------------------------------------------------------------------------------
 // noise streams: Philox4x32-10, counter (env_lo, env_hi, tick, stream<<16 | block), key (seed_lo, seed_hi ^ episode)
 // ------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// Polynomial coefficients of the device-side noise transforms live in constant memory: an FP64 instruction takes a
+// constant-bank operand for free, whereas a 64-bit literal costs two uniform-register moves (two issue slots) per use.
+__constant__ double ON_K[40] = {
+    // [0..9] atanh series 1/3 .. 1/21
+    1.0 / 3.0, 1.0 / 5.0, 1.0 / 7.0, 1.0 / 9.0, 1.0 / 11.0, 1.0 / 13.0, 1.0 / 15.0, 1.0 / 17.0, 1.0 / 19.0, 1.0 / 21.0,
+    // [10..16] sin Taylor -1/3! .. -1/15!
+    -1.0 / 6.0, 1.0 / 120.0, -1.0 / 5040.0, 1.0 / 362880.0, -1.0 / 39916800.0, 1.0 / 6227020800.0, -1.0 / 1307674368000.0,
+    // [17..24] cos Taylor -1/2! .. 1/16!
+    -0.5, 1.0 / 24.0, -1.0 / 720.0, 1.0 / 40320.0, -1.0 / 3628800.0, 1.0 / 479001600.0, -1.0 / 87178291200.0, 1.0 / 20922789888000.0,
+    // [25..27] sqrt2, -2 ln2, (pi/4) / 2^29
+    1.4142135623730951, -2.0 * 0.6931471805599453, 0.78539816339744831 / 536870912.0,
+    // [28..39] exp Taylor 1/2! .. 1/13!
+    0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, 1.0 / 720.0, 1.0 / 5040.0, 1.0 / 40320.0, 1.0 / 362880.0, 1.0 / 3628800.0,
+    1.0 / 39916800.0, 1.0 / 479001600.0, 1.0 / 6227020800.0};
+#endif
 #ifdef __CUDA_ARCH__
 // -2 ln((x + 1) / 2^32) for a 32-bit draw x: the argument is an integer times a power of two, so the exponent and a
 // mantissa in [1/sqrt2, sqrt2) come from integer operations and ln m = 2 atanh((m - 1)/(m + 1)) needs eleven odd terms
@@ -54,13 +70,13 @@ __device__ __forceinline__ double neg2_log_u32(uint32_t x)
     const int lz = __clz((int)n);
     double m = (double)(n << lz) * (1.0 / 2147483648.0);     // [1, 2)
     int e = -1 - lz;
-    if (m > 1.4142135623730951) { m *= 0.5; e += 1; }
+    if (m > ON_K[25]) { m *= 0.5; e += 1; }
     const double sq = (m - 1.0) * frcp(m + 1.0), s2 = sq * sq;
-    double p = fma(s2, 1.0 / 21.0, 1.0 / 19.0);
-    p = fma(p, s2, 1.0 / 17.0); p = fma(p, s2, 1.0 / 15.0); p = fma(p, s2, 1.0 / 13.0); p = fma(p, s2, 1.0 / 11.0);
-    p = fma(p, s2, 1.0 / 9.0); p = fma(p, s2, 1.0 / 7.0); p = fma(p, s2, 1.0 / 5.0); p = fma(p, s2, 1.0 / 3.0);
+    double p = fma(s2, ON_K[9], ON_K[8]);
+    p = fma(p, s2, ON_K[7]); p = fma(p, s2, ON_K[6]); p = fma(p, s2, ON_K[5]); p = fma(p, s2, ON_K[4]);
+    p = fma(p, s2, ON_K[3]); p = fma(p, s2, ON_K[2]); p = fma(p, s2, ON_K[1]); p = fma(p, s2, ON_K[0]);
     const double lnm = fma(sq * s2, p, sq);                  // atanh(s)
-    return fma((double)e, -2.0 * 0.6931471805599453, -4.0 * lnm);
+    return fma((double)e, ON_K[26], -4.0 * lnm);
 }
 // sin and cos of 2 pi j / 2^32: the octant comes from the top three bits, the remainder (reflected in odd octants, exactly,
 // on the integer) is an angle in [0, pi/4] for two short Taylor polynomials (truncation < 1e-17).
@@ -69,14 +85,14 @@ __device__ __forceinline__ void sincos_2pi_u32(uint32_t j, double &sn, double &c
     const uint32_t oct = j >> 29;
     uint32_t fr = j & 0x1FFFFFFFu;
     if (oct & 1u) fr = 0x20000000u - fr;
-    const double a = (double)fr * (0.78539816339744831 / 536870912.0), a2 = a * a;
-    double ps = fma(a2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0);
-    ps = fma(ps, a2, -1.0 / 39916800.0); ps = fma(ps, a2, 1.0 / 362880.0); ps = fma(ps, a2, -1.0 / 5040.0);
-    ps = fma(ps, a2, 1.0 / 120.0); ps = fma(ps, a2, -1.0 / 6.0);
+    const double a = (double)fr * ON_K[27], a2 = a * a;
+    double ps = fma(a2, ON_K[16], ON_K[15]);
+    ps = fma(ps, a2, ON_K[14]); ps = fma(ps, a2, ON_K[13]); ps = fma(ps, a2, ON_K[12]);
+    ps = fma(ps, a2, ON_K[11]); ps = fma(ps, a2, ON_K[10]);
     const double si = fma(a * a2, ps, a);
-    double pc = fma(a2, 1.0 / 20922789888000.0, -1.0 / 87178291200.0);
-    pc = fma(pc, a2, 1.0 / 479001600.0); pc = fma(pc, a2, -1.0 / 3628800.0); pc = fma(pc, a2, 1.0 / 40320.0);
-    pc = fma(pc, a2, -1.0 / 720.0); pc = fma(pc, a2, 1.0 / 24.0); pc = fma(pc, a2, -0.5);
+    double pc = fma(a2, ON_K[24], ON_K[23]);
+    pc = fma(pc, a2, ON_K[22]); pc = fma(pc, a2, ON_K[21]); pc = fma(pc, a2, ON_K[20]);
+    pc = fma(pc, a2, ON_K[19]); pc = fma(pc, a2, ON_K[18]); pc = fma(pc, a2, ON_K[17]);
     const double co = fma(a2, pc, 1.0);
     const bool swap = ((oct + 1u) & 2u) != 0u;               // octants 1, 2, 5, 6
     double s0 = swap ? co : si, c0 = swap ? si : co;
@@ -220,6 +236,23 @@ ON_HD Rot rk4_rotation(const OpNavParams &P, const Rot &x0, const double (&u)[ON
 //   x += P * (n + push),  push = e * copysign(e, -x),  e = 1/exp(b^3),  b = max((2 bound - s)/s, 1e-10 bound),
 //   s = |x| if |x| > 1e-10 bound else bound.
 // For b >= 7.2 the push underflows to zero; for b^3 < 1e-17 it is exactly +-1 (the attitude states: bound 1e-18 deg).
+#ifdef __CUDA_ARCH__
+// exp(-y), 0 <= y < 400: reduction by ln 2 (two-term Cody-Waite), degree-13 Taylor polynomial on |r| <= ln2/2 (truncation
+// 4e-18), exponent patched in; no special operands on this path.
+__device__ __forceinline__ double exp_neg(double y)
+{
+    const double t = fma(y, -1.4426950408889634, 6755399441055744.0);
+    const int kk = __double2loint(t);
+    const double kd = t - 6755399441055744.0;
+    double r = fma(kd, -6.93147180369123816490e-01, -y);
+    r = fma(kd, -1.90821492927058770002e-10, r);
+    double p = fma(r, ON_K[39], ON_K[38]);
+    p = fma(p, r, ON_K[37]); p = fma(p, r, ON_K[36]); p = fma(p, r, ON_K[35]); p = fma(p, r, ON_K[34]); p = fma(p, r, ON_K[33]);
+    p = fma(p, r, ON_K[32]); p = fma(p, r, ON_K[31]); p = fma(p, r, ON_K[30]); p = fma(p, r, ON_K[29]); p = fma(p, r, ON_K[28]);
+    p = fma(p, r, 1.0); p = fma(p, r, 1.0);
+    return __hiloint2double(__double2hiint(p) + (kk << 20), __double2loint(p));
+}
+#endif
 ON_HD double gm_step(double xs, double bound, double pm, double rn)
 {
     const double ax = fabs(xs);
@@ -233,7 +266,7 @@ ON_HD double gm_step(double xs, double bound, double pm, double rn)
     if (bc < 7.2) {
         const double b3 = bc * bc * bc;
 #ifdef __CUDA_ARCH__
-        const double ex = b3 < 1e-17 ? 1.0 : exp(-b3);
+        const double ex = b3 < 1e-17 ? 1.0 : exp_neg(b3);
 #else
         const double ex = b3 < 1e-17 ? 1.0 : 1.0 / exp(b3);
 #endif
@@ -328,15 +361,15 @@ ON_HD_NOINLINE V3 css_wls(const OpNavParams &P, V3 sHat_B, double shadow)
         double m00 = HtH[0], m01 = HtH[1], m02 = HtH[2], m11 = HtH[3], m12 = HtH[4], m22 = HtH[5];
         double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
         double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
-        double det = m00 * c00 + m01 * c01 + m02 * c02, id = 1.0 / det;
+        double det = m00 * c00 + m01 * c01 + m02 * c02, id = frcp(det);
         d = mk((c00 * Hty[0] + c01 * Hty[1] + c02 * Hty[2]) * id, (c01 * Hty[0] + c11 * Hty[1] + c12 * Hty[2]) * id,
                (c02 * Hty[0] + c12 * Hty[1] + c22 * Hty[2]) * id);
     } else if (n == 2) {
-        double a = dot(H0, H0), b = dot(H0, H1), c = dot(H1, H1), det = a * c - b * b;
-        double l0 = (c * y0 - b * y1) / det, l1 = (a * y1 - b * y0) / det;
+        double a = dot(H0, H0), b = dot(H0, H1), c = dot(H1, H1), idet = frcp(a * c - b * b);
+        double l0 = (c * y0 - b * y1) * idet, l1 = (a * y1 - b * y0) * idet;
         d = H0 * l0 + H1 * l1;
     } else if (n == 1) {
-        d = H0 * (y0 / dot(H0, H0));
+        d = H0 * (y0 * frcp(dot(H0, H0)));
     }
     return n > 0 ? unit_or_zero(d) : mk(0, 0, 0);
 }

@@ -79,7 +79,6 @@ static void m33Inverse(double m[3][3], double r[3][3])
     t[2][2] = (m[0][0] * m[1][1] - m[0][1] * m[1][0]) / det;
     memcpy(r, t, sizeof(t));
 }
-static double safeAcos(double x) { return x > 1. ? acos(1.) : (x < -1. ? acos(-1.) : acos(x)); }
 
 /* ================================ counter-based noise streams =================================== */
 /* Philox4x32-10 (Salmon et al. 2011), the same generator the product uses for its device-side initial
