@@ -410,6 +410,41 @@ ON_HD void two_body_rk4(double (&x)[6], double mu, double dt)
 #pragma unroll
     for (int i = 0; i < 6; i++) x[i] += acc[i];
 }
+// G independent two-body RK4 steps in lockstep: every operation is emitted G times in a row, so the in-order issue of a warp
+// always has G independent FP64 chains to fill the 8-cycle DFMA latency (tests/...: same arithmetic per point as two_body_rk4)
+template <int G>
+ON_HD void two_body_rk4_group(double (&x)[G][6], double mu, double dt)
+{
+    double k[G][6], s[G][6], acc[G][6];
+#pragma unroll
+    for (int st = 0; st < 4; st++) {
+        const double cin = st == 0 ? 0.0 : (st == 3 ? dt : 0.5 * dt);
+        const double cw = (st == 0 || st == 3) ? dt / 6.0 : dt / 3.0;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int g = 0; g < G; g++) s[g][i] = st == 0 ? x[g][i] : x[g][i] + cin * k[g][i];
+        double r2[G], ir[G], gg[G];
+#pragma unroll
+        for (int g = 0; g < G; g++) r2[g] = s[g][0] * s[g][0] + s[g][1] * s[g][1] + s[g][2] * s[g][2];
+#pragma unroll
+        for (int g = 0; g < G; g++) ir[g] = rsq(r2[g]);
+#pragma unroll
+        for (int g = 0; g < G; g++) gg[g] = -mu * (ir[g] * ir[g] * ir[g]);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int g = 0; g < G; g++) { k[g][i] = s[g][3 + i]; k[g][3 + i] = gg[g] * s[g][i]; }
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int g = 0; g < G; g++) acc[g][i] = st == 0 ? cw * k[g][i] : acc[g][i] + cw * k[g][i];
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+        for (int g = 0; g < G; g++) x[g][i] += acc[g][i];
+}
 // L L^T -= x x^T (hyperbolic sweep); returns false when the result is not positive definite
 ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
 {
@@ -454,19 +489,29 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int idx = 0; idx < 12; idx++) {
-        const int i = idx >> 1;
-        const double g = (idx & 1) ? -P.ukf_gamma : P.ukf_gamma;
-        double Y[6];
+#ifndef ON_UKF_GROUP
+#define ON_UKF_GROUP 1
+#endif
+    for (int idx = 0; idx < 12; idx += ON_UKF_GROUP) {
+        double Y[ON_UKF_GROUP][6];
 #pragma unroll
-        for (int r = 0; r < 6; r++) Y[r] = fmad(g, f.C[i * 6 + r], f.x[r]);
-        two_body_rk4(Y, P.mu_fsw, dt);
+        for (int g = 0; g < ON_UKF_GROUP; g++) {
+            const int i = (idx + g) >> 1;
+            const double gam = ((idx + g) & 1) ? -P.ukf_gamma : P.ukf_gamma;
 #pragma unroll
-        for (int r = 0; r < 6; r++) { Y[r] -= Y0[r]; ms[r] += Y[r]; }
+            for (int r = 0; r < 6; r++) Y[g][r] = fmad(gam, f.C[i * 6 + r], f.x[r]);
+        }
+        two_body_rk4_group<ON_UKF_GROUP>(Y, P.mu_fsw, dt);
+#pragma unroll
+        for (int g = 0; g < ON_UKF_GROUP; g++)
+#pragma unroll
+            for (int r = 0; r < 6; r++) { Y[g][r] -= Y0[r]; ms[r] += Y[g][r]; }
 #pragma unroll
         for (int a = 0; a < 6; a++)
 #pragma unroll
-            for (int b = 0; b <= a; b++) A[TRI(a, b)] = fmad(Y[a], Y[b], A[TRI(a, b)]);
+            for (int b = 0; b <= a; b++)
+#pragma unroll
+                for (int g = 0; g < ON_UKF_GROUP; g++) A[TRI(a, b)] = fmad(Y[g][a], Y[g][b], A[TRI(a, b)]);
     }
     double m[6], L[21];
 #pragma unroll
