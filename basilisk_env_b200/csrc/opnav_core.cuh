@@ -466,11 +466,12 @@ ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
 }
 // Filter state as the kernel holds it during a launch: estimate, square-root covariance as a full column-major 6 x 6 (column c
 // at C[6c .. 6c+5], zeros above the diagonal: a sigma-point column is six consecutive words), mean shift of the last time
-// update; then the cold per-env data of the launch (four Sun nodes of the interval, Sun-heading / eclipse latches, nav Sun
-// heading).  An odd stride (67 doubles) keeps the per-thread copies in shared memory free of bank conflicts; the cold
-// fields are read through volatile accesses so that they are re-loaded at their (rare) points of use instead of being
-// carried in registers through the tick loop.
-struct Ukf { double x[6]; double C[36]; double m[6]; double sun[12]; double cold[7]; };   // + Sun nodes, cold per-env latches: 67 doubles
+// update.  `Cold` is the cold per-env data of the dynamics side (four Sun nodes of the interval, Sun-heading / eclipse
+// latches, nav Sun heading).  Odd strides (49, 19 doubles) keep the per-thread copies in shared memory free of bank
+// conflicts; the cold fields are read through volatile accesses so that they are re-loaded at their (rare) points of use
+// instead of being carried in registers through the tick loop.
+struct Ukf { double x[6]; double C[36]; double m[6]; double pad; };      // 49 doubles
+struct Cold { double sun[12]; double cold[7]; };                         // 19 doubles: Sun nodes, cold per-env latches
 #define SC(r, c) C[(c) * 6 + (r)]
 // relODuKFTimeUpdate over dt.  The twelve deviations are accumulated into the 21 independent entries of the Gram
 // matrix (no serial dependence between sigma points; propagating the +/- pair of a column side by side was measured and
@@ -682,50 +683,102 @@ ON_HD void opnav_reset_env(const OpNavParams &P, double *S, int64_t *I, int64_t 
 // ------------------------------------------------------------------------------------------------
 struct StepOut { double ob[4]; double debug[12]; double reward; int done; int reason; };
 
-// `f` is scratch storage for the filter during the call (per-thread shared memory on the device, a stack object on the host)
-ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out, Ukf &f)
-{
-#define SD(f) S[(int64_t)(f) * stride + e]
-#define SI(f) I[(int64_t)(f) * stride + e]
-    const int64_t genv = P.first_env_index + e, episode = SI(OI_EPISODE);
-    // ---- opNavEnv.step prologue (ONE:94-95) and run_sim mode switching (ONS:237-254) ----
-    int over = (int)SI(OI_OVER), reason = 0;
-    const int64_t curr_step = SI(OI_STEP);
-    if (curr_step >= P.max_length) { over = 1; reason |= 1; }
-    int mode = (int)SI(OI_MODE), camera = (int)SI(OI_CAMERA);
-    const int modeCounter = (int)SI(OI_MODECNT) + 1;
-    if (action == 0) { mode = 0; if (P.camera_reenable) camera = 1; }
-    else if (action == 1) { mode = 1; camera = 0; }
-    if (SI(OI_FIRST)) mode = 0;          // pending 'OpNavOD' event fires at the first ExecuteSimulation (ONS:157, ONF:219-224)
-    // ---- load the persistent state ----
-    Truth x;
-    x.r = mk(SD(OF_R), SD(OF_R + 1), SD(OF_R + 2)); x.v = mk(SD(OF_V), SD(OF_V + 1), SD(OF_V + 2));
-    x.s = mk(SD(OF_SIG), SD(OF_SIG + 1), SD(OF_SIG + 2)); x.w = mk(SD(OF_OMG), SD(OF_OMG + 1), SD(OF_OMG + 2));
-    double rwcmd[ON_NRW], nerr[15];
-    for (int i = 0; i < ON_NRW; i++) { x.Om[i] = SD(OF_WHL + i); rwcmd[i] = SD(OF_RWCMD + i); }
-    for (int i = 0; i < 15; i++) nerr[i] = SD(OF_NAVERR + i);
-    volatile double *cold = f.cold;            // [0..2] sun_point_data, [3] eclipse message, [4..6] nav Sun heading
-    cold[0] = SD(OF_SUNPT); cold[1] = SD(OF_SUNPT + 1); cold[2] = SD(OF_SUNPT + 2);
-    int sunpt_w = (int)SI(OI_SUNPT_W);
-    cold[3] = SD(OF_SHADOW);
-    cold[4] = 0.0; cold[5] = 0.0; cold[6] = 1.0;
-    for (int i = 0; i < 6; i++) { f.x[i] = SD(OF_FSTATE + i); f.m[i] = 0.0; }
-    for (int r = 0; r < 6; r++)
-        for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? SD(OF_FS + TRI(r, c)) : 0.0;
-    int64_t ftick = SI(OI_FTICK), n_meas = SI(OI_NMEAS), n_bad = SI(OI_NBAD), n_img = SI(OI_NIMG), n_switch = SI(OI_SWITCH);
-    const int64_t tick0 = SI(OI_TICK);
-    const int64_t k_first = tick0 + 1, k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;   // stop time inclusive
-    // ---- Sun over this interval ----
-    const double sun_t0 = (double)(tick0 < 0 ? 0 : tick0) * P.dt, sun_T = (double)P.ticks_per_step * P.dt;
-    volatile double *sunn = f.sun;
-    for (int j = 0; j < 4; j++) {
-        V3 p = sun_from_mars(P, sun_t0 + (double)j * sun_T / 3.0).r;
-        sunn[3 * j] = p.x; sunn[3 * j + 1] = p.y; sunn[3 * j + 2] = p.z;
+// A tick has three dependency chains of similar length that only meet through small messages:
+//   NoiseRole   the bounded random walk of simple_nav's 15 error states (depends on nothing but its own stream);
+//   DynRole     wheel latch, CSS, eclipse, truth RK4, nav message, camera, guidance, control (and the circle -> pixelLine
+//               measurement when a frame is due): consumes the error states, produces the measurement;
+//   FilterRole  relativeODuKF: one time update per tick, a measurement update when the dynamics side produced one.
+// opnav_step_env() runs them in sequence in one thread (host-compiled core); the warp-specialised kernel of opnav.cu gives
+// them to three warps of a block, each one tick behind the previous, with the messages in shared mailboxes.
+struct Meas { bool valid; double obs[3]; double R[6]; };
+
+// simple_nav's Gauss-Markov error states: a bounded random walk driven by the per-env Philox stream, independent of the
+// dynamics (SimpleNav::computeErrors, OND:236-258).  tick(k) advances the 15 states to tick k.
+struct NoiseRole {
+    double nerr[15];
+    int64_t genv, episode, k_first, k_last;
+    ON_HD void load(const OpNavParams &P, const double *S, const int64_t *I, int64_t stride, int64_t e)
+    {
+        for (int i = 0; i < 15; i++) nerr[i] = S[(int64_t)(OF_NAVERR + i) * stride + e];
+        genv = P.first_env_index + e; episode = I[(int64_t)OI_EPISODE * stride + e];
+        const int64_t tick0 = I[(int64_t)OI_TICK * stride + e];
+        k_first = tick0 + 1; k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;
     }
+    ON_HD void tick(const OpNavParams &P, int64_t k)
+    {
+        if (!P.nav_noise) return;
+        const double ndt = k > 0 ? P.dt : 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) nerr[i] += ndt * nerr[3 + i];
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-    for (int64_t k = k_first; k <= k_last; k++) {
+        for (int b = 0; b < 4; b++) {                                 // four normals per Philox block, 15 walk states
+            double n4[4];
+            normals4(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {                             // four independent walk states side by side
+                const int i = 4 * b + j;
+                if (i < 15) nerr[i] = gm_step(nerr[i], P.navBound[i], P.navP[i], n4[j]);
+            }
+        }
+    }
+    ON_HD void finish(double *S, int64_t stride, int64_t e) const
+    {
+        for (int i = 0; i < 15; i++) S[(int64_t)(OF_NAVERR + i) * stride + e] = nerr[i];
+    }
+};
+
+struct DynRole {
+    Truth x;
+    double rwcmd[ON_NRW];
+    int mode, camera, sunpt_w, over, reason, modeCounter;
+    int64_t n_img, n_switch, curr_step, k_first, k_last, genv, episode;
+    double sun_t0, sun_T;
+
+    ON_HD void load(const OpNavParams &P, const double *S, const int64_t *I, int64_t stride, int64_t e, int action, Cold &c)
+    {
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+        genv = P.first_env_index + e; episode = SI(OI_EPISODE);
+        // ---- opNavEnv.step prologue (ONE:94-95) and run_sim mode switching (ONS:237-254) ----
+        over = (int)SI(OI_OVER); reason = 0;
+        curr_step = SI(OI_STEP);
+        if (curr_step >= P.max_length) { over = 1; reason |= 1; }
+        mode = (int)SI(OI_MODE); camera = (int)SI(OI_CAMERA);
+        modeCounter = (int)SI(OI_MODECNT) + 1;
+        if (action == 0) { mode = 0; if (P.camera_reenable) camera = 1; }
+        else if (action == 1) { mode = 1; camera = 0; }
+        if (SI(OI_FIRST)) mode = 0;      // pending 'OpNavOD' event fires at the first ExecuteSimulation (ONS:157, ONF:219-224)
+        x.r = mk(SD(OF_R), SD(OF_R + 1), SD(OF_R + 2)); x.v = mk(SD(OF_V), SD(OF_V + 1), SD(OF_V + 2));
+        x.s = mk(SD(OF_SIG), SD(OF_SIG + 1), SD(OF_SIG + 2)); x.w = mk(SD(OF_OMG), SD(OF_OMG + 1), SD(OF_OMG + 2));
+        for (int i = 0; i < ON_NRW; i++) { x.Om[i] = SD(OF_WHL + i); rwcmd[i] = SD(OF_RWCMD + i); }
+        volatile double *cold = c.cold;        // [0..2] sun_point_data, [3] eclipse message, [4..6] nav Sun heading
+        cold[0] = SD(OF_SUNPT); cold[1] = SD(OF_SUNPT + 1); cold[2] = SD(OF_SUNPT + 2);
+        sunpt_w = (int)SI(OI_SUNPT_W);
+        cold[3] = SD(OF_SHADOW);
+        cold[4] = 0.0; cold[5] = 0.0; cold[6] = 1.0;
+        n_img = SI(OI_NIMG); n_switch = SI(OI_SWITCH);
+        const int64_t tick0 = SI(OI_TICK);
+        k_first = tick0 + 1; k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;   // stop time inclusive
+        // ---- Sun over this interval ----
+        sun_t0 = (double)(tick0 < 0 ? 0 : tick0) * P.dt; sun_T = (double)P.ticks_per_step * P.dt;
+        volatile double *sunn = c.sun;
+        for (int j = 0; j < 4; j++) {
+            V3 p = sun_from_mars(P, sun_t0 + (double)j * sun_T / 3.0).r;
+            sunn[3 * j] = p.x; sunn[3 * j + 1] = p.y; sunn[3 * j + 2] = p.z;
+        }
+#undef SD
+#undef SI
+    }
+
+    // one tick of the dynamics process and of the flight software except the filter; `nerr` = simple_nav's error states at
+    // this tick (NoiseRole), `m` receives the measurement of this tick
+    template <class NE>
+    ON_HD void tick(const OpNavParams &P, int64_t k, Cold &c, const NE &nerr, Meas &m)
+    {
+        volatile double *cold = c.cold;
+        volatile double *sunn = c.sun;
         const double t = (double)k * P.dt;
         // ================= DynamicsTask =================
         // ReactionWheelStateEffector (prio 301): latch last pass's motor torques; publish Omega before the integration
@@ -763,24 +816,7 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
         }
         // SpiceInterface (prio 200): the Sun message of this tick is evaluated where it is consumed (here at the last tick
         // for the nav Sun heading, at the next tick by the CSS and the eclipse model)
-        // SimpleNav (prio 109)
-        if (P.nav_noise) {
-            const double ndt = k > 0 ? P.dt : 0.0;
-#pragma unroll
-            for (int i = 0; i < 3; i++) nerr[i] += ndt * nerr[3 + i];
-#if defined(__CUDA_ARCH__)
-#pragma unroll 1
-#endif
-            for (int b = 0; b < 4; b++) {                             // four normals per Philox block, 15 walk states
-                double n4[4];
-                normals4(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
-#pragma unroll
-                for (int j = 0; j < 4; j++) {                         // four independent walk states side by side
-                    const int i = 4 * b + j;
-                    if (i < 15) nerr[i] = gm_step(nerr[i], P.navBound[i], P.navP[i], n4[j]);
-                }
-            }
-        }
+        // SimpleNav (prio 109): error states from the noise role, applied to the truth
         const V3 nav_r = x.r + mk(nerr[0], nerr[1], nerr[2]), nav_v = x.v + mk(nerr[3], nerr[4], nerr[5]);
         const V3 nav_s = P.nav_noise ? mrp_add(x.s, mk(nerr[6], nerr[7], nerr[8])) : mrp_inner(x.s);
         const V3 nav_w = x.w + mk(nerr[9], nerr[10], nerr[11]);
@@ -824,75 +860,135 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
 #pragma unroll
             for (int i = 0; i < ON_NRW; i++) rwcmd[i] = dot(arr(P.Umap[i]), Lr);
         }
-        { // relativeODuKF (opNavODTask: after imageProcessing + pixelLine; sunSafePointTask: time update only)
-            bool meas = false;
-            double c[3], obs[3], R[6];
-            if (mode == 0 && frame) {
-                MrpRot BN = mrp_rot(x.s);
-                meas = project_circle(P, rot_BN(BN, x.s, -x.r), c);
-                if (meas) {
-                    if (P.pixel_noise_std > 0.0) {
-                        double n4[4];
-                        normals4(P, genv, episode, (uint32_t)k, 2u, 0u, n4);
-                        c[0] += P.pixel_noise_std * n4[0]; c[1] += P.pixel_noise_std * n4[1]; c[2] += P.pixel_noise_std * n4[2];
-                    }
-                    pixel_line(P, c, nav_s, obs, R);
+        // opNavODTask front end: imageProcessing stand-in + pixelLine (the filter itself is the other role)
+        m.valid = false;
+        if (mode == 0 && frame) {
+            double cc[3];
+            MrpRot BN = mrp_rot(x.s);
+            m.valid = project_circle(P, rot_BN(BN, x.s, -x.r), cc);
+            if (m.valid) {
+                if (P.pixel_noise_std > 0.0) {
+                    double n4[4];
+                    normals4(P, genv, episode, (uint32_t)k, 2u, 0u, n4);
+                    cc[0] += P.pixel_noise_std * n4[0]; cc[1] += P.pixel_noise_std * n4[1]; cc[2] += P.pixel_noise_std * n4[2];
                 }
-            }
-            const double fdt = (double)(k - ftick) * P.dt;
-            bool tu_ok = true;
-            if (meas || k > ftick) {
-                tu_ok = ukf_time_update(P, f, fdt);
-                if (tu_ok) ftick = k; else n_bad++;          // relODuKFCleanUpdate: the filter keeps its previous state and time
-            }
-            if (meas && tu_ok) {
-                if (ukf_meas_update(P, f, fdt, obs, R)) n_meas++; else n_bad++;
+                pixel_line(P, cc, nav_s, m.obs, m.R);
             }
         }
     }
-    // ---- observation (ONS:263-293) ----
-    const double nr2 = f.x[0] * f.x[0] + f.x[1] * f.x[1] + f.x[2] * f.x[2], inr = 1.0 / sqrt(nr2);
+
+    // observation (ONS:263-293), opNavEnv.step epilogue (ONE:100-125, :139-152) and the dynamics side of the state;
+    // fx = filter position estimate, psig = sqrt of the first three covariance diagonal entries
+    ON_HD void finish(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, const double (&fx)[3],
+                      const double (&psig)[3], Cold &c, StepOut &out)
     {
-        MrpRot BN = mrp_rot(x.s);
-        V3 pos_B = -rot_BN(BN, x.s, mk(f.x[0], f.x[1], f.x[2]) * inr);
-        V3 nav_sun_B = mk(cold[4], cold[5], cold[6]);
-        V3 sh = nav_sun_B * (1.0 / norm(nav_sun_B));
-        out.ob[0] = dot(pos_B, sh);
-        double p00 = f.SC(0, 0) * f.SC(0, 0);
-        double p11 = f.SC(1, 0) * f.SC(1, 0) + f.SC(1, 1) * f.SC(1, 1);
-        double p22 = f.SC(2, 0) * f.SC(2, 0) + f.SC(2, 1) * f.SC(2, 1) + f.SC(2, 2) * f.SC(2, 2);
-        out.ob[1] = sqrt(p00) * inr; out.ob[2] = sqrt(p11) * inr; out.ob[3] = sqrt(p22) * inr;
-    }
-    out.debug[0] = f.x[0]; out.debug[1] = f.x[1]; out.debug[2] = f.x[2];
-    out.debug[3] = x.r.x; out.debug[4] = x.r.y; out.debug[5] = x.r.z;
-    out.debug[6] = x.v.x; out.debug[7] = x.v.y; out.debug[8] = x.v.z;
-    out.debug[9] = x.s.x; out.debug[10] = x.s.y; out.debug[11] = x.s.z;
-    // ---- opNavEnv.step epilogue (ONE:100-125, :139-152) ----
-    double reward = 0.0;
-    if (action == 1) {
-        V3 real = x.r, nav = (mk(f.x[0], f.x[1], f.x[2]) - real) * (1.0 / norm(real));
-        reward = fabs(P.reward_mult / (1.0 + dot(nav, nav)));
-    }
-    if (modeCounter >= P.numModes) { over = 1; reason |= 2; }
-    out.reward = reward; out.done = over; out.reason = reason;
-    // ---- store ----
-    SD(OF_R) = x.r.x; SD(OF_R + 1) = x.r.y; SD(OF_R + 2) = x.r.z; SD(OF_V) = x.v.x; SD(OF_V + 1) = x.v.y; SD(OF_V + 2) = x.v.z;
-    SD(OF_SIG) = x.s.x; SD(OF_SIG + 1) = x.s.y; SD(OF_SIG + 2) = x.s.z; SD(OF_OMG) = x.w.x; SD(OF_OMG + 1) = x.w.y; SD(OF_OMG + 2) = x.w.z;
-    for (int i = 0; i < ON_NRW; i++) { SD(OF_WHL + i) = x.Om[i]; SD(OF_RWCMD + i) = rwcmd[i]; }
-    for (int i = 0; i < 15; i++) SD(OF_NAVERR + i) = nerr[i];
-    SD(OF_SUNPT) = cold[0]; SD(OF_SUNPT + 1) = cold[1]; SD(OF_SUNPT + 2) = cold[2];
-    SD(OF_SHADOW) = cold[3];
-    for (int i = 0; i < 6; i++) SD(OF_FSTATE + i) = f.x[i];
-    for (int r = 0; r < 6; r++)
-        for (int c = 0; c <= r; c++) SD(OF_FS + TRI(r, c)) = f.SC(r, c);
-    SD(OF_EPRET) = SD(OF_EPRET) + reward;
-    for (int i = 0; i < 4; i++) SD(OF_OBS + i) = out.ob[i];
-    for (int i = 0; i < 12; i++) SD(OF_DEBUG + i) = out.debug[i];
-    SI(OI_TICK) = k_last; SI(OI_STEP) = curr_step + 1; SI(OI_MODE) = mode; SI(OI_CAMERA) = camera; SI(OI_MODECNT) = modeCounter;
-    SI(OI_FIRST) = 0; SI(OI_SWITCH) = n_switch; SI(OI_OVER) = over; SI(OI_NMEAS) = n_meas; SI(OI_NBAD) = n_bad;
-    SI(OI_FTICK) = ftick; SI(OI_SUNPT_W) = sunpt_w; SI(OI_NIMG) = n_img;
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+        volatile double *cold = c.cold;
+        const double nr2 = fx[0] * fx[0] + fx[1] * fx[1] + fx[2] * fx[2], inr = 1.0 / sqrt(nr2);
+        {
+            MrpRot BN = mrp_rot(x.s);
+            V3 pos_B = -rot_BN(BN, x.s, mk(fx[0], fx[1], fx[2]) * inr);
+            V3 nav_sun_B = mk(cold[4], cold[5], cold[6]);
+            V3 sh = nav_sun_B * (1.0 / norm(nav_sun_B));
+            out.ob[0] = dot(pos_B, sh);
+            out.ob[1] = psig[0] * inr; out.ob[2] = psig[1] * inr; out.ob[3] = psig[2] * inr;
+        }
+        out.debug[0] = fx[0]; out.debug[1] = fx[1]; out.debug[2] = fx[2];
+        out.debug[3] = x.r.x; out.debug[4] = x.r.y; out.debug[5] = x.r.z;
+        out.debug[6] = x.v.x; out.debug[7] = x.v.y; out.debug[8] = x.v.z;
+        out.debug[9] = x.s.x; out.debug[10] = x.s.y; out.debug[11] = x.s.z;
+        double reward = 0.0;
+        if (action == 1) {
+            V3 real = x.r, nav = (mk(fx[0], fx[1], fx[2]) - real) * (1.0 / norm(real));
+            reward = fabs(P.reward_mult / (1.0 + dot(nav, nav)));
+        }
+        if (modeCounter >= P.numModes) { over = 1; reason |= 2; }
+        out.reward = reward; out.done = over; out.reason = reason;
+        SD(OF_R) = x.r.x; SD(OF_R + 1) = x.r.y; SD(OF_R + 2) = x.r.z; SD(OF_V) = x.v.x; SD(OF_V + 1) = x.v.y; SD(OF_V + 2) = x.v.z;
+        SD(OF_SIG) = x.s.x; SD(OF_SIG + 1) = x.s.y; SD(OF_SIG + 2) = x.s.z; SD(OF_OMG) = x.w.x; SD(OF_OMG + 1) = x.w.y; SD(OF_OMG + 2) = x.w.z;
+        for (int i = 0; i < ON_NRW; i++) { SD(OF_WHL + i) = x.Om[i]; SD(OF_RWCMD + i) = rwcmd[i]; }
+        SD(OF_SUNPT) = cold[0]; SD(OF_SUNPT + 1) = cold[1]; SD(OF_SUNPT + 2) = cold[2];
+        SD(OF_SHADOW) = cold[3];
+        SD(OF_EPRET) = SD(OF_EPRET) + reward;
+        for (int i = 0; i < 4; i++) SD(OF_OBS + i) = out.ob[i];
+        for (int i = 0; i < 12; i++) SD(OF_DEBUG + i) = out.debug[i];
+        SI(OI_TICK) = k_last; SI(OI_STEP) = curr_step + 1; SI(OI_MODE) = mode; SI(OI_CAMERA) = camera; SI(OI_MODECNT) = modeCounter;
+        SI(OI_FIRST) = 0; SI(OI_SWITCH) = n_switch; SI(OI_OVER) = over; SI(OI_SUNPT_W) = sunpt_w; SI(OI_NIMG) = n_img;
 #undef SD
 #undef SI
+    }
+};
+
+struct FilterRole {
+    int64_t ftick, n_meas, n_bad, k_first, k_last;
+
+    ON_HD void load(const OpNavParams &P, const double *S, const int64_t *I, int64_t stride, int64_t e, Ukf &f)
+    {
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+        for (int i = 0; i < 6; i++) { f.x[i] = SD(OF_FSTATE + i); f.m[i] = 0.0; }
+        for (int r = 0; r < 6; r++)
+            for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? SD(OF_FS + TRI(r, c)) : 0.0;
+        ftick = SI(OI_FTICK); n_meas = SI(OI_NMEAS); n_bad = SI(OI_NBAD);
+        const int64_t tick0 = SI(OI_TICK);
+        k_first = tick0 + 1; k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;
+#undef SD
+#undef SI
+    }
+    // relativeODuKF (opNavODTask: after imageProcessing + pixelLine; sunSafePointTask: time update only)
+    ON_HD void tick(const OpNavParams &P, Ukf &f, int64_t k, bool meas, const double (&obs)[3], const double (&R)[6])
+    {
+        const double fdt = (double)(k - ftick) * P.dt;
+        bool tu_ok = true;
+        if (meas || k > ftick) {
+            tu_ok = ukf_time_update(P, f, fdt);
+            if (tu_ok) ftick = k; else n_bad++;              // relODuKFCleanUpdate: the filter keeps its previous state and time
+        }
+        if (meas && tu_ok) {
+            if (ukf_meas_update(P, f, fdt, obs, R)) n_meas++; else n_bad++;
+        }
+    }
+    ON_HD void finish(double *S, int64_t *I, int64_t stride, int64_t e, const Ukf &f, double (&fx)[3], double (&psig)[3])
+    {
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+        fx[0] = f.x[0]; fx[1] = f.x[1]; fx[2] = f.x[2];
+        psig[0] = sqrt(f.SC(0, 0) * f.SC(0, 0));
+        psig[1] = sqrt(f.SC(1, 0) * f.SC(1, 0) + f.SC(1, 1) * f.SC(1, 1));
+        psig[2] = sqrt(f.SC(2, 0) * f.SC(2, 0) + f.SC(2, 1) * f.SC(2, 1) + f.SC(2, 2) * f.SC(2, 2));
+        for (int i = 0; i < 6; i++) SD(OF_FSTATE + i) = f.x[i];
+        for (int r = 0; r < 6; r++)
+            for (int c = 0; c <= r; c++) SD(OF_FS + TRI(r, c)) = f.SC(r, c);
+        SI(OI_NMEAS) = n_meas; SI(OI_NBAD) = n_bad; SI(OI_FTICK) = ftick;
+#undef SD
+#undef SI
+    }
+};
+
+// Both roles in one thread (host-compiled core; single-role kernel).  `f` and `c` are scratch storage for the call.
+ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out,
+                          Ukf &f, Cold &c)
+{
+    DynRole d;
+    FilterRole fr;
+    NoiseRole nz;
+    d.load(P, S, I, stride, e, action, c);
+    fr.load(P, S, I, stride, e, f);
+    nz.load(P, S, I, stride, e);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int64_t k = d.k_first; k <= d.k_last; k++) {
+        Meas m;
+        nz.tick(P, k);
+        d.tick(P, k, c, nz.nerr, m);
+        fr.tick(P, f, k, m.valid, m.obs, m.R);
+    }
+    double fx[3], psig[3];
+    nz.finish(S, stride, e);
+    fr.finish(S, I, stride, e, f, fx, psig);
+    d.finish(P, S, I, stride, e, action, fx, psig, c, out);
 }
 
 }  // namespace opnav

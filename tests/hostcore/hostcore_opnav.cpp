@@ -56,7 +56,8 @@ void hco_step(HCO *h, const int32_t *actions, double *obs, double *reward, uint8
     for (int64_t e = 0; e < h->n; e++) {
         opnav::StepOut o;
         opnav::Ukf f;
-        opnav::opnav_step_env(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o, f);
+        opnav::Cold c;
+        opnav::opnav_step_env(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o, f, c);
         for (int k = 0; k < 4; k++) obs[4 * e + k] = o.ob[k];
         if (debug) for (int k = 0; k < 12; k++) debug[12 * e + k] = o.debug[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
