@@ -18,7 +18,7 @@
 #include "opnav_host.h"
 
 #ifndef ON_MIN_BLOCKS
-#define ON_MIN_BLOCKS 4          // resident blocks per SM: 4 x 96 threads x 168 registers
+#define ON_MIN_BLOCKS 2
 #endif
 
 namespace {
@@ -32,132 +32,62 @@ __device__ __forceinline__ double warp_sum_d(double v)
     return v;
 }
 
-// Work distribution: a block steps groups of ON_ENVS consecutive envs; when there are more groups than resident blocks the
-// grid is one resident set and the blocks pull groups from an atomic queue (same scheme as the LEO step kernel).
+// One warp steps a group of 32 consecutive envs; when there are more groups than resident warps the grid is one
+// resident set and the warps pull groups from an atomic queue (same scheme as the LEO step kernel).
 struct OnSched { int *sched; int n_groups; int dynamic; };
 
-#define ON_ENVS 32                                      // envs per block: one warp per role
-#define ON_THREADS (3 * ON_ENVS)                        // noise warp, dynamics warp, filter warp
-struct OnShared {
-    // per-env scratch of the dynamics and filter roles, thread-contiguous with odd strides (conflict-free 64-bit accesses)
-    opnav::Cold cold[ON_ENVS];
-    opnav::Ukf filt[ON_ENVS];
-    // simple_nav error states, double-buffered by tick parity: [buffer][state][env]
-    double nerr[2][15][ON_ENVS];
-    // measurement mailbox, double-buffered by tick parity: [buffer][field][env]; field 0 = valid flag, 1..3 obs, 4..9 R
-    double mail[2][10][ON_ENVS];
-    // decision-boundary hand-over from the filter side: position estimate (3), sqrt of the covariance diagonal (3), counters (2)
-    double fin[8][ON_ENVS];
-    int group;
-};
-struct NerrView {           // the dynamics role reads the error states of its tick straight from the mailbox
-    const double *p;        // &nerr[buffer][0][slot]
-    __device__ __forceinline__ double operator[](int i) const { return p[i * ON_ENVS]; }
-};
+#ifdef ON_MAXNREG
+#define ON_STEP_BOUNDS __maxnreg__(ON_MAXNREG)          // tuning builds: explicit register cap instead of an occupancy target
+#else
+#define ON_STEP_BOUNDS __launch_bounds__(ON_BLOCK, ON_MIN_BLOCKS)
+#endif
 
-__device__ __forceinline__ void block_barrier() { asm volatile("bar.sync 0;" ::: "memory"); }
+// per-thread scratch in shared memory: filter (49 doubles) + cold dynamics data (19) + 1 pad = 69, an odd stride (conflict-free)
+struct OnScratch { opnav::Ukf f; opnav::Cold c; double pad; };
 
-// Warp-specialised step.  A block owns ON_ENVS envs and three warps: warp 0 advances simple_nav's error walk (tick j at
-// iteration j), warp 1 the dynamics / flight-software half (tick j at iteration j + 1), warp 2 the relative-OD filter
-// (tick j at iteration j + 2).  The three dependency chains of a tick -- which only meet through the 15 error states and the
-// occasional measurement -- advance side by side instead of one after the other; one block barrier per tick orders the
-// double-buffered mailboxes.  No arithmetic is replicated: the per-env instruction count is that of the single-thread form.
-__global__ void __launch_bounds__(ON_THREADS, ON_MIN_BLOCKS)
+// One thread runs the three roles of opnav_core.cuh (noise walk, dynamics + flight software, filter) of one env in sequence.
+// A warp-specialised form (one warp per role, mailboxes in shared memory, one block barrier per tick) was built and is
+// parity-green (git history, profiles/README.md): its pipeline latency is 26 ms instead of 45 ms per interval, but at equal
+// residency it delivers 0.54 M env-steps/s against 0.58 M of this form, so the simpler kernel stays.
+__global__ void ON_STEP_BOUNDS
 opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                   int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                   double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
                   double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc)
 {
-    extern __shared__ __align__(16) unsigned char on_smem_raw[];
-    OnShared &sh = *reinterpret_cast<OnShared *>(on_smem_raw);
-    const int lane = threadIdx.x & 31;
-    const int slot = threadIdx.x % ON_ENVS;                 // env slot of this thread within the block's group
-    const int role = threadIdx.x / ON_ENVS;                 // warp-uniform: 0 noise, 1 dynamics, 2 filter
-    const int T = P.ticks_per_step;
+    extern __shared__ double on_smem[];
+    OnScratch &scr = *reinterpret_cast<OnScratch *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratch) / sizeof(double)));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (bool more = true; more; more = sc.dynamic != 0) {
         int g;
         if (sc.dynamic) {
-            if (threadIdx.x == 0) sh.group = atomicAdd(&sc.sched[0], 1);
-            __syncthreads();
-            g = sh.group;
-            __syncthreads();
+            g = 0;
+            if (lane == 0) g = atomicAdd(&sc.sched[0], 1);
+            g = __shfl_sync(0xffffffffu, g, 0);
             if (g >= sc.n_groups) break;
         } else {
-            g = blockIdx.x;
+            g = blockIdx.x * (ON_BLOCK / 32) + warp;
         }
-        const int64_t e = (int64_t)g * ON_ENVS + slot;
+        const int64_t e = (int64_t)g * 32 + lane;
         const bool valid = e < n;
-        // every role runs T + 4 iterations with one barrier each; iteration j handles tick k_last - T + (j - role)
-        // (envs in their first interval have T + 1 ticks: they also run the tick of offset 0)
-        if (role == 0) {
-            // ---------------- noise warp ----------------
-            opnav::NoiseRole nz;
-            if (valid) nz.load(P, S, I, stride, e);
-#pragma unroll 1
-            for (int j = 0; j <= T + 3; j++) {
-                if (valid && j <= T) {
-                    const int64_t k = nz.k_last - T + j;
-                    if (k >= nz.k_first) {
-                        nz.tick(P, k);
-#pragma unroll
-                        for (int q = 0; q < 15; q++) sh.nerr[j & 1][q][slot] = nz.nerr[q];
-                    }
-                }
-                block_barrier();
-            }
-            if (valid) nz.finish(S, stride, e);
-        } else if (role == 1) {
-            // ---------------- dynamics / flight-software warp ----------------
-            opnav::StepOut o;
-            o.done = 0; o.reason = 0; o.reward = 0.;
-            double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
-            opnav::DynRole d;
-            opnav::Cold &c = sh.cold[slot];
-            const int action = valid ? actions[e] : 0;
-            if (valid) d.load(P, S, I, stride, e, action, c);
-#pragma unroll 1
-            for (int j = 0; j <= T + 3; j++) {
-                const int jt = j - 1;
-                if (valid && jt >= 0 && jt <= T) {
-                    const int64_t k = d.k_last - T + jt;
-                    if (k >= d.k_first) {
-                        opnav::Meas m;
-                        NerrView nv;
-                        nv.p = &sh.nerr[jt & 1][0][slot];
-                        d.tick(P, k, c, nv, m);
-                        sh.mail[jt & 1][0][slot] = m.valid ? 1.0 : 0.0;
-                        if (m.valid) {
-#pragma unroll
-                            for (int q = 0; q < 3; q++) sh.mail[jt & 1][1 + q][slot] = m.obs[q];
-#pragma unroll
-                            for (int q = 0; q < 6; q++) sh.mail[jt & 1][4 + q][slot] = m.R[q];
-                        }
-                    }
-                }
-                block_barrier();
-            }
-            // iteration T + 3 was the filter's last tick + hand-over: its decision-boundary values are in sh.fin
-            if (valid) {
-                double fx[3] = {sh.fin[0][slot], sh.fin[1][slot], sh.fin[2][slot]};
-                double psig[3] = {sh.fin[3][slot], sh.fin[4][slot], sh.fin[5][slot]};
-                d_meas = sh.fin[6][slot]; d_bad = sh.fin[7][slot];
-                d.finish(P, S, I, stride, e, action, fx, psig, c, o);
-                reward[e] = o.reward;
-                done[e] = (uint8_t)o.done;
-                reason[e] = (uint8_t)o.reason;
-                if (debug)
-                    for (int k = 0; k < 12; k++) debug[e * 12 + k] = o.debug[k];
-                if (o.done) {
-                    ep_ret = S[(int64_t)OF_EPRET * stride + e];
-                    ep_len = (double)I[(int64_t)OI_STEP * stride + e];
-                    if (term_obs)
-                        for (int k = 0; k < 4; k++) term_obs[e * 4 + k] = o.ob[k];
-                }
-            }
-            // the noise and filter warps store their halves of the state before the next barrier; an auto-reset must follow it
-            block_barrier();
-            if (valid) {
-                if (o.done && P.auto_reset) {
+        opnav::StepOut o;
+        o.done = 0; o.reason = 0; o.reward = 0.;
+        double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
+        if (valid) {
+            const int64_t m0 = I[(int64_t)OI_NMEAS * stride + e], b0 = I[(int64_t)OI_NBAD * stride + e];
+            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o, scr.f, scr.c);
+            d_meas = (double)(I[(int64_t)OI_NMEAS * stride + e] - m0); d_bad = (double)(I[(int64_t)OI_NBAD * stride + e] - b0);
+            reward[e] = o.reward;
+            done[e] = (uint8_t)o.done;
+            reason[e] = (uint8_t)o.reason;
+            if (debug)
+                for (int k = 0; k < 12; k++) debug[e * 12 + k] = o.debug[k];
+            if (o.done) {
+                ep_ret = S[(int64_t)OF_EPRET * stride + e];
+                ep_len = (double)I[(int64_t)OI_STEP * stride + e];
+                if (term_obs)
+                    for (int k = 0; k < 4; k++) term_obs[e * 4 + k] = o.ob[k];
+                if (P.auto_reset) {
                     int64_t ep = I[(int64_t)OI_EPISODE * stride + e] + 1;
                     I[(int64_t)OI_EPISODE * stride + e] = ep;
                     double ic[OPNAV_IC_DIM];
@@ -165,65 +95,31 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
                     for (int k = 0; k < OPNAV_IC_DIM; k++) ics[(int64_t)k * stride + e] = ic[k];
                     opnav::opnav_reset_env(P, S, I, stride, e, ic, o.ob);
                 }
-                for (int k = 0; k < 4; k++) obs[e * 4 + k] = o.ob[k];
             }
-            if (stats) {
-                const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
-                if (any_done) {
-                    double v_ret = warp_sum_d(o.done ? ep_ret : 0.), v_len = warp_sum_d(o.done ? ep_len : 0.);
-                    int c_all = __popc(any_done);
-                    int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
-                    int c_s = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
-                    if (lane == 0) {
-                        atomicAdd(&stats[OST_RET], v_ret); atomicAdd(&stats[OST_LEN], v_len);
-                        atomicAdd(&stats[OST_COUNT], (double)c_all); atomicAdd(&stats[OST_MAXLEN], (double)c_m);
-                        atomicAdd(&stats[OST_MODES], (double)c_s);
-                    }
-                }
-                const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
-                double v_meas = warp_sum_d(d_meas), v_bad = warp_sum_d(d_bad);
-                if (lane == 0 && c_valid) {
-                    atomicAdd(&stats[OST_STEPS], (double)c_valid);
-                    atomicAdd(&stats[OST_MEAS], v_meas);
-                    if (v_bad != 0.0) atomicAdd(&stats[OST_BAD], v_bad);
+            for (int k = 0; k < 4; k++) obs[e * 4 + k] = o.ob[k];
+        }
+        if (stats) {
+            const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
+            if (any_done) {
+                double v_ret = warp_sum_d(o.done ? ep_ret : 0.), v_len = warp_sum_d(o.done ? ep_len : 0.);
+                int c_all = __popc(any_done);
+                int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
+                int c_s = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
+                if (lane == 0) {
+                    atomicAdd(&stats[OST_RET], v_ret); atomicAdd(&stats[OST_LEN], v_len);
+                    atomicAdd(&stats[OST_COUNT], (double)c_all); atomicAdd(&stats[OST_MAXLEN], (double)c_m);
+                    atomicAdd(&stats[OST_MODES], (double)c_s);
                 }
             }
-        } else {
-            // ---------------- filter warp ----------------
-            opnav::FilterRole fr;
-            opnav::Ukf &f = sh.filt[slot];
-            int64_t m0 = 0, b0 = 0;
-            if (valid) { fr.load(P, S, I, stride, e, f); m0 = fr.n_meas; b0 = fr.n_bad; }
-#pragma unroll 1
-            for (int j = 0; j <= T + 3; j++) {
-                const int jt = j - 2;
-                if (valid && jt >= 0 && jt <= T) {
-                    const int64_t k = fr.k_last - T + jt;
-                    if (k >= fr.k_first) {
-                        const int bsel = jt & 1;
-                        const bool meas = sh.mail[bsel][0][slot] != 0.0;
-                        double ob[3] = {0., 0., 0.}, R[6] = {0., 0., 0., 0., 0., 0.};
-                        if (meas) {
-#pragma unroll
-                            for (int q = 0; q < 3; q++) ob[q] = sh.mail[bsel][1 + q][slot];
-#pragma unroll
-                            for (int q = 0; q < 6; q++) R[q] = sh.mail[bsel][4 + q][slot];
-                        }
-                        fr.tick(P, f, k, meas, ob, R);
-                    }
-                }
-                if (j == T + 3 && valid) {      // last iteration (no tick left for this role): publish and store
-                    double fx[3], psig[3];
-                    fr.finish(S, I, stride, e, f, fx, psig);
-                    sh.fin[0][slot] = fx[0]; sh.fin[1][slot] = fx[1]; sh.fin[2][slot] = fx[2];
-                    sh.fin[3][slot] = psig[0]; sh.fin[4][slot] = psig[1]; sh.fin[5][slot] = psig[2];
-                    sh.fin[6][slot] = (double)(fr.n_meas - m0); sh.fin[7][slot] = (double)(fr.n_bad - b0);
-                }
-                block_barrier();
+            const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
+            double v_meas = warp_sum_d(d_meas), v_bad = warp_sum_d(d_bad);
+            if (lane == 0 && c_valid) {
+                atomicAdd(&stats[OST_STEPS], (double)c_valid);
+                atomicAdd(&stats[OST_MEAS], v_meas);
+                if (v_bad != 0.0) atomicAdd(&stats[OST_BAD], v_bad);
             }
         }
-        if (role != 1) block_barrier();                     // pairs with the dynamics warp's pre-reset barrier
-        __syncthreads();                                    // state written by this group is visible before the next group starts
+        __syncwarp();
     }
 }
 
@@ -299,9 +195,10 @@ struct bskenv_opnav_handle {
 static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double *obs, double *rew, uint8_t *done,
                              uint8_t *reason, double *debug, double *term_obs, cudaStream_t st)
 {
-    const int64_t groups = (h->n + ON_ENVS - 1) / ON_ENVS;
+    const int wpb = ON_BLOCK / 32;
+    const int64_t groups = (h->n + 31) / 32;
     const int resident = h->sm_count * ON_MIN_BLOCKS;
-    int grid = (int)groups;
+    int grid = (int)((groups + wpb - 1) / wpb);
     OnSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
     if (grid > resident) {
@@ -309,13 +206,13 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
         grid = resident;
         ON_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
     }
-    const size_t smem = sizeof(OnShared);
+    const size_t smem = sizeof(OnScratch) * ON_BLOCK;
     static bool attr_set[64] = {false};             // opt in to > 48 KB of dynamic shared memory once per device
     if (!attr_set[h->device & 63]) {
         ON_TRY(h, cudaFuncSetAttribute(opnav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = true;
     }
-    opnav_step_kernel<<<grid, ON_THREADS, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
+    opnav_step_kernel<<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
                                                  term_obs, h->stats, sc);
     ON_TRY(h, cudaGetLastError());
     h->launches++;
