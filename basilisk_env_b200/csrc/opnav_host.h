@@ -117,7 +117,7 @@ static inline std::string build_params(const bskenv_opnav_config &c, OpNavParams
 
 // FP64 flop per env-decision-step of the opNav kernel AS BUILT (FMA = 2, add/mul = 1, one per MUFU seed), from the
 // operation list of opnav_core.cuh and matched to ncu's executed 2*DFMA + DMUL + DADD thread-instruction counters
-// (profiles/ncu_opnav_r01e.md: 5.765e11 per 32768-env launch = 5864 per tick and env with the 50/50 action mix):
+// (profiles/ncu_opnav_r01f.md: 5.774e11 per 32768-env launch = 5874 per tick and env with the 50/50 action mix):
 //   filter time update   13 two-body RK4 steps (4 x 44 + 6), sigma points and deviations 6 x 60, Gram matrix 6 x 84,
 //                        covariance assembly 100, 6 x 6 Cholesky 185                                        ~ 3400
 //   truth RK4            4 x eom (gravity 20, wheel momentum and torque 52, gyroscopics + inverse 45, MRP kinematics 40,
