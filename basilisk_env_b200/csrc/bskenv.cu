@@ -360,6 +360,8 @@ int bskenv_step_host(bskenv_handle *h, const int32_t *actions, double *obs, doub
         CU_TRY(h, cudaMallocHost(&h->h_rew, n * sizeof(double))); CU_TRY(h, cudaMallocHost(&h->h_done, n)); CU_TRY(h, cudaMallocHost(&h->h_reason, n));
     }
     cudaStream_t st = h->own_stream;
+    // the handle's stream does not synchronise with the caller's streams: wait for any bskenv_step / reset still in flight
+    CU_TRY(h, cudaDeviceSynchronize());
     memcpy(h->h_act, actions, n * sizeof(int32_t));
     CU_TRY(h, cudaMemcpyAsync(h->d_act, h->h_act, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     int rc = launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_reason, nullptr, st);

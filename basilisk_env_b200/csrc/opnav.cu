@@ -339,6 +339,8 @@ int bskenv_opnav_step_host(bskenv_opnav_handle *h, const int32_t *actions, doubl
         ON_TRY(h, cudaMallocHost(&h->h_done, n)); ON_TRY(h, cudaMallocHost(&h->h_reason, n));
     }
     cudaStream_t st = h->own_stream;
+    // the handle's stream does not synchronise with the caller's streams: wait for any step / reset still in flight
+    ON_TRY(h, cudaDeviceSynchronize());
     memcpy(h->h_act, actions, n * sizeof(int32_t));
     ON_TRY(h, cudaMemcpyAsync(h->d_act, h->h_act, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     int rc = opnav_launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_reason, debug ? h->d_dbg : nullptr, nullptr, st);

@@ -112,7 +112,8 @@ int bskenv_step(bskenv_handle *h, const int32_t *actions_dev, double *obs_dev, d
                 uint8_t *done_dev, uint8_t *done_reason_dev, double *term_obs_dev, void *stream);
 /* Same call with HOST buffers (the reference-facing plugin path): copies actions to the device,
  * launches, copies obs/reward/done/reason back through pinned staging owned by the handle, and
- * synchronises.  This is what bench.py times as `e2e`. */
+ * synchronises.  It first waits for work already queued on the device (a preceding bskenv_step / reset on any stream),
+ * so the two entry points can be mixed freely.  This is what bench.py times as `e2e`. */
 int bskenv_step_host(bskenv_handle *h, const int32_t *actions, double *obs, double *reward,
                      uint8_t *done, uint8_t *done_reason);
 

@@ -288,3 +288,29 @@ def test_full_size_properties_65536_envs(bsk):
     rw = r[acts == 0]
     assert bool((r[acts != 0] <= 0).all()) and float(rw[rw > 0].max()) <= 1.0 / 540 + 1e-15
     env.close()
+
+
+def test_step_and_step_host_can_be_mixed(bsk):
+    """`step` queues on the caller's stream, `step_host` on the handle's own: the host entry point waits for the
+    device first, so an un-synchronised mix gives the same trajectory as a serial one (and counts every episode once)."""
+    import torch
+    n = 4096
+    acts = np.random.RandomState(3).randint(0, 3, size=(6, n)).astype(np.int32)
+    outs = []
+    for mixed in (False, True):
+        env = _vec(bsk, n, seed=11, auto_reset=True, step_duration=20.0, max_length=2)
+        env.reset()
+        for t in range(6):
+            if mixed and t % 2 == 1:
+                ob = env.step_host(acts[t])[0].copy()
+            else:
+                ob = env.step(torch.as_tensor(acts[t], device="cuda"))[0]
+                if not mixed:
+                    torch.cuda.synchronize()
+                    ob = ob.cpu().numpy()
+        torch.cuda.synchronize()
+        ob = ob if isinstance(ob, np.ndarray) else ob.cpu().numpy()
+        outs.append((ob, env.episode_stats()))
+        env.close()
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    assert outs[0][1] == outs[1][1] and outs[0][1]["episodes"] == 2 * n
