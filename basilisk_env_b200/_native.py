@@ -24,7 +24,8 @@ class Config(C.Structure):
                 ("thrForceSign", C.c_int32), ("maxCounterValue", C.c_int32),
                 ("max_length", C.c_int32), ("auto_reset", C.c_int32),
                 ("wheel_limit_rpm", C.c_double), ("power_max", C.c_double), ("failure_penalty", C.c_double),
-                ("use_j2", C.c_int32), ("hill_cel_pun", C.c_int32), ("rw_set", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("use_j2", C.c_int32), ("hill_cel_pun", C.c_int32), ("rw_set", C.c_int32), ("precision", C.c_int32),
+                ("reserved", C.c_int32 * 6)]
 
 
 class OpNavConfig(C.Structure):

@@ -52,9 +52,9 @@ __device__ __forceinline__ double warp_sum(double v)
 //   sched[0] = queue head (zeroed before the launch)
 struct LeoSched { int *sched; int n_groups; int dynamic; };
 
-template <int NRW, bool J2, bool DIAG>
+template <int NRW, bool J2, bool DIAG, bool F32>
 __global__ void LEO_STEP_BOUNDS
-leo_step_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ LeoParamsF PF, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                 int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                 double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
                 double *__restrict__ term_obs, double *__restrict__ stats, const LeoSched sc)
@@ -80,7 +80,7 @@ leo_step_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int
         o.done = 0; o.reason = 0; o.reward = 0.;
         double ep_ret = 0., ep_len = 0.;
         if (valid) {
-            leo::leo_step_env<NRW, J2, DIAG>(P, S, I, stride, e, bus, actions[e], o);
+            leo::leo_step_env<NRW, J2, DIAG, F32>(P, S, I, stride, e, bus, actions[e], o, PF);
             reward[e] = o.reward;
             done[e] = (uint8_t)o.done;
             reason[e] = (uint8_t)o.reason;
@@ -188,6 +188,7 @@ thread_local std::string g_create_error;
 struct bskenv_handle {
     bskenv_config cfg;
     LeoParams P;
+    LeoParamsF PF;
     int device;
     int64_t n, stride;
     double *S, *ics, *stats;
@@ -225,19 +226,23 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
         grid = resident;
         CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
     }
-#define LEO_LAUNCH(NRW, J2, DIAG)                                                                              \
+#define LEO_LAUNCH(NRW, J2, DIAG, F32)                                                                         \
     do {                                                                                                       \
         static bool attr_set[64] = {false};      /* opt in to > 48 KB of dynamic shared memory once per device */  \
         if (!attr_set[h->device & 63]) {                                                                       \
-            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEO_BUS_BYTES)); \
+            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEO_BUS_BYTES)); \
             attr_set[h->device & 63] = true;                                                                   \
         }                                                                                                      \
-        leo_step_kernel<NRW, J2, DIAG><<<grid, LEO_BLOCK, LEO_BUS_BYTES, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
-                                                                                rew, done, reason, term_obs, h->stats, sc); \
+        leo_step_kernel<NRW, J2, DIAG, F32><<<grid, LEO_BLOCK, LEO_BUS_BYTES, st>>>(h->P, h->PF, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
+                                                                                     rew, done, reason, term_obs, h->stats, sc); \
     } while (0)
-    if (h->P.nrw == 4) { if (h->cfg.use_j2) LEO_LAUNCH(4, true, false); else LEO_LAUNCH(4, false, false); }
-    else if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(3, true, true); else LEO_LAUNCH(3, true, false); }
-    else                    { if (h->P.diag) LEO_LAUNCH(3, false, true); else LEO_LAUNCH(3, false, false); }
+    if (h->P.mixed) {         // mixed precision: built for the stress configuration and the reference configuration
+        if (h->P.nrw == 4 && h->cfg.use_j2) LEO_LAUNCH(4, true, false, true);
+        else LEO_LAUNCH(3, false, true, true);
+    }
+    else if (h->P.nrw == 4) { if (h->cfg.use_j2) LEO_LAUNCH(4, true, false, false); else LEO_LAUNCH(4, false, false, false); }
+    else if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(3, true, true, false); else LEO_LAUNCH(3, true, false, false); }
+    else                    { if (h->P.diag) LEO_LAUNCH(3, false, true, false); else LEO_LAUNCH(3, false, false, false); }
 #undef LEO_LAUNCH
     CU_TRY(h, cudaGetLastError());
     h->launches++;
@@ -267,6 +272,11 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     h->cfg = *cfg;
     std::string perr = leo_host::build_params(*cfg, h->P);
     if (!perr.empty()) { g_create_error = "bskenv_create: " + perr; delete h; return BSKENV_EINVAL; }
+    if (h->P.mixed && !((h->P.nrw == 4 && cfg->use_j2) || (h->P.nrw == 3 && !cfg->use_j2 && h->P.diag))) {
+        g_create_error = "bskenv_create: precision = 1 is built for the reference configuration and for the stress configuration (rw_set = 1, use_j2 = 1)";
+        delete h; return BSKENV_EINVAL;
+    }
+    leo_host::build_params_f(h->P, h->PF);
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
     h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;

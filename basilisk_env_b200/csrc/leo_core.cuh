@@ -1042,9 +1042,14 @@ LEO_HD double exp_bounded(double x)
 #endif
 }
 
-template <int NRW, bool J2, bool DIAG>
+}  // namespace leo
+#include "leo_f32.cuh"      // mixed-precision tick (BASELINE config 5); needs everything above
+namespace leo {
+
+// F32 = false: the FP64 kernel (the reference's arithmetic; every parity claim).  F32 = true: mixed precision, see leo_f32.cuh.
+template <int NRW, bool J2, bool DIAG, bool F32 = false>
 LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
-                         MBus m, int action, StepOut &out)
+                         MBus m, int action, StepOut &out, const LeoParamsF &PF = LeoParamsF())
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
@@ -1101,6 +1106,14 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     const double dyn_d = (double)P.dyn_ns;
     double sun_d = (double)((n_base - 1) * P.dyn_ns);          // write time of the Sun message in force
     sun_latch_to_bus(P, m, (n_base - 1) * P.dyn_ns);
+    // FP32 shadows of the Sun latch and its eclipse constants (mixed-precision variant only)
+    V3f sunr_f = mkf(0.f, 0.f, 0.f), sunv_f = mkf(0.f, 0.f, 0.f);
+    float ecf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (F32) {
+        sunr_f = tof(mld3(m, M_SUNR)); sunv_f = tof(mld3(m, M_SUNV));
+#pragma unroll
+        for (int q = 0; q < 6; q++) ecf[q] = (float)mld(m, M_ECL + q);
+    }
     int phase = (int)((n_base - 1) % tpf);                     // (n mod ticks_per_fsw) of the tick about to run
     double now_d = sun_d;                                      // exact: n * dyn_ns
     int desat_ran = 0, desat_quiet = 0;                        // the chain's quiet state is re-established once per launch
@@ -1118,7 +1131,14 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
             // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule); the
             // message is then newer than the start of this integration step (quirk Q18)
-            if (n > 0 && n == n_end) { sun_d = now_d; sun_latch_to_bus(P, m, n * P.dyn_ns); wrapped = true; }
+            if (n > 0 && n == n_end) {
+                sun_d = now_d; sun_latch_to_bus(P, m, n * P.dyn_ns); wrapped = true;
+                if (F32) {
+                    sunr_f = tof(mld3(m, M_SUNR)); sunv_f = tof(mld3(m, M_SUNV));
+#pragma unroll
+                    for (int q = 0; q < 6; q++) ecf[q] = (float)mld(m, M_ECL + q);
+                }
+            }
         }
         // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
         const double prev_d = j < 0 ? 0.0 : now_d - dyn_d;     // tick 0 integrates over an empty interval
@@ -1146,8 +1166,17 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         } else {
             // Sun at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
             const double dtsm = t_mul(prev_d - sun_d, 1e-9) + 0.5 * h;
-            a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
-            x = rk4_step<J2, DIAG>(P, x, a, thr_active != 0, m);
+            if (F32) {
+                StageInF af;
+                af.h = (float)h; af.rho = (float)a.rho;
+                af.Lc = tof(a.Lc); af.HB = tof(a.HB); af.tau_u = tof(a.tau_u);
+                af.gsun = sun_accelf(PF, sunr_f + sunv_f * (float)dtsm, tof(x.r) + tof(x.v) * (0.5f * af.h));
+                const bool thr_on = thr_active != 0;
+                x = rk4_step_mixed<J2, DIAG>(PF, x, af, thr_on, thr_on ? tof(mld3(m, M_FM)) : mkf(0.f, 0.f, 0.f));
+            } else {
+                a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+                x = rk4_step<J2, DIAG>(P, x, a, thr_active != 0, m);
+            }
         }
         // the wheel invariant advances with the motor torque held over the step
         a.HB = a.HB + a.tau_u * h;
@@ -1162,9 +1191,17 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             if (s2 > 1.0000000000000002) { x.s = x.s * (-frcp(s2)); nswitch++; }
         }
         // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
-        const double r2 = dot(x.r, x.r), ir = rsq(r2);
-        // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
-        a.rho = P.rho0 * exp_bounded(-(r2 * ir - P.Rp_atmo) * P.inv_H);
+        double r2 = 0., ir = 0.;
+        V3f xr_f = mkf(0.f, 0.f, 0.f);
+        float r2f = 0.f;
+        if (F32) {
+            xr_f = tof(x.r); r2f = dot(xr_f, xr_f);
+            a.rho = (double)(PF.rho0 * expf(-(r2f * rsqf(r2f) - PF.Rp_atmo) * PF.inv_H));
+        } else {
+            r2 = dot(x.r, x.r); ir = rsq(r2);
+            // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
+            a.rho = P.rho0 * exp_bounded(-(r2 * ir - P.Rp_atmo) * P.inv_H);
+        }
         // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
         {
             double W[NRW];
@@ -1184,7 +1221,33 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             }
         }
         // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
-        {
+        if (F32) {
+            const V3f r_SBf = sunr_f - xr_f;
+            const float d2f = dot(r_SBf, r_SBf), idf = rsqf(d2f);
+            float shf = eclipse_coref(PF, ecf, sunr_f, xr_f, r2f, d2f);
+            double shadow = (double)shf;
+            if (shf < 0.f) {                                   // cone-surface band / penumbra: the FP64 evaluation
+                const V3 sun_r = mld3(m, M_SUNR);
+                const V3 r_SB = sun_r - x.r;
+                const double r2d = dot(x.r, x.r), d2 = dot(r_SB, r_SB);
+                const double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
+                shadow = eclipse_core(P, ec, sun_r, x.r, r2d, rsq(r2d), r_SB, d2, rsq(d2));
+                shf = (float)shadow;
+            }
+            mst(m, M_SHADOW, shadow);
+            const V3f sf = tof(x.s);
+            MrpRotF R = mrp_rotf(sf);
+            V3f n_N = rot_NBf(R, sf, arrf(PF.nHat_B));
+            float proj = dot(n_N, r_SBf) * idf;
+            if (proj < 0.f) proj = 0.f;
+            const float panel = PF.panel_coef * proj * (idf * idf) * shf;
+            if (j >= 0) {
+                double E = mld(m, M_CHARGE) + ((double)panel + P.sink_power) * h;
+                if (E > P.capacity) E = P.capacity;
+                if (E < 0.) E = 0.;
+                mst(m, M_CHARGE, E);
+            }
+        } else {
             const V3 sun_r = mld3(m, M_SUNR);
             const V3 r_SB = sun_r - x.r;                       // spacecraft -> Sun
             const double d2 = dot(r_SB, r_SB), id = rsq(d2);

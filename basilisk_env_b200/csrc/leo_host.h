@@ -63,6 +63,8 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
     p.mu_c = 0.3986004415e15; p.mu_sun = 1.32712440018e20;       // [BSK: simIncludeGravBody]
     p.j2k = 1.5 * 1.08262668355e-3 * p.mu_c * (6378136.6 * 6378136.6);
     p.hill_cel_pun = c.hill_cel_pun; p.use_j2 = c.use_j2 ? 1 : 0;
+    if (c.precision != 0 && c.precision != 1) return "precision must be 0 (FP64) or 1 (mixed: FP32 stages, FP64 accumulation)";
+    p.mixed = c.precision;
     // Honeywell HR16 at 50 Nms ([BSK: simIncludeRW.Honeywell_HR16]): three along the body axes (AP:20-37), or the
     // four-wheel pyramid of the opNav spacecraft (opNav_models/BSK_OpNavDynamics.py:269-293:
     // gsHat = M3(-az) M2(el) e_x = (cos el cos az, cos el sin az, sin el))
@@ -171,6 +173,19 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
     // '2021 MAY 04 07:47:48.965 (UTC)' (SIM:219) as days of TT from J2000: JD 2459338.5 + UTC seconds + 69.184 s
     p.epoch_days = 7793.5 + (28068.965 + 69.184) / 86400.0;
     return "";
+}
+
+static inline void build_params_f(const LeoParams &p, LeoParamsF &f)
+{
+    memset(&f, 0, sizeof(f));
+    f.mu_c = (float)p.mu_c; f.mu_sun = (float)p.mu_sun; f.j2k = (float)p.j2k;
+    for (int i = 0; i < 9; i++) { f.D[i] = (float)p.D[i]; f.Dinv[i] = (float)p.Dinv[i]; }
+    for (int a = 0; a < 3; a++) {
+        f.dragKa[a] = (float)p.dragKa[a]; f.dragKd[a] = (float)p.dragKd[a]; f.nHat_B[a] = (float)p.nHat_B[a];
+        for (int b = 0; b < 3; b++) { f.dragMa[a][b] = (float)p.dragMa[a][b]; f.dragMd[a][b] = (float)p.dragMd[a][b]; }
+    }
+    f.rho0 = (float)p.rho0; f.inv_H = (float)p.inv_H; f.Rp_atmo = (float)p.Rp_atmo;
+    f.R_sun = (float)p.R_sun; f.R_planet = (float)p.R_planet; f.panel_coef = (float)p.panel_coef;
 }
 
 // FP64 flop per env-decision-step of the step kernel AS BUILT (DESIGN.md "Flop model"): FMA = 2, add/mul = 1,

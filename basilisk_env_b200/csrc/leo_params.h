@@ -28,6 +28,7 @@ struct LeoParams {
     double mu_c, mu_sun;
     double j2k;           // 1.5 * J2 * mu * Req^2 (only when the J2 template flag is on)
     int32_t use_j2, hill_cel_pun;
+    int32_t mixed, pad2;   // 1: FP32 stage arithmetic with FP64 accumulation (leo_f32.cuh); stress-config trade-off only
     int32_t diag, pad1;    // 1: diagonal hub inertia, three wheels along the body axes, drag facets on their normal axis
                            //    (the reference set-up): fast EOM path
     // ---- reaction wheels ----
@@ -70,6 +71,15 @@ struct LeoParams {
     // ---- IC sampling ----
     uint64_t seed;
     int64_t first_env_index;
+};
+
+// FP32 copies of the parameters the mixed-precision tick reads (leo_f32.cuh); second __grid_constant__ kernel argument
+struct LeoParamsF {
+    float mu_c, mu_sun, j2k;
+    float D[9], Dinv[9];
+    float dragKa[3], dragKd[3], dragMa[3][3], dragMd[3][3];
+    float rho0, inv_H, Rp_atmo, R_sun, R_planet;
+    float nHat_B[3], panel_coef;
 };
 
 // ---- persistent per-env state: double fields (SoA, field-major, stride = padded env count) ----

@@ -74,7 +74,11 @@ typedef struct bskenv_config {
                                     1: four HR16 in the opNav pyramid, elevation 40 deg, azimuth 45/135/225/315 deg
                                     (opNav_models/BSK_OpNavDynamics.py:269-293): BASELINE stress config.  The fourth
                                     wheel starts at the mean of the three sampled speeds. */
-    int32_t reserved[7];
+    int32_t precision;           /* 0: FP64 everywhere (the reference's arithmetic; every parity claim is about this setting).
+                                    1: mixed precision for the accuracy / throughput trade-off of the stress config: the RK4 stage
+                                    arithmetic, density, eclipse cone tests and panel projection in FP32; state accumulation,
+                                    clocks, battery, flight software, wheel limits and thruster logic in FP64 */
+    int32_t reserved[6];
 } bskenv_config;
 
 typedef struct bskenv_handle bskenv_handle;

@@ -11,6 +11,7 @@
 
 struct HC {
     LeoParams P;
+    LeoParamsF PF;
     int64_t n;
     std::vector<double> S, ics;
     std::vector<int64_t> I;
@@ -24,6 +25,7 @@ HC *hc_create(const bskenv_config *cfg, int64_t n)
     HC *h = new HC();
     std::string err = leo_host::build_params(*cfg, h->P);
     if (!err.empty()) { delete h; return nullptr; }
+    leo_host::build_params_f(h->P, h->PF);
     h->n = n;
     h->S.assign((size_t)LEO_ND * n, 0.0);
     h->I.assign((size_t)LEO_NI * n, 0);
@@ -58,7 +60,10 @@ void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t
     for (int64_t e = 0; e < h->n; e++) {
         leo::StepOut o;
         const bool diag = h->P.diag && !h->force_general;
-        if (h->P.nrw == 4) {
+        if (h->P.mixed) {      // mixed-precision variant (leo_f32.cuh): the two configurations the library builds
+            if (h->P.nrw == 4) leo::leo_step_env<4, true, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF);
+            else leo::leo_step_env<3, false, true, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF);
+        } else if (h->P.nrw == 4) {
             if (h->P.use_j2) leo::leo_step_env<4, true, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
             else leo::leo_step_env<4, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
         } else if (h->P.use_j2) {

@@ -118,3 +118,26 @@ def test_max_length_rule(orc, hostcore):
     dones = [bool(hc.step([1])[2][0]) for _ in range(4)]
     assert dones == [False, False, False, True]
     assert hc.step([1])[3][0] & 1
+
+
+def test_mixed_precision_variant_tracks_fp64(hostcore, orc):
+    """precision = 1 (leo_f32.cuh: FP32 stage arithmetic, FP64 accumulation / clocks / flight software / events) against the
+    FP64 core on the same inputs: discrete outcomes equal, continuous states within the FP32 increment error per interval
+    (position ~0.1 m, attitude ~1e-7).  This is the accuracy side of BASELINE config 5; parity claims are about FP64 only."""
+    rows = parity.sample_rows(orc, 12, seed=5)
+    for kw in (dict(), dict(use_j2=1, rw_set=1)):
+        h64 = hostcore.HostCore(12, **kw); h32 = hostcore.HostCore(12, precision=1, **kw)
+        np.testing.assert_array_equal(h64.reset_ics(rows), h32.reset_ics(rows))
+        rng = np.random.RandomState(1)
+        for t in range(3):
+            a = rng.randint(0, 2, 12)                       # modes 0/1 (thruster timing is exercised on the GPU)
+            o64, o32 = h64.step(a), h32.step(a)
+            S64, I64 = h64.state(); S32, I32 = h32.state()
+            assert np.linalg.norm(S64[0:3] - S32[0:3], axis=0).max() < 1.0          # m
+            assert np.linalg.norm(S64[3:6] - S32[3:6], axis=0).max() < 5e-3         # m/s
+            assert np.abs(S64[6:9] - S32[6:9]).max() < 1e-6 and np.abs(S64[9:12] - S32[9:12]).max() < 1e-7
+            np.testing.assert_allclose(o32[0], o64[0], atol=2e-6, rtol=0)
+            np.testing.assert_array_equal(o32[2], o64[2]); np.testing.assert_array_equal(o32[3], o64[3])
+            np.testing.assert_array_equal(I64[parity.F("MRPSwitchCount")], I32[parity.F("MRPSwitchCount")])
+    with pytest.raises(AssertionError):
+        hostcore.HostCore(2, precision=2)
