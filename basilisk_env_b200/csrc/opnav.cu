@@ -42,6 +42,45 @@ struct OnSched { int *sched; int n_groups; int dynamic; };
 #define ON_STEP_BOUNDS __launch_bounds__(ON_BLOCK, ON_MIN_BLOCKS)
 #endif
 
+// Lane assignment.  The two flight-software task sets execute different code every tick (hillPoint + tracking error vs CSS +
+// eclipse + cssWlsEst + sunSafePoint); with one env per lane in index order a warp of mixed actions runs both, 3000 times.
+// Before the step, envs are therefore bucketed by the task set they WILL run (first-interval event, action, or the mode in
+// force for an unknown action) and the warps of the step kernel take 32 envs of one bucket: the persistent state is read and
+// written once per decision (gathered, 97 fields per env), the tick loop is divergence-free.  sched[1..2] = bucket sizes,
+// sched[3..4] = bucket cursors.
+__device__ __forceinline__ int opnav_task_set(const int64_t *__restrict__ I, int64_t stride, int64_t e, int action)
+{
+    if (I[(int64_t)OI_FIRST * stride + e]) return 0;
+    return action == 0 ? 0 : (action == 1 ? 1 : (int)I[(int64_t)OI_MODE * stride + e]);
+}
+__global__ void __launch_bounds__(256)
+opnav_bucket_count_kernel(const int64_t *__restrict__ I, int64_t stride, int64_t n, const int32_t *__restrict__ actions, int *__restrict__ sched)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < n;
+    const int cls = valid ? opnav_task_set(I, stride, e, actions[e]) : -1;
+    const unsigned m0 = __ballot_sync(0xffffffffu, cls == 0);
+    if ((threadIdx.x & 31) == 0 && m0) atomicAdd(&sched[1], __popc(m0));
+}
+__global__ void __launch_bounds__(256)
+opnav_bucket_fill_kernel(const int64_t *__restrict__ I, int64_t stride, int64_t n, const int32_t *__restrict__ actions, int *__restrict__ sched,
+                         int32_t *__restrict__ perm)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = e < n;
+    const int cls = valid ? opnav_task_set(I, stride, e, actions[e]) : -1;
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int c = 0; c < 2; c++) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (!m) continue;
+        int base = 0;
+        if (lane == __ffs(m) - 1) base = atomicAdd(&sched[3 + c], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        if (cls == c) perm[(c == 0 ? 0 : sched[1]) + base + __popc(m & ((1u << lane) - 1))] = (int32_t)e;
+    }
+}
+
 // per-thread scratch in shared memory: filter (49 doubles) + cold dynamics data (19) + 1 pad = 69, an odd stride (conflict-free)
 struct OnScratch { opnav::Ukf f; opnav::Cold c; double pad; };
 
@@ -53,7 +92,8 @@ __global__ void ON_STEP_BOUNDS
 opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                   int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                   double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
-                  double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc)
+                  double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc,
+                  const int32_t *__restrict__ perm)
 {
     extern __shared__ double on_smem[];
     OnScratch &scr = *reinterpret_cast<OnScratch *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratch) / sizeof(double)));
@@ -68,8 +108,9 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
         } else {
             g = blockIdx.x * (ON_BLOCK / 32) + warp;
         }
-        const int64_t e = (int64_t)g * 32 + lane;
-        const bool valid = e < n;
+        const int64_t slot = (int64_t)g * 32 + lane;
+        const bool valid = slot < n;
+        const int64_t e = valid ? (int64_t)perm[slot] : 0;      // envs of one flight-software task set per warp
         opnav::StepOut o;
         o.done = 0; o.reason = 0; o.reward = 0.;
         double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
@@ -175,6 +216,7 @@ struct bskenv_opnav_handle {
     double *S, *ics, *stats;
     int64_t *I;
     int *sched;
+    int32_t *perm;              // lane assignment of the step kernel (envs bucketed by task set)
     int sm_count;
     int32_t *d_act; double *d_obs, *d_rew, *d_dbg; uint8_t *d_done, *d_reason;
     int32_t *h_act; double *h_obs, *h_rew, *h_dbg; uint8_t *h_done, *h_reason;
@@ -201,10 +243,15 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
     int grid = (int)((groups + wpb - 1) / wpb);
     OnSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
+    ON_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int) * 8, st));
+    {   // bucket the envs by flight-software task set (two small launches; see opnav_bucket_*_kernel)
+        const int bgrid = (int)((h->n + 255) / 256);
+        opnav_bucket_count_kernel<<<bgrid, 256, 0, st>>>(h->I, h->stride, h->n, act, h->sched);
+        opnav_bucket_fill_kernel<<<bgrid, 256, 0, st>>>(h->I, h->stride, h->n, act, h->sched, h->perm);
+    }
     if (grid > resident) {
         sc.dynamic = 1;
         grid = resident;
-        ON_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
     }
     const size_t smem = sizeof(OnScratch) * ON_BLOCK;
     static bool attr_set[64] = {false};             // opt in to > 48 KB of dynamic shared memory once per device
@@ -213,7 +260,7 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
         attr_set[h->device & 63] = true;
     }
     opnav_step_kernel<<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
-                                                 term_obs, h->stats, sc);
+                                                 term_obs, h->stats, sc, h->perm);
     ON_TRY(h, cudaGetLastError());
     h->launches++;
     return BSKENV_OK;
@@ -244,12 +291,13 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
     if (!perr.empty()) { g_opnav_create_error = "bskenv_opnav_create: " + perr; delete h; return BSKENV_EINVAL; }
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
-    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr;
     h->d_act = nullptr; h->d_obs = h->d_rew = h->d_dbg = nullptr; h->d_done = h->d_reason = nullptr;
     h->h_act = nullptr; h->h_obs = h->h_rew = h->h_dbg = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * OPNAV_ND * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * OPNAV_NI * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * OPNAV_IC_DIM * h->stride);
@@ -271,7 +319,7 @@ int bskenv_opnav_destroy(bskenv_opnav_handle *h)
 {
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_dbg); cudaFree(h->d_done); cudaFree(h->d_reason);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_dbg); cudaFreeHost(h->h_done);
     cudaFreeHost(h->h_reason);
