@@ -48,7 +48,7 @@ EXPORTS = ["bskenv_abi_version", "bskenv_default_config", "bskenv_create", "bske
            "bskenv_num_envs", "bskenv_reset_seeded", "bskenv_reset_ics", "bskenv_reset_init", "bskenv_get_ics",
            "bskenv_step", "bskenv_step_host", "bskenv_state_dims", "bskenv_get_state", "bskenv_set_state",
            "bskenv_state_field", "bskenv_episode_stats", "bskenv_launch_count", "bskenv_fp64_peak",
-           "bskenv_flops_per_step"]
+           "bskenv_flops_per_step", "bskenv_set_ephemeris", "bskenv_set_gravity_degree2"]
 
 
 def lib_path():
@@ -89,6 +89,8 @@ def lib():
     L.bskenv_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double)]
     L.bskenv_flops_per_step.restype = C.c_double
     L.bskenv_flops_per_step.argtypes = [vp]
+    L.bskenv_set_ephemeris.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp]
+    L.bskenv_set_gravity_degree2.argtypes = [vp, C.c_int, vp]
     L.bskenv_opnav_default_config.argtypes = [C.POINTER(OpNavConfig)]
     L.bskenv_opnav_create.argtypes = [C.POINTER(OpNavConfig), C.c_int, i64, i64, C.POINTER(vp)]
     L.bskenv_opnav_destroy.argtypes = [vp]

@@ -25,6 +25,7 @@
 #define LEO_MIN_BLOCKS 3        // resident blocks per SM: 3 x 128 threads x 168 registers
 #endif
 #define LEO_BUS_BYTES ((size_t)leo::LEO_NM * LEO_BLOCK * sizeof(double))   // shared-memory message bus of one block
+#define LEO_BUS_BYTES_PFIX ((size_t)leo::LEO_NM_PFIX * LEO_BLOCK * sizeof(double))   // ... of the planet-fixed gravity variant
 
 namespace {
 
@@ -52,7 +53,7 @@ __device__ __forceinline__ double warp_sum(double v)
 //   sched[0] = queue head (zeroed before the launch)
 struct LeoSched { int *sched; int n_groups; int dynamic; };
 
-template <int NRW, bool J2, bool DIAG, bool F32>
+template <int NRW, int J2, bool DIAG, bool F32>
 __global__ void LEO_STEP_BOUNDS
 leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ LeoParamsF PF, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                 int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
@@ -194,6 +195,7 @@ struct bskenv_handle {
     double *S, *ics, *stats;
     int64_t *I;
     int *sched;                 // work queue head of the step kernel
+    double *d_eph[2];           // device copies of the ephemeris tables (Sun position, Earth orientation angles)
     int sm_count;
     // staging for the host-buffer entry point
     int32_t *d_act; double *d_obs, *d_rew; uint8_t *d_done, *d_reason;
@@ -229,20 +231,26 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
 #define LEO_LAUNCH(NRW, J2, DIAG, F32)                                                                         \
     do {                                                                                                       \
         static bool attr_set[64] = {false};      /* opt in to > 48 KB of dynamic shared memory once per device */  \
+        const size_t bus_bytes = (J2) == 2 ? LEO_BUS_BYTES_PFIX : LEO_BUS_BYTES;                                \
         if (!attr_set[h->device & 63]) {                                                                       \
-            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LEO_BUS_BYTES)); \
+            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bus_bytes)); \
             attr_set[h->device & 63] = true;                                                                   \
         }                                                                                                      \
-        leo_step_kernel<NRW, J2, DIAG, F32><<<grid, LEO_BLOCK, LEO_BUS_BYTES, st>>>(h->P, h->PF, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
-                                                                                     rew, done, reason, term_obs, h->stats, sc); \
+        leo_step_kernel<NRW, J2, DIAG, F32><<<grid, LEO_BLOCK, bus_bytes, st>>>(h->P, h->PF, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
+                                                                                 rew, done, reason, term_obs, h->stats, sc); \
     } while (0)
-    if (h->P.mixed) {         // mixed precision: built for the stress configuration and the reference configuration
-        if (h->P.nrw == 4 && h->cfg.use_j2) LEO_LAUNCH(4, true, false, true);
-        else LEO_LAUNCH(3, false, true, true);
+    if (h->P.grav_pfix) {     // degree-2 field in the planet-fixed frame (general EOM path)
+        if (h->P.nrw == 4) LEO_LAUNCH(4, 2, false, false);
+        else if (h->P.diag) LEO_LAUNCH(3, 2, true, false);
+        else LEO_LAUNCH(3, 2, false, false);
     }
-    else if (h->P.nrw == 4) { if (h->cfg.use_j2) LEO_LAUNCH(4, true, false, false); else LEO_LAUNCH(4, false, false, false); }
-    else if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(3, true, true, false); else LEO_LAUNCH(3, true, false, false); }
-    else                    { if (h->P.diag) LEO_LAUNCH(3, false, true, false); else LEO_LAUNCH(3, false, false, false); }
+    else if (h->P.mixed) {         // mixed precision: built for the stress configuration and the reference configuration
+        if (h->P.nrw == 4 && h->cfg.use_j2) LEO_LAUNCH(4, 1, false, true);
+        else LEO_LAUNCH(3, 0, true, true);
+    }
+    else if (h->P.nrw == 4) { if (h->cfg.use_j2) LEO_LAUNCH(4, 1, false, false); else LEO_LAUNCH(4, 0, false, false); }
+    else if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(3, 1, true, false); else LEO_LAUNCH(3, 1, false, false); }
+    else                    { if (h->P.diag) LEO_LAUNCH(3, 0, true, false); else LEO_LAUNCH(3, 0, false, false); }
 #undef LEO_LAUNCH
     CU_TRY(h, cudaGetLastError());
     h->launches++;
@@ -280,6 +288,7 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
     h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;
+    h->d_eph[0] = h->d_eph[1] = nullptr;
     h->d_act = nullptr; h->d_obs = h->d_rew = nullptr; h->d_done = h->d_reason = nullptr;
     h->h_act = nullptr; h->h_obs = h->h_rew = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
     cudaError_t e = cudaSetDevice(device);
@@ -307,10 +316,43 @@ int bskenv_destroy(bskenv_handle *h)
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
     cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched);
+    cudaFree(h->d_eph[0]); cudaFree(h->d_eph[1]);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_reason);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done); cudaFreeHost(h->h_reason);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+    return BSKENV_OK;
+}
+
+int bskenv_set_gravity_degree2(bskenv_handle *h, int enable, const double *cbar)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!enable) { h->P.grav_pfix = 0; return BSKENV_OK; }
+    if (h->P.mixed) { h->err = "bskenv_set_gravity_degree2: not built for precision = 1"; return BSKENV_EINVAL; }
+    leo_host::set_degree2(h->P, cbar);
+    return BSKENV_OK;
+}
+
+int bskenv_set_ephemeris(bskenv_handle *h, int kind, double t0, double seg_len, int n_seg, int n_coef, const double *coef)
+{
+    if (!h || kind < 0 || kind > 1) return BSKENV_EINVAL;
+    CU_TRY(h, cudaSetDevice(h->device));
+    CU_TRY(h, cudaDeviceSynchronize());                         // a launch in flight may still read the old table
+    LeoEph &E = kind == 0 ? h->P.eph_sun : h->P.eph_orient;
+    cudaFree(h->d_eph[kind]); h->d_eph[kind] = nullptr;
+    E.coef = nullptr; E.nseg = 0; E.ncoef = 0; E.t0 = 0.; E.seg_len = 0.;
+    if (n_seg <= 0) return BSKENV_OK;                           // back to the analytic model
+    if (!coef || n_coef < 1 || n_coef > 64 || !(seg_len > 0.)) { h->err = "bskenv_set_ephemeris: bad table shape"; return BSKENV_EINVAL; }
+    // an episode runs from sim time 0 to (max_length + 1) decision intervals: the table has to cover it
+    const double t_end = (double)(h->P.max_length + 1) * (double)h->P.step_ns * 1e-9;
+    if (t0 > 0. || t0 + seg_len * n_seg < t_end) {
+        h->err = "bskenv_set_ephemeris: the table does not cover one episode [0, (max_length + 1) * step_duration]";
+        return BSKENV_EINVAL;
+    }
+    const size_t bytes = sizeof(double) * (size_t)n_seg * 3 * (size_t)n_coef;
+    CU_TRY(h, cudaMalloc(&h->d_eph[kind], bytes));
+    CU_TRY(h, cudaMemcpy(h->d_eph[kind], coef, bytes, cudaMemcpyHostToDevice));
+    E.coef = h->d_eph[kind]; E.nseg = n_seg; E.ncoef = n_coef; E.t0 = t0; E.seg_len = seg_len;
     return BSKENV_OK;
 }
 

@@ -202,6 +202,29 @@ struct SunLatch {
     double inv_hp;      // 1/|s_HP|
     double c1off, c2off, tan1, tan2;   // R_p/sin f_1, R_p/sin f_2, tan f_1, tan f_2
 };
+// Chebyshev table look-up (layout of SPK type 2 / binary PCK type 2 records): value by Clenshaw's
+// recurrence on the T_k series, rate as the derivative of the same polynomial (Clenshaw on sum (k+1) a_{k+1} U_k).
+// Times outside the table use its first / last segment (bskenv_set_ephemeris checks that an episode is covered).
+LEO_HD_NOINLINE void cheb_eval(const LeoEph &E, double t, V3 &val, V3 &rate)
+{
+    int i = (int)floor((t - E.t0) / E.seg_len);
+    i = i < 0 ? 0 : (i >= E.nseg ? E.nseg - 1 : i);
+    const double half = 0.5 * E.seg_len, sc = (t - (E.t0 + (i + 0.5) * E.seg_len)) / half, s2 = 2. * sc;
+    double v[3], d[3];
+    for (int c = 0; c < 3; c++) {
+        const double *a = E.coef + ((int64_t)i * 3 + c) * E.ncoef;
+        double b1 = 0., b2 = 0., d1 = 0., d2 = 0.;
+        for (int k = E.ncoef - 1; k >= 1; k--) {
+            const double ak = a[k];
+            const double b0 = ak + s2 * b1 - b2, d0 = (double)k * ak + s2 * d1 - d2;
+            b2 = b1; b1 = b0; d2 = d1; d1 = d0;
+        }
+        v[c] = a[0] + sc * b1 - b2;
+        d[c] = d1 / half;
+    }
+    val = mk(v[0], v[1], v[2]); rate = mk(d[0], d[1], d[2]);
+}
+
 LEO_HD_NOINLINE SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
 {
     const double D2R = 3.14159265358979323846 / 180.0;
@@ -223,6 +246,7 @@ LEO_HD_NOINLINE SunLatch sun_latch(const LeoParams &P, int64_t msg_ns)
     SunLatch s;
     s.r = u * R;
     s.v = u * Rd + ud * R;
+    if (P.eph_sun.nseg > 0) cheb_eval(P.eph_sun, t, s.r, s.v);      // ephemeris table instead of the analytic Sun
     s.hp2 = dot(s.r, s.r);
     double hp = sqrt(s.hp2);
     s.inv_hp = 1. / hp;
@@ -670,7 +694,11 @@ enum LeoMField : int {
     M_TNEXT = 53,    // earliest expiry of a burning thruster
     M_CHARGE = 54,        // storedCharge
     M_SHADOW = 55,   // shadowFactor of the last environment tick
-    LEO_NM = 56
+    LEO_NM = 56,
+    // only allocated by the planet-fixed gravity variant (J2 == 2):
+    M_PFIX = 56,     // J20002Pfix of the last SPICE message (9, row-major)
+    M_PFIXD = 65,    // J20002Pfix_dot (9)
+    LEO_NM_PFIX = 74
 };
 #define LEO_M_MIRROR 28          // number of leading bus fields that mirror state fields starting at F_GUID
 struct MBus {
@@ -704,6 +732,36 @@ LEO_HD_NOINLINE void sun_latch_to_bus(const LeoParams &P, MBus m, int64_t msg_ns
     mst3(m, M_SUNR, s.r); mst3(m, M_SUNV, s.v);
     mst(m, M_ECL, s.hp2); mst(m, M_ECL + 1, s.inv_hp); mst(m, M_ECL + 2, s.c1off);
     mst(m, M_ECL + 3, s.c2off); mst(m, M_ECL + 4, s.tan1); mst(m, M_ECL + 5, s.tan2);
+}
+
+// Earth orientation at a SPICE message time (spice_interface with computeOrient): J2000 -> planet-fixed
+// DCM P = R3(W) R1(pi/2 - DEC) R3(pi/2 + RA) and its time derivative (pxform_c / sxform_c).  Angles from the
+// orientation table when one is loaded, else the IAU rotation model of the SPICE text kernel pck00010.tpc
+// (BODY399_POLE_RA = 0 - 0.641 T, POLE_DEC = 90 - 0.557 T, PM = 190.147 + 360.9856235 d).
+LEO_HD_NOINLINE void pfix_latch_to_bus(const LeoParams &P, MBus m, int64_t msg_ns)
+{
+    const double D2R = 3.14159265358979323846 / 180.0, HPI = 0.5 * 3.14159265358979323846;
+    const double t = ns2sec(msg_ns);
+    V3 ang, rate;
+    if (P.eph_orient.nseg > 0) {
+        cheb_eval(P.eph_orient, t, ang, rate);
+    } else {
+        const double d = P.epoch_days + t / 86400.0, T = d / 36525.0;
+        ang = mk((0.0 - 0.641 * T) * D2R, (90.0 - 0.557 * T) * D2R, (190.147 + 360.9856235 * d) * D2R);
+        rate = mk(-0.641 / 36525.0 / 86400.0 * D2R, -0.557 / 36525.0 / 86400.0 * D2R, 360.9856235 / 86400.0 * D2R);
+    }
+    const double th = HPI - ang.y, ph = HPI + ang.x, thd = -rate.y, phd = rate.x, Wd = rate.z;
+    const double cw = cos(ang.z), sw = sin(ang.z), ct = cos(th), st = sin(th), cp = cos(ph), sp = sin(ph);
+    // A = R1(th) R3(ph) and its derivative
+    const V3 A0 = mk(cp, sp, 0.), A1 = mk(-ct * sp, ct * cp, st), A2 = mk(st * sp, -st * cp, ct);
+    const V3 dA0 = mk(-sp * phd, cp * phd, 0.);
+    const V3 dA1 = mk(st * sp * thd - ct * cp * phd, -st * cp * thd - ct * sp * phd, ct * thd);
+    const V3 dA2 = mk(ct * sp * thd + st * cp * phd, -ct * cp * thd + st * sp * phd, -st * thd);
+    const V3 P0 = A0 * cw + A1 * sw, P1 = A1 * cw - A0 * sw;
+    mst3(m, M_PFIX, P0); mst3(m, M_PFIX + 3, P1); mst3(m, M_PFIX + 6, A2);
+    mst3(m, M_PFIXD, P1 * Wd + dA0 * cw + dA1 * sw);
+    mst3(m, M_PFIXD + 3, dA1 * cw - dA0 * sw - P0 * Wd);
+    mst3(m, M_PFIXD + 6, dA2);
 }
 
 // One flight-software pass at time now_ns (the priority 100/50 tasks run before DynTask at equal times).
@@ -792,13 +850,14 @@ struct StageIn {
     V3 gsun;                       // Sun third-body acceleration
     V3 HB, tau_u;                  // wheel momentum invariant at the start of the step and motor torque sum_i g_i u_i (see Dyn)
     double rho, h;
+    double dtp;                    // planet-fixed gravity only: time since the SPICE message that carries the orientation
 };
 
 // One evaluation of SpacecraftPlus::equationsOfMotion for the scenario's effector set at stage time t0 + ct.
 //   DIAG   fast path of the reference configuration: diagonal hub inertia, three wheels along the body axes
 //          (AP:20-37) and drag facets located on their own normal axis (SIM:274-281) -- the same arithmetic
 //          with the structural zeros dropped
-template <bool J2, bool DIAG>
+template <int J2, bool DIAG>
 LEO_HD void eom(const LeoParams &P, const Dyn &x, Dyn &k, const StageIn &a, double ct, bool thr_on, MBus m)
 {
     // gravity: central point mass (+J2) + Sun third body (gravityEffector)
@@ -807,7 +866,22 @@ LEO_HD void eom(const LeoParams &P, const Dyn &x, Dyn &k, const StageIn &a, doub
         double ir = rsq(dot(x.r, x.r));
         double ir3 = ir * ir * ir;
         g = a.gsun + x.r * (-P.mu_c * ir3);
-        if (J2) {
+        if (J2 == 2) {
+            // degree-2 field in the planet-fixed frame (GravBodyData::computeGravityInertial with spherical harmonics):
+            // dcm_PfixN = J20002Pfix + J20002Pfix_dot dt, g_N += dcm^T grad U_2(dcm r), with the closed-form gradient of
+            // U_2 = (r^T M r) / |r|^5:  grad U_2 = 2 M r / |r|^5 - 5 (r^T M r) r / |r|^7   (gm2 = mu Req^2 M)
+            const V3 D0 = mld3(m, M_PFIX) + mld3(m, M_PFIXD) * a.dtp;
+            const V3 D1 = mld3(m, M_PFIX + 3) + mld3(m, M_PFIXD + 3) * a.dtp;
+            const V3 D2 = mld3(m, M_PFIX + 6) + mld3(m, M_PFIXD + 6) * a.dtp;
+            const V3 rp = mk(dot(D0, x.r), dot(D1, x.r), dot(D2, x.r));
+            const double ip = rsq(dot(rp, rp)), ip2 = ip * ip, ip5 = ip2 * ip2 * ip;
+            const V3 Mr = mk(P.gm2[0] * rp.x + P.gm2[3] * rp.y + P.gm2[4] * rp.z,
+                             P.gm2[3] * rp.x + P.gm2[1] * rp.y + P.gm2[5] * rp.z,
+                             P.gm2[4] * rp.x + P.gm2[5] * rp.y + P.gm2[2] * rp.z);
+            const double q5 = -5. * dot(rp, Mr) * ip5 * ip2;
+            const V3 gp = Mr * (2. * ip5) + rp * q5;
+            g = g + D0 * gp.x + D1 * gp.y + D2 * gp.z;
+        } else if (J2) {
             double ir2 = ir * ir, z2 = 5. * x.r.z * x.r.z * ir2, kk = -P.j2k * ir3 * ir2;
             g = g + mk(kk * x.r.x * (1. - z2), kk * x.r.y * (1. - z2), kk * x.r.z * (3. - z2));
         }
@@ -864,7 +938,7 @@ LEO_HD void eom(const LeoParams &P, const Dyn &x, Dyn &k, const StageIn &a, doub
 // within 0.4 km of that point and the deviations of the first and last stage cancel in the RK4 weights -- the
 // net effect is < 1e-10 m of position per decision interval (1e-17 relative); the thrust is constant over the
 // step.  Steps in which a thruster may switch, and the step whose Sun clock wraps, go through rk4_general().
-template <bool J2, bool DIAG>
+template <int J2, bool DIAG>
 LEO_HD Dyn rk4_step(const LeoParams &P, const Dyn &x, const StageIn &a, bool thr_on, MBus m)
 {
     const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
@@ -893,7 +967,7 @@ LEO_HD Dyn rk4_step(const LeoParams &P, const Dyn &x, const StageIn &a, bool thr
 // accumulation order.
 struct SunDt { double d0, dm, d1; };
 struct ThrEventOut { Dyn x; int factor, active; };
-template <bool J2, bool DIAG>
+template <int J2, bool DIAG>
 LEO_HD_NOINLINE ThrEventOut rk4_general(const LeoParams &P, const double *S, int64_t stride, int64_t e, MBus m, Dyn x,
                                         StageIn a, SunDt dts, double tBefore, double tauPrev, int thr_factor, int thr_active)
 {
@@ -905,6 +979,7 @@ LEO_HD_NOINLINE ThrEventOut rk4_general(const LeoParams &P, const double *S, int
         const double dt = (st == 0) ? dts.d0 : (st == 3 ? dts.d1 : dts.dm);
         const double ct = (st == 0) ? 0.0 : (st == 3 ? h : hh);
         a.gsun = sun_accel(P, sun_r + sun_v * dt, xs.r);
+        a.dtp = dt;
         V3 Fm = mk(0., 0., 0.), Lx = L_ext;
         const bool thr_on = thr_active != 0;
         if (thr_on) {
@@ -1047,7 +1122,7 @@ LEO_HD double exp_bounded(double x)
 namespace leo {
 
 // F32 = false: the FP64 kernel (the reference's arithmetic; every parity claim).  F32 = true: mixed precision, see leo_f32.cuh.
-template <int NRW, bool J2, bool DIAG, bool F32 = false>
+template <int NRW, int J2, bool DIAG, bool F32 = false>
 LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
                          MBus m, int action, StepOut &out, const LeoParamsF &PF = LeoParamsF())
 {
@@ -1106,6 +1181,8 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     const double dyn_d = (double)P.dyn_ns;
     double sun_d = (double)((n_base - 1) * P.dyn_ns);          // write time of the Sun message in force
     sun_latch_to_bus(P, m, (n_base - 1) * P.dyn_ns);
+    if (J2 == 2) pfix_latch_to_bus(P, m, (n_base - 1) * P.dyn_ns);
+    a.dtp = 0.;
     // FP32 shadows of the Sun latch and its eclipse constants (mixed-precision variant only)
     V3f sunr_f = mkf(0.f, 0.f, 0.f), sunv_f = mkf(0.f, 0.f, 0.f);
     float ecf[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -1133,6 +1210,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             // message is then newer than the start of this integration step (quirk Q18)
             if (n > 0 && n == n_end) {
                 sun_d = now_d; sun_latch_to_bus(P, m, n * P.dyn_ns); wrapped = true;
+                if (J2 == 2) pfix_latch_to_bus(P, m, n * P.dyn_ns);
                 if (F32) {
                     sunr_f = tof(mld3(m, M_SUNR)); sunv_f = tof(mld3(m, M_SUNV));
 #pragma unroll
@@ -1172,9 +1250,10 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
                 af.Lc = tof(a.Lc); af.HB = tof(a.HB); af.tau_u = tof(a.tau_u);
                 af.gsun = sun_accelf(PF, sunr_f + sunv_f * (float)dtsm, tof(x.r) + tof(x.v) * (0.5f * af.h));
                 const bool thr_on = thr_active != 0;
-                x = rk4_step_mixed<J2, DIAG>(PF, x, af, thr_on, thr_on ? tof(mld3(m, M_FM)) : mkf(0.f, 0.f, 0.f));
+                x = rk4_step_mixed<(J2 != 0), DIAG>(PF, x, af, thr_on, thr_on ? tof(mld3(m, M_FM)) : mkf(0.f, 0.f, 0.f));
             } else {
                 a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+                if (J2 == 2) a.dtp = dtsm;     // orientation held at the step's mid time, like the Sun
                 x = rk4_step<J2, DIAG>(P, x, a, thr_active != 0, m);
             }
         }

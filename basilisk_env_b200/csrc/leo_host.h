@@ -175,6 +175,21 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
     return "";
 }
 
+// normalised degree-2 coefficients (C20, C21, S21, C22, S22; the form gravity-model files carry and
+// Basilisk's loadGravFromFile reads) -> mu Req^2 [M] of the closed-form gradient used by the kernel.
+// Un-normalisation: C_nm = Cbar_nm sqrt((2 - delta_0m)(2n + 1)(n - m)!/(n + m)!).
+static inline void set_degree2(LeoParams &p, const double cbar[5])
+{
+    static const double ggm03s[5] = {-4.8416537173459064e-04, -2.0661550900e-10, 1.3844138138e-09, 2.4393836573e-06, -1.4002737040e-06};
+    if (!cbar) cbar = ggm03s;
+    const double C20 = cbar[0] * sqrt(5.0), C21 = cbar[1] * sqrt(5.0 / 3.0), S21 = cbar[2] * sqrt(5.0 / 3.0);
+    const double C22 = cbar[3] * sqrt(5.0 / 12.0), S22 = cbar[4] * sqrt(5.0 / 12.0);
+    const double k = p.mu_c * (6378136.6 * 6378136.6);
+    p.gm2[0] = k * (-0.5 * C20 + 3.0 * C22); p.gm2[1] = k * (-0.5 * C20 - 3.0 * C22); p.gm2[2] = k * C20;
+    p.gm2[3] = k * 3.0 * S22; p.gm2[4] = k * 1.5 * C21; p.gm2[5] = k * 1.5 * S21;
+    p.grav_pfix = 1;
+}
+
 static inline void build_params_f(const LeoParams &p, LeoParamsF &f)
 {
     memset(&f, 0, sizeof(f));
@@ -205,7 +220,8 @@ static inline double flops_per_step(const LeoParams &p)
     const double F_rk4 = 204.0, F_tick = 236.0;
     double F_fsw = 360.0;
     if (!p.diag) F_eom += 36.0 + 8.0 * (p.nrw - 3);        // full 3x3 D / Dinv / drag moment arms, wheel invariants
-    if (p.use_j2) F_eom += 14.0;
+    if (p.grav_pfix) F_eom += 92.0;      // DCM Euler step 18, r_Pfix 15, |r|^-5/-7 9, M r + quadratic form 29, g_Pfix 9, back-rotation 15 (- point-mass share 3)
+    else if (p.use_j2) F_eom += 14.0;
     if (p.nrw == 4) F_fsw += 5.0;
     double ticks = (double)p.ticks_per_fsw * p.fsw_per_step;
     return ticks * (4 * F_eom + F_rk4 + F_tick) + p.fsw_per_step * F_fsw;

@@ -15,6 +15,11 @@
 #define LEO_BLOCK 128          // threads per block of the step kernel = stride of the shared-memory message bus
 #endif
 
+// Chebyshev ephemeris table in the layout of SPICE SPK type 2 / binary PCK type 2 records: nseg segments
+// of equal length from t0 [s of sim time], three components x ncoef coefficients each, coef[nseg][3][ncoef] in device
+// memory (every thread of a warp reads the same address: one broadcast transaction).  nseg = 0: no table.
+struct LeoEph { const double *coef; double t0, seg_len; int32_t nseg, ncoef; };
+
 struct LeoParams {
     // ---- task rates as integer nanoseconds (Basilisk sec2nano) and derived loop counts ----
     int64_t dyn_ns, fsw_ns, step_ns;
@@ -28,6 +33,12 @@ struct LeoParams {
     double mu_c, mu_sun;
     double j2k;           // 1.5 * J2 * mu * Req^2 (only when the J2 template flag is on)
     int32_t use_j2, hill_cel_pun;
+    // degree-2 field in the planet-fixed frame (bskenv_set_gravity_degree2).  gm2 = mu Req^2 [M] with
+    // U_2 = mu Req^2 (r^T M r) / |r|^5 for the un-normalised C20, C21, S21, C22, S22: xx, yy, zz, xy, xz, yz
+    int32_t grav_pfix, pad3;
+    double gm2[6];
+    LeoEph eph_sun;       // Sun position relative to Earth [m] (replaces the analytic Sun, deviation D1)
+    LeoEph eph_orient;    // Earth orientation angles RA, DEC, W [rad] (replaces the IAU rotation model)
     int32_t mixed, pad2;   // 1: FP32 stage arithmetic with FP64 accumulation (leo_f32.cuh); stress-config trade-off only
     int32_t diag, pad1;    // 1: diagonal hub inertia, three wheels along the body axes, drag facets on their normal axis
                            //    (the reference set-up): fast EOM path

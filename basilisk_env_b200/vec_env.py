@@ -107,6 +107,30 @@ class LeoPowerAttVecEnv:
         return m, C.c_void_p(m.data_ptr())
 
     # ------------------------------------------------------------------------------------------
+    # ---- ephemeris tables and the planet-fixed degree-2 field (set before reset) ----
+    def set_ephemeris(self, kind, table):
+        """Load a Chebyshev ephemeris table (`basilisk_env_b200.ephemeris.ChebTable`, or None to go back to the analytic
+        model).  kind: "sun" (Sun position relative to Earth [m]) or "orientation" (Earth RA, DEC, W [rad])."""
+        k = {"sun": 0, "orientation": 1}[kind]
+        if table is None:
+            self._check(self._L.bskenv_set_ephemeris(self._h, k, 0.0, 0.0, 0, 0, None), "set_ephemeris")
+            return
+        coef = np.ascontiguousarray(table.coef, dtype=np.float64)
+        nseg, three, ncoef = coef.shape
+        assert three == 3
+        self._check(self._L.bskenv_set_ephemeris(self._h, k, float(table.t0), float(table.seg_len), nseg, ncoef,
+                                                 coef.ctypes.data), "set_ephemeris")
+
+    def set_gravity_degree2(self, enable=True, cbar=None):
+        """Earth's degree-2 field (normalised C20, C21, S21, C22, S22; None = built-in GGM03S-class values) evaluated in
+        the planet-fixed frame with the orientation Euler-stepped from the last SPICE message."""
+        ptr = None
+        if cbar is not None:
+            cbar = np.ascontiguousarray(cbar, dtype=np.float64)
+            assert cbar.shape == (5,)
+            ptr = cbar.ctypes.data
+        self._check(self._L.bskenv_set_gravity_degree2(self._h, int(bool(enable)), ptr), "set_gravity_degree2")
+
     def reset(self, seed=None, mask=None):
         """Sample fresh initial conditions on the device and return the initial observation [N,5]."""
         if seed is not None:

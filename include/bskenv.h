@@ -95,6 +95,26 @@ int bskenv_destroy(bskenv_handle *h);
 const char *bskenv_last_error(const bskenv_handle *h); /* h may be NULL: last create() error */
 int64_t bskenv_num_envs(const bskenv_handle *h);
 
+/* SURVEY 8(f)-4 -- optional force-model / ephemeris upgrades of a handle (all off = the reference wiring; call before
+ * reset).  They close the gap to a SPICE-driven Basilisk run: the reference loads de430.bsp / pck00010.tpc through
+ * Basilisk's spice_interface (simulators/leoPowerAttitudeSimulator.py:219-225); here the same data arrive as tables.
+ *
+ * bskenv_set_ephemeris: Chebyshev table in the layout of SPICE SPK type 2 / binary PCK type 2 records, host memory,
+ * coef[n_seg][3][n_coef]; segment i covers sim time [t0 + i*seg_len, t0 + (i+1)*seg_len] seconds (sim time 0 = the
+ * scenario epoch '2021 MAY 04 07:47:48.965 (UTC)', :219); value = sum_k a_k T_k(s), rate = its derivative.
+ *   kind BSKENV_EPH_SUN    Sun position relative to Earth, J2000 axes [m]: replaces the analytic Sun (DESIGN D1)
+ *   kind BSKENV_EPH_ORIENT Earth orientation angles RA, DEC, W [rad]: replaces the IAU rotation model
+ * n_seg = 0 unloads the table.  The table must cover one episode, [0, (max_length + 1) * step_duration].
+ *
+ * bskenv_set_gravity_degree2: Earth's degree-2 field C20, C21, S21, C22, S22 (normalised, as gravity-model files
+ * carry them; NULL = GGM03S-class defaults) evaluated in the planet-fixed frame, whose orientation comes with the
+ * SPICE message every step_duration and is Euler-stepped in between (Basilisk GravBodyData::computeGravityInertial).
+ * Overrides use_j2 (which keeps the zonal term on the inertial z axis). */
+#define BSKENV_EPH_SUN 0
+#define BSKENV_EPH_ORIENT 1
+int bskenv_set_ephemeris(bskenv_handle *h, int kind, double t0, double seg_len, int n_seg, int n_coef, const double *coef);
+int bskenv_set_gravity_degree2(bskenv_handle *h, int enable, const double *cbar /* [5] or NULL */);
+
 /* reset(): sample fresh initial conditions on the device (distributions and clipping of
  * initial_conditions/leo_orbit.py:25-39, sc_attitudes.py:3-13, simulators/...Simulator.py:152-167).
  * `mask_dev` (uint8[n], may be NULL = all) selects the envs to reset.  `obs_dev` (double[n*5], may be

@@ -290,7 +290,8 @@ static void msg_stamp(MsgHdr *h, uint64_t now) { h->write_ns = now; h->count++; 
 static int msg_written(const MsgHdr *h) { return h->count > 0; } /* ReadMessage returns false if never written */
 
 typedef struct { MsgHdr h; double r_BN_N[3], v_BN_N[3], sigma_BN[3], omega_BN_B[3]; } SCPlusStatesMsg;
-typedef struct { MsgHdr h; double J2000Current, PositionVector[3], VelocityVector[3]; } SpicePlanetStateMsg;
+typedef struct { MsgHdr h; double J2000Current, PositionVector[3], VelocityVector[3];
+                 double J20002Pfix[3][3], J20002Pfix_dot[3][3]; int computeOrient; } SpicePlanetStateMsg;
 typedef struct { MsgHdr h; double neutralDensity; } AtmoPropsMsg;
 typedef struct { MsgHdr h; double sigma_BN[3], omega_BN_B[3], vehSunPntBdy[3]; } NavAttMsg;
 typedef struct { MsgHdr h; double r_BN_N[3], v_BN_N[3]; } NavTransMsg;
@@ -471,13 +472,161 @@ static void log_all_messages(orc_leo_sim *s)
     }
 }
 
+/* ================================ SURVEY 8(f)-4: ephemeris tables, planet-fixed degree-2 field ======
+ * (a) Chebyshev ephemeris tables in the layout of SPICE SPK type 2 / binary PCK type 2 records: n_seg
+ *     segments of equal length, three components with n_coef Chebyshev coefficients each; the value is
+ *     sum a_k T_k(s), s = (t - mid) / (len/2), the rate is the derivative of the same polynomial (what
+ *     spkezr / sxform return for these record types).  Test infrastructure: the tables are process-global.
+ *     kind 0: Sun position relative to Earth [m]; kind 1: Earth orientation angles (RA, DEC, W) [rad].
+ * (b) Earth orientation without a table: IAU rotation model as in the SPICE text kernel pck00010.tpc
+ *     (BODY399_POLE_RA = 0 - 0.641 T, POLE_DEC = 90 - 0.557 T, PM = 190.147 + 360.9856235 d), J2000 -> IAU_EARTH
+ *     = R3(W) R1(pi/2 - DEC) R3(pi/2 + RA) (pxform_c), rate from the product rule (sxform_c).
+ * (c) [BSK: gravityEffector.cpp GravBodyData::computeGravityInertial + sphericalHarmonics::computeField]:
+ *     dcm_PfixN = J20002Pfix + J20002Pfix_dot * dt (dt since the SPICE message was written), Pines' recursion with
+ *     normalised coefficients in the planet-fixed frame, rotated back with the transpose.  Restated here for
+ *     max degree 2; confidence M (recalled).  Pinned by tests/test_oracle_physics.py against the closed-form
+ *     gradient of the degree-2 potential. */
+typedef struct { int nseg, ncoef; double t0, seg_len; double *coef; } EphTable;
+static EphTable g_eph[2];
+static double g_cbar[5] = {-4.8416537173459064e-04, -2.0661550900e-10, 1.3844138138e-09, 2.4393836573e-06, -1.4002737040e-06};
+                           /* C20 = -J2_EARTH / sqrt 5 (the J2 of use_j2); C21, S21, C22, S22: GGM03S-class values, confidence L;
+                              orc_set_gravity_coeffs replaces them */
+int orc_set_ephemeris(int kind, double t0, double seg_len, int nseg, int ncoef, const double *coef)
+{
+    if (kind < 0 || kind > 1) return -1;
+    free(g_eph[kind].coef); memset(&g_eph[kind], 0, sizeof(EphTable));
+    if (nseg <= 0) return 0;
+    if (ncoef < 1 || !(seg_len > 0) || !coef) return -1;
+    g_eph[kind].coef = (double *)malloc(sizeof(double) * (size_t)nseg * 3 * (size_t)ncoef);
+    memcpy(g_eph[kind].coef, coef, sizeof(double) * (size_t)nseg * 3 * (size_t)ncoef);
+    g_eph[kind].nseg = nseg; g_eph[kind].ncoef = ncoef; g_eph[kind].t0 = t0; g_eph[kind].seg_len = seg_len;
+    return 0;
+}
+void orc_set_gravity_coeffs(const double cbar[5]) { for (int k = 0; k < 5; k++) g_cbar[k] = cbar[k]; }
+int orc_eph_eval(int kind, double t, double val[3], double rate[3])
+{ /* forward recurrences T_{k+1} = 2 s T_k - T_{k-1}, U_{k+1} = 2 s U_k - U_{k-1}, T_k' = k U_{k-1} */
+    const EphTable *E = &g_eph[kind];
+    if (E->nseg <= 0) return -1;
+    int i = (int)floor((t - E->t0) / E->seg_len);
+    if (i < 0) i = 0;
+    if (i >= E->nseg) i = E->nseg - 1;
+    double half = 0.5 * E->seg_len, mid = E->t0 + (i + 0.5) * E->seg_len, sc = (t - mid) / half;
+    for (int c = 0; c < 3; c++) {
+        const double *a = E->coef + ((size_t)i * 3 + c) * E->ncoef;
+        double Tm = 1.0, T = sc, Um = 0.0, U = 1.0;     /* T_0, T_1, U_{-1}, U_0 */
+        double v = a[0], d = 0.0;
+        for (int k = 1; k < E->ncoef; k++) {
+            v += a[k] * T; d += a[k] * k * U;
+            double Tn = 2.0 * sc * T - Tm, Un = 2.0 * sc * U - Um;
+            Tm = T; T = Tn; Um = U; U = Un;
+        }
+        val[c] = v; rate[c] = d / half;
+    }
+    return 0;
+}
+static void rot1(double a, double R[3][3]) { double c = cos(a), s = sin(a); double M[3][3] = {{1, 0, 0}, {0, c, s}, {0, -s, c}}; memcpy(R, M, sizeof(M)); }
+static void rot3(double a, double R[3][3]) { double c = cos(a), s = sin(a); double M[3][3] = {{c, s, 0}, {-s, c, 0}, {0, 0, 1}}; memcpy(R, M, sizeof(M)); }
+static void drot1(double a, double R[3][3]) { double c = cos(a), s = sin(a); double M[3][3] = {{0, 0, 0}, {0, -s, c}, {0, -c, -s}}; memcpy(R, M, sizeof(M)); }
+static void drot3(double a, double R[3][3]) { double c = cos(a), s = sin(a); double M[3][3] = {{-s, c, 0}, {-c, -s, 0}, {0, 0, 0}}; memcpy(R, M, sizeof(M)); }
+static void mm3(double A[3][3], double B[3][3], double C[3][3])
+{
+    double T[3][3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) { T[i][j] = 0; for (int k = 0; k < 3; k++) T[i][j] += A[i][k] * B[k][j]; }
+    memcpy(C, T, sizeof(T));
+}
+void orc_earth_orientation(double t, double P[3][3], double Pdot[3][3])
+{
+    double ang[3], rate[3];
+    if (orc_eph_eval(1, t, ang, rate) != 0) {
+        const double D2R = PI_D / 180.0;
+        double d = EPOCH_DAYS_TT_FROM_J2000 + t / 86400.0, T = d / 36525.0;
+        ang[0] = (0.0 - 0.641 * T) * D2R; ang[1] = (90.0 - 0.557 * T) * D2R; ang[2] = (190.147 + 360.9856235 * d) * D2R;
+        rate[0] = -0.641 / 36525.0 / 86400.0 * D2R; rate[1] = -0.557 / 36525.0 / 86400.0 * D2R; rate[2] = 360.9856235 / 86400.0 * D2R;
+    }
+    double W[3][3], A[3][3], F[3][3], dW[3][3], dA[3][3], dF[3][3], T1[3][3], T2[3][3], T3[3][3];
+    double th = 0.5 * PI_D - ang[1], ph = 0.5 * PI_D + ang[0];
+    rot3(ang[2], W); rot1(th, A); rot3(ph, F);
+    drot3(ang[2], dW); drot1(th, dA); drot3(ph, dF);
+    mm3(A, F, T1); mm3(W, T1, P);
+    mm3(A, F, T1); mm3(dW, T1, T1);              /* W' A F * Wdot */
+    mm3(dA, F, T2); mm3(W, T2, T2);              /* W A' F * thdot, thdot = -DECdot */
+    mm3(A, dF, T3); mm3(W, T3, T3);              /* W A F' * phdot, phdot = RAdot */
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)
+        Pdot[i][j] = rate[2] * T1[i][j] - rate[1] * T2[i][j] + rate[0] * T3[i][j];
+}
+static double sh_getK(int m) { return m == 0 ? 1.0 : 2.0; }
+void orc_grav_degree2_pfix(double mu, double radEquator, const double cbar[5], const double pos[3], double acc[3])
+{ /* sphericalHarmonics::computeField(pos_Pfix, degree = 2, include_zero_degree = false), Pines' formulation */
+    enum { N = 2 };
+    double cB[N + 2][N + 2] = {{0}}, sB[N + 2][N + 2] = {{0}}, aBar[N + 3][N + 3] = {{0}};
+    double n1[N + 3][N + 3] = {{0}}, n2[N + 3][N + 3] = {{0}}, nq1[N + 3][N + 3] = {{0}}, nq2[N + 3][N + 3] = {{0}};
+    cB[0][0] = 1.0; cB[2][0] = cbar[0]; cB[2][1] = cbar[1]; sB[2][1] = cbar[2]; cB[2][2] = cbar[3]; sB[2][2] = cbar[4];
+    /* initializeParameters */
+    for (int l = 0; l <= N + 1; l++) {
+        if (l == 0) aBar[l][l] = 1.0;
+        else aBar[l][l] = sqrt((2.0 * l + 1.0) * sh_getK(l) / (2.0 * l * sh_getK(l - 1))) * aBar[l - 1][l - 1];
+        for (int m = 0; m <= l; m++) {
+            if (l >= m + 2) {
+                n1[l][m] = sqrt((2.0 * l + 1.0) * (2.0 * l - 1.0) / ((double)(l - m) * (l + m)));
+                n2[l][m] = sqrt((double)(l + m - 1) * (2.0 * l + 1.0) * (l - m - 1) / ((double)(l + m) * (l - m) * (2.0 * l - 3.0)));
+            }
+        }
+    }
+    for (int l = 0; l <= N; l++)
+        for (int m = 0; m <= l; m++) {
+            if (m < l) nq1[l][m] = sqrt((double)(l - m) * sh_getK(m) * (l + m + 1) / sh_getK(m + 1));
+            nq2[l][m] = sqrt((double)(l + m + 2) * (l + m + 1) * (2.0 * l + 1.0) * sh_getK(m) / ((2.0 * l + 3.0) * sh_getK(m + 1)));
+        }
+    /* computeField */
+    double x = pos[0], y = pos[1], z = pos[2];
+    double r = sqrt(x * x + y * y + z * z), sx = x / r, ty = y / r, u = z / r;
+    for (int l = 1; l <= N + 1; l++) aBar[l][l - 1] = sqrt((2.0 * l) * sh_getK(l - 1) / sh_getK(l)) * aBar[l][l] * u;
+    for (int m = 0; m <= N + 1; m++)
+        for (int l = m + 2; l <= N + 1; l++) aBar[l][m] = u * n1[l][m] * aBar[l - 1][m] - n2[l][m] * aBar[l - 2][m];
+    double rE[N + 2], iM[N + 2], rhol[N + 3];
+    rE[0] = 1.0; iM[0] = 0.0;
+    for (int m = 1; m <= N + 1; m++) { rE[m] = sx * rE[m - 1] - ty * iM[m - 1]; iM[m] = sx * iM[m - 1] + ty * rE[m - 1]; }
+    double rho = radEquator / r;
+    rhol[0] = mu / r; rhol[1] = rhol[0] * rho;
+    double a1 = 0, a2 = 0, a3 = 0, a4 = 0;
+    for (int l = 1; l <= N; l++) {       /* degree 1 carries zero coefficients */
+        rhol[l + 1] = rho * rhol[l];
+        double s1 = 0, s2 = 0, s3 = 0, s4 = 0;
+        for (int m = 0; m <= l; m++) {
+            double D = cB[l][m] * rE[m] + sB[l][m] * iM[m], E = 0, F = 0;
+            if (m > 0) { E = cB[l][m] * rE[m - 1] + sB[l][m] * iM[m - 1]; F = sB[l][m] * rE[m - 1] - cB[l][m] * iM[m - 1]; }
+            s1 += m * aBar[l][m] * E; s2 += m * aBar[l][m] * F;
+            if (m < l) s3 += nq1[l][m] * aBar[l][m + 1] * D;
+            s4 += nq2[l][m] * aBar[l + 1][m + 1] * D;
+        }
+        a1 += rhol[l + 1] / radEquator * s1; a2 += rhol[l + 1] / radEquator * s2;
+        a3 += rhol[l + 1] / radEquator * s3; a4 -= rhol[l + 1] / radEquator * s4;
+    }
+    acc[0] = a1 + sx * a4; acc[1] = a2 + ty * a4; acc[2] = a3 + u * a4;
+}
+static void grav_degree2_pfix(const SpicePlanetStateMsg *b, uint64_t systemClock, const double r_I[3], double out[3])
+{
+    double dt = (double)(systemClock - b->h.write_ns) * NANO2SEC;      /* unsigned clock difference, as the body position */
+    double D[3][3], rp[3], gp[3];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) D[i][j] = b->J20002Pfix[i][j] + b->J20002Pfix_dot[i][j] * dt;
+    for (int i = 0; i < 3; i++) rp[i] = D[i][0] * r_I[0] + D[i][1] * r_I[1] + D[i][2] * r_I[2];
+    orc_grav_degree2_pfix(MU_EARTH, REQ_EARTH_KM * 1000.0, g_cbar, rp, gp);
+    for (int j = 0; j < 3; j++) out[j] = D[0][j] * gp[0] + D[1][j] * gp[1] + D[2][j] * gp[2];
+}
+
 /* ================================ SPICE stand-in ([BSK: spice_interface.cpp]) =================== */
 static void spice_update(orc_leo_sim *s, uint64_t now)
 { /* zeroBase = "earth" (SIM:225): Earth at the origin, Sun relative to Earth */
     double et;
     if (s->scenario == 1) orc_sun_from_mars(now * NANO2SEC, s->sunMsg.PositionVector, s->sunMsg.VelocityVector, &et);
-    else
-    orc_sun_ephemeris(now * NANO2SEC, s->sunMsg.PositionVector, s->sunMsg.VelocityVector, &et);
+    else {
+        orc_sun_ephemeris(now * NANO2SEC, s->sunMsg.PositionVector, s->sunMsg.VelocityVector, &et);
+        orc_eph_eval(0, now * NANO2SEC, s->sunMsg.PositionVector, s->sunMsg.VelocityVector);   /* table, when one is loaded */
+        if (s->cfg.grav_pfix) {   /* computeOrient: pxform_c / sxform_c at the message time */
+            orc_earth_orientation(now * NANO2SEC, s->earthMsg.J20002Pfix, s->earthMsg.J20002Pfix_dot);
+            s->earthMsg.computeOrient = 1;
+        }
+    }
     s->sunMsg.J2000Current = et;
     s->earthMsg.J2000Current = et;
     v3SetZero(s->earthMsg.PositionVector); v3SetZero(s->earthMsg.VelocityVector);
@@ -535,7 +684,8 @@ static void gravity_compute(orc_leo_sim *s, const double r_cF_N[3])
     grav_body_position(&s->gravEarth, s->sysTimeNanos, r_PN_N);
     v3Subtract(r_cN_N, r_PN_N, r_cP_N);
     grav_point_mass(s->mu_central, r_cP_N, tmp);
-    if (s->cfg.use_j2) { double j[3]; grav_j2(r_cP_N, j); v3Add(tmp, j, tmp); }
+    if (s->cfg.grav_pfix) { double j[3]; grav_degree2_pfix(&s->gravEarth, s->sysTimeNanos, r_cP_N, j); v3Add(tmp, j, tmp); }
+    else if (s->cfg.use_j2) { double j[3]; grav_j2(r_cP_N, j); v3Add(tmp, j, tmp); }
     v3Add(acc, tmp, acc);
     v3Copy(acc, s->g_N);
 }

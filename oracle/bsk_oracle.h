@@ -40,7 +40,9 @@ typedef struct {
     int    rw_set;           /* 0: balancedHR16Triad (actuatorPrimatives.py:20-37); 1: the four-wheel HR16 pyramid of
                                 opNav_models/BSK_OpNavDynamics.py:269-293 (stress config); fourth wheel starts at the
                                 mean of the three sampled speeds */
-    int    reserved[5];
+    int    grav_pfix;        /* 1 = degree-2 field (C20, C21, S21, C22, S22) evaluated in the planet-fixed
+                                frame, orientation from the SPICE message Euler-stepped like the body positions */
+    int    reserved[4];
 } orc_leo_cfg;
 
 /* Everything a parity test wants to see at a decision boundary. */
@@ -97,6 +99,14 @@ int  orc_max_threads(void);
 void orc_elem2rv(double mu, double a, double e, double i, double Omega, double omega, double f,
                  double r[3], double v[3]);
 void orc_sun_ephemeris(double t_sim_sec, double r[3], double v[3], double *j2000_et);
+/* SURVEY 8(f)-4 (process-global test settings): Chebyshev ephemeris tables (kind 0: Sun position rel. Earth [m],
+ * kind 1: Earth orientation angles RA, DEC, W [rad]; coef[nseg][3][ncoef]; nseg = 0 unloads) and the normalised
+ * degree-2 coefficients C20, C21, S21, C22, S22. */
+int orc_set_ephemeris(int kind, double t0, double seg_len, int nseg, int ncoef, const double *coef);
+int orc_eph_eval(int kind, double t, double val[3], double rate[3]);
+void orc_set_gravity_coeffs(const double cbar[5]);
+void orc_earth_orientation(double t_sim_sec, double P[3][3], double Pdot[3][3]);
+void orc_grav_degree2_pfix(double mu, double radEquator, const double cbar[5], const double pos[3], double acc[3]);
 double orc_eclipse_shadow(const double r_sun[3], const double r_planet[3], const double r_sc[3], double planet_radius);
 void orc_MRP2C(const double q[3], double C[3][3]);
 void orc_C2MRP(double C[3][3], double q[3]);

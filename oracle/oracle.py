@@ -23,7 +23,8 @@ class LeoIC(C.Structure):
 
 class LeoCfg(C.Structure):
     _fields_ = [("dynRate", C.c_double), ("fswRate", C.c_double), ("step_duration", C.c_double),
-                ("use_j2", C.c_int), ("hill_cel_pun", C.c_int), ("rw_set", C.c_int), ("reserved", C.c_int * 5)]
+                ("use_j2", C.c_int), ("hill_cel_pun", C.c_int), ("rw_set", C.c_int), ("grav_pfix", C.c_int),
+                ("reserved", C.c_int * 4)]
 
 
 class LeoState(C.Structure):
@@ -73,6 +74,12 @@ def lib():
         L.orc_max_threads.restype = C.c_int
         L.orc_elem2rv.argtypes = [C.c_double] * 7 + [C.POINTER(C.c_double)] * 2
         L.orc_sun_ephemeris.argtypes = [C.c_double] + [C.POINTER(C.c_double)] * 3
+        dp = C.POINTER(C.c_double)
+        L.orc_set_ephemeris.argtypes = [C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, dp]
+        L.orc_eph_eval.argtypes = [C.c_int, C.c_double, dp, dp]
+        L.orc_set_gravity_coeffs.argtypes = [dp]
+        L.orc_earth_orientation.argtypes = [C.c_double, dp, dp]
+        L.orc_grav_degree2_pfix.argtypes = [C.c_double, C.c_double, dp, dp, dp]
         L.orc_eclipse_shadow.restype = C.c_double
         L.orc_eclipse_shadow.argtypes = [C.POINTER(C.c_double)] * 3 + [C.c_double]
         L.orc_MRP2C.argtypes = [C.POINTER(C.c_double)] * 2
@@ -239,6 +246,42 @@ class LeoEnvBatch:
         done = np.array([o.done for o in self._outs], dtype=bool)
         reason = np.array([o.reason for o in self._outs], dtype=np.int32)
         return ob, rew, done, reason
+
+
+# ---- ephemeris tables and planet-fixed degree-2 field (process-global settings of the oracle) ----
+GGM03S_CBAR = np.array([-4.8416537173459064e-04, -2.0661550900e-10, 1.3844138138e-09, 2.4393836573e-06, -1.4002737040e-06])
+
+
+def set_ephemeris(kind, table):
+    """kind 0: Sun position rel. Earth [m]; 1: Earth RA, DEC, W [rad].  table: object with t0, seg_len, coef[nseg,3,ncoef]; None unloads."""
+    if table is None:
+        assert lib().orc_set_ephemeris(kind, 0.0, 0.0, 0, 0, None) == 0
+        return
+    coef = np.ascontiguousarray(table.coef, dtype=np.float64)
+    assert lib().orc_set_ephemeris(kind, float(table.t0), float(table.seg_len), coef.shape[0], coef.shape[2], _p(coef)) == 0
+
+
+def eph_eval(kind, t):
+    v, r = np.zeros(3), np.zeros(3)
+    assert lib().orc_eph_eval(kind, float(t), _p(v), _p(r)) == 0
+    return v, r
+
+
+def set_gravity_coeffs(cbar=None):
+    c = np.ascontiguousarray(GGM03S_CBAR if cbar is None else cbar, dtype=np.float64)
+    lib().orc_set_gravity_coeffs(_p(c))
+
+
+def earth_orientation(t):
+    P, Pd = np.zeros((3, 3)), np.zeros((3, 3))
+    lib().orc_earth_orientation(float(t), _p(P), _p(Pd))
+    return P, Pd
+
+
+def grav_degree2_pfix(cbar, pos, mu=MU_EARTH, req=6378136.6):
+    c = np.ascontiguousarray(cbar, dtype=np.float64); r = np.ascontiguousarray(pos, dtype=np.float64); a = np.zeros(3)
+    lib().orc_grav_degree2_pfix(mu, req, _p(c), _p(r), _p(a))
+    return a
 
 
 def max_threads():

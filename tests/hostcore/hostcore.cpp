@@ -16,6 +16,7 @@ struct HC {
     std::vector<double> S, ics;
     std::vector<int64_t> I;
     int force_general = 0;
+    std::vector<double> eph[2];
 };
 
 extern "C" {
@@ -55,11 +56,16 @@ void hc_reset_seeded(HC *h, uint64_t seed, int64_t first_env, double *ics_out, d
 }
 void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t *done, uint8_t *reason)
 {
-    double bus[leo::LEO_NM];
+    double bus[leo::LEO_NM_PFIX];
     leo::MBus m; m.a = 0; m.p = bus;
     for (int64_t e = 0; e < h->n; e++) {
         leo::StepOut o;
         const bool diag = h->P.diag && !h->force_general;
+        if (h->P.grav_pfix) {  // planet-fixed degree-2 field
+            if (h->P.nrw == 4) leo::leo_step_env<4, 2, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            else if (diag) leo::leo_step_env<3, 2, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            else leo::leo_step_env<3, 2, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+        } else
         if (h->P.mixed) {      // mixed-precision variant (leo_f32.cuh): the two configurations the library builds
             if (h->P.nrw == 4) leo::leo_step_env<4, true, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF);
             else leo::leo_step_env<3, false, true, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF);
@@ -76,6 +82,18 @@ void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t
         for (int k = 0; k < 5; k++) obs[5 * e + k] = o.ob[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
     }
+}
+// the same two settings the C ABI offers (bskenv_set_ephemeris / bskenv_set_gravity_degree2)
+void hc_set_gravity_degree2(HC *h, int enable, const double *cbar)
+{
+    if (!enable) h->P.grav_pfix = 0; else leo_host::set_degree2(h->P, cbar);
+}
+void hc_set_ephemeris(HC *h, int kind, double t0, double seg_len, int nseg, int ncoef, const double *coef)
+{
+    LeoEph &E = kind == 0 ? h->P.eph_sun : h->P.eph_orient;
+    std::vector<double> &store = h->eph[kind];
+    store.assign(coef, coef + (size_t)(nseg > 0 ? nseg : 0) * 3 * ncoef);
+    E.coef = nseg > 0 ? store.data() : nullptr; E.nseg = nseg > 0 ? nseg : 0; E.ncoef = ncoef; E.t0 = t0; E.seg_len = seg_len;
 }
 void hc_get_state(HC *h, double *S, int64_t *I)
 {

@@ -41,6 +41,8 @@ def lib():
         L.hc_thr_force_mapping.argtypes = [vp, vp, vp]
         L.hc_force_general.argtypes = [vp, C.c_int]
         L.hc_eclipse.argtypes = [vp, C.c_int64, vp, C.c_int64, vp, vp]
+        L.hc_set_gravity_degree2.argtypes = [vp, C.c_int, vp]
+        L.hc_set_ephemeris.argtypes = [vp, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, vp]
         _LIB = L
     return _LIB
 
@@ -94,6 +96,17 @@ class HostCore:
         S = np.zeros((self.nd, self.n)); I = np.zeros((self.ni, self.n), np.int64)
         self.L.hc_get_state(self.h, S.ctypes.data, I.ctypes.data)
         return S, I
+
+    def set_gravity_degree2(self, enable=True, cbar=None):
+        c = None if cbar is None else np.ascontiguousarray(cbar, dtype=np.float64)
+        self.L.hc_set_gravity_degree2(self.h, int(enable), None if c is None else c.ctypes.data)
+
+    def set_ephemeris(self, kind, table):
+        if table is None:
+            self.L.hc_set_ephemeris(self.h, kind, 0.0, 1.0, 0, 1, None)
+            return
+        coef = np.ascontiguousarray(table.coef, dtype=np.float64)
+        self.L.hc_set_ephemeris(self.h, kind, float(table.t0), float(table.seg_len), coef.shape[0], coef.shape[2], coef.ctypes.data)
 
     def force_general(self, on=True):
         """Run the general (non-DIAG) EOM path even for the reference configuration."""

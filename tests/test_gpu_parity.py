@@ -344,3 +344,71 @@ def test_mixed_precision_variant_on_the_stress_config(bsk):
         e.close()
     with pytest.raises(Exception):
         _vec(bsk, 8, use_j2=1, precision=1)         # built for the reference and the stress configuration only
+
+
+def test_ephemeris_tables_and_degree2_field(bsk, orc):
+    """SURVEY 8(f)-4 through the C ABI: Sun and Earth-orientation Chebyshev tables (bskenv_set_ephemeris) and the
+    planet-fixed degree-2 field (bskenv_set_gravity_degree2) against the oracle (Pines recursion, forward Chebyshev
+    recurrences), reference wheel set and the four-wheel stress set, all three modes, full 180 s intervals."""
+    from basilisk_env_b200 import ephemeris as eph
+    from basilisk_env_b200.vec_env import BskEnvError
+    sun = eph.ChebTable.fit(lambda t: eph.analytic_sun(t + 40 * 86400.0) * 1.01, 0.0, 16 * 3600.0, 2, 9)
+    orient = eph.ChebTable.fit(lambda t: eph.iau_earth_angles(t) + np.array([0.01, -0.02, 0.5]), 0.0, 16 * 3600.0, 2, 5)
+    try:
+        for case, (kw, tables) in enumerate([(dict(), False), (dict(rw_set=1), True)]):
+            n = 40
+            rows = parity.sample_rows(orc, n, seed=90 + case)
+            rows[:6, 15:18] = np.random.RandomState(91).uniform(1500, 2900, size=(6, 3)) * np.array([1, -1, 1])
+            acts = np.random.RandomState(92 + case).randint(0, 3, size=(3, n))
+            acts[:2, :6] = 2
+            env = _vec(bsk, n, max_length=100, **kw)
+            env.set_gravity_degree2(True)
+            orc.set_gravity_coeffs(None)
+            orc.set_ephemeris(0, sun if tables else None); orc.set_ephemeris(1, orient if tables else None)
+            env.set_ephemeris("sun", sun if tables else None); env.set_ephemeris("orientation", orient if tables else None)
+            batch = orc.LeoEnvBatch(rows, orc.default_cfg(grav_pfix=1, **kw))
+            np.testing.assert_allclose(env.reset_ics(rows).cpu().numpy(), batch.obs0, rtol=1e-14, atol=0)
+            for t in range(len(acts)):
+                o, r, d, info = env.step(acts[t])
+                obs = o.cpu().numpy()
+                S, I = _state_np(env)
+                o_ob, o_rew, o_done, o_reason = batch.step(acts[t])
+                np.testing.assert_array_equal(d.cpu().numpy().astype(bool), o_done)
+                for e in range(n):
+                    where = f"case {case} step {t} env {e} action {acts[t][e]}"
+                    parity.compare_obs(obs[e], o_ob[e], where)
+                    parity.compare_state(batch.envs[e].state(), S[:, e], I[:, e], where)
+            if case == 0:
+                # the tesseral terms are really in the kernel: the zonal-only inertial J2 build ends somewhere else
+                env2 = _vec(bsk, n, max_length=100, use_j2=1)
+                env2.reset_ics(rows)
+                for t in range(len(acts)):
+                    env2.step(acts[t])
+                S2, _ = _state_np(env2)
+                d = np.linalg.norm(S[0:3] - S2[0:3], axis=0)
+                assert d.max() > 0.05 and d.max() < 500.0           # metres after nine minutes
+                env2.close()
+            # a table that does not cover an episode is refused; unloading goes back to the analytic model
+            with pytest.raises(BskEnvError):
+                env.set_ephemeris("sun", eph.ChebTable.fit(eph.analytic_sun, 0.0, 600.0, 2, 4))
+            env.close()
+    finally:
+        orc.set_ephemeris(0, None); orc.set_ephemeris(1, None); orc.set_gravity_coeffs(None)
+
+
+def test_sun_table_fitted_to_the_analytic_model_changes_nothing(bsk):
+    """A Sun table fitted to the built-in series reproduces the table-free run to the fit error (1e-11 relative)."""
+    import torch
+    from basilisk_env_b200 import ephemeris as eph
+    n = 256
+    a = _vec(bsk, n, seed=5); b = _vec(bsk, n, seed=5)
+    b.set_ephemeris("sun", eph.ChebTable.fit(eph.analytic_sun, 0.0, 86400.0, 2, 9))
+    a.reset(); b.reset()
+    acts = torch.randint(0, 3, (3, n), dtype=torch.int32, device="cuda", generator=torch.Generator("cuda").manual_seed(1))
+    for t in range(3):
+        oa = a.step(acts[t])[0]; ob = b.step(acts[t])[0]
+    Sa, Ia = _state_np(a); Sb, Ib = _state_np(b)
+    np.testing.assert_array_equal(Ia, Ib)
+    np.testing.assert_allclose(Sb[0:6], Sa[0:6], rtol=1e-12)
+    np.testing.assert_allclose(ob.cpu().numpy(), oa.cpu().numpy(), atol=1e-7)
+    a.close(); b.close()
