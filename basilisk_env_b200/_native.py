@@ -42,7 +42,8 @@ OPNAV_EXPORTS = ["bskenv_opnav_default_config", "bskenv_opnav_create", "bskenv_o
                  "bskenv_opnav_num_envs", "bskenv_opnav_reset_seeded", "bskenv_opnav_reset_ics", "bskenv_opnav_reset_init",
                  "bskenv_opnav_get_ics", "bskenv_opnav_step", "bskenv_opnav_step_host", "bskenv_opnav_state_dims",
                  "bskenv_opnav_get_state", "bskenv_opnav_set_state", "bskenv_opnav_state_field",
-                 "bskenv_opnav_episode_stats", "bskenv_opnav_launch_count", "bskenv_opnav_flops_per_step"]
+                 "bskenv_opnav_episode_stats", "bskenv_opnav_launch_count", "bskenv_opnav_flops_per_step",
+                 "bskenv_opnav_set_ephemeris"]
 
 EXPORTS = ["bskenv_abi_version", "bskenv_default_config", "bskenv_create", "bskenv_destroy", "bskenv_last_error",
            "bskenv_num_envs", "bskenv_reset_seeded", "bskenv_reset_ics", "bskenv_reset_init", "bskenv_get_ics",
@@ -113,6 +114,7 @@ def lib():
     L.bskenv_opnav_launch_count.argtypes = [vp]
     L.bskenv_opnav_flops_per_step.restype = C.c_double
     L.bskenv_opnav_flops_per_step.argtypes = [vp]
+    L.bskenv_opnav_set_ephemeris.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, vp]
     if L.bskenv_abi_version() != 1:
         raise RuntimeError("libbskenv.so ABI version mismatch")
     _LIB = L

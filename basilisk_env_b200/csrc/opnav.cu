@@ -217,6 +217,7 @@ struct bskenv_opnav_handle {
     int64_t *I;
     int *sched;
     int32_t *perm;              // lane assignment of the step kernel (envs bucketed by task set)
+    double *d_eph;              // device copy of the Sun ephemeris table
     int sm_count;
     int32_t *d_act; double *d_obs, *d_rew, *d_dbg; uint8_t *d_done, *d_reason;
     int32_t *h_act; double *h_obs, *h_rew, *h_dbg; uint8_t *h_done, *h_reason;
@@ -291,7 +292,7 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
     if (!perr.empty()) { g_opnav_create_error = "bskenv_opnav_create: " + perr; delete h; return BSKENV_EINVAL; }
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
-    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr; h->d_eph = nullptr;
     h->d_act = nullptr; h->d_obs = h->d_rew = h->d_dbg = nullptr; h->d_done = h->d_reason = nullptr;
     h->h_act = nullptr; h->h_obs = h->h_rew = h->h_dbg = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
     cudaError_t e = cudaSetDevice(device);
@@ -319,12 +320,34 @@ int bskenv_opnav_destroy(bskenv_opnav_handle *h)
 {
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm); cudaFree(h->d_eph);
     cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_dbg); cudaFree(h->d_done); cudaFree(h->d_reason);
     cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_dbg); cudaFreeHost(h->h_done);
     cudaFreeHost(h->h_reason);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     delete h;
+    return BSKENV_OK;
+}
+
+int bskenv_opnav_set_ephemeris(bskenv_opnav_handle *h, double t0, double seg_len, int n_seg, int n_coef, const double *coef)
+{
+    if (!h) return BSKENV_EINVAL;
+    ON_TRY(h, cudaSetDevice(h->device));
+    ON_TRY(h, cudaDeviceSynchronize());
+    LeoEph &E = h->P.eph_sun;
+    cudaFree(h->d_eph); h->d_eph = nullptr;
+    E.coef = nullptr; E.nseg = 0; E.ncoef = 0; E.t0 = 0.; E.seg_len = 0.;
+    if (n_seg <= 0) return BSKENV_OK;
+    if (!coef || n_coef < 1 || n_coef > 64 || !(seg_len > 0.)) { h->err = "bskenv_opnav_set_ephemeris: bad table shape"; return BSKENV_EINVAL; }
+    const double t_end = (double)(h->P.max_length + 1) * (double)h->P.ticks_per_step * h->P.dt;
+    if (t0 > 0. || t0 + seg_len * n_seg < t_end) {
+        h->err = "bskenv_opnav_set_ephemeris: the table does not cover one episode [0, (max_length + 1) * step_duration]";
+        return BSKENV_EINVAL;
+    }
+    const size_t bytes = sizeof(double) * (size_t)n_seg * 3 * (size_t)n_coef;
+    ON_TRY(h, cudaMalloc(&h->d_eph, bytes));
+    ON_TRY(h, cudaMemcpy(h->d_eph, coef, bytes, cudaMemcpyHostToDevice));
+    E.coef = h->d_eph; E.nseg = n_seg; E.ncoef = n_coef; E.t0 = t0; E.seg_len = seg_len;
     return BSKENV_OK;
 }
 

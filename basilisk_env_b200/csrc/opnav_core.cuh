@@ -131,6 +131,11 @@ ON_HD_NOINLINE void normals4(const OpNavParams &P, int64_t env, int64_t episode,
 struct SunState { V3 r, v; };
 ON_HD_NOINLINE SunState sun_from_mars(const OpNavParams &P, double t)
 {
+    if (P.eph_sun.nseg > 0) {          // ephemeris table instead of the analytic series
+        SunState o;
+        leo::cheb_eval(P.eph_sun, t, o.r, o.v);
+        return o;
+    }
     const double PI = 3.14159265358979323846, D2R = PI / 180.0, AUm = 149597870700.0;
     double days = P.epoch_days + t / 86400.0;
     double T = days / 36525.0;

@@ -8,6 +8,7 @@
 //   /root/reference/basilisk_env/envs/opNavEnvironment.py                      (ONE:line)
 #pragma once
 #include <stdint.h>
+#include "leo_params.h"      // LeoEph: Chebyshev ephemeris table
 
 #define ON_NRW 4
 #define ON_NCSS 8
@@ -46,6 +47,7 @@ struct OpNavParams {
     double rN0[3], vN0[3];
     // ---- epoch: TT days from J2000 at sim time 0 ('2019 DECEMBER 12 18:00:00.0', OND:396) ----
     double epoch_days;
+    LeoEph eph_sun;                 // optional table: Sun position relative to the Mars barycentre [m] (bskenv_opnav_set_ephemeris)
     uint64_t seed;                  // noise / IC stream key
     int64_t first_env_index;
 };

@@ -119,6 +119,16 @@ class OpNavVecEnv:
             raise ValueError("mask must have one entry per env")
         return m, C.c_void_p(m.data_ptr())
 
+    def set_ephemeris(self, table):
+        """Sun position relative to the Mars barycentre [m] from a Chebyshev table
+        (`basilisk_env_b200.ephemeris.ChebTable`; None = back to the analytic series).  Set before reset."""
+        if table is None:
+            self._check(self._L.bskenv_opnav_set_ephemeris(self._h, 0.0, 0.0, 0, 0, None), "set_ephemeris")
+            return
+        coef = np.ascontiguousarray(table.coef, dtype=np.float64)
+        self._check(self._L.bskenv_opnav_set_ephemeris(self._h, float(table.t0), float(table.seg_len), coef.shape[0],
+                                                       coef.shape[2], coef.ctypes.data), "set_ephemeris")
+
     def reset(self, seed=None, mask=None):
         """Sample fresh initial conditions on the device; returns the initial observation [N,4] (zeros)."""
         if seed is not None:

@@ -210,6 +210,10 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
 int bskenv_opnav_destroy(bskenv_opnav_handle *h);
 const char *bskenv_opnav_last_error(const bskenv_opnav_handle *h);
 int64_t bskenv_opnav_num_envs(const bskenv_opnav_handle *h);
+/* Chebyshev table (layout as bskenv_set_ephemeris) of the Sun position relative to the Mars barycentre,
+ * J2000 axes [m], sim time 0 = '2019 DECEMBER 12 18:00:00.0' (opNav_models/BSK_OpNavDynamics.py:396-401: de430.bsp through
+ * spice_interface with zeroBase 'mars barycenter'); replaces the analytic Keplerian series.  n_seg = 0 unloads. */
+int bskenv_opnav_set_ephemeris(bskenv_opnav_handle *h, double t0, double seg_len, int n_seg, int n_coef, const double *coef);
 /* reset(): device-sampled ICs (filter initial error U(+-1e5 m), U(+-1e3 m/s), opNavSimulator.py:187-188; orbit fixed or
  * sampled); `obs_dev` (double[n*4], may be NULL) receives the initial observation (zeros, opNavSimulator.py:152). */
 int bskenv_opnav_reset_seeded(bskenv_opnav_handle *h, uint64_t seed, const uint8_t *mask_dev, double *obs_dev, void *stream);

@@ -487,13 +487,13 @@ static void log_all_messages(orc_leo_sim *s)
  *     max degree 2; confidence M (recalled).  Pinned by tests/test_oracle_physics.py against the closed-form
  *     gradient of the degree-2 potential. */
 typedef struct { int nseg, ncoef; double t0, seg_len; double *coef; } EphTable;
-static EphTable g_eph[2];
+static EphTable g_eph[3];   /* kind 2: Sun relative to the Mars barycentre [m] (opNav scenario) */
 static double g_cbar[5] = {-4.8416537173459064e-04, -2.0661550900e-10, 1.3844138138e-09, 2.4393836573e-06, -1.4002737040e-06};
                            /* C20 = -J2_EARTH / sqrt 5 (the J2 of use_j2); C21, S21, C22, S22: GGM03S-class values, confidence L;
                               orc_set_gravity_coeffs replaces them */
 int orc_set_ephemeris(int kind, double t0, double seg_len, int nseg, int ncoef, const double *coef)
 {
-    if (kind < 0 || kind > 1) return -1;
+    if (kind < 0 || kind > 2) return -1;
     free(g_eph[kind].coef); memset(&g_eph[kind], 0, sizeof(EphTable));
     if (nseg <= 0) return 0;
     if (ncoef < 1 || !(seg_len > 0) || !coef) return -1;

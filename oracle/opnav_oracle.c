@@ -30,6 +30,7 @@
 #define NSP 13
 
 void orc_sun_from_mars(double t, double r[3], double v[3], double *j2000_et); /* bsk_oracle.c */
+int orc_eph_eval(int kind, double t, double val[3], double rate[3]);          /* bsk_oracle.c */
 
 static const double MU_MARS_DYN = 4.2828371901284001E+13;  /* OND:386 */
 static const double MU_MARS_FSW = 42828.314 * 1E9;         /* [BSK: astroConstants.h MU_MARS]*1e9; also ONF:507 */
@@ -475,6 +476,7 @@ static void sc_update(orc_opnav_sim *s, uint64_t now)
 static void spice_update(orc_opnav_sim *s, uint64_t now)
 { /* SpiceInterface (prio 200), zeroBase "mars barycenter" (OND:401): analytic stand-in, documented deviation */
     orc_sun_from_mars(now * NANO2SEC, s->sunMsg.pos, s->sunMsg.vel, 0);
+    orc_eph_eval(2, now * NANO2SEC, s->sunMsg.pos, s->sunMsg.vel);      /* the table, when one is loaded */
     s->sunMsg.h.written = 1;
 }
 static const double NAV_P[15] = {10.0, 10.0, 10.0, 0.001, 0.001, 0.001,                       /* OND:238-247 */

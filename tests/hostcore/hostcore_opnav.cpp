@@ -14,9 +14,11 @@ struct HCO {
     int64_t n;
     std::vector<double> S, ics;
     std::vector<int64_t> I;
+    std::vector<double> eph;
 };
 
 extern "C" {
+void hco_set_ephemeris(struct HCO *h, double t0, double seg_len, int nseg, int ncoef, const double *coef);
 void hco_default_config(bskenv_opnav_config *c) { opnav_host::default_config(c); }
 HCO *hco_create(const bskenv_opnav_config *cfg, int64_t n, int64_t first_env)
 {
@@ -105,5 +107,11 @@ int hco_ukf_meas_update(HCO *h, double *x, double *S, const double *m, double dt
     for (int i = 0; i < 6; i++) x[i] = f.x[i];
     for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c <= r; c++) S[k++] = f.SC(r, c);
     return ok ? 1 : 0;
+}
+void hco_set_ephemeris(HCO *h, double t0, double seg_len, int nseg, int ncoef, const double *coef)
+{   // the setting bskenv_opnav_set_ephemeris offers
+    h->eph.assign(coef, coef + (size_t)(nseg > 0 ? nseg : 0) * 3 * ncoef);
+    LeoEph &E = h->P.eph_sun;
+    E.coef = nseg > 0 ? h->eph.data() : nullptr; E.nseg = nseg > 0 ? nseg : 0; E.ncoef = ncoef; E.t0 = t0; E.seg_len = seg_len;
 }
 }

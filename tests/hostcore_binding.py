@@ -157,6 +157,7 @@ def lib_opnav():
         L.hco_step.argtypes = [vp] * 7
         L.hco_get_state.argtypes = [vp] * 3
         L.hco_dims.argtypes = [C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.hco_set_ephemeris.argtypes = [vp, C.c_double, C.c_double, C.c_int, C.c_int, vp]
         L.hco_normals.argtypes = [vp, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32, C.c_uint32, vp]
         L.hco_sun.argtypes = [vp, C.c_double, vp, vp]
         L.hco_eclipse.restype = C.c_double
@@ -193,6 +194,13 @@ class HostCoreOpNav:
         obs = np.zeros((self.n, 4))
         self.L.hco_reset_ics(self.h, rows.ctypes.data, obs.ctypes.data)
         return obs
+
+    def set_ephemeris(self, table):
+        if table is None:
+            self.L.hco_set_ephemeris(self.h, 0.0, 1.0, 0, 1, None)
+            return
+        coef = np.ascontiguousarray(table.coef, dtype=np.float64)
+        self.L.hco_set_ephemeris(self.h, float(table.t0), float(table.seg_len), coef.shape[0], coef.shape[2], coef.ctypes.data)
 
     def reset_seeded(self, seed):
         ics = np.zeros((self.n, 12)); obs = np.zeros((self.n, 4))

@@ -26,10 +26,12 @@ def _state_np(env):
     return d.cpu().numpy(), i.cpu().numpy()
 
 
-def _run_against_oracle(bsk, rows, action_seq, host_path=False, first_env=0, seed=77, **cfg):
+def _run_against_oracle(bsk, rows, action_seq, host_path=False, first_env=0, seed=77, sun_table=None, **cfg):
     from oracle import opnav as on
     n = len(rows)
     env = _vec(n, first_env_index=first_env, noise_seed=seed, **cfg)
+    if sun_table is not None:
+        env.set_ephemeris(sun_table)
     batch = on.OpNavEnvBatch(rows, on.default_cfg(seed=seed, **{k: v for k, v in cfg.items() if k in ORC_KEYS}), first_env_index=first_env)
     ob0 = env.reset_ics(rows).cpu().numpy()
     np.testing.assert_array_equal(ob0, np.zeros((n, 4)))
@@ -181,4 +183,25 @@ def test_opnav_gym_surface(bsk):
     assert reward == 0
     sim = env.simulator
     assert sim.modeCounter == 2 and sim.simTime == 100.0
+    env.close()
+
+
+def test_opnav_sun_ephemeris_table(bsk):
+    """SURVEY 8(f)-4 for the opNav env through the C ABI: a perturbed Sun-from-Mars Chebyshev table on both sides."""
+    from oracle import opnav as on
+    from oracle import oracle as orc
+    from basilisk_env_b200.vec_env import BskEnvError
+    from tests.test_opnav_hostcore import mars_sun_table
+    tab = mars_sun_table(scale=0.97, shift_days=60.0, n_seg=5, seg_len=8 * 3600.0)      # covers the 41 x 50 min episode
+    rows = par.sample_rows(on, 48, seed=21)
+    acts = np.random.RandomState(22).randint(0, 2, size=(2, 48))
+    try:
+        orc.set_ephemeris(2, tab)
+        _run_against_oracle(bsk, rows, acts, first_env=5, camera_reenable=1, sun_table=tab)
+    finally:
+        orc.set_ephemeris(2, None)
+    env = _vec(8)
+    with pytest.raises(BskEnvError):
+        env.set_ephemeris(mars_sun_table(n_seg=1, seg_len=3600.0))       # does not cover an episode
+    env.set_ephemeris(None)
     env.close()

@@ -10,9 +10,11 @@ from tests import opnav_parity as par
 from tests.hostcore_binding import HostCoreOpNav
 
 
-def _run(rows, acts, first_env=0, **kw):
+def _run(rows, acts, first_env=0, sun_table=None, **kw):
     cfg = on.default_cfg(seed=77, **kw)
     hc = HostCoreOpNav(len(rows), first_env=first_env, noise_seed=77, **kw)
+    if sun_table is not None:
+        hc.set_ephemeris(sun_table)
     ob0 = hc.reset_ics(rows)
     np.testing.assert_array_equal(ob0, np.zeros_like(ob0))
     batch = on.OpNavEnvBatch(rows, cfg, first_env_index=first_env)
@@ -164,3 +166,37 @@ def test_episode_bookkeeping_matches_oracle_to_the_end():
     hc, batch = _run(rows, acts, step_duration_min=1.0, camera_reenable=1)
     S, I = hc.state()
     assert list(I[par.F("curr_step")]) == [42, 42] and list(I[par.F("episode_over")]) == [1, 1]
+
+
+def mars_sun_table(scale=1.0, shift_days=0.0, n_seg=3, n_coef=8, seg_len=8 * 3600.0):
+    """Chebyshev table fitted to the oracle's analytic Sun-from-Mars series (optionally perturbed, so that a test can tell
+    the table from the built-in model)."""
+    from basilisk_env_b200 import ephemeris as eph
+    L = on.lib()
+
+    def fn(t):
+        r, v, et = np.zeros(3), np.zeros(3), np.zeros(1)
+        L.orc_sun_from_mars(t + shift_days * 86400.0, on._p(r), on._p(v), on._p(et))
+        return r * scale
+    return eph.ChebTable.fit(fn, 0.0, seg_len, n_seg, n_coef)
+
+
+def test_sun_table_replaces_the_analytic_series():
+    """SURVEY 8(f)-4 for the opNav env: with a (perturbed) Sun table loaded on both sides the fused schedule still matches
+    the oracle, the table is what the core evaluates, and the sun-safe observation really changes."""
+    from oracle import oracle as orc
+    tab = mars_sun_table(scale=0.97, shift_days=60.0)
+    rows = par.sample_rows(on, 3, seed=9)
+    acts = np.array([[0, 1, 1], [1, 1, 0]])
+    kw = dict(step_duration_min=10.0, camera_reenable=1)
+    try:
+        orc.set_ephemeris(2, tab)
+        hc, batch = _run(rows, acts, sun_table=tab, **kw)
+        rk, vk = hc.sun(700.0)
+        np.testing.assert_allclose(rk, tab(700.0)[0], rtol=1e-14)
+        np.testing.assert_allclose(vk, tab(700.0)[1], rtol=1e-10)
+    finally:
+        orc.set_ephemeris(2, None)
+    hc0, _ = _run(rows, acts, **kw)
+    S1, _ = hc.state(); S0, _ = hc0.state()
+    assert np.abs(S1[par.F("sigma_BN"):par.F("sigma_BN") + 3] - S0[par.F("sigma_BN"):par.F("sigma_BN") + 3]).max() > 1e-3
