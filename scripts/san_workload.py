@@ -15,3 +15,19 @@ for t in range(4):
     on.step(torch.full((100,), t % 2, dtype=torch.int32, device="cuda"))
 on.step_host(np.zeros(100, np.int32))
 print("opnav", on.episode_stats()); on.close()
+# SURVEY 8(f)-4 paths: ephemeris tables (global-memory look-ups) and the planet-fixed degree-2 variant (larger bus)
+from basilisk_env_b200 import ephemeris as eph
+env = LeoPowerAttVecEnv(200, device=0, auto_reset=True, step_duration=20.0, max_length=2, rw_set=1)
+env.set_gravity_degree2(True)
+env.set_ephemeris("sun", eph.ChebTable.fit(eph.analytic_sun, 0.0, 40.0, 3, 6))
+env.set_ephemeris("orientation", eph.ChebTable.fit(eph.iau_earth_angles, 0.0, 100.0, 1, 4))
+env.reset(seed=3)
+for t in range(4):
+    env.step(torch.full((200,), (t + 1) % 3, dtype=torch.int32, device="cuda"))
+print("leo degree2+tables", env.episode_stats()); env.close()
+on = OpNavVecEnv(100, device=0, auto_reset=True, step_duration_min=2.0, max_length=2, camera_reenable=1)
+on.set_ephemeris(eph.ChebTable.fit(lambda t: np.array([2.0e11, 5.0e10, 1.0e10]) + 2.0e4 * t * np.array([-0.2, 1.0, 0.4]), 0.0, 200.0, 2, 3))
+on.reset(seed=4)
+for t in range(3):
+    on.step(torch.full((100,), t % 2, dtype=torch.int32, device="cuda"))
+print("opnav table", on.episode_stats()); on.close()
