@@ -67,6 +67,18 @@ def sampled_400km(rng=None):
     return oe, rN, vN
 
 
+def inclined_circular_300km():
+    """leo_orbit.py:6-23 (not used by the reference env, kept for API parity): circular, i = 45 deg, 300 km."""
+    oe = ClassicElements(a=6371 * 1000.0 + 300. * 1000, e=0.0, i=45.0 * D2R, Omega=0.0 * D2R, omega=0.0 * D2R, f=0.0 * D2R)
+    rN, vN = elem2rv(MU_EARTH, oe)
+    return oe, rN, vN
+
+
+def static_inertial():
+    """sc_attitudes.py:15-23 (not used by the reference env): zero MRP, zero body rate."""
+    return np.zeros([3, ]), np.zeros([3, ])
+
+
 def random_tumble(maxSpinRate=0.001, rng=None):
     """sc_attitudes.py:3-13."""
     R = np.random if rng is None else rng

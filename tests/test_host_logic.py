@@ -118,3 +118,15 @@ def test_device_sampler_distributions(hostcore):
     np.testing.assert_allclose(obs[:, 2], np.linalg.norm(ics[:, 15:18], axis=1) / (3000 * 2 * np.pi / 60), rtol=1e-15)
     np.testing.assert_allclose(obs[:, 3], ics[:, 18] / 3600. / 20., rtol=1e-15)
     assert np.all(obs[:, 4] == 0)
+
+
+def test_unused_reference_ic_helpers():
+    """leo_orbit.inclined_circular_300km (leo_orbit.py:6-23) and sc_attitudes.static_inertial (sc_attitudes.py:15-23)."""
+    from basilisk_env_b200 import initial_conditions as icm
+    oe, r, v = icm.inclined_circular_300km()
+    a = 6671e3
+    assert oe.e == 0.0 and abs(np.linalg.norm(r) - a) < 1e-6
+    np.testing.assert_allclose(np.linalg.norm(v), np.sqrt(icm.MU_EARTH / a), rtol=1e-14)       # circular speed
+    np.testing.assert_allclose(np.cross(r, v) / np.linalg.norm(np.cross(r, v)), [0.0, -np.sin(np.pi / 4), np.cos(np.pi / 4)], atol=1e-15)
+    s, w = icm.static_inertial()
+    assert s.shape == (3,) and w.shape == (3,) and not s.any() and not w.any()
