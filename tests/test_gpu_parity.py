@@ -412,3 +412,37 @@ def test_sun_table_fitted_to_the_analytic_model_changes_nothing(bsk):
     np.testing.assert_allclose(Sb[0:6], Sa[0:6], rtol=1e-12)
     np.testing.assert_allclose(ob.cpu().numpy(), oa.cpu().numpy(), atol=1e-7)
     a.close(); b.close()
+
+
+def test_one_million_envs_sharded_eight_ways_equals_one_handle(bsk):
+    """BASELINE configs[2] at its full size: 2^20 envs with device-sampled random orbits.  One handle on one GPU and the
+    eight index shards a box of 8 GPUs would own ([g * 131072, (g + 1) * 131072), here run back to back on the same device)
+    give bit-identical observations, rewards, flags and state after a full 180 s decision interval with auto-reset."""
+    import torch
+    n, shards = 1 << 20, 8
+    per = n // shards
+    acts = torch.randint(0, 3, (n,), dtype=torch.int32, device="cuda", generator=torch.Generator("cuda").manual_seed(11))
+    env = _vec(bsk, n, seed=77, auto_reset=True)
+    ob0 = env.reset()
+    o, r, d, info = env.step(acts)
+    S, I = env.get_state()
+    tick = I[parity.F("tick")]
+    assert bool(torch.isfinite(o).all()) and bool(((tick == 1800) | ((tick == -1) & d.bool())).all())     # -1: re-initialised in the launch
+    ref = (ob0.clone(), o.clone(), r.clone(), d.clone(), S[:12].clone(), S[parity.F("storedCharge")].clone())
+    stats = env.episode_stats()
+    env.close()
+    del env, S, I
+    torch.cuda.empty_cache()
+    steps = 0.0
+    for g in range(shards):
+        lo = g * per
+        sh = _vec(bsk, per, first_env_index=lo, seed=77, auto_reset=True)
+        s_ob0 = sh.reset()
+        so, sr, sd, _ = sh.step(acts[lo:lo + per])
+        sS, _ = sh.get_state()
+        assert torch.equal(s_ob0, ref[0][lo:lo + per]) and torch.equal(so, ref[1][lo:lo + per])
+        assert torch.equal(sr, ref[2][lo:lo + per]) and torch.equal(sd, ref[3][lo:lo + per])
+        assert torch.equal(sS[:12], ref[4][:, lo:lo + per]) and torch.equal(sS[parity.F("storedCharge")], ref[5][lo:lo + per])
+        steps += sh.episode_stats()["env_steps"]
+        sh.close()
+    assert steps == stats["env_steps"] == float(n)
