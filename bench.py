@@ -350,6 +350,16 @@ def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None):
             "sample": f"{n} envs x {steps} decision steps (oracle/opnav_oracle.c, OpenMP over envs, {el:.1f} s)"}
 
 
+def opnav_traffic(n):
+    """DRAM bytes per launch of opnav_step_kernel from the latest `ncu --set full` capture (profiles/traffic_opnav.json,
+    taken at the default 32768 envs); None for any other size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_opnav.json"))).get("dram_bytes_per_launch")
+        return t if n == 32768 else None
+    except (OSError, ValueError):
+        return None
+
+
 def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
     from basilisk_env_b200.opnav_env import OpNavVecEnv
     env = OpNavVecEnv(n, device=dev.index, seed=5, auto_reset=True, sample_orbit=1, camera_reenable=1)
@@ -408,7 +418,7 @@ def run_opnav(args):
             "config": {"workload": r["workload"], "envs_per_gpu": n, "ticks_per_step": 3000,
                        "l2": f"{(OPNAV_STATE_BYTES_PER_ENV + 12 * 8) * n / 2**20:.0f} MiB of per-env state, touched once per launch; "
                              "the kernel is FP64-pipe / latency bound, not memory bound"},
-            "roofline": dict(r["roofline"], traffic=None), "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks,
+            "roofline": dict(r["roofline"], traffic=opnav_traffic(n)), "e2e": r["e2e"], "gpu_launches": r["gpu_launches"], "clocks": clocks,
             "episode_stats": r["episode_stats"], "checksum": r["checksum"], "cpu_baseline": r.get("cpu_baseline")}
     print(json.dumps(line), flush=True)
 
