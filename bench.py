@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env and opNav side measurements")
     ap.add_argument("--workload", default="leo", choices=["leo", "opnav"],
                     help="leo: the headline line (default); opnav: the same JSON line for BASELINE configs[3] (N=1 only)")
-    ap.add_argument("--opnav-envs", type=int, default=32768)
+    ap.add_argument("--opnav-envs", type=int, default=75776,
+                    help="opNav batch: two resident sets of the step kernel (148 SMs x 2 blocks x 128 threads = 37888 envs each)")
     return ap.parse_args()
 
 
@@ -324,7 +325,7 @@ OPNAV_D2H_BYTES_PER_ENV = 4 * 8 + 8 + 1 + 1 + 12 * 8
 
 
 def opnav_workload_name(n):
-    return (f"opNav env, {n} envs on one GPU (BASELINE configs[3]): Mars orbits from the reference's element ranges, filter "
+    return (f"opNav env, {n} envs on one GPU (BASELINE configs[3]; {n / 37888:.2f} resident sets of 148 SMs x 2 blocks x 128 threads): Mars orbits from the reference's element ranges, filter "
             "initial error U(+-1e5 m, +-1e3 m/s), simple_nav noise on, one synthetic circle measurement per 60 s while imaging, "
             "i.i.d. uniform actions {0,1}, camera re-enabled by action 0, auto-reset, FP64; one step = 50 min = 3000 ticks")
 
@@ -352,10 +353,10 @@ def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None):
 
 def opnav_traffic(n):
     """DRAM bytes per launch of opnav_step_kernel from the latest `ncu --set full` capture (profiles/traffic_opnav.json,
-    taken at the default 32768 envs); None for any other size."""
+    of a launch with the same env count); None for any other size."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic_opnav.json"))).get("dram_bytes_per_launch")
-        return t if n == 32768 else None
+        j = json.load(open(os.path.join(ROOT, "profiles", "traffic_opnav.json")))
+        return j.get("dram_bytes_per_launch") if (j.get("envs") or 32768) == n else None
     except (OSError, ValueError):
         return None
 

@@ -72,7 +72,12 @@ def raw():
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
     if rd is not None and wr is not None:
         tb = rd * scale.get(d["dram__bytes_read.sum"][1], 1) + wr * scale.get(d["dram__bytes_write.sum"][1], 1)
-        json.dump({"tag": tag, "dram_bytes_per_launch": tb, "kernel": d.get("Kernel Name", ("", ""))[0][:80]},
+        envs = None
+        try:    # env count of the captured launch = the bench line of the same tag
+            envs = json.loads(open(os.path.join(G, f"bench_{tag}.json")).read().strip().splitlines()[-1])["config"]["envs_per_gpu"]
+        except (OSError, ValueError, KeyError, IndexError):
+            pass
+        json.dump({"tag": tag, "envs": envs, "dram_bytes_per_launch": tb, "kernel": d.get("Kernel Name", ("", ""))[0][:80]},
                   open(os.path.join(ROOT, "profiles", "traffic_opnav.json" if tag.startswith("opnav") else "traffic.json"), "w"))
         out.append(f"DRAM traffic per launch: {tb / 1e6:.1f} MB (read {rd} + write {wr} {d['dram__bytes_read.sum'][1]})\n")
     return rep
