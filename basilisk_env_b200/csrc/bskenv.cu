@@ -51,7 +51,24 @@ __device__ __forceinline__ double warp_sum(double v)
 // the tail is spread over all SMs (131072 envs on 148 SMs: 16.15 ms with one block per 128 envs, 15.7 ms with
 // the queue; an early-retiring third block per SM was measured as well and does not help).
 //   sched[0] = queue head (zeroed before the launch)
-struct LeoSched { int *sched; int n_groups; int dynamic; };
+// Work items of the queue are (chunk, group) pairs, chunk-major: the decision interval of a group is cut into n_chunks
+// consecutive chunks (leo_core.cuh: leo_step_env; leo_host::step_chunks), so the tail of a launch is one chunk long instead
+// of one interval long (131072 envs = 2.3 resident sets: the last 0.3 set used to run alone at one warp per sub-partition
+// for 4.6 ms).  Chunk c of a group may start when chunk c - 1 has been published in progress[group] (release / acquire at
+// GPU scope); its predecessor was handed out n_groups items earlier, so in practice nobody waits.  Without the queue
+// (grid covers all groups) each warp runs the chunks of its own group back to back.
+struct LeoSched { int *sched; int n_groups; int dynamic; int n_chunks; int *progress; };
+
+__device__ __forceinline__ void chunk_publish(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" : : "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int chunk_peek(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 template <int NRW, int J2, bool DIAG, bool F32>
 __global__ void LEO_STEP_BOUNDS
@@ -66,12 +83,19 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
     bus.p = nullptr;
     bus.a = (uint32_t)__cvta_generic_to_shared(bus_smem) + threadIdx.x * (uint32_t)sizeof(double);
     for (bool more = true; more; more = sc.dynamic != 0) {
-        int g;
+        int g, c_first = 0, c_end = sc.n_chunks;
         if (sc.dynamic) {
             g = 0;
             if (lane == 0) g = atomicAdd(&sc.sched[0], 1);
             g = __shfl_sync(0xffffffffu, g, 0);
-            if (g >= sc.n_groups) break;
+            if (g >= sc.n_groups * sc.n_chunks) break;
+            c_first = g / sc.n_groups; c_end = c_first + 1;
+            g -= c_first * sc.n_groups;
+            if (c_first > 0) {                                  // chunk c_first - 1 of this group must be in memory
+                if (lane == 0)
+                    while (chunk_peek(sc.progress + g) < c_first) __nanosleep(200);
+                __syncwarp();
+            }
         } else {
             g = blockIdx.x * (LEO_BLOCK / 32) + warp;
         }
@@ -80,8 +104,17 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
         leo::StepOut o;
         o.done = 0; o.reason = 0; o.reward = 0.;
         double ep_ret = 0., ep_len = 0.;
+        for (int c = c_first; c < c_end; c++) {
+        if (valid) leo::leo_step_env<NRW, J2, DIAG, F32>(P, S, I, stride, e, bus, actions[e], o, PF, c, sc.n_chunks);
+        if (c + 1 < sc.n_chunks) {                              // chunk boundary inside the interval: publish and go on
+            if (sc.dynamic) {
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) chunk_publish(sc.progress + g, c + 1);
+            }
+            continue;
+        }
         if (valid) {
-            leo::leo_step_env<NRW, J2, DIAG, F32>(P, S, I, stride, e, bus, actions[e], o, PF);
             reward[e] = o.reward;
             done[e] = (uint8_t)o.done;
             reason[e] = (uint8_t)o.reason;
@@ -122,6 +155,7 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
             const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
             if (lane == 0 && c_valid) atomicAdd(&stats[ST_STEPS], (double)c_valid);
         }
+        }   // chunks of this item
         __syncwarp();
     }
 }
@@ -223,10 +257,11 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
     int grid = (int)((groups + wpb - 1) / wpb);
     LeoSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
+    sc.n_chunks = leo_host::step_chunks(h->P); sc.progress = h->sched + 4;
     if (grid > resident) {
         sc.dynamic = 1;
         grid = resident;
-        CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int), st));
+        CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int) * (size_t)(4 + groups), st));    // queue head + chunk progress per group
     }
 #define LEO_LAUNCH(NRW, J2, DIAG, F32)                                                                         \
     do {                                                                                                       \
@@ -293,7 +328,7 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     h->h_act = nullptr; h->h_obs = h->h_rew = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * (size_t)(4 + (n_envs + 31) / 32));
     if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * LEO_ND * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * LEO_NI * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * 19 * h->stride);

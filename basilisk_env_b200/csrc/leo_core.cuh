@@ -1123,8 +1123,13 @@ namespace leo {
 
 // F32 = false: the FP64 kernel (the reference's arithmetic; every parity claim).  F32 = true: mixed precision, see leo_f32.cuh.
 template <int NRW, int J2, bool DIAG, bool F32 = false>
+// `chunk` / `n_chunks`: the decision interval may be executed as n_chunks consecutive calls of ticks/n_chunks dynamics
+// ticks each (chunk 0 applies the mode switch, the last chunk samples the observation and does the gym bookkeeping); the
+// persistent state carries everything across a chunk boundary exactly as it does across a decision boundary, and the
+// Sun / orientation latch keeps the time of the interval's SPICE message.  The kernel uses this to cut one launch into
+// finer work items (bskenv.cu: smaller tail); leo_host::step_chunks() fixes the split as a function of the rates only.
 LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
-                         MBus m, int action, StepOut &out, const LeoParamsF &PF = LeoParamsF())
+                         MBus m, int action, StepOut &out, const LeoParamsF &PF = LeoParamsF(), int chunk = 0, int n_chunks = 1)
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
@@ -1161,7 +1166,8 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     int nswitch = 0;
 
     // ---------------- mode switch (SIM:543-588); modeRequest = str(action) ----------------
-    if (action == 0) mask = LEO_TASK_NADIR | LEO_TASK_MRP;
+    if (chunk > 0) {}                                          // the mode was switched by chunk 0 (mask is persistent)
+    else if (action == 0) mask = LEO_TASK_NADIR | LEO_TASK_MRP;
     else if (action == 1) mask = LEO_TASK_SUN | LEO_TASK_MRP;
     else if (action == 2) {
         mask = LEO_TASK_SUN | LEO_TASK_MRP | LEO_TASK_DESAT;
@@ -1175,13 +1181,15 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     // ---------------- clock: all tick times are integers below 2^53 ns, held exactly in doubles ----------------
     const bool first = tick < 0;                               // tick 0 (t = 0, h = 0) only runs right after a reset
     const int tpf = P.ticks_per_fsw;
-    const int ticks = tpf * P.fsw_per_step;
+    const int ticks_step = tpf * P.fsw_per_step;               // dynamics ticks of a decision interval
+    const int ticks = ticks_step / n_chunks;                   // ... of this call
     const int64_t n_base = (first ? 0 : tick) + 1;             // loop index j executes tick n = n_base + j
-    const int64_t n_end = n_base - 1 + ticks;                  // inclusive (ConfigureStopTime is inclusive)
+    const int64_t n_step0 = ((n_base - 1) / ticks_step) * ticks_step;   // tick at which this decision interval started
+    const int64_t n_end = n_step0 + ticks_step;                // last tick of the interval, inclusive (ConfigureStopTime is inclusive)
     const double dyn_d = (double)P.dyn_ns;
-    double sun_d = (double)((n_base - 1) * P.dyn_ns);          // write time of the Sun message in force
-    sun_latch_to_bus(P, m, (n_base - 1) * P.dyn_ns);
-    if (J2 == 2) pfix_latch_to_bus(P, m, (n_base - 1) * P.dyn_ns);
+    double sun_d = (double)(n_step0 * P.dyn_ns);               // write time of the Sun message in force
+    sun_latch_to_bus(P, m, n_step0 * P.dyn_ns);
+    if (J2 == 2) pfix_latch_to_bus(P, m, n_step0 * P.dyn_ns);
     a.dtp = 0.;
     // FP32 shadows of the Sun latch and its eclipse constants (mixed-precision variant only)
     V3f sunr_f = mkf(0.f, 0.f, 0.f), sunv_f = mkf(0.f, 0.f, 0.f);
@@ -1192,7 +1200,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         for (int q = 0; q < 6; q++) ecf[q] = (float)mld(m, M_ECL + q);
     }
     int phase = (int)((n_base - 1) % tpf);                     // (n mod ticks_per_fsw) of the tick about to run
-    double now_d = sun_d;                                      // exact: n * dyn_ns
+    double now_d = (double)((n_base - 1) * P.dyn_ns);          // exact: n * dyn_ns
     int desat_ran = 0, desat_quiet = 0;                        // the chain's quiet state is re-established once per launch
 
 #pragma unroll 1
@@ -1347,10 +1355,24 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         }
     }
 
-    // ---------------- observation sampling (SIM:598-642) + gym bookkeeping (ENV:98-145) ----------------
     for (int f = 0; f < LEO_M_MIRROR; f++) SD(F_GUID + f) = mld(m, f);
     double W[NRW];
     wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
+    if (chunk + 1 < n_chunks) {
+        // ---------------- chunk boundary inside the interval: persist the state, nothing else ----------------
+        SD(F_R) = x.r.x; SD(F_R + 1) = x.r.y; SD(F_R + 2) = x.r.z;
+        SD(F_V) = x.v.x; SD(F_V + 1) = x.v.y; SD(F_V + 2) = x.v.z;
+        SD(F_SIG) = x.s.x; SD(F_SIG + 1) = x.s.y; SD(F_SIG + 2) = x.s.z;
+        SD(F_OMG) = x.w.x; SD(F_OMG + 1) = x.w.y; SD(F_OMG + 2) = x.w.z;
+#pragma unroll
+        for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = W[i]; SD(F_UCUR + i) = mld(m, M_U + i); }
+        SD(F_RHO) = a.rho; SD(F_E) = mld(m, M_CHARGE); SD(F_SHADOW) = mld(m, M_SHADOW);
+        SI(I_TICK) = n_base - 1 + ticks; SI(I_MASK) = mask; SI(I_SWITCH) = SI(I_SWITCH) + nswitch;
+        SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_RWSAT) = rw_sat;
+        out.done = 0; out.reason = 0; out.reward = 0.;
+        return;
+    }
+    // ---------------- observation sampling (SIM:598-642) + gym bookkeeping (ENV:98-145) ----------------
     double ob0 = norm(mld3(m, M_GUID));
     double ob1 = norm(x.w);
     double wn = 0.;

@@ -190,6 +190,18 @@ static inline void set_degree2(LeoParams &p, const double cbar[5])
     p.grav_pfix = 1;
 }
 
+// Number of chunks a decision interval is executed in (leo_step_env): a function of the task rates only, so that a
+// trajectory never depends on the batch size, the sharding or the entry point.  Six chunks of 300 ticks at the reference
+// rates; one when the interval does not split into whole flight-software periods.
+#ifndef LEO_STEP_CHUNKS
+#define LEO_STEP_CHUNKS 6
+#endif
+static inline int step_chunks(const LeoParams &p)
+{
+    const int c = LEO_STEP_CHUNKS;
+    return (c > 1 && p.fsw_per_step % c == 0) ? c : 1;
+}
+
 static inline void build_params_f(const LeoParams &p, LeoParamsF &f)
 {
     memset(&f, 0, sizeof(f));

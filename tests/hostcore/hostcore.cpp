@@ -58,27 +58,30 @@ void hc_step(HC *h, const int32_t *actions, double *obs, double *reward, uint8_t
 {
     double bus[leo::LEO_NM_PFIX];
     leo::MBus m; m.a = 0; m.p = bus;
-    for (int64_t e = 0; e < h->n; e++) {
+    const int nch = leo_host::step_chunks(h->P);                // the same split of the interval as the CUDA kernel
+    for (int64_t e = 0; e < h->n; e++)
+    for (int ch = 0; ch < nch; ch++) {
         leo::StepOut o;
         const bool diag = h->P.diag && !h->force_general;
         if (h->P.grav_pfix) {  // planet-fixed degree-2 field
-            if (h->P.nrw == 4) leo::leo_step_env<4, 2, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
-            else if (diag) leo::leo_step_env<3, 2, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
-            else leo::leo_step_env<3, 2, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            if (h->P.nrw == 4) leo::leo_step_env<4, 2, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
+            else if (diag) leo::leo_step_env<3, 2, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
+            else leo::leo_step_env<3, 2, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
         } else
         if (h->P.mixed) {      // mixed-precision variant (leo_f32.cuh): the two configurations the library builds
-            if (h->P.nrw == 4) leo::leo_step_env<4, true, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF);
-            else leo::leo_step_env<3, false, true, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF);
+            if (h->P.nrw == 4) leo::leo_step_env<4, true, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF, ch, nch);
+            else leo::leo_step_env<3, false, true, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, h->PF, ch, nch);
         } else if (h->P.nrw == 4) {
-            if (h->P.use_j2) leo::leo_step_env<4, true, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
-            else leo::leo_step_env<4, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            if (h->P.use_j2) leo::leo_step_env<4, true, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
+            else leo::leo_step_env<4, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
         } else if (h->P.use_j2) {
-            if (diag) leo::leo_step_env<3, true, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
-            else leo::leo_step_env<3, true, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            if (diag) leo::leo_step_env<3, true, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
+            else leo::leo_step_env<3, true, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
         } else {
-            if (diag) leo::leo_step_env<3, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
-            else leo::leo_step_env<3, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o);
+            if (diag) leo::leo_step_env<3, false, true>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
+            else leo::leo_step_env<3, false, false>(h->P, h->S.data(), h->I.data(), h->n, e, m, actions[e], o, LeoParamsF(), ch, nch);
         }
+        if (ch + 1 < nch) continue;
         for (int k = 0; k < 5; k++) obs[5 * e + k] = o.ob[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
     }
