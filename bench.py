@@ -271,7 +271,9 @@ def main():
                        "parallelism": f"env-sharded x{world}, no collective on the step path"},
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                         "kernel": "leo_step_kernel<3,false,true>", "kernel_ms": kern_ms, "flop_per_env_step": flops,
+                         "traffic_note": "ncu capture at 131072 envs (profiles/traffic.json); above the algorithmic bytes by design: the "
+                                         "interval runs as 6 chunks with a state round trip each (DESIGN.md section 5), < 2 % of HBM bandwidth",
+                         "kernel": "leo_step_kernel<3,0,true,false>", "kernel_ms": kern_ms, "flop_per_env_step": flops,
                          "flop_source": "operation list of the kernel as built (bskenv_flops_per_step), equal to the executed "
                                         "2*DFMA+DMUL+DADD count of ncu (profiles/ncu_r01c.md: 2.074e6 per env-step); the un-fused "
                                         "Basilisk formulation of SURVEY 8(d) would be 4.29e6",
