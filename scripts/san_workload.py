@@ -31,3 +31,9 @@ on.reset(seed=4)
 for t in range(3):
     on.step(torch.full((100,), t % 2, dtype=torch.int32, device="cuda"))
 print("opnav table", on.episode_stats()); on.close()
+# chunked work items through the queue (more groups than resident warps): 60000 envs, 6 s intervals = 6 chunks of 10 ticks
+env = LeoPowerAttVecEnv(60000, device=0, auto_reset=True, step_duration=6.0, max_length=3, seed=5)
+env.reset()
+for t in range(3):
+    env.step(torch.full((60000,), t % 3, dtype=torch.int32, device="cuda"))
+print("leo queue+chunks", env.episode_stats()); env.close()
