@@ -49,7 +49,8 @@ EXPORTS = ["bskenv_abi_version", "bskenv_default_config", "bskenv_create", "bske
            "bskenv_num_envs", "bskenv_reset_seeded", "bskenv_reset_ics", "bskenv_reset_init", "bskenv_get_ics",
            "bskenv_step", "bskenv_step_host", "bskenv_state_dims", "bskenv_get_state", "bskenv_set_state",
            "bskenv_state_field", "bskenv_episode_stats", "bskenv_launch_count", "bskenv_fp64_peak",
-           "bskenv_flops_per_step", "bskenv_set_ephemeris", "bskenv_set_gravity_degree2"]
+           "bskenv_flops_per_step", "bskenv_set_ephemeris", "bskenv_set_gravity_degree2", "bskenv_step_info",
+           "bskenv_step_host_async", "bskenv_step_host_wait", "bskenv_alloc_host", "bskenv_free_host", "bskenv_kernel_name"]
 
 
 def lib_path():
@@ -80,6 +81,11 @@ def lib():
     L.bskenv_get_ics.argtypes = [vp, vp, vp]
     L.bskenv_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     L.bskenv_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.bskenv_step_info.argtypes = [vp] * 10
+    L.bskenv_step_host_async.argtypes = [vp] * 9
+    L.bskenv_step_host_wait.argtypes = [vp]
+    L.bskenv_alloc_host.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.bskenv_free_host.argtypes = [vp]
     L.bskenv_state_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.bskenv_get_state.argtypes = [vp, vp, vp, vp]
     L.bskenv_set_state.argtypes = [vp, vp, vp, vp]
@@ -87,6 +93,8 @@ def lib():
     L.bskenv_episode_stats.argtypes = [vp, vp]
     L.bskenv_launch_count.restype = i64
     L.bskenv_launch_count.argtypes = [vp]
+    L.bskenv_kernel_name.restype = C.c_char_p
+    L.bskenv_kernel_name.argtypes = [vp]
     L.bskenv_fp64_peak.argtypes = [C.c_int, C.c_double, C.POINTER(C.c_double)]
     L.bskenv_flops_per_step.restype = C.c_double
     L.bskenv_flops_per_step.argtypes = [vp]

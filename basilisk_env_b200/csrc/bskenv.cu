@@ -75,7 +75,8 @@ __global__ void LEO_STEP_BOUNDS
 leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ LeoParamsF PF, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                 int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                 double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
-                double *__restrict__ term_obs, double *__restrict__ stats, const LeoSched sc)
+                double *__restrict__ term_obs, double *__restrict__ stats, const LeoSched sc,
+                double *__restrict__ ep_return, int64_t *__restrict__ ep_length)
 {
     extern __shared__ double bus_smem[];          // [LEO_NM][LEO_BLOCK]: per-thread message bus (leo_core.cuh: MBus)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -118,9 +119,15 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
             reward[e] = o.reward;
             done[e] = (uint8_t)o.done;
             reason[e] = (uint8_t)o.reason;
-            if (o.done) {
+            if (o.done || ep_return) {
                 ep_ret = S[(int64_t)F_EPRET * stride + e];
                 ep_len = (double)I[(int64_t)I_STEP * stride + e];
+            }
+            if (ep_return) {       // ENV:130-136: info['episode'] = {'r': reward_total, 'l': curr_step (before its increment)}
+                ep_return[e] = ep_ret;
+                ep_length[e] = (int64_t)ep_len - 1;
+            }
+            if (o.done) {
                 if (term_obs)
                     for (int k = 0; k < 5; k++) term_obs[e * 5 + k] = o.ob[k];
                 if (P.auto_reset) {
@@ -231,11 +238,14 @@ struct bskenv_handle {
     int *sched;                 // work queue head of the step kernel
     double *d_eph[2];           // device copies of the ephemeris tables (Sun position, Earth orientation angles)
     int sm_count;
-    // staging for the host-buffer entry point
-    int32_t *d_act; double *d_obs, *d_rew; uint8_t *d_done, *d_reason;
-    int32_t *h_act; double *h_obs, *h_rew; uint8_t *h_done, *h_reason;
+    // host-buffer entry points: page-locked staging (only for pageable caller buffers), own stream, ordering events
+    void *h_stage[8];           // actions, obs, reward, done, reason, ep_return, ep_length, term_obs
+    void *pend_user[8]; size_t pend_bytes[8]; int host_pending;
     cudaStream_t own_stream;
+    cudaEvent_t ev_last;        // recorded after every launch queued through the device-buffer entry points
+    int ev_valid;
     int64_t launches;
+    const char *kernel_name;    // the step-kernel instantiation of the last launch
     std::string err;
 };
 
@@ -248,8 +258,20 @@ struct bskenv_handle {
         }                                                                                            \
     } while (0)
 
+// Launches queued on the caller's streams are ordered before a later host-buffer step (which runs on the handle's own
+// stream) through this event; the host-buffer step itself is complete when bskenv_step_host[_wait] returns.
+static cudaError_t note_launch(bskenv_handle *h, cudaStream_t st)
+{
+    h->ev_valid = 1;
+    return cudaEventRecord(h->ev_last, st);
+}
+#define NO_HOST_PENDING(h, what)                                                                                        \
+    do {                                                                                                                \
+        if ((h)->host_pending) { (h)->err = what ": a host-buffer step is in flight (call bskenv_step_host_wait first)"; return BSKENV_EINVAL; } \
+    } while (0)
+
 static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double *rew, uint8_t *done, uint8_t *reason,
-                       double *term_obs, cudaStream_t st)
+                       double *term_obs, cudaStream_t st, double *ep_return = nullptr, int64_t *ep_length = nullptr)
 {
     const int wpb = LEO_BLOCK / 32;
     const int64_t groups = (h->n + 31) / 32;
@@ -271,8 +293,9 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
             CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bus_bytes)); \
             attr_set[h->device & 63] = true;                                                                   \
         }                                                                                                      \
+        h->kernel_name = "leo_step_kernel<" #NRW "," #J2 "," #DIAG "," #F32 ">";                                \
         leo_step_kernel<NRW, J2, DIAG, F32><<<grid, LEO_BLOCK, bus_bytes, st>>>(h->P, h->PF, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
-                                                                                 rew, done, reason, term_obs, h->stats, sc); \
+                                                                                 rew, done, reason, term_obs, h->stats, sc, ep_return, ep_length); \
     } while (0)
     if (h->P.grav_pfix) {     // degree-2 field in the planet-fixed frame (general EOM path)
         if (h->P.nrw == 4) LEO_LAUNCH(4, 2, false, false);
@@ -289,6 +312,7 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
 #undef LEO_LAUNCH
     CU_TRY(h, cudaGetLastError());
     h->launches++;
+    if (st != h->own_stream || !st) CU_TRY(h, note_launch(h, st));
     return BSKENV_OK;
 }
 
@@ -299,6 +323,7 @@ void bskenv_default_config(bskenv_config *cfg) { leo_host::default_config(cfg); 
 const char *bskenv_last_error(const bskenv_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 int64_t bskenv_num_envs(const bskenv_handle *h) { return h ? h->n : 0; }
 int64_t bskenv_launch_count(const bskenv_handle *h) { return h ? h->launches : 0; }
+const char *bskenv_kernel_name(const bskenv_handle *h) { return (h && h->kernel_name) ? h->kernel_name : ""; }
 double bskenv_flops_per_step(const bskenv_handle *h) { return h ? leo_host::flops_per_step(h->P) : 0.0; }
 
 int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t first_env_index, bskenv_handle **out)
@@ -321,12 +346,13 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     }
     leo_host::build_params_f(h->P, h->PF);
     h->P.first_env_index = first_env_index;
-    h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
+    h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0; h->kernel_name = nullptr;
     h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;
     h->d_eph[0] = h->d_eph[1] = nullptr;
-    h->d_act = nullptr; h->d_obs = h->d_rew = nullptr; h->d_done = h->d_reason = nullptr;
-    h->h_act = nullptr; h->h_obs = h->h_rew = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
+    for (int k = 0; k < 8; k++) { h->h_stage[k] = nullptr; h->pend_user[k] = nullptr; h->pend_bytes[k] = 0; }
+    h->host_pending = 0; h->own_stream = nullptr; h->ev_last = nullptr; h->ev_valid = 0;
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * (size_t)(4 + (n_envs + 31) / 32));
     if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * LEO_ND * h->stride);
@@ -352,9 +378,9 @@ int bskenv_destroy(bskenv_handle *h)
     cudaSetDevice(h->device);
     cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched);
     cudaFree(h->d_eph[0]); cudaFree(h->d_eph[1]);
-    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_done); cudaFree(h->d_reason);
-    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_done); cudaFreeHost(h->h_reason);
-    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    for (int k = 0; k < 8; k++) cudaFreeHost(h->h_stage[k]);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
     delete h;
     return BSKENV_OK;
 }
@@ -379,7 +405,7 @@ int bskenv_set_ephemeris(bskenv_handle *h, int kind, double t0, double seg_len, 
     if (n_seg <= 0) return BSKENV_OK;                           // back to the analytic model
     if (!coef || n_coef < 1 || n_coef > 64 || !(seg_len > 0.)) { h->err = "bskenv_set_ephemeris: bad table shape"; return BSKENV_EINVAL; }
     // an episode runs from sim time 0 to (max_length + 1) decision intervals: the table has to cover it
-    const double t_end = (double)(h->P.max_length + 1) * (double)h->P.step_ns * 1e-9;
+    const double t_end = ((double)h->P.max_length + 1.0) * (double)h->P.step_ns * 1e-9;   // max_length may be INT_MAX
     if (t0 > 0. || t0 + seg_len * n_seg < t_end) {
         h->err = "bskenv_set_ephemeris: the table does not cover one episode [0, (max_length + 1) * step_duration]";
         return BSKENV_EINVAL;
@@ -394,10 +420,12 @@ int bskenv_set_ephemeris(bskenv_handle *h, int kind, double t0, double seg_len, 
 static int do_reset(bskenv_handle *h, int mode, const double *ics_in, const uint8_t *mask, double *obs, void *stream)
 {
     if (!h) return BSKENV_EINVAL;
+    NO_HOST_PENDING(h, "bskenv_reset");
     CU_TRY(h, cudaSetDevice(h->device));
     const int grid = (int)((h->n + 255) / 256);
     leo_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, mode, ics_in, mask, obs);
     CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, note_launch(h, (cudaStream_t)stream));
     return BSKENV_OK;
 }
 int bskenv_reset_seeded(bskenv_handle *h, uint64_t seed, const uint8_t *mask_dev, double *obs_dev, void *stream)
@@ -429,37 +457,113 @@ int bskenv_step(bskenv_handle *h, const int32_t *actions_dev, double *obs_dev, d
 {
     if (!h) return BSKENV_EINVAL;
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev || !done_reason_dev) { h->err = "bskenv_step: null buffer"; return BSKENV_EINVAL; }
+    NO_HOST_PENDING(h, "bskenv_step");
     CU_TRY(h, cudaSetDevice(h->device));
     return launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, done_reason_dev, term_obs_dev, (cudaStream_t)stream);
 }
 
-int bskenv_step_host(bskenv_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done, uint8_t *done_reason)
+int bskenv_step_info(bskenv_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev,
+                     uint8_t *done_reason_dev, double *term_obs_dev, double *ep_return_dev, int64_t *ep_length_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev || !done_reason_dev) { h->err = "bskenv_step_info: null buffer"; return BSKENV_EINVAL; }
+    if ((ep_return_dev == nullptr) != (ep_length_dev == nullptr)) { h->err = "bskenv_step_info: ep_return and ep_length go together"; return BSKENV_EINVAL; }
+    NO_HOST_PENDING(h, "bskenv_step_info");
+    CU_TRY(h, cudaSetDevice(h->device));
+    return launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, done_reason_dev, term_obs_dev, (cudaStream_t)stream,
+                       ep_return_dev, ep_length_dev);
+}
+
+// ---- host-buffer entry points (the reference-facing plugin path) ----------------------------------------------------
+// The step kernel reads the actions from and writes its results to PINNED HOST memory directly (zero-copy over PCIe:
+// 4 B in and 50 B out per env, spread over the whole launch, so no transfer is exposed after the kernel).  Caller buffers
+// that are already page-locked (bskenv_alloc_host, cudaHostRegister, torch pin_memory) are used in place; pageable ones go
+// through page-locked staging owned by the handle plus one memcpy each.
+namespace {
+struct HostMap { void *dev; void *stage; };          // device-visible address, and the staging block behind it (or null)
+bool host_pinned(const void *p, void **dev)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    *dev = a.devicePointer;
+    return true;
+}
+}  // namespace
+
+static int host_map(bskenv_handle *h, const void *user, size_t bytes, int slot, HostMap *m)
+{
+    m->stage = nullptr;
+    if (host_pinned(user, &m->dev)) return BSKENV_OK;
+    if (!h->h_stage[slot]) CU_TRY(h, cudaHostAlloc(&h->h_stage[slot], bytes, cudaHostAllocMapped));
+    m->stage = h->h_stage[slot];
+    CU_TRY(h, cudaHostGetDevicePointer(&m->dev, m->stage, 0));
+    return BSKENV_OK;
+}
+
+int bskenv_step_host_async(bskenv_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done,
+                           uint8_t *done_reason, double *term_obs, double *ep_return, int64_t *ep_length)
 {
     if (!h) return BSKENV_EINVAL;
     if (!actions || !obs || !reward || !done || !done_reason) { h->err = "bskenv_step_host: null buffer"; return BSKENV_EINVAL; }
+    if ((ep_return == nullptr) != (ep_length == nullptr)) { h->err = "bskenv_step_host: ep_return and ep_length go together"; return BSKENV_EINVAL; }
+    if (h->host_pending) { h->err = "bskenv_step_host_async: the previous host step has not been waited for"; return BSKENV_EINVAL; }
     CU_TRY(h, cudaSetDevice(h->device));
-    const int64_t n = h->n;
-    if (!h->own_stream) {
-        CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-        CU_TRY(h, cudaMalloc(&h->d_act, n * sizeof(int32_t))); CU_TRY(h, cudaMalloc(&h->d_obs, n * 5 * sizeof(double)));
-        CU_TRY(h, cudaMalloc(&h->d_rew, n * sizeof(double))); CU_TRY(h, cudaMalloc(&h->d_done, n)); CU_TRY(h, cudaMalloc(&h->d_reason, n));
-        CU_TRY(h, cudaMallocHost(&h->h_act, n * sizeof(int32_t))); CU_TRY(h, cudaMallocHost(&h->h_obs, n * 5 * sizeof(double)));
-        CU_TRY(h, cudaMallocHost(&h->h_rew, n * sizeof(double))); CU_TRY(h, cudaMallocHost(&h->h_done, n)); CU_TRY(h, cudaMallocHost(&h->h_reason, n));
-    }
+    const size_t n = (size_t)h->n;
+    if (!h->own_stream) CU_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     cudaStream_t st = h->own_stream;
-    // the handle's stream does not synchronise with the caller's streams: wait for any bskenv_step / reset still in flight
-    CU_TRY(h, cudaDeviceSynchronize());
-    memcpy(h->h_act, actions, n * sizeof(int32_t));
-    CU_TRY(h, cudaMemcpyAsync(h->d_act, h->h_act, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    int rc = launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_reason, nullptr, st);
+    HostMap m[8];
+    int rc;
+    if ((rc = host_map(h, actions, n * sizeof(int32_t), 0, &m[0]))) return rc;
+    if ((rc = host_map(h, obs, n * 5 * sizeof(double), 1, &m[1]))) return rc;
+    if ((rc = host_map(h, reward, n * sizeof(double), 2, &m[2]))) return rc;
+    if ((rc = host_map(h, done, n, 3, &m[3]))) return rc;
+    if ((rc = host_map(h, done_reason, n, 4, &m[4]))) return rc;
+    m[5].dev = m[6].dev = m[7].dev = nullptr; m[5].stage = m[6].stage = m[7].stage = nullptr;
+    if (term_obs && (rc = host_map(h, term_obs, n * 5 * sizeof(double), 7, &m[7]))) return rc;
+    if (ep_return) {
+        if ((rc = host_map(h, ep_return, n * sizeof(double), 5, &m[5]))) return rc;
+        if ((rc = host_map(h, ep_length, n * sizeof(int64_t), 6, &m[6]))) return rc;
+    }
+    if (m[0].stage) memcpy(m[0].stage, actions, n * sizeof(int32_t));
+    // order after whatever the caller queued through bskenv_step / reset / set_state on its own streams
+    if (h->ev_valid) CU_TRY(h, cudaStreamWaitEvent(st, h->ev_last, 0));
+    rc = launch_step(h, (const int32_t *)m[0].dev, (double *)m[1].dev, (double *)m[2].dev, (uint8_t *)m[3].dev, (uint8_t *)m[4].dev,
+                     (double *)m[7].dev, st, (double *)m[5].dev, (int64_t *)m[6].dev);
     if (rc) return rc;
-    CU_TRY(h, cudaMemcpyAsync(h->h_obs, h->d_obs, n * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaMemcpyAsync(h->h_reason, h->d_reason, n, cudaMemcpyDeviceToHost, st));
-    CU_TRY(h, cudaStreamSynchronize(st));
-    memcpy(obs, h->h_obs, n * 5 * sizeof(double)); memcpy(reward, h->h_rew, n * sizeof(double));
-    memcpy(done, h->h_done, n); memcpy(done_reason, h->h_reason, n);
+    void *user[8] = {nullptr, obs, reward, done, done_reason, ep_return, ep_length, term_obs};
+    const size_t bytes[8] = {0, n * 5 * sizeof(double), n * sizeof(double), n, n, n * sizeof(double), n * sizeof(int64_t), n * 5 * sizeof(double)};
+    for (int k = 0; k < 8; k++) { h->pend_user[k] = m[k].stage ? user[k] : nullptr; h->pend_bytes[k] = bytes[k]; }
+    h->host_pending = 1;
+    return BSKENV_OK;
+}
+
+int bskenv_step_host_wait(bskenv_handle *h)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!h->host_pending) return BSKENV_OK;
+    h->host_pending = 0;
+    CU_TRY(h, cudaStreamSynchronize(h->own_stream));
+    for (int k = 1; k < 8; k++)
+        if (h->pend_user[k]) memcpy(h->pend_user[k], h->h_stage[k], h->pend_bytes[k]);
+    return BSKENV_OK;
+}
+
+int bskenv_step_host(bskenv_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done, uint8_t *done_reason)
+{
+    int rc = bskenv_step_host_async(h, actions, obs, reward, done, done_reason, nullptr, nullptr, nullptr);
+    return rc ? rc : bskenv_step_host_wait(h);
+}
+
+int bskenv_alloc_host(size_t bytes, void **out)
+{
+    if (!out || bytes == 0) return BSKENV_EINVAL;
+    if (cudaHostAlloc(out, bytes, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); *out = nullptr; return BSKENV_ECUDA; }
+    return BSKENV_OK;
+}
+int bskenv_free_host(void *p)
+{
+    if (p && cudaFreeHost(p) != cudaSuccess) { cudaGetLastError(); return BSKENV_ECUDA; }
     return BSKENV_OK;
 }
 
@@ -488,6 +592,7 @@ int bskenv_set_state(bskenv_handle *h, const double *dstate_dev, const int64_t *
     if (dstate_dev) copy_fields_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(dstate_dev, h->n, h->S, h->stride, h->n, LEO_ND);
     if (istate_dev) copy_fields_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(istate_dev, h->n, h->I, h->stride, h->n, LEO_NI);
     CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, note_launch(h, (cudaStream_t)stream));
     return BSKENV_OK;
 }
 int bskenv_state_field(const char *name, int32_t *is_int)

@@ -51,7 +51,9 @@ struct OnSched { int *sched; int n_groups; int dynamic; };
 __device__ __forceinline__ int opnav_task_set(const int64_t *__restrict__ I, int64_t stride, int64_t e, int action)
 {
     if (I[(int64_t)OI_FIRST * stride + e]) return 0;
-    return action == 0 ? 0 : (action == 1 ? 1 : (int)I[(int64_t)OI_MODE * stride + e]);
+    // an unknown action keeps the mode in force; any non-zero mode field (also a foreign one injected through
+    // bskenv_opnav_set_state) is the sun-safe set, so that every env lands in exactly one of the two buckets
+    return action == 0 ? 0 : (action == 1 ? 1 : (I[(int64_t)OI_MODE * stride + e] != 0 ? 1 : 0));
 }
 __global__ void __launch_bounds__(256)
 opnav_bucket_count_kernel(const int64_t *__restrict__ I, int64_t stride, int64_t n, const int32_t *__restrict__ actions, int *__restrict__ sched)
@@ -79,6 +81,12 @@ opnav_bucket_fill_kernel(const int64_t *__restrict__ I, int64_t stride, int64_t 
         base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
         if (cls == c) perm[(c == 0 ? 0 : sched[1]) + base + __popc(m & ((1u << lane) - 1))] = (int32_t)e;
     }
+}
+
+__global__ void opnav_perm_identity_kernel(int32_t *__restrict__ perm, int64_t stride, int64_t n)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < stride) perm[e] = (int32_t)(e < n ? e : n - 1);
 }
 
 // per-thread scratch in shared memory: filter (49 doubles) + cold dynamics data (19) + 1 pad = 69, an odd stride (conflict-free)
@@ -219,9 +227,10 @@ struct bskenv_opnav_handle {
     int32_t *perm;              // lane assignment of the step kernel (envs bucketed by task set)
     double *d_eph;              // device copy of the Sun ephemeris table
     int sm_count;
-    int32_t *d_act; double *d_obs, *d_rew, *d_dbg; uint8_t *d_done, *d_reason;
-    int32_t *h_act; double *h_obs, *h_rew, *h_dbg; uint8_t *h_done, *h_reason;
+    void *h_stage[6];           // page-locked staging for pageable caller buffers: actions, obs, reward, done, reason, debug
     cudaStream_t own_stream;
+    cudaEvent_t ev_last;        // recorded after every launch queued through the device-buffer entry points
+    int ev_valid;
     int64_t launches;
     std::string err;
 };
@@ -264,6 +273,7 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
                                                  term_obs, h->stats, sc, h->perm);
     ON_TRY(h, cudaGetLastError());
     h->launches++;
+    if (st != h->own_stream || !st) { h->ev_valid = 1; ON_TRY(h, cudaEventRecord(h->ev_last, st)); }
     return BSKENV_OK;
 }
 
@@ -293,9 +303,10 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
     h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr; h->d_eph = nullptr;
-    h->d_act = nullptr; h->d_obs = h->d_rew = h->d_dbg = nullptr; h->d_done = h->d_reason = nullptr;
-    h->h_act = nullptr; h->h_obs = h->h_rew = h->h_dbg = nullptr; h->h_done = h->h_reason = nullptr; h->own_stream = nullptr;
+    for (int k = 0; k < 6; k++) h->h_stage[k] = nullptr;
+    h->own_stream = nullptr; h->ev_last = nullptr; h->ev_valid = 0;
     cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * h->stride);
@@ -307,6 +318,10 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
     if (e == cudaSuccess) e = cudaMemset(h->I, 0, sizeof(int64_t) * OPNAV_NI * h->stride);
     if (e == cudaSuccess) e = cudaMemset(h->ics, 0, sizeof(double) * OPNAV_IC_DIM * h->stride);
     if (e == cudaSuccess) e = cudaMemset(h->stats, 0, sizeof(double) * OST_N);
+    if (e == cudaSuccess) {              // lane assignment starts as the identity (every slot names a valid env)
+        opnav_perm_identity_kernel<<<(int)((h->stride + 255) / 256), 256>>>(h->perm, h->stride, h->n);
+        e = cudaGetLastError();
+    }
     if (e != cudaSuccess) {
         g_opnav_create_error = std::string("bskenv_opnav_create: ") + cudaGetErrorString(e);
         bskenv_opnav_destroy(h);
@@ -321,10 +336,9 @@ int bskenv_opnav_destroy(bskenv_opnav_handle *h)
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
     cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm); cudaFree(h->d_eph);
-    cudaFree(h->d_act); cudaFree(h->d_obs); cudaFree(h->d_rew); cudaFree(h->d_dbg); cudaFree(h->d_done); cudaFree(h->d_reason);
-    cudaFreeHost(h->h_act); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_rew); cudaFreeHost(h->h_dbg); cudaFreeHost(h->h_done);
-    cudaFreeHost(h->h_reason);
-    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
+    for (int k = 0; k < 6; k++) cudaFreeHost(h->h_stage[k]);
+    if (h->ev_last) cudaEventDestroy(h->ev_last);
     delete h;
     return BSKENV_OK;
 }
@@ -339,7 +353,7 @@ int bskenv_opnav_set_ephemeris(bskenv_opnav_handle *h, double t0, double seg_len
     E.coef = nullptr; E.nseg = 0; E.ncoef = 0; E.t0 = 0.; E.seg_len = 0.;
     if (n_seg <= 0) return BSKENV_OK;
     if (!coef || n_coef < 1 || n_coef > 64 || !(seg_len > 0.)) { h->err = "bskenv_opnav_set_ephemeris: bad table shape"; return BSKENV_EINVAL; }
-    const double t_end = (double)(h->P.max_length + 1) * (double)h->P.ticks_per_step * h->P.dt;
+    const double t_end = ((double)h->P.max_length + 1.0) * (double)h->P.ticks_per_step * h->P.dt;   // max_length may be INT_MAX
     if (t0 > 0. || t0 + seg_len * n_seg < t_end) {
         h->err = "bskenv_opnav_set_ephemeris: the table does not cover one episode [0, (max_length + 1) * step_duration]";
         return BSKENV_EINVAL;
@@ -358,6 +372,7 @@ static int opnav_do_reset(bskenv_opnav_handle *h, int mode, const double *ics_in
     const int grid = (int)((h->n + 255) / 256);
     opnav_reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, mode, ics_in, mask, obs);
     ON_TRY(h, cudaGetLastError());
+    h->ev_valid = 1; ON_TRY(h, cudaEventRecord(h->ev_last, (cudaStream_t)stream));
     return BSKENV_OK;
 }
 int bskenv_opnav_reset_seeded(bskenv_opnav_handle *h, uint64_t seed, const uint8_t *mask_dev, double *obs_dev, void *stream)
@@ -393,38 +408,45 @@ int bskenv_opnav_step(bskenv_opnav_handle *h, const int32_t *actions_dev, double
     return opnav_launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, done_reason_dev, debug_dev, term_obs_dev, (cudaStream_t)stream);
 }
 
+// Host-buffer entry point: zero-copy, as bskenv_step_host (bskenv.cu) -- the kernel reads the actions from and writes its
+// results to page-locked host memory directly; pageable caller buffers go through staging owned by the handle.
+static int opnav_host_map(bskenv_opnav_handle *h, const void *user, size_t bytes, int slot, void **dev, void **stage)
+{
+    *stage = nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, user) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer) { *dev = a.devicePointer; return BSKENV_OK; }
+    cudaGetLastError();
+    if (!h->h_stage[slot]) ON_TRY(h, cudaHostAlloc(&h->h_stage[slot], bytes, cudaHostAllocMapped));
+    *stage = h->h_stage[slot];
+    ON_TRY(h, cudaHostGetDevicePointer(dev, *stage, 0));
+    return BSKENV_OK;
+}
+
 int bskenv_opnav_step_host(bskenv_opnav_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done,
                            uint8_t *done_reason, double *debug)
 {
     if (!h) return BSKENV_EINVAL;
     if (!actions || !obs || !reward || !done || !done_reason) { h->err = "bskenv_opnav_step_host: null buffer"; return BSKENV_EINVAL; }
     ON_TRY(h, cudaSetDevice(h->device));
-    const int64_t n = h->n;
-    if (!h->own_stream) {
-        ON_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
-        ON_TRY(h, cudaMalloc(&h->d_act, n * sizeof(int32_t))); ON_TRY(h, cudaMalloc(&h->d_obs, n * 4 * sizeof(double)));
-        ON_TRY(h, cudaMalloc(&h->d_rew, n * sizeof(double))); ON_TRY(h, cudaMalloc(&h->d_dbg, n * 12 * sizeof(double)));
-        ON_TRY(h, cudaMalloc(&h->d_done, n)); ON_TRY(h, cudaMalloc(&h->d_reason, n));
-        ON_TRY(h, cudaMallocHost(&h->h_act, n * sizeof(int32_t))); ON_TRY(h, cudaMallocHost(&h->h_obs, n * 4 * sizeof(double)));
-        ON_TRY(h, cudaMallocHost(&h->h_rew, n * sizeof(double))); ON_TRY(h, cudaMallocHost(&h->h_dbg, n * 12 * sizeof(double)));
-        ON_TRY(h, cudaMallocHost(&h->h_done, n)); ON_TRY(h, cudaMallocHost(&h->h_reason, n));
-    }
+    const size_t n = (size_t)h->n;
+    if (!h->own_stream) ON_TRY(h, cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     cudaStream_t st = h->own_stream;
-    // the handle's stream does not synchronise with the caller's streams: wait for any step / reset still in flight
-    ON_TRY(h, cudaDeviceSynchronize());
-    memcpy(h->h_act, actions, n * sizeof(int32_t));
-    ON_TRY(h, cudaMemcpyAsync(h->d_act, h->h_act, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    int rc = opnav_launch_step(h, h->d_act, h->d_obs, h->d_rew, h->d_done, h->d_reason, debug ? h->d_dbg : nullptr, nullptr, st);
+    void *user[6] = {(void *)actions, obs, reward, done, done_reason, debug};
+    const size_t bytes[6] = {n * sizeof(int32_t), n * 4 * sizeof(double), n * sizeof(double), n, n, n * 12 * sizeof(double)};
+    void *dev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, *stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 6; k++) {
+        if (!user[k]) continue;
+        int rc = opnav_host_map(h, user[k], bytes[k], k, &dev[k], &stage[k]);
+        if (rc) return rc;
+    }
+    if (stage[0]) memcpy(stage[0], actions, bytes[0]);
+    if (h->ev_valid) ON_TRY(h, cudaStreamWaitEvent(st, h->ev_last, 0));     // after the caller's device-buffer steps / resets
+    int rc = opnav_launch_step(h, (const int32_t *)dev[0], (double *)dev[1], (double *)dev[2], (uint8_t *)dev[3], (uint8_t *)dev[4],
+                               (double *)dev[5], nullptr, st);
     if (rc) return rc;
-    ON_TRY(h, cudaMemcpyAsync(h->h_obs, h->d_obs, n * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    ON_TRY(h, cudaMemcpyAsync(h->h_rew, h->d_rew, n * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (debug) ON_TRY(h, cudaMemcpyAsync(h->h_dbg, h->d_dbg, n * 12 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    ON_TRY(h, cudaMemcpyAsync(h->h_done, h->d_done, n, cudaMemcpyDeviceToHost, st));
-    ON_TRY(h, cudaMemcpyAsync(h->h_reason, h->d_reason, n, cudaMemcpyDeviceToHost, st));
     ON_TRY(h, cudaStreamSynchronize(st));
-    memcpy(obs, h->h_obs, n * 4 * sizeof(double)); memcpy(reward, h->h_rew, n * sizeof(double));
-    if (debug) memcpy(debug, h->h_dbg, n * 12 * sizeof(double));
-    memcpy(done, h->h_done, n); memcpy(done_reason, h->h_reason, n);
+    for (int k = 1; k < 6; k++)
+        if (stage[k]) memcpy(user[k], stage[k], bytes[k]);
     return BSKENV_OK;
 }
 
@@ -453,6 +475,7 @@ int bskenv_opnav_set_state(bskenv_opnav_handle *h, const double *dstate_dev, con
     if (dstate_dev) opnav_copy_fields_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(dstate_dev, h->n, h->S, h->stride, h->n, OPNAV_ND);
     if (istate_dev) opnav_copy_fields_kernel<int64_t><<<grid, 256, 0, (cudaStream_t)stream>>>(istate_dev, h->n, h->I, h->stride, h->n, OPNAV_NI);
     ON_TRY(h, cudaGetLastError());
+    h->ev_valid = 1; ON_TRY(h, cudaEventRecord(h->ev_last, (cudaStream_t)stream));
     return BSKENV_OK;
 }
 int bskenv_opnav_state_field(const char *name, int32_t *is_int)

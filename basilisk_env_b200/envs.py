@@ -88,7 +88,10 @@ def _decode_action(action):
     return int(s) if s in ("0", "1", "2") else -1
 
 
-class leoPowerAttEnv:
+_GymEnv = spaces.gym_env_base()
+
+
+class leoPowerAttEnv(_GymEnv):
     """Simple attitude/orbit control problem: decide when to point at the ground (reward), at the
     Sun (power) or to dump wheel momentum.  gym API of the reference environment."""
 

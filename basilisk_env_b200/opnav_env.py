@@ -274,7 +274,10 @@ class scenario_OpNav:
             self._vec = None
 
 
-class opNavEnv:
+_GymEnv = spaces.gym_env_base()
+
+
+class opNavEnv(_GymEnv):
     """OpNav scenario (opNavEnvironment.py:11-177): decide when to image Mars and when to point at the Sun."""
 
     def __init__(self, device=0, **config):

@@ -61,3 +61,16 @@ class Discrete:
 
     def __eq__(self, other):
         return isinstance(other, Discrete) and self.n == other.n
+
+
+def gym_env_base():
+    """`gym.Env` when a gym is importable (the reference declares `class leoPowerAttEnv(gym.Env)`,
+    /root/reference/basilisk_env/envs/leoPowerAttitudeEnvironment.py:14, so wrappers that isinstance-check accept the
+    env), else `object`: gym / gymnasium are not installed in the build image."""
+    import importlib
+    for modname in ("gym", "gymnasium"):
+        try:
+            return importlib.import_module(modname).Env
+        except Exception:       # not installed (or a broken install): the env classes stand alone
+            continue
+    return object

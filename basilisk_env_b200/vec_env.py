@@ -71,6 +71,9 @@ class LeoPowerAttVecEnv:
             self.reward = torch.zeros(n, dtype=torch.float64, device=self.device)
             self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
             self.done_reason = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            # ENV:130-136 per env: reward_total and curr_step, the `info['episode']` record where done
+            self.episode_r = torch.zeros(n, dtype=torch.float64, device=self.device)
+            self.episode_l = torch.zeros(n, dtype=torch.int64, device=self.device)
         self.observation_space = spaces.Box(-1e16, 1e16, shape=(OBS_DIM, 1))
         self.action_space = spaces.Discrete(3)
         self.max_length = int(self.cfg.max_length)
@@ -176,27 +179,59 @@ class LeoPowerAttVecEnv:
         a = actions.to(device=self.device, dtype=torch.int32).contiguous()
         if a.numel() != self.num_envs:
             raise ValueError("one action per env")
-        self._check(self._L.bskenv_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(self.obs.data_ptr()),
-                                        C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
-                                        C.c_void_p(self.done_reason.data_ptr()), C.c_void_p(self.term_obs.data_ptr()),
-                                        self._stream()), "bskenv_step")
+        self._check(self._L.bskenv_step_info(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                                             C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
+                                             C.c_void_p(self.done_reason.data_ptr()), C.c_void_p(self.term_obs.data_ptr()),
+                                             C.c_void_p(self.episode_r.data_ptr()), C.c_void_p(self.episode_l.data_ptr()),
+                                             self._stream()), "bskenv_step_info")
         self._last_actions = a          # keep alive until the launch has consumed it
-        info = {"done_reason": self.done_reason, "terminal_obs": self.term_obs}
+        # episode_r / episode_l: the reference's info['episode'] = {'r', 'l'} (ENV:130-136) for the envs with done set
+        info = {"done_reason": self.done_reason, "terminal_obs": self.term_obs, "episode_r": self.episode_r,
+                "episode_l": self.episode_l}
         return self.obs, self.reward, self.done, info
 
-    def step_host(self, actions, out=None):
-        """Host-buffer step (the plugin path a CPU-side RL trainer calls): numpy int32 [N] in, numpy
-        (obs, reward, done, done_reason) out; copies and synchronisation happen inside the C call."""
-        a = np.ascontiguousarray(actions, dtype=np.int32)
+    def host_buffers(self, episode=False):
+        """Page-locked, device-mapped numpy buffers for `step_host`: (actions int32 [N], (obs [N,5], reward [N], done u8 [N],
+        done_reason u8 [N][, episode_r f64 [N], episode_l i64 [N]])).  The step kernel reads / writes them in place
+        (zero-copy over PCIe); ordinary numpy arrays work too, through staging and one memcpy each.  With `episode` the
+        tuple also carries the per-env episode record and terminal_obs [N,5] (rows of finished envs only)."""
+        n = self.num_envs
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()     # noqa: E731
+        out = [pin((n, OBS_DIM), torch.float64), pin(n, torch.float64), pin(n, torch.uint8), pin(n, torch.uint8)]
+        if episode:
+            out += [pin(n, torch.float64), pin(n, torch.int64), pin((n, OBS_DIM), torch.float64)]
+        return pin(n, torch.int32), tuple(out)
+
+    def step_host_async(self, actions, out=None):
+        """Queue one host-buffer step and return; `step_host_wait()` delivers the results.  `out` as returned by
+        `host_buffers()` (4 arrays, or 7 with the per-env episode record and the terminal observations)."""
+        a = actions if (isinstance(actions, np.ndarray) and actions.dtype == np.int32 and actions.flags.c_contiguous) \
+            else np.ascontiguousarray(actions, dtype=np.int32)
         if a.size != self.num_envs:
             raise ValueError("one action per env")
         if out is None:
             out = (np.empty((self.num_envs, OBS_DIM)), np.empty(self.num_envs), np.empty(self.num_envs, np.uint8),
                    np.empty(self.num_envs, np.uint8))
-        obs, rew, done, reason = out
-        self._check(self._L.bskenv_step_host(self._h, a.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
-                                             reason.ctypes.data), "bskenv_step_host")
-        return obs, rew, done, reason
+        ep_r = out[4].ctypes.data if len(out) > 4 else None
+        ep_l = out[5].ctypes.data if len(out) > 4 else None
+        term = out[6].ctypes.data if len(out) > 6 else None
+        self._check(self._L.bskenv_step_host_async(self._h, a.ctypes.data, out[0].ctypes.data, out[1].ctypes.data,
+                                                   out[2].ctypes.data, out[3].ctypes.data, term, ep_r, ep_l),
+                    "bskenv_step_host_async")
+        self._host_pending = (a, out)       # keep the buffers alive while the launch is in flight
+        return out
+
+    def step_host_wait(self):
+        self._check(self._L.bskenv_step_host_wait(self._h), "bskenv_step_host_wait")
+        pend, self._host_pending = getattr(self, "_host_pending", None), None
+        return pend[1] if pend else None
+
+    def step_host(self, actions, out=None):
+        """Host-buffer step (the plugin path a CPU-side RL trainer calls): numpy int32 [N] in, numpy
+        (obs, reward, done, done_reason[, episode_r, episode_l]) out; the transfers and the synchronisation happen inside
+        the C calls."""
+        self.step_host_async(actions, out)
+        return self.step_host_wait()
 
     # ------------------------------------------------------------------------------------------
     def get_state(self):
@@ -234,6 +269,10 @@ class LeoPowerAttVecEnv:
 
     def launch_count(self):
         return int(self._L.bskenv_launch_count(self._h))
+
+    def kernel_name(self):
+        """The step-kernel instantiation the last step launched (as ncu lists it)."""
+        return self._L.bskenv_kernel_name(self._h).decode()
 
     def flops_per_step(self):
         return float(self._L.bskenv_flops_per_step(self._h))

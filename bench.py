@@ -30,6 +30,8 @@ H2D_BYTES_PER_ENV = 4          # int32 action
 D2H_BYTES_PER_ENV = 5 * 8 + 8 + 1 + 1   # obs[5] f64, reward f64, done u8, done_reason u8
 # ALGORITHMIC bytes per env-step: persistent state read + written once, plus the step I/O
 STATE_BYTES_PER_ENV = (89 + 22) * 8
+# the ncu capture of the shipped build whose executed-flop count the roofline numerator is checked against
+FLOP_CAPTURE = "profiles/ncu_r01j.md: 2.082e6 per env-step"
 
 
 def parse():
@@ -101,15 +103,20 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
-def cpu_arm(envs_per_core_step, seconds, min_steps, warmup, threads=None, fixed_steps=None):
+CPU_BUILDS = {"parity": "-O2 -ffp-contract=off (the build every parity test runs against)",
+              "fast": "-O3 -march=native (contraction allowed; compiled on this box)"}
+
+
+def cpu_arm(envs_per_core_step, seconds, min_steps, warmup, threads=None, fixed_steps=None, build="fast"):
     """Times the oracle port (oracle/bsk_oracle.c, OpenMP over envs) on the host cores: the same
     workload definition (random initial orbits, i.i.d. uniform actions), bounded sample."""
     from oracle import oracle as orc
     from tests import parity
     threads = threads or host_threads()
+    L = orc.fast_lib() if build == "fast" else orc.lib()
     n = envs_per_core_step * threads
     rows = parity.sample_rows(orc, n, seed=7)
-    batch = orc.LeoEnvBatch(rows)
+    batch = orc.LeoEnvBatch(rows, L=L)
     rng = np.random.RandomState(3)
     for _ in range(warmup):
         batch.step(rng.randint(0, 3, n), nthreads=threads)
@@ -123,23 +130,39 @@ def cpu_arm(envs_per_core_step, seconds, min_steps, warmup, threads=None, fixed_
                 break
         elif el >= seconds and steps >= min_steps:
             break
-    return {"value": n * steps / el, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": f"{n} envs x {steps} decision steps (oracle/bsk_oracle.c, OpenMP over envs, {el:.1f} s)",
+    return {"value": n * steps / el, "unit": UNIT, "cores": threads, "kind": "port", "build": build, "build_flags": CPU_BUILDS[build],
+            "sample": f"{n} envs x {steps} decision steps (oracle/bsk_oracle.c, gcc {CPU_BUILDS[build].split(' (')[0]}, OpenMP over envs, "
+                      f"{threads} thread{'s' if threads > 1 else ''}, {el:.1f} s)",
             "ms_per_step": el / steps * 1e3, "envs": n, "steps": steps}
+
+
+def cpu_baseline_block(seconds):
+    """the restated CPU path with 1 thread and with all host threads, as the parity build and as an
+    optimised build.  The block's own value is the strongest of the four (optimised build, all threads)."""
+    per = max(seconds / 4.0, 1.0)
+    variants = [cpu_arm(8, per, 1, 1, threads=1, build="parity"), cpu_arm(8, per, 1, 1, threads=1, build="fast"),
+                cpu_arm(4, per, 2, 1, build="parity"), cpu_arm(4, per, 2, 1, build="fast")]
+    best = max(variants[2:], key=lambda v: v["value"])
+    keys = ("value", "unit", "cores", "kind", "sample", "build_flags")
+    out = {k: best[k] for k in keys}
+    out["variants"] = [{k: v[k] for k in ("value", "cores", "build_flags", "sample")} for v in variants]
+    out["note"] = ("in-repo FP64 restatement of the Basilisk 1.x algorithms (Basilisk itself cannot be built here); scalar code, one env "
+                   "per thread")
+    return out
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    res = cpu_arm(envs_per_core_step=32, seconds=0.0, min_steps=1, warmup=args.warmup, fixed_steps=args.steps)
+    res = cpu_arm(envs_per_core_step=32, seconds=0.0, min_steps=1, warmup=args.warmup, fixed_steps=args.steps, build="fast")
     line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.envs_per_gpu), "note":
                        "CPU arm = in-repo FP64 restatement of the Basilisk 1.x algorithms (Basilisk itself cannot be built "
-                       "or installed in this image: no Eigen/SWIG/conan/CSPICE, no network); each step is a bounded sample of "
-                       f"{res['envs']} envs of the same workload"},
-            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                       "or installed in this image: no Eigen/SWIG/conan/CSPICE, no network), optimised host build "
+                       f"({CPU_BUILDS['fast']}), all host threads; each step is a bounded sample of {res['envs']} envs of the same workload"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -184,7 +207,7 @@ def main():
                                   "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms_per_step"],
                                   "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                                   "data": "synthetic", "config": {"workload": opnav_workload_name(args.opnav_envs)},
-                                  "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                                  "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")},
                                   "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                                   "gpu_launches": 0}), flush=True)
             return
@@ -211,7 +234,9 @@ def main():
     n_act = K + W
     actions_dev = torch.randint(0, 3, (n_act, E), dtype=torch.int32, device=dev, generator=g)
     actions_host = actions_dev.cpu().numpy()
-    outs = (np.empty((E, 5)), np.empty(E), np.empty(E, np.uint8), np.empty(E, np.uint8))
+    # host side of the plugin call: page-locked buffers the library hands out (env.host_buffers -> zero-copy); a caller
+    # with ordinary numpy arrays gets the same result through staging + one memcpy per buffer
+    act_pinned, outs = env.host_buffers()
 
     # FP64 roofline denominator: measured live (MEASURED_PEAKS.json carries HBM and bf16 only)
     peak_tf = fp64_peak_tflops(local_rank, 0.5) if rank == 0 else None
@@ -222,17 +247,20 @@ def main():
     total_ms, per_ms = time_device_steps(env, actions_dev, K, W, torch, dist, world)
     # ---- end to end through the host-buffer C-ABI entry point (bskenv_step_host) ----
     for t in range(min(W, 3)):
-        env.step_host(actions_host[t], outs)
+        act_pinned[:] = actions_host[t]
+        env.step_host(act_pinned, outs)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0 = time.perf_counter()
     for t in range(K):
-        env.step_host(actions_host[W + t], outs)      # H2D copy, launch, D2H copies and sync inside the call
+        act_pinned[:] = actions_host[W + t]           # the trainer's actions of this step (host memory)
+        env.step_host(act_pinned, outs)               # actions in, results out and the sync: all inside the call
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - e0) * 1e3
     t_mark1 = time.perf_counter()
     launches = env.launch_count() - l0 - W - min(W, 3)
+    kernel_name = env.kernel_name()
     clocks = sampler.stop(t_mark0, t_mark1) if sampler else None
     checksum = float(outs[1].sum())
 
@@ -273,9 +301,9 @@ def main():
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "traffic_note": "ncu capture at 131072 envs (profiles/traffic.json); above the algorithmic bytes by design: the "
                                          "interval runs as 6 chunks with a state round trip each (DESIGN.md section 5), < 2 % of HBM bandwidth",
-                         "kernel": "leo_step_kernel<3,0,true,false>", "kernel_ms": kern_ms, "flop_per_env_step": flops,
+                         "kernel": kernel_name, "kernel_ms": kern_ms, "flop_per_env_step": flops,
                          "flop_source": "operation list of the kernel as built (bskenv_flops_per_step), equal to the executed "
-                                        "2*DFMA+DMUL+DADD count of ncu (profiles/ncu_r01c.md: 2.074e6 per env-step); the un-fused "
+                                        f"2*DFMA+DMUL+DADD count of ncu ({FLOP_CAPTURE}); the un-fused "
                                         "Basilisk formulation of SURVEY 8(d) would be 4.29e6",
                          "peak_source": "DFMA-chain microbenchmark run in this process (bskenv_fp64_peak); MEASURED_PEAKS.json "
                                         "has no FP64 figure; nominal 148 SM x 64 FMA/clk x 1.965 GHz = 37.2 TFLOP/s",
@@ -283,18 +311,19 @@ def main():
                                  "frac": alg_bytes / (kern_ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes_per_launch": alg_bytes,
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": H2D_BYTES_PER_ENV * E, "d2h_bytes_per_step": D2H_BYTES_PER_ENV * E,
-                    "ms_per_step": e2e_ms / K, "api": "bskenv_step_host (host numpy buffers, pinned staging inside the library)"},
+                    "ms_per_step": e2e_ms / K, "api": "bskenv_step_host with page-locked host buffers (env.host_buffers): the kernel reads the actions from and writes "
+                           "obs / reward / done / reason to host memory in place, over PCIe, inside the launch"},
             "gpu_launches": int(launches), "clocks": clocks,
             "episode_stats": stats, "checksum": checksum,
         }
         if not args.no_extra:
-            line["batch4096"] = side_batch(4096, torch, dev, flops, peak_tf)
+            line["batch4096"] = side_batch(4096, torch, dev, peak_tf)
             if world == 1:
+                line["stress"] = side_stress(65536, torch, dev, peak_tf)
                 line["opnav"] = side_opnav(args.opnav_envs, torch, dev, peak_tf, steps=3, warmup=3,
                                            cpu_seconds=0.0 if args.no_cpu_baseline else 4.0)
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_arm(envs_per_core_step=4, seconds=args.cpu_seconds, min_steps=2, warmup=1)
-            line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            line["cpu_baseline"] = cpu_baseline_block(args.cpu_seconds)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line), flush=True)
@@ -304,18 +333,59 @@ def main():
         dist.destroy_process_group()
 
 
-def side_batch(n, torch, dev, flops, peak_tf):
-    """BASELINE configs[1]: 4096 envs on one GPU (latency-bound: 128 warps on 148 SMs)."""
+def side_batch(n, torch, dev, peak_tf):
+    """BASELINE configs[1]: 4096 envs on one GPU (fewer env groups than SM sub-partitions: the small-batch organisation
+    of the step kernel)."""
     from basilisk_env_b200.vec_env import LeoPowerAttVecEnv
     env = LeoPowerAttVecEnv(n, device=dev.index, seed=5, auto_reset=True)
     env.reset()
-    acts = torch.randint(0, 3, (8, n), dtype=torch.int32, device=dev)
-    total_ms, per = time_device_steps(env, acts, 5, 3, torch, None, 1)
+    acts = torch.randint(0, 3, (13, n), dtype=torch.int32, device=dev)
+    total_ms, per = time_device_steps(env, acts, 10, 3, torch, None, 1)
+    flops, name = env.flops_per_step(), env.kernel_name()
     env.close()
-    ms = total_ms / 5
+    ms = total_ms / 10
     tf = flops * n / (ms * 1e-3) / 1e12
     return {"envs": n, "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "fp64_tflops": tf,
-            "frac": tf / peak_tf if peak_tf else None}
+            "frac": tf / peak_tf if peak_tf else None, "kernel": name}
+
+
+def side_stress(n, torch, dev, peak_tf, steps=5, warmup=3):
+    """BASELINE configs[4]: J2 + drag + eclipse + four-wheel pyramid with momentum dumping, 65536 envs per GPU, FP64 and
+    the mixed-precision build (precision = 1), with the deviation of the mixed trajectories from the FP64 ones after the
+    timed steps (same initial conditions, same actions, no auto-reset so that the envs stay comparable)."""
+    from basilisk_env_b200.vec_env import LeoPowerAttVecEnv
+    from basilisk_env_b200 import _native
+    F = lambda name: _native.state_field(name)[0]      # noqa: E731
+    g = torch.Generator(device=dev).manual_seed(99)
+    acts = torch.randint(0, 3, (steps + warmup, n), dtype=torch.int32, device=dev, generator=g)
+    out, states = {"envs": n, "config": "use_j2=1, rw_set=1 (four-wheel pyramid), i.i.d. actions {0,1,2}"}, {}
+    for prec, key in ((0, "fp64"), (1, "mixed")):
+        env = LeoPowerAttVecEnv(n, device=dev.index, seed=17, use_j2=1, rw_set=1, precision=prec)
+        env.reset()
+        total_ms, per = time_device_steps(env, acts, steps, warmup, torch, None, 1)
+        ms = float(np.mean(per))
+        flops = env.flops_per_step()
+        tf = flops * n / (ms * 1e-3) / 1e12
+        d, i = env.get_state()
+        states[key] = (d.clone(), i.clone(), env.done.clone())
+        out[key] = {"value": n * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps, "kernel": env.kernel_name()}
+        if prec == 0:
+            out[key]["roofline"] = {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
+                                    "frac": tf / peak_tf if peak_tf else None, "kernel_ms": ms, "flop_per_env_step": flops}
+        env.close()
+    d0, i0, dn0 = states["fp64"]; d1, i1, dn1 = states["mixed"]
+
+    def q(x):
+        x = x.flatten().double().cpu().numpy()
+        return {"median": float(np.median(x)), "p99": float(np.percentile(x, 99))}
+    out["speedup_mixed_over_fp64"] = out["fp64"]["ms_per_step"] / out["mixed"]["ms_per_step"]
+    out["deviation_after_steps"] = steps + warmup
+    out["deviation"] = {"position_m": q((d0[F("r_BN_N"):F("r_BN_N") + 3] - d1[F("r_BN_N"):F("r_BN_N") + 3]).norm(dim=0)),
+                        "sigma_BN": q((d0[F("sigma_BN"):F("sigma_BN") + 3] - d1[F("sigma_BN"):F("sigma_BN") + 3]).abs().max(dim=0).values),
+                        "wheel_rad_s": q((d0[F("Omega"):F("Omega") + 4] - d1[F("Omega"):F("Omega") + 4]).abs().max(dim=0).values),
+                        "done_flags_equal_frac": float((dn0 == dn1).double().mean()),
+                        "fire_counters_equal_frac": float((i0[F("fireCounter"):F("fireCounter") + 8] == i1[F("fireCounter"):F("fireCounter") + 8]).all(dim=0).double().mean())}
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
@@ -332,14 +402,13 @@ def opnav_workload_name(n):
             "i.i.d. uniform actions {0,1}, camera re-enabled by action 0, auto-reset, FP64; one step = 50 min = 3000 ticks")
 
 
-def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None):
+def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None, build="fast"):
     from oracle import opnav as on
-    from oracle import oracle as orc
     from tests import opnav_parity as par
     threads = threads or host_threads()
     n = envs_per_core * threads
     rows = par.sample_rows(on, n, seed=7)
-    batch = on.OpNavEnvBatch(rows, on.default_cfg(seed=5, camera_reenable=1))
+    batch = on.OpNavEnvBatch(rows, on.default_cfg(seed=5, camera_reenable=1), L=on.lib(fast=(build == "fast")))
     rng = np.random.RandomState(3)
     batch.step(rng.randint(0, 2, n), nthreads=threads)
     steps, t0 = 0, time.perf_counter()
@@ -350,7 +419,9 @@ def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None):
         if (fixed_steps is not None and steps >= fixed_steps) or (fixed_steps is None and el >= seconds):
             break
     return {"value": n * steps / el, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": el / steps * 1e3,
-            "sample": f"{n} envs x {steps} decision steps (oracle/opnav_oracle.c, OpenMP over envs, {el:.1f} s)"}
+            "build_flags": CPU_BUILDS[build],
+            "sample": f"{n} envs x {steps} decision steps (oracle/opnav_oracle.c, gcc {CPU_BUILDS[build].split(' (')[0]}, OpenMP over envs, "
+                      f"{threads} threads, {el:.1f} s)"}
 
 
 def opnav_traffic(n):
@@ -396,7 +467,7 @@ def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
            "gpu_launches": int(launches), "episode_stats": stats, "checksum": float(outs[0].sum())}
     if cpu_seconds > 0:
         cb = opnav_cpu_arm(2, cpu_seconds)
-        out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")}
     return out
 
 

@@ -16,6 +16,7 @@
  */
 #ifndef BSKENV_H
 #define BSKENV_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -134,12 +135,39 @@ int bskenv_get_ics(bskenv_handle *h, double *ics_dev, void *stream);
  * first observation of the new episode and `term_obs_dev` (double[n*5], may be NULL) the terminal one. */
 int bskenv_step(bskenv_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
                 uint8_t *done_dev, uint8_t *done_reason_dev, double *term_obs_dev, void *stream);
-/* Same call with HOST buffers (the reference-facing plugin path): copies actions to the device,
- * launches, copies obs/reward/done/reason back through pinned staging owned by the handle, and
- * synchronises.  It first waits for work already queued on the device (a preceding bskenv_step / reset on any stream),
- * so the two entry points can be mixed freely.  This is what bench.py times as `e2e`. */
+/* Same call with HOST buffers (the reference-facing plugin path), synchronous: on return the results are in the
+ * caller's buffers.  It is ordered after work queued earlier through the device-buffer entry points of this handle
+ * (event on the stream of the last such call), so the two kinds of entry point can be mixed freely.  See
+ * bskenv_step_host_async below for how the bytes move.  This is what bench.py times as `e2e`. */
 int bskenv_step_host(bskenv_handle *h, const int32_t *actions, double *obs, double *reward,
                      uint8_t *done, uint8_t *done_reason);
+
+/* SURVEY 8(f)-1 -- per-env episode bookkeeping of the reference's `info['episode'] = {'r': self.reward_total,
+ * 'l': self.curr_step}` (envs/leoPowerAttitudeEnvironment.py:130-136).  bskenv_step with two more caller-owned device
+ * outputs, written for EVERY env at every step (they are the episode record where done[e] != 0; with auto_reset they are
+ * taken before the in-kernel reset):
+ *   ep_return_dev double[n]  reward_total after this step (penalties included, :105,113,122)
+ *   ep_length_dev int64[n]   curr_step before its increment (:144), i.e. the reference's 'l'
+ * Both may be NULL (then this is bskenv_step). */
+int bskenv_step_info(bskenv_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
+                     uint8_t *done_dev, uint8_t *done_reason_dev, double *term_obs_dev, double *ep_return_dev,
+                     int64_t *ep_length_dev, void *stream);
+
+/* Host-buffer step, split in two (the shape of a VecEnv's step_async / step_wait): _async queues the launch on the handle's
+ * own stream and returns; _wait blocks until the results are in the caller's buffers.  One step may be in flight per handle;
+ * device-buffer calls on the same handle are refused until it has been waited for.  ep_return / ep_length as in
+ * bskenv_step_info (host memory, may both be NULL).
+ * ZERO-COPY: buffers that are page-locked and device-mapped (bskenv_alloc_host, cudaHostAlloc / cudaHostRegister, torch
+ * pin_memory) are read and written by the kernel in place -- the 4 B in and 50 B out per env cross PCIe while the launch
+ * runs, nothing is exposed after it.  Pageable buffers go through page-locked staging inside the handle and one memcpy
+ * each.  bskenv_step_host == _async + _wait. */
+int bskenv_step_host_async(bskenv_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done,
+                           uint8_t *done_reason, double *term_obs /* [n*5], may be NULL; rows of finished envs only */,
+                           double *ep_return, int64_t *ep_length);
+int bskenv_step_host_wait(bskenv_handle *h);
+/* page-locked, device-mapped host memory for the host-buffer entry points (any handle, any device) */
+int bskenv_alloc_host(size_t bytes, void **out);
+int bskenv_free_host(void *p);
 
 /* Checkpoint / parity injection: the whole persistent state as two SoA blocks,
  * double[n_double_fields][n] and int64[n_int_fields][n] (field-major). */
@@ -157,6 +185,8 @@ int bskenv_episode_stats(bskenv_handle *h, double *stats_host);
 
 /* Number of step-path kernel launches issued through this handle (bench.py's gpu_launches). */
 int64_t bskenv_launch_count(const bskenv_handle *h);
+/* Name of the step-kernel instantiation the last bskenv_step* call launched (as ncu lists it), "" before the first. */
+const char *bskenv_kernel_name(const bskenv_handle *h);
 
 /* FP64 FMA-pipe microbenchmark used as the roofline denominator (MEASURED_PEAKS.json has none):
  * returns achieved TFLOP/s of a register-resident DFMA chain kernel on `device`. */
@@ -226,7 +256,8 @@ int bskenv_opnav_get_ics(bskenv_opnav_handle *h, double *ics_dev, void *stream);
  *   debug double[n*12] (may be NULL: info['full_states']); term_obs double[n*4] (may be NULL; auto_reset only). */
 int bskenv_opnav_step(bskenv_opnav_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
                       uint8_t *done_dev, uint8_t *done_reason_dev, double *debug_dev, double *term_obs_dev, void *stream);
-/* same with HOST buffers (pinned staging inside the handle, synchronous): what bench.py times as e2e */
+/* same with HOST buffers (zero-copy for page-locked caller buffers, staging for pageable ones, as bskenv_step_host;
+ * synchronous): what bench.py times as e2e */
 int bskenv_opnav_step_host(bskenv_opnav_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done,
                            uint8_t *done_reason, double *debug);
 int bskenv_opnav_state_dims(const bskenv_opnav_handle *h, int32_t *n_double_fields, int32_t *n_int_fields);

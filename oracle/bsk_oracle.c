@@ -1464,6 +1464,11 @@ orc_leo_env *orc_env_create(const orc_leo_cfg *cfg)
 }
 void orc_env_destroy(orc_leo_env *e) { if (e->sim) orc_leo_destroy(e->sim); free(e); }
 orc_leo_sim *orc_env_sim(orc_leo_env *e) { return e->sim; }
+/* the env attributes a user of the reference may change before reset (ENV:25, :41: reward_mult = 1/max_length) */
+void orc_env_set_max_length(orc_leo_env *e, int max_length) { e->max_length = max_length; e->reward_mult = 1. / max_length; }
+/* ENV:130-136: the episode record `info['episode'] = {'r': self.reward_total, 'l': self.curr_step}` is assembled BEFORE
+ * `self.curr_step += 1` (ENV:144); orc_env_step has already incremented, hence the - 1 */
+void orc_env_episode(const orc_leo_env *e, double *r, int *l) { *r = e->reward_total; *l = e->curr_step - 1; }
 void orc_env_reset(orc_leo_env *e, const orc_leo_ic *ic, double ob[5])
 { /* ENV:172-191 / 202-216 */
     e->episode_over = 0; e->curr_step = 0; e->reward_total = 0;

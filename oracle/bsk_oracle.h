@@ -90,6 +90,8 @@ void orc_env_destroy(orc_leo_env *e);
 void orc_env_reset(orc_leo_env *e, const orc_leo_ic *ic, double ob[5]);
 void orc_env_step(orc_leo_env *e, int action, orc_env_out *out);
 orc_leo_sim *orc_env_sim(orc_leo_env *e);
+void orc_env_set_max_length(orc_leo_env *e, int max_length);
+void orc_env_episode(const orc_leo_env *e, double *reward_total, int *curr_step_at_info);   /* ENV:130-136 */
 
 /* Batched driver for the CPU baseline: steps n independent envs, OpenMP over envs. */
 void orc_env_step_batch(orc_leo_env **envs, int n, const int *actions, orc_env_out *outs, int nthreads);

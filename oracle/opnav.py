@@ -52,13 +52,13 @@ class Ukf(C.Structure):
                 ("n_bad", C.c_int64)]
 
 
-_BOUND = False
+_BOUND = set()
 
 
-def lib():
-    global _BOUND
-    L = _o.lib()
-    if not _BOUND:
+def lib(fast=False):
+    """fast=True: the -O3 -march=native host build of the same sources (bench.py's optimised CPU baseline)."""
+    L = _o.fast_lib() if fast else _o.lib()
+    if id(L) not in _BOUND:
         dp, vp = C.POINTER(C.c_double), C.c_void_p
         L.orc_opnav_default_cfg.argtypes = [C.POINTER(OpNavCfg)]
         L.orc_opnav_reference_orbit.argtypes = [C.POINTER(OpNavIC)]
@@ -90,7 +90,7 @@ def lib():
         L.orc_ukf_time_update.argtypes = [C.POINTER(Ukf), C.c_double]
         L.orc_ukf_meas_update.argtypes = [C.POINTER(Ukf), dp, dp]
         L.orc_sun_from_mars.argtypes = [C.c_double, dp, dp, dp]
-        _BOUND = True
+        _BOUND.add(id(L))
     return L
 
 
@@ -165,8 +165,8 @@ class OpNavSim:
 class OpNavEnv:
     """Oracle restatement of opNavEnv.reset/step for one env."""
 
-    def __init__(self, cfg=None):
-        self._L = lib()
+    def __init__(self, cfg=None, L=None):
+        self._L = L if L is not None else lib()
         self.cfg = cfg if cfg is not None else default_cfg()
         self._h = self._L.orc_opnav_env_create(C.byref(self.cfg))
 
@@ -195,11 +195,11 @@ class OpNavEnv:
 class OpNavEnvBatch:
     """n independent oracle envs stepped with OpenMP over envs (the CPU baseline)."""
 
-    def __init__(self, ic_rows, cfg=None, first_env_index=0):
-        self._L = lib()
+    def __init__(self, ic_rows, cfg=None, first_env_index=0, L=None):
+        self._L = L if L is not None else lib()
         self.cfg = cfg if cfg is not None else default_cfg()
         self.n = len(ic_rows)
-        self.envs = [OpNavEnv(self.cfg) for _ in range(self.n)]
+        self.envs = [OpNavEnv(self.cfg, self._L) for _ in range(self.n)]
         self.obs0 = np.stack([e.reset(r, first_env_index + k, 0) for k, (e, r) in enumerate(zip(self.envs, ic_rows))])
         self._handles = (C.c_void_p * self.n)(*[e._h for e in self.envs])
         self._outs = (OpNavOut * self.n)()

@@ -51,10 +51,48 @@ def build(force=False):
     return so
 
 
+def build_fast():
+    """The same sources as an optimised host build (-O3 -march=native, contraction allowed): bench.py's second CPU
+    baseline.  -march=native ties the binary to the CPU it was compiled on, so it is built where it runs, into
+    oracle/_fast/ under a name derived from that CPU's model and flags (the GPU box is not this container)."""
+    import hashlib
+    try:
+        info = open("/proc/cpuinfo").read()
+        key = "".join(l for l in info.splitlines()[:40] if l.startswith(("model name", "flags")))
+    except OSError:
+        key = "unknown"
+    tag = hashlib.sha1(key.encode()).hexdigest()[:10]
+    d = os.path.join(_HERE, "_fast")
+    os.makedirs(d, exist_ok=True)
+    so = os.path.join(d, f"libbsk_oracle_fast_{tag}.so")
+    srcs = [os.path.join(_HERE, f) for f in ("bsk_oracle.c", "bsk_oracle.h", "opnav_oracle.c", "opnav_oracle.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(so) < os.path.getmtime(f) for f in srcs):
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-fopenmp", "-std=c99", "-shared", "-o", so,
+                               os.path.join(_HERE, "bsk_oracle.c"), os.path.join(_HERE, "opnav_oracle.c"), "-lm"])
+    return so
+
+
+FAST_FLAGS = "-O3 -march=native"
+PARITY_FLAGS = "-O2 -ffp-contract=off"
+_FAST = None
+
+
+def fast_lib():
+    global _FAST
+    if _FAST is None:
+        _FAST = _bind(C.CDLL(build_fast()))
+    return _FAST
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        L = C.CDLL(build())
+        _LIB = _bind(C.CDLL(build()))
+    return _LIB
+
+
+def _bind(L):
+    if True:
         L.orc_leo_default_cfg.argtypes = [C.POINTER(LeoCfg)]
         L.orc_leo_create.restype = C.c_void_p
         L.orc_leo_create.argtypes = [C.POINTER(LeoIC), C.POINTER(LeoCfg)]
@@ -70,6 +108,8 @@ def lib():
         L.orc_env_step.argtypes = [C.c_void_p, C.c_int, C.POINTER(EnvOut)]
         L.orc_env_sim.restype = C.c_void_p
         L.orc_env_sim.argtypes = [C.c_void_p]
+        L.orc_env_set_max_length.argtypes = [C.c_void_p, C.c_int]
+        L.orc_env_episode.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.orc_env_step_batch.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int), C.POINTER(EnvOut), C.c_int]
         L.orc_max_threads.restype = C.c_int
         L.orc_elem2rv.argtypes = [C.c_double] * 7 + [C.POINTER(C.c_double)] * 2
@@ -87,8 +127,7 @@ def lib():
         L.orc_subMRP.argtypes = [C.POINTER(C.c_double)] * 3
         L.orc_addMRP.argtypes = [C.POINTER(C.c_double)] * 3
         L.orc_thr_force_mapping.argtypes = [C.POINTER(C.c_double)] * 3
-        _LIB = L
-    return _LIB
+    return L
 
 
 def _p(a):
@@ -199,10 +238,18 @@ class LeoSim:
 class LeoEnv:
     """Oracle restatement of leoPowerAttEnv.reset/step for one env."""
 
-    def __init__(self, cfg=None):
-        self._L = lib()
+    def __init__(self, cfg=None, max_length=None, L=None):
+        self._L = L if L is not None else lib()
         self.cfg = cfg if cfg is not None else default_cfg()
         self._h = self._L.orc_env_create(C.byref(self.cfg))
+        if max_length is not None:
+            self._L.orc_env_set_max_length(self._h, int(max_length))
+
+    def episode(self):
+        """(reward_total, curr_step) as the reference puts them into info['episode'] (ENV:130-136)."""
+        r, l = C.c_double(0.0), C.c_int(0)
+        self._L.orc_env_episode(self._h, C.byref(r), C.byref(l))
+        return r.value, l.value
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -229,11 +276,11 @@ class LeoEnv:
 class LeoEnvBatch:
     """n independent oracle envs stepped with OpenMP over envs (the CPU baseline)."""
 
-    def __init__(self, ic_rows, cfg=None):
-        self._L = lib()
+    def __init__(self, ic_rows, cfg=None, max_length=None, L=None):
+        self._L = L if L is not None else lib()
         self.cfg = cfg if cfg is not None else default_cfg()
         self.n = len(ic_rows)
-        self.envs = [LeoEnv(self.cfg) for _ in range(self.n)]
+        self.envs = [LeoEnv(self.cfg, max_length, self._L) for _ in range(self.n)]
         self.obs0 = np.stack([e.reset(r) for e, r in zip(self.envs, ic_rows)])
         self._handles = (C.c_void_p * self.n)(*[e._h for e in self.envs])
         self._outs = (EnvOut * self.n)()

@@ -278,7 +278,9 @@ def test_full_size_properties_65536_envs(bsk):
     rel = ((E1 - E0) / E0.abs()).abs()
     perigee_alt = r0.norm(dim=0).minimum(r1.norm(dim=0)) - 6378136.6
     assert float(rel[perigee_alt > 300e3].max()) < 1e-5           # drag is the only dissipation
-    assert bool((E1 <= E0 + 1e-3 * E0.abs() * 1e-6).all() or True)
+    # drag only removes two-body energy; what can add some is the Sun's tide: <= 2 mu_sun r / d^3 * v * 180 s = 0.8 J/kg,
+    # i.e. 3e-8 of |E0| = mu / 2a = 2.9e7 J/kg
+    assert bool((E1 <= E0 + 1e-7 * E0.abs()).all())
     assert float(d1[6:9].norm(dim=0).max()) <= 1.0 + 1e-12        # MRP switched to the inner set
     assert float(d1[parity.F("storedCharge")].min()) >= 0.0 and float(d1[parity.F("storedCharge")].max()) <= 72000.0
     assert bool((o[:, 4] >= 0).all()) and bool((o[:, 4] <= 1).all())
