@@ -945,7 +945,11 @@ LEO_HD Dyn rk4_step(const LeoParams &P, const Dyn &x, const StageIn &a, bool thr
     Dyn k, acc;
     k.r = k.v = k.s = k.w = acc.r = acc.v = acc.s = acc.w = mk(0., 0., 0.);
     double c = 0.;
+#if LEO_UNROLL_STAGES
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int st = 0; st < 4; st++) {
         Dyn xs;
         xs.r = x.r + k.r * c; xs.v = x.v + k.v * c; xs.s = x.s + k.s * c; xs.w = x.w + k.w * c;

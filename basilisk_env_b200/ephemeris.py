@@ -46,6 +46,36 @@ class ChebTable:
             coef[i] = c.T
         return cls(t0, seg_len, coef)
 
+    @classmethod
+    def from_nodes(cls, t0, seg_len, pos, vel):
+        """Table through recorded states: pos[k], vel[k] (each [n_seg + 1, 3]) at t0 + k*seg_len -- e.g. the Sun messages a
+        Basilisk run logged once per decision interval.  One cubic per segment that reproduces position AND velocity at
+        both ends (Hermite data written in the Chebyshev basis), so a look-up at a node returns what was recorded."""
+        pos = np.asarray(pos, dtype=np.float64); vel = np.asarray(vel, dtype=np.float64)
+        if pos.ndim != 2 or pos.shape[1] != 3 or pos.shape != vel.shape or pos.shape[0] < 2:
+            raise ValueError("pos and vel must be [n_seg + 1, 3]")
+        half = 0.5 * float(seg_len)
+        p0, p1, m0, m1 = pos[:-1], pos[1:], vel[:-1] * half, vel[1:] * half
+        a2 = (m1 - m0) / 8.0
+        a3 = ((m1 + m0) / 2.0 - (p1 - p0) / 2.0) / 8.0
+        a1 = (p1 - p0) / 2.0 - a3
+        a0 = (p1 + p0) / 2.0 - a2
+        return cls(t0, seg_len, np.stack([a0, a1, a2, a3], axis=2))
+
+    def extended(self, n_seg_total):
+        """The same table padded with straight-line segments (last position, last velocity) up to n_seg_total segments:
+        `bskenv_set_ephemeris` wants a table that covers a whole episode even when the recorded trace is shorter."""
+        n = self.coef.shape[0]
+        if n_seg_total <= n:
+            return self
+        val, rate = self(self.t0 + n * self.seg_len)
+        pad = np.zeros((n_seg_total - n, 3, self.coef.shape[2]))
+        for k in range(n_seg_total - n):
+            pad[k, :, 0] = val + rate * self.seg_len * (k + 0.5)
+            if self.coef.shape[2] > 1:
+                pad[k, :, 1] = rate * 0.5 * self.seg_len
+        return ChebTable(self.t0, self.seg_len, np.concatenate([self.coef, pad], axis=0))
+
     def __call__(self, t):
         """value (3,), rate (3,) at sim time t [s] -- numpy's own Chebyshev evaluation (not the kernel's recurrence)."""
         from numpy.polynomial import chebyshev as ch

@@ -39,8 +39,9 @@ def vec_err(a, b, floor=0.0):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), floor, 1e-300))
 
 
-def compare_state(st, S, I, where=""):
-    """st: oracle LeoState; S, I: one env's column of the double / int64 state blocks."""
+def compare_state(st, S, I, where="", check_continuous=True):
+    """st: oracle LeoState; S, I: one env's column of the double / int64 state blocks.  Returns the continuous deviations;
+    with check_continuous=False only the discrete quantities are asserted here (the caller applies its own bounds)."""
     errs = {}
     errs["r"] = vec_err(S[F("r_BN_N"):F("r_BN_N") + 3], st.r_BN_N[:])
     errs["v"] = vec_err(S[F("v_BN_N"):F("v_BN_N") + 3], st.v_BN_N[:])
@@ -54,7 +55,7 @@ def compare_state(st, S, I, where=""):
     errs["u"] = vec_err(S[F("u_current"):F("u_current") + 4], st.u_current[:4], floor=1e-3)
     for k, v in errs.items():
         tol = SHADOW_ATOL if k == "shadow" else RTOL
-        assert v <= tol, f"{where}: {k} differs by {v:.3e} (> {tol})"
+        assert not check_continuous or v <= tol, f"{where}: {k} differs by {v:.3e} (> {tol})"
     # discrete quantities: bit-exact
     assert int(I[F("MRPSwitchCount")]) == st.mrp_switch_count, f"{where}: MRP switch count"
     assert int(I[F("task_mask")]) == st.task_mask, f"{where}: task mask"
@@ -66,7 +67,8 @@ def compare_state(st, S, I, where=""):
     assert int(I[F("tick")]) * 100000000 == st.sim_nanos, f"{where}: sim clock"
     # commanded on-times are compared exactly as well: they gate discrete firing decisions
     on_k = S[F("ThrustOnCmd"):F("ThrustOnCmd") + 8]
-    np.testing.assert_allclose(on_k, np.array(st.thrOnCmd[:]), rtol=1e-9, atol=1e-12, err_msg=f"{where}: ThrustOnCmd")
+    if check_continuous:
+        np.testing.assert_allclose(on_k, np.array(st.thrOnCmd[:]), rtol=1e-9, atol=1e-12, err_msg=f"{where}: ThrustOnCmd")
     return errs
 
 
