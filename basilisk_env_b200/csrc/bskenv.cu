@@ -21,6 +21,9 @@
 #include "leo_core.cuh"
 #include "leo_host.h"
 
+#ifndef LEO_LANES
+#define LEO_LANES 32            // envs per warp (tuning builds: 16 / 8 leave the upper lanes idle)
+#endif
 #ifndef LEO_MIN_BLOCKS
 #define LEO_MIN_BLOCKS 3        // resident blocks per SM: 3 x 128 threads x 168 registers
 #endif
@@ -39,9 +42,9 @@ __device__ __forceinline__ double warp_sum(double v)
 }
 
 #ifdef LEO_MAXNREG
-#define LEO_STEP_BOUNDS __maxnreg__(LEO_MAXNREG)       // tuning builds: explicit register cap instead of an occupancy target
+#define LEO_STEP_BOUNDS(MINB) __maxnreg__(LEO_MAXNREG)       // tuning builds: explicit register cap instead of an occupancy target
 #else
-#define LEO_STEP_BOUNDS __launch_bounds__(LEO_BLOCK, LEO_MIN_BLOCKS)
+#define LEO_STEP_BOUNDS(MINB) __launch_bounds__(LEO_BLOCK, MINB)
 #endif
 
 // Work distribution.  One warp steps one group of 32 consecutive envs through the whole decision interval and
@@ -70,8 +73,13 @@ __device__ __forceinline__ int chunk_peek(const int *p)
     return v;
 }
 
-template <int NRW, int J2, bool DIAG, bool F32>
-__global__ void LEO_STEP_BOUNDS
+// MINB = resident blocks per SM the register allocation is made for.  LEO_MIN_BLOCKS (3 blocks x 128 threads x 168 registers,
+// a few spilled values) is the throughput organisation.  MINB = 1 is the SMALL-BATCH organisation (BASELINE configs[1], 4096
+// envs): when the whole batch fits one block per SM anyway, every warp runs alone on its SM sub-partition at its dependent-
+// issue latency, occupancy buys nothing and the full register file (255 registers, nothing spilled onto the dependency
+// chain) is worth 20 %.
+template <int NRW, int J2, bool DIAG, bool F32, int MINB>
+__global__ void LEO_STEP_BOUNDS(MINB)
 leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ LeoParamsF PF, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                 int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                 double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
@@ -100,8 +108,8 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
         } else {
             g = blockIdx.x * (LEO_BLOCK / 32) + warp;
         }
-        const int64_t e = (int64_t)g * 32 + lane;
-        const bool valid = e < n;
+        const int64_t e = (int64_t)g * LEO_LANES + lane;
+        const bool valid = lane < LEO_LANES && e < n;
         leo::StepOut o;
         o.done = 0; o.reason = 0; o.reward = 0.;
         double ep_ret = 0., ep_len = 0.;
@@ -274,9 +282,10 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
                        double *term_obs, cudaStream_t st, double *ep_return = nullptr, int64_t *ep_length = nullptr)
 {
     const int wpb = LEO_BLOCK / 32;
-    const int64_t groups = (h->n + 31) / 32;
+    const int64_t groups = (h->n + LEO_LANES - 1) / LEO_LANES;
     const int resident = h->sm_count * LEO_MIN_BLOCKS;          // blocks of one full resident set
     int grid = (int)((groups + wpb - 1) / wpb);
+    const bool small = grid <= h->sm_count;                     // at most one block per SM: the small-batch organisation
     LeoSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
     sc.n_chunks = leo_host::step_chunks(h->P); sc.progress = h->sched + 4;
@@ -285,18 +294,25 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
         grid = resident;
         CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int) * (size_t)(4 + groups), st));    // queue head + chunk progress per group
     }
-#define LEO_LAUNCH(NRW, J2, DIAG, F32)                                                                         \
+#define LEO_STR_(x) #x
+#define LEO_STR(x) LEO_STR_(x)
+#define LEO_LAUNCH_B(NRW, J2, DIAG, F32, MINB)                                                                 \
     do {                                                                                                       \
         static bool attr_set[64] = {false};      /* opt in to > 48 KB of dynamic shared memory once per device */  \
         const size_t bus_bytes = (J2) == 2 ? LEO_BUS_BYTES_PFIX : LEO_BUS_BYTES;                                \
         if (!attr_set[h->device & 63]) {                                                                       \
-            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bus_bytes)); \
+            CU_TRY(h, cudaFuncSetAttribute(leo_step_kernel<NRW, J2, DIAG, F32, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bus_bytes)); \
             attr_set[h->device & 63] = true;                                                                   \
         }                                                                                                      \
-        h->kernel_name = "leo_step_kernel<" #NRW "," #J2 "," #DIAG "," #F32 ">";                                \
-        leo_step_kernel<NRW, J2, DIAG, F32><<<grid, LEO_BLOCK, bus_bytes, st>>>(h->P, h->PF, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
+        h->kernel_name = "leo_step_kernel<" #NRW "," #J2 "," #DIAG "," #F32 "," LEO_STR(MINB) ">";              \
+        leo_step_kernel<NRW, J2, DIAG, F32, MINB><<<grid, LEO_BLOCK, bus_bytes, st>>>(h->P, h->PF, h->S, h->I, h->ics, h->stride, h->n, act, obs, \
                                                                                  rew, done, reason, term_obs, h->stats, sc, ep_return, ep_length); \
     } while (0)
+#define LEO_LAUNCH(NRW, J2, DIAG, F32) LEO_LAUNCH_B(NRW, J2, DIAG, F32, LEO_MIN_BLOCKS)
+    // small-batch organisation: built for the reference configuration and for the stress configuration
+    if (small && !h->P.grav_pfix && !h->P.mixed && h->P.nrw == 3 && !h->cfg.use_j2 && h->P.diag) LEO_LAUNCH_B(3, 0, true, false, 1);
+    else if (small && !h->P.grav_pfix && !h->P.mixed && h->P.nrw == 4 && h->cfg.use_j2) LEO_LAUNCH_B(4, 1, false, false, 1);
+    else
     if (h->P.grav_pfix) {     // degree-2 field in the planet-fixed frame (general EOM path)
         if (h->P.nrw == 4) LEO_LAUNCH(4, 2, false, false);
         else if (h->P.diag) LEO_LAUNCH(3, 2, true, false);
@@ -310,6 +326,7 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
     else if (h->cfg.use_j2) { if (h->P.diag) LEO_LAUNCH(3, 1, true, false); else LEO_LAUNCH(3, 1, false, false); }
     else                    { if (h->P.diag) LEO_LAUNCH(3, 0, true, false); else LEO_LAUNCH(3, 0, false, false); }
 #undef LEO_LAUNCH
+#undef LEO_LAUNCH_B
     CU_TRY(h, cudaGetLastError());
     h->launches++;
     if (st != h->own_stream || !st) CU_TRY(h, note_launch(h, st));
@@ -354,7 +371,7 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
-    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * (size_t)(4 + (n_envs + 31) / 32));
+    if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * (size_t)(4 + (n_envs + LEO_LANES - 1) / LEO_LANES));
     if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * LEO_ND * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * LEO_NI * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * 19 * h->stride);

@@ -23,6 +23,15 @@
 #define LEO_HD_NOINLINE static inline
 #endif
 
+#ifndef LEO_TUNE_A
+#define LEO_TUNE_A 0
+#endif
+#ifndef LEO_TUNE_B
+#define LEO_TUNE_B 0
+#endif
+#ifndef LEO_TUNE_C
+#define LEO_TUNE_C 0
+#endif
 #ifndef LEO_UNROLL_STAGES
 #define LEO_UNROLL_STAGES 0
 #endif
@@ -557,7 +566,10 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double i
 // cones of two spheres), so outside the band both give exactly 0.0 or 1.0 (tests/test_hostcore_eclipse.py).
 //   s2 = r.r, ir = 1/|r|, r_HB = sun_r - r, hb2 = r_HB.r_HB, id = 1/|r_HB|
 #define ECL_BAND 1e-7
-LEO_HD double eclipse_core(const LeoParams &P, const double (&ec)[6], V3 sun_r, V3 r, double s2, double ir, V3 r_HB, double hb2, double id)
+// Cone tests only: returns the shadow factor where it is decided by the cones (1.0 lit / outside the gate, 0.0 umbra) and sets
+// `penumbra` when the disk-overlap formula has to be evaluated (the rare, divergent part: the tick loop calls it out of line
+// AFTER the common-path arithmetic of the tick, so that the cone tests stay in one straight-line block with the rest).
+LEO_HD double eclipse_cones(const LeoParams &P, const double (&ec)[6], V3 sun_r, V3 r, double s2, double hb2, bool &penumbra)
 {
     const double hp2 = ec[0], inv_hp = ec[1], c1off = ec[2], c2off = ec[3], tan1 = ec[4], tan2 = ec[5];
     const double s0 = -dot(r, sun_r) * inv_hp;
@@ -568,9 +580,15 @@ LEO_HD double eclipse_core(const LeoParams &P, const double (&ec)[6], V3 sun_r, 
     const bool lit = (hb2 < hp2)                            // spacecraft on the sunny side of the planet
                      || (l2sq > p2 * (1. + ECL_BAND) && l2sq > u2 * (1. + ECL_BAND));       // outside both cones
     const bool dark = l2sq < u2 * (1. - ECL_BAND) && c2 < 0. && P.R_sun > P.R_planet;      // inside the umbra, before its apex
-    double f = lit ? 1.0 : 0.0;
     // eclipse.cpp gate `fabs(l) < fabs(l_2) || fabs(l) < fabs(l_1)`, on the squares
-    if (!lit && !dark) f = (l2sq < u2 || l2sq < p2) ? penumbra_fraction(P, ir, id, dot(r, r_HB)) : 1.0;
+    penumbra = !lit && !dark && (l2sq < u2 || l2sq < p2);
+    return (lit || !dark) ? 1.0 : 0.0;
+}
+LEO_HD double eclipse_core(const LeoParams &P, const double (&ec)[6], V3 sun_r, V3 r, double s2, double ir, V3 r_HB, double hb2, double id)
+{
+    bool pen;
+    double f = eclipse_cones(P, ec, sun_r, r, s2, hb2, pen);
+    if (pen) f = penumbra_fraction(P, ir, id, dot(r, r_HB));
     return f;
 }
 LEO_HD double eclipse_factor(const LeoParams &P, const SunLatch &sun, V3 r, double s2, V3 r_HB, double hb2)
@@ -1157,7 +1175,6 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     }
     for (int f = 0; f < LEO_M_MIRROR; f++) mst(m, f, SD(F_GUID + f));
     a.rho = SD(F_RHO);
-    mst(m, M_CHARGE, SD(F_E)); mst(m, M_SHADOW, SD(F_SHADOW));
     {
         const V3 L_ext = mk(SD(F_LDIST), SD(F_LDIST + 1), SD(F_LDIST + 2));
         mst3(m, M_LEXT, L_ext); mst3(m, M_FM, mk(0., 0., 0.));
@@ -1203,13 +1220,35 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
 #pragma unroll
         for (int q = 0; q < 6; q++) ecf[q] = (float)mld(m, M_ECL + q);
     }
-    int phase = (int)((n_base - 1) % tpf);                     // (n mod ticks_per_fsw) of the tick about to run
-    double now_d = (double)((n_base - 1) * P.dyn_ns);          // exact: n * dyn_ns
+    // ---------------- the tick loop ----------------
+    // Layout for latency: a tick is [flight software, every ticks_per_fsw-th tick, out of line] -> [RK4: one rolled loop of four
+    // stages] -> ONE straight-line block with everything else that runs every tick -- wheel invariant, MRP switch (as a
+    // select), |r|, atmosphere, wheel-limit flags, eclipse cone tests, panel geometry, and the clock and Sun third-body
+    // term of the NEXT tick -- -> [rare, out of line: command latches; penumbra] -> battery.  The independent dependency
+    // chains of the block (rsqrt / exp / rcp seeds, cone tests, rotations) are interleaved by the instruction scheduler,
+    // which cannot move code across the branches that used to separate them; a single resident warp (small batches)
+    // otherwise waits out every chain in turn.  Battery charge and shadow factor live in registers.
+    const int j0 = first ? -1 : 0;                             // tick 0 (t = 0, h = 0) only runs right after a reset
+    int phase = (int)((n_base + j0) % tpf);                    // (n mod ticks_per_fsw) of the tick about to run
+    double now_d = (double)((n_base + j0) * P.dyn_ns);         // exact: n * dyn_ns
     int desat_ran = 0, desat_quiet = 0;                        // the chain's quiet state is re-established once per launch
+    double charge = SD(F_E), shadow = SD(F_SHADOW);
+#if LEO_TUNE_A
+    mst(m, M_CHARGE, charge);
+#endif
+    // clock of the first tick: CurrentSimNanos * NANO2SEC of this and of the previous tick (tick 0 integrates over an empty
+    // interval); for the later ticks prevTime is the previous newTime
+    double newTime = t_mul(now_d, 1e-9);
+    double prevTime = j0 < 0 ? 0.0 : t_mul(now_d - dyn_d, 1e-9);
+    double h = t_sub(newTime, prevTime);
+    // Sun at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
+    double dtsm = t_mul((j0 < 0 ? 0.0 : now_d - dyn_d) - sun_d, 1e-9) + 0.5 * h;
+#if !LEO_TUNE_B
+    if (!F32) a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+#endif
 
 #pragma unroll 1
-    for (int j = -1; j < ticks; j++, now_d += dyn_d, phase = (phase + 1 == tpf) ? 0 : phase + 1) {
-        if (j < 0 && !first) continue;                         // keeps the lanes of a warp on the same FSW phase
+    for (int j = j0; j < ticks; j++) {
         bool wrapped = false;
         // ================= flight software every ticks_per_fsw-th tick =================
         if (phase == 0) {
@@ -1231,14 +1270,11 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             }
         }
         // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
-        const double prev_d = j < 0 ? 0.0 : now_d - dyn_d;     // tick 0 integrates over an empty interval
-        const double newTime = t_mul(now_d, 1e-9);             // CurrentSimNanos * NANO2SEC
-        const double prevTime = t_mul(prev_d, 1e-9);
-        const double h = t_sub(newTime, prevTime);
         a.h = h;
         if (wrapped || (thr_active && !(newTime + LEO_THR_MARGIN <= mld(m, M_TNEXT)))) {
             // a thruster may switch within this step (exact per-stage evaluation, then refresh the held thrust),
             // or the Sun clock wraps: every stage gets its own Sun position
+            const double prev_d = j < 0 ? 0.0 : now_d - dyn_d;
             const double tBefore = t_sub(newTime, h);
             SunDt dts;
             dts.d0 = t_mul(prev_d - sun_d, 1e-9); dts.dm = dts.d0 + 0.5 * h; dts.d1 = dts.d0 + h;
@@ -1253,22 +1289,21 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             x = o.x; thr_factor = o.factor; thr_active = o.active;
             ThrRefresh th = thr_refresh(P, S, stride, e, m, thr_active ? thr_factor : 0, a.tau_u);
             a.Lc = th.Lc; mst3(m, M_LTHR, th.L_thr); mst(m, M_TNEXT, th.t_next);
+        } else if (F32) {
+            StageInF af;
+            af.h = (float)h; af.rho = (float)a.rho;
+            af.Lc = tof(a.Lc); af.HB = tof(a.HB); af.tau_u = tof(a.tau_u);
+            af.gsun = sun_accelf(PF, sunr_f + sunv_f * (float)dtsm, tof(x.r) + tof(x.v) * (0.5f * af.h));
+            const bool thr_on = thr_active != 0;
+            x = rk4_step_mixed<(J2 != 0), DIAG>(PF, x, af, thr_on, thr_on ? tof(mld3(m, M_FM)) : mkf(0.f, 0.f, 0.f));
         } else {
-            // Sun at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
-            const double dtsm = t_mul(prev_d - sun_d, 1e-9) + 0.5 * h;
-            if (F32) {
-                StageInF af;
-                af.h = (float)h; af.rho = (float)a.rho;
-                af.Lc = tof(a.Lc); af.HB = tof(a.HB); af.tau_u = tof(a.tau_u);
-                af.gsun = sun_accelf(PF, sunr_f + sunv_f * (float)dtsm, tof(x.r) + tof(x.v) * (0.5f * af.h));
-                const bool thr_on = thr_active != 0;
-                x = rk4_step_mixed<(J2 != 0), DIAG>(PF, x, af, thr_on, thr_on ? tof(mld3(m, M_FM)) : mkf(0.f, 0.f, 0.f));
-            } else {
-                a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
-                if (J2 == 2) a.dtp = dtsm;     // orientation held at the step's mid time, like the Sun
-                x = rk4_step<J2, DIAG>(P, x, a, thr_active != 0, m);
-            }
+            if (J2 == 2) a.dtp = dtsm;     // orientation held at the step's mid time, like the Sun
+#if LEO_TUNE_B
+            a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+#endif
+            x = rk4_step<J2, DIAG>(P, x, a, thr_active != 0, m);
         }
+        // ================= everything else that runs every tick: one straight-line block =================
         // the wheel invariant advances with the motor torque held over the step
         a.HB = a.HB + a.tau_u * h;
         if (!DIAG) {
@@ -1276,89 +1311,122 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             for (int i = 0; i < NRW; i++) C[i] = fmad(uJ[i], h, C[i]);
         }
         // HubEffector::modifyStates -- MRP shadow-set switch: |sigma| > 1 with the correctly rounded norm, i.e.
-        // sigma.sigma > 1 + 2^-52 (sqrt(1 + 2^-52) rounds to 1)
+        // sigma.sigma > 1 + 2^-52 (sqrt(1 + 2^-52) rounds to 1).  A select, not a branch.
         {
             const double s2 = dot(x.s, x.s);
+#if LEO_TUNE_C
             if (s2 > 1.0000000000000002) { x.s = x.s * (-frcp(s2)); nswitch++; }
+#else
+            const bool sw = s2 > 1.0000000000000002;
+            const double f = -frcp(sw ? s2 : 1.0);
+            x.s = mk(sw ? x.s.x * f : x.s.x, sw ? x.s.y * f : x.s.y, sw ? x.s.z * f : x.s.z);
+            nswitch += sw ? 1 : 0;
+#endif
         }
         // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
-        double r2 = 0., ir = 0.;
+        double r2 = 0., ir = 0., id = 0., rdh = 0., pgeo = 0.;
+        bool penumbra = false;
+        float shf = 0.f, panel_f = 0.f;
         V3f xr_f = mkf(0.f, 0.f, 0.f);
-        float r2f = 0.f;
         if (F32) {
-            xr_f = tof(x.r); r2f = dot(xr_f, xr_f);
+            xr_f = tof(x.r);
+            const float r2f = dot(xr_f, xr_f);
             a.rho = (double)(PF.rho0 * expf(-(r2f * rsqf(r2f) - PF.Rp_atmo) * PF.inv_H));
+            // EnvTask in FP32: eclipse cone tests, panel projection
+            const V3f r_SBf = sunr_f - xr_f;
+            const float d2f = dot(r_SBf, r_SBf), idf = rsqf(d2f);
+            shf = eclipse_coref(PF, ecf, sunr_f, xr_f, r2f, d2f);
+            penumbra = shf < 0.f;                              // cone-surface band / penumbra: the FP64 evaluation below
+            const V3f sf = tof(x.s);
+            MrpRotF R = mrp_rotf(sf);
+            V3f n_N = rot_NBf(R, sf, arrf(PF.nHat_B));
+            float proj = dot(n_N, r_SBf) * idf;
+            if (proj < 0.f) proj = 0.f;
+            panel_f = PF.panel_coef * proj * (idf * idf);
         } else {
             r2 = dot(x.r, x.r); ir = rsq(r2);
             // exponentialAtmosphere (density latched for the NEXT step, zero-order hold)
             a.rho = P.rho0 * exp_bounded(-(r2 * ir - P.Rp_atmo) * P.inv_H);
         }
-        // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
-        {
-            double W[NRW];
-            wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
-            int lim = 0;
+        // wheel-limit flags (the latch itself is a rare event, below)
+        double W[NRW];
+        wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
+        int lim = 0;
 #pragma unroll
-            for (int i = 0; i < NRW; i++) lim |= (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
-            if (rw_sat | lim | desat_ran) {
-                PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, W, mld3(m, M_LTHR), desat_ran, (int64_t)now_d, thr_factor);
-#pragma unroll
-                for (int i = 0; i < NRW; i++) uJ[i] = po.uJ[i];
-                a.Lc = po.Lc; a.tau_u = po.tau_u;
-                rw_sat = lim;
-                if (po.thr_active >= 0) { thr_active = po.thr_active; mst(m, M_TNEXT, -1.0); }   // burning set: re-derive exactly
-                if (desat_ran) desat_quiet = po.quiet;
-                desat_ran = 0;
-            }
+        for (int i = 0; i < NRW; i++) lim |= (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
+        if (!F32) {
+            // EnvTask: eclipse cone tests and solar-panel geometry
+            const V3 sun_r = mld3(m, M_SUNR);
+            const V3 r_SB = sun_r - x.r;                       // spacecraft -> Sun
+            const double d2 = dot(r_SB, r_SB);
+            id = rsq(d2);
+            const double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
+            shadow = eclipse_cones(P, ec, sun_r, x.r, r2, d2, penumbra);
+            rdh = dot(x.r, r_SB);
+            MrpRot R = mrp_rot(x.s);
+            V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
+            double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
+            if (proj < 0.) proj = 0.;
+            pgeo = P.panel_coef * proj * (id * id);
         }
-        // ================= EnvTask: eclipse -> solar panel -> battery -> sink =================
-        if (F32) {
-            const V3f r_SBf = sunr_f - xr_f;
-            const float d2f = dot(r_SBf, r_SBf), idf = rsqf(d2f);
-            float shf = eclipse_coref(PF, ecf, sunr_f, xr_f, r2f, d2f);
-            double shadow = (double)shf;
-            if (shf < 0.f) {                                   // cone-surface band / penumbra: the FP64 evaluation
+        // clock and Sun third body of the NEXT tick (its state is final: the rare events below do not touch x)
+        const double h_this = h;
+        now_d += dyn_d;
+        phase = (phase + 1 == tpf) ? 0 : phase + 1;
+        prevTime = newTime;
+        newTime = t_mul(now_d, 1e-9);
+        h = t_sub(newTime, prevTime);
+        dtsm = t_mul((now_d - dyn_d) - sun_d, 1e-9) + 0.5 * h;
+#if !LEO_TUNE_B
+        if (!F32) a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+#endif
+        // ================= rare, out of line =================
+        // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
+        if (rw_sat | lim | desat_ran) {
+            PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, W, mld3(m, M_LTHR), desat_ran, (int64_t)(now_d - dyn_d), thr_factor);
+#pragma unroll
+            for (int i = 0; i < NRW; i++) uJ[i] = po.uJ[i];
+            a.Lc = po.Lc; a.tau_u = po.tau_u;
+            rw_sat = lim;
+            if (po.thr_active >= 0) { thr_active = po.thr_active; mst(m, M_TNEXT, -1.0); }   // burning set: re-derive exactly
+            if (desat_ran) desat_quiet = po.quiet;
+            desat_ran = 0;
+        }
+        // penumbra / cone-surface band: the disk-overlap formula
+        if (penumbra) {
+            if (F32) {
                 const V3 sun_r = mld3(m, M_SUNR);
                 const V3 r_SB = sun_r - x.r;
                 const double r2d = dot(x.r, x.r), d2 = dot(r_SB, r_SB);
                 const double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
                 shadow = eclipse_core(P, ec, sun_r, x.r, r2d, rsq(r2d), r_SB, d2, rsq(d2));
                 shf = (float)shadow;
+            } else {
+                shadow = penumbra_fraction(P, ir, id, rdh);
             }
-            mst(m, M_SHADOW, shadow);
-            const V3f sf = tof(x.s);
-            MrpRotF R = mrp_rotf(sf);
-            V3f n_N = rot_NBf(R, sf, arrf(PF.nHat_B));
-            float proj = dot(n_N, r_SBf) * idf;
-            if (proj < 0.f) proj = 0.f;
-            const float panel = PF.panel_coef * proj * (idf * idf) * shf;
-            if (j >= 0) {
-                double E = mld(m, M_CHARGE) + ((double)panel + P.sink_power) * h;
-                if (E > P.capacity) E = P.capacity;
-                if (E < 0.) E = 0.;
-                mst(m, M_CHARGE, E);
-            }
-        } else {
-            const V3 sun_r = mld3(m, M_SUNR);
-            const V3 r_SB = sun_r - x.r;                       // spacecraft -> Sun
-            const double d2 = dot(r_SB, r_SB), id = rsq(d2);
-            const double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
-            const double shadow = eclipse_core(P, ec, sun_r, x.r, r2, ir, r_SB, d2, id);
-            mst(m, M_SHADOW, shadow);
-            MrpRot R = mrp_rot(x.s);
-            V3 n_N = rot_NB(R, x.s, arr(P.nHat_B));            // panel normal in the inertial frame
-            double proj = dot(n_N, r_SB) * id;                 // sHat_B . nHat_B
-            if (proj < 0.) proj = 0.;
-            double panel = P.panel_coef * proj * (id * id) * shadow;
-            if (j >= 0) {                                      // quirk Q2: the sink message does not exist at tick 0
-                double E = mld(m, M_CHARGE) + (panel + P.sink_power) * h;
-                if (E > P.capacity) E = P.capacity;
-                if (E < 0.) E = 0.;
-                mst(m, M_CHARGE, E);
-            }
+        } else if (F32) {
+            shadow = (double)shf;
+        }
+        // ================= battery (quirk Q2: the sink message does not exist at tick 0) =================
+        {
+            const double panel = F32 ? (double)(panel_f * shf) : pgeo * shadow;
+#if LEO_TUNE_A
+            const double c0 = mld(m, M_CHARGE);
+            double E = c0 + (panel + P.sink_power) * h_this;
+            if (E > P.capacity) E = P.capacity;
+            if (E < 0.) E = 0.;
+            mst(m, M_CHARGE, j >= 0 ? E : c0);
+#else
+            double E = charge + (panel + P.sink_power) * h_this;
+            if (E > P.capacity) E = P.capacity;
+            if (E < 0.) E = 0.;
+            charge = j >= 0 ? E : charge;
+#endif
         }
     }
-
+#if LEO_TUNE_A
+    charge = mld(m, M_CHARGE);
+#endif
     for (int f = 0; f < LEO_M_MIRROR; f++) SD(F_GUID + f) = mld(m, f);
     double W[NRW];
     wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
@@ -1370,7 +1438,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         SD(F_OMG) = x.w.x; SD(F_OMG + 1) = x.w.y; SD(F_OMG + 2) = x.w.z;
 #pragma unroll
         for (int i = 0; i < NRW; i++) { SD(F_WHL + i) = W[i]; SD(F_UCUR + i) = mld(m, M_U + i); }
-        SD(F_RHO) = a.rho; SD(F_E) = mld(m, M_CHARGE); SD(F_SHADOW) = mld(m, M_SHADOW);
+        SD(F_RHO) = a.rho; SD(F_E) = charge; SD(F_SHADOW) = shadow;
         SI(I_TICK) = n_base - 1 + ticks; SI(I_MASK) = mask; SI(I_SWITCH) = SI(I_SWITCH) + nswitch;
         SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_RWSAT) = rw_sat;
         out.done = 0; out.reason = 0; out.reward = 0.;
@@ -1382,7 +1450,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     double wn = 0.;
 #pragma unroll
     for (int i = 0; i < NRW; i++) wn += W[i] * W[i];
-    const double E = mld(m, M_CHARGE), shadow = mld(m, M_SHADOW);
+    const double E = charge;
     double ob2 = sqrt(wn), ob3 = E / 3600., ob4 = shadow;
     int sim_over = norm(x.r) < P.decay_radius;
     int64_t curr_step = SI(I_STEP);

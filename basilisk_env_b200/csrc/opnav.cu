@@ -89,8 +89,9 @@ __global__ void opnav_perm_identity_kernel(int32_t *__restrict__ perm, int64_t s
     if (e < stride) perm[e] = (int32_t)(e < n ? e : n - 1);
 }
 
-// per-thread scratch in shared memory: filter (49 doubles) + cold dynamics data (19) + 1 pad = 69, an odd stride (conflict-free)
-struct OnScratch { opnav::Ukf f; opnav::Cold c; double pad; };
+// per-thread scratch in shared memory: filter (49 doubles) + cold dynamics data (19) + walk states (15) = 83, an odd stride
+// (conflict-free); 83 x 8 B x 128 threads = 85 KB per block, two blocks per SM
+struct OnScratch { opnav::Ukf f; opnav::Cold c; opnav::Walk w; };
 
 // One thread runs the three roles of opnav_core.cuh (noise walk, dynamics + flight software, filter) of one env in sequence.
 // A warp-specialised form (one warp per role, mailboxes in shared memory, one block barrier per tick) was built and is
@@ -124,7 +125,7 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
         double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
         if (valid) {
             const int64_t m0 = I[(int64_t)OI_NMEAS * stride + e], b0 = I[(int64_t)OI_NBAD * stride + e];
-            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o, scr.f, scr.c);
+            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o, scr.f, scr.c, scr.w);
             d_meas = (double)(I[(int64_t)OI_NMEAS * stride + e] - m0); d_bad = (double)(I[(int64_t)OI_NBAD * stride + e] - b0);
             reward[e] = o.reward;
             done[e] = (uint8_t)o.done;

@@ -20,6 +20,7 @@
 //
 // Everything is __host__ __device__ (tests/hostcore compiles it with g++); the product only runs it on the GPU.
 #pragma once
+#include <type_traits>
 #include "leo_core.cuh"
 #include "opnav_params.h"
 
@@ -100,8 +101,10 @@ __device__ __forceinline__ void sincos_2pi_u32(uint32_t j, double &sn, double &c
     cs = ((oct + 2u) & 4u) ? -c0 : c0;                       // octants 2..5
 }
 #endif
-ON_HD_NOINLINE void normals4(const OpNavParams &P, int64_t env, int64_t episode, uint32_t tick, uint32_t stream, uint32_t block,
-                             double (&out)[4])
+// Inline form (the caller's `out` stays in registers: used in the rolled loop of the noise walk, where the code exists once
+// anyway); normals4() below is the out-of-line form for the rare pixel-noise draw.
+ON_HD void normals4_inl(const OpNavParams &P, int64_t env, int64_t episode, uint32_t tick, uint32_t stream, uint32_t block,
+                        double (&out)[4])
 {
     uint32_t x[4];
     philox4x32((uint32_t)(uint64_t)env, (uint32_t)((uint64_t)env >> 32), tick, (stream << 16) | block, (uint32_t)P.seed,
@@ -122,6 +125,11 @@ ON_HD_NOINLINE void normals4(const OpNavParams &P, int64_t env, int64_t episode,
         out[2 * p] = rr * c;
         out[2 * p + 1] = rr * s;
     }
+}
+ON_HD_NOINLINE void normals4(const OpNavParams &P, int64_t env, int64_t episode, uint32_t tick, uint32_t stream, uint32_t block,
+                             double (&out)[4])
+{
+    normals4_inl(P, env, episode, tick, stream, block, out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -398,6 +406,15 @@ ON_HD_NOINLINE AttGuid sun_safe_point(V3 sHat, V3 omega_BN_B)
 // relative-OD square-root UKF (see the header comment).  S: lower triangle, row-major, S(i,j) = S[i(i+1)/2+j].
 // ------------------------------------------------------------------------------------------------
 #define TRI(i, j) ((i) * ((i) + 1) / 2 + (j))
+// compile-time loop: f(std::integral_constant<int, I>) for I = B .. E-1 (every index is a constant when the body is generated)
+template <int B, int E, class F>
+ON_HD void static_for(F &&f)
+{
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
 ON_HD void two_body_rk4(double (&x)[6], double mu, double dt)
 {
     double k[6], s[6], acc[6];
@@ -477,6 +494,11 @@ ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
 // instead of being carried in registers through the tick loop.
 struct Ukf { double x[6]; double C[36]; double m[6]; double pad; };      // 49 doubles
 struct Cold { double sun[12]; double cold[7]; };                         // 19 doubles: Sun nodes, cold per-env latches
+// simple_nav's 15 walk states: parked in the per-thread shared scratch as well.  The walk advances in a ROLLED loop (four
+// states per Philox block; the noise transform exists once in the instruction stream), i.e. the states are indexed at run
+// time -- in a per-thread array that means local memory (the kernel's former 752-byte stack: ~140 LDL / STL per tick and
+// 2.5x the algorithmic DRAM traffic from its write-backs); in shared memory it is an LDS / STS with an immediate stride.
+struct Walk { double e[15]; };
 #define SC(r, c) C[(c) * 6 + (r)]
 // relODuKFTimeUpdate over dt.  The twelve deviations are accumulated into the 21 independent entries of the Gram
 // matrix (no serial dependence between sigma points; propagating the +/- pair of a column side by side was measured and
@@ -519,7 +541,7 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
 #pragma unroll
                 for (int g = 0; g < ON_UKF_GROUP; g++) A[TRI(a, b)] = fmad(Y[g][a], Y[g][b], A[TRI(a, b)]);
     }
-    double m[6], L[21];
+    double m[6];
 #pragma unroll
     for (int r = 0; r < 6; r++) m[r] = P.ukf_w * ms[r];
     const double qp = P.ukf_sq_pos * (dt * dt / 2), qv = P.ukf_sq_vel * dt;
@@ -531,28 +553,29 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
             if (a == b) v += a < 3 ? qp * qp : qv * qv;
             A[TRI(a, b)] = v;
         }
+    // 6 x 6 Cholesky, in place on the 21 accumulators.  The triangular loops are unrolled by template recursion, not by
+    // `#pragma unroll`: with loop bounds that depend on an outer loop variable the optimiser unrolls too late to promote the
+    // arrays to registers and A / L end up in local memory (36 LDL / STL per tick, the kernel's former "stack").
     bool ok = true;
-#pragma unroll
-    for (int j = 0; j < 6; j++) {
+    static_for<0, 6>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
         double t = A[TRI(j, j)];
-#pragma unroll
-        for (int k = 0; k < j; k++) t -= L[TRI(j, k)] * L[TRI(j, k)];
+        static_for<0, j>([&](auto kc) { constexpr int k = decltype(kc)::value; t -= A[TRI(j, k)] * A[TRI(j, k)]; });
         if (!(t > 0.0)) { ok = false; t = 1.0; }
         const double ir = rsq(t);
-        L[TRI(j, j)] = t * ir;
-#pragma unroll
-        for (int i = j + 1; i < 6; i++) {
+        A[TRI(j, j)] = t * ir;
+        static_for<j + 1, 6>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
             double v = A[TRI(i, j)];
-#pragma unroll
-            for (int k = 0; k < j; k++) v -= L[TRI(i, k)] * L[TRI(j, k)];
-            L[TRI(i, j)] = v * ir;
-        }
-    }
+            static_for<0, j>([&](auto kc) { constexpr int k = decltype(kc)::value; v -= A[TRI(i, k)] * A[TRI(j, k)]; });
+            A[TRI(i, j)] = v * ir;
+        });
+    });
     if (!ok) return false;
 #pragma unroll
     for (int c = 0; c < 6; c++)
 #pragma unroll
-        for (int r = c; r < 6; r++) f.SC(r, c) = L[TRI(r, c)];
+        for (int r = c; r < 6; r++) f.SC(r, c) = A[TRI(r, c)];
 #pragma unroll
     for (int i = 0; i < 6; i++) { f.x[i] = Y0[i]; f.m[i] = m[i]; }
     return true;
@@ -700,10 +723,11 @@ struct Meas { bool valid; double obs[3]; double R[6]; };
 // simple_nav's Gauss-Markov error states: a bounded random walk driven by the per-env Philox stream, independent of the
 // dynamics (SimpleNav::computeErrors, OND:236-258).  tick(k) advances the 15 states to tick k.
 struct NoiseRole {
-    double nerr[15];
+    double *nerr;                 // Walk::e of this env (shared scratch on the device)
     int64_t genv, episode, k_first, k_last;
-    ON_HD void load(const OpNavParams &P, const double *S, const int64_t *I, int64_t stride, int64_t e)
+    ON_HD void load(const OpNavParams &P, const double *S, const int64_t *I, int64_t stride, int64_t e, Walk &w)
     {
+        nerr = w.e;
         for (int i = 0; i < 15; i++) nerr[i] = S[(int64_t)(OF_NAVERR + i) * stride + e];
         genv = P.first_env_index + e; episode = I[(int64_t)OI_EPISODE * stride + e];
         const int64_t tick0 = I[(int64_t)OI_TICK * stride + e];
@@ -720,7 +744,7 @@ struct NoiseRole {
 #endif
         for (int b = 0; b < 4; b++) {                                 // four normals per Philox block, 15 walk states
             double n4[4];
-            normals4(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
+            normals4_inl(P, genv, episode, (uint32_t)k, 1u, (uint32_t)b, n4);
 #pragma unroll
             for (int j = 0; j < 4; j++) {                             // four independent walk states side by side
                 const int i = 4 * b + j;
@@ -779,8 +803,7 @@ struct DynRole {
 
     // one tick of the dynamics process and of the flight software except the filter; `nerr` = simple_nav's error states at
     // this tick (NoiseRole), `m` receives the measurement of this tick
-    template <class NE>
-    ON_HD void tick(const OpNavParams &P, int64_t k, Cold &c, const NE &nerr, Meas &m)
+    ON_HD void tick(const OpNavParams &P, int64_t k, Cold &c, const double *nerr, Meas &m)
     {
         volatile double *cold = c.cold;
         volatile double *sunn = c.sun;
@@ -973,14 +996,14 @@ struct FilterRole {
 
 // Both roles in one thread (host-compiled core; single-role kernel).  `f` and `c` are scratch storage for the call.
 ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out,
-                          Ukf &f, Cold &c)
+                          Ukf &f, Cold &c, Walk &w)
 {
     DynRole d;
     FilterRole fr;
     NoiseRole nz;
     d.load(P, S, I, stride, e, action, c);
     fr.load(P, S, I, stride, e, f);
-    nz.load(P, S, I, stride, e);
+    nz.load(P, S, I, stride, e, w);
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
