@@ -23,15 +23,6 @@
 #define LEO_HD_NOINLINE static inline
 #endif
 
-#ifndef LEO_TUNE_A
-#define LEO_TUNE_A 0
-#endif
-#ifndef LEO_TUNE_B
-#define LEO_TUNE_B 0
-#endif
-#ifndef LEO_TUNE_C
-#define LEO_TUNE_C 0
-#endif
 #ifndef LEO_UNROLL_STAGES
 #define LEO_UNROLL_STAGES 0
 #endif
@@ -710,13 +701,11 @@ enum LeoMField : int {
     M_U = 46,        // latched wheel motor torques u_current (4)
     M_LTHR = 50,     // held thruster torque (3), zero outside burns
     M_TNEXT = 53,    // earliest expiry of a burning thruster
-    M_CHARGE = 54,        // storedCharge
-    M_SHADOW = 55,   // shadowFactor of the last environment tick
-    LEO_NM = 56,
+    LEO_NM = 54,     // (battery charge and shadow factor are carried in registers)
     // only allocated by the planet-fixed gravity variant (J2 == 2):
-    M_PFIX = 56,     // J20002Pfix of the last SPICE message (9, row-major)
-    M_PFIXD = 65,    // J20002Pfix_dot (9)
-    LEO_NM_PFIX = 74
+    M_PFIX = 54,     // J20002Pfix of the last SPICE message (9, row-major)
+    M_PFIXD = 63,    // J20002Pfix_dot (9)
+    LEO_NM_PFIX = 72
 };
 #define LEO_M_MIRROR 28          // number of leading bus fields that mirror state fields starting at F_GUID
 struct MBus {
@@ -913,7 +902,9 @@ LEO_HD void eom(const LeoParams &P, const Dyn &x, Dyn &k, const StageIn &a, doub
     double Sp;
     {
         double ax = fabs(vB.x), ay = fabs(vB.y), az = fabs(vB.z);
-        Sp = P.dragKa[0] * ax + P.dragKa[1] * ay + P.dragKa[2] * az + P.dragKd[0] * vB.x + P.dragKd[1] * vB.y + P.dragKd[2] * vB.z;
+        // DIAG also means equal + / - facet areas on every axis (SIM:274-281: 0.06 / 0.06, 2.02 / 2.02, 0.03 / 0.03): Kd = 0
+        Sp = P.dragKa[0] * ax + P.dragKa[1] * ay + P.dragKa[2] * az;
+        if (!DIAG) Sp += P.dragKd[0] * vB.x + P.dragKd[1] * vB.y + P.dragKd[2] * vB.z;
         if (DIAG) {
             Mp = mk(P.dragMa[0][0] * ax + P.dragMd[0][0] * vB.x, P.dragMa[1][1] * ay + P.dragMd[1][1] * vB.y,
                     P.dragMa[2][2] * az + P.dragMd[2][2] * vB.z);
@@ -1115,21 +1106,35 @@ LEO_HD void wheel_speeds(const LeoParams &P, V3 HB, const double (&C)[NRW], V3 w
     }
 }
 
+#if defined(__CUDACC__)
+// 64-bit literals of the per-tick code live in constant memory: an FP64 instruction takes a constant-bank operand for free,
+// whereas a literal that does not fit the 32-bit immediate form costs two uniform-register moves (two issue slots) per use.
+__constant__ double LEO_K[16] = {
+    1.4426950408889634, 6755399441055744.0, -6.93147180369123816490e-01, -1.90821492927058770002e-10,    // exp: log2 e, 2^52 + 2^51, -ln2 hi / lo
+    1. / 6., 1. / 24., 1. / 120., 1. / 720., 1. / 5040., 1. / 40320., 1. / 362880., 1. / 3628800., 1. / 39916800.,
+    1. / 479001600., 1. / 6227020800.,                                                                   // exp: Taylor 1/3! .. 1/13!
+    1e-9};                                                                                               // NANO2SEC
+#endif
+#if defined(__CUDA_ARCH__)
+#define LEO_NANO2SEC LEO_K[15]
+#else
+#define LEO_NANO2SEC 1e-9
+#endif
 // exp(x) for |x| <= 700 without special-operand handling (the atmosphere's argument): Cody-Waite reduction by
 // ln 2, degree-13 Taylor polynomial on |r| <= ln2/2 in Estrin form (truncation 4e-18), exponent patched in.
 LEO_HD double exp_bounded(double x)
 {
 #ifdef __CUDA_ARCH__
     x = fmin(fmax(x, -700.0), 700.0);
-    const double t = fma(x, 1.4426950408889634, 6755399441055744.0);
+    const double t = fma(x, LEO_K[0], LEO_K[1]);
     const int kk = __double2loint(t);
-    const double kd = t - 6755399441055744.0;
-    double r = fma(kd, -6.93147180369123816490e-01, x);
-    r = fma(kd, -1.90821492927058770002e-10, r);
+    const double kd = t - LEO_K[1];
+    double r = fma(kd, LEO_K[2], x);
+    r = fma(kd, LEO_K[3], r);
     const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double a0 = fma(r, 1.0, 1.0), a1 = fma(r, 1. / 6., 0.5), a2 = fma(r, 1. / 120., 1. / 24.), a3 = fma(r, 1. / 5040., 1. / 720.);
-    const double a4 = fma(r, 1. / 362880., 1. / 40320.), a5 = fma(r, 1. / 39916800., 1. / 3628800.);
-    const double a6 = fma(r, 1. / 6227020800., 1. / 479001600.);
+    const double a0 = r + 1.0, a1 = fma(r, LEO_K[4], 0.5), a2 = fma(r, LEO_K[6], LEO_K[5]), a3 = fma(r, LEO_K[8], LEO_K[7]);
+    const double a4 = fma(r, LEO_K[10], LEO_K[9]), a5 = fma(r, LEO_K[12], LEO_K[11]);
+    const double a6 = fma(r, LEO_K[14], LEO_K[13]);
     const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
     const double d0 = fma(b1, r4, b0), d1 = fma(a6, r4, b2);
     const double p = fma(d1, r8, d0);
@@ -1233,19 +1238,14 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     double now_d = (double)((n_base + j0) * P.dyn_ns);         // exact: n * dyn_ns
     int desat_ran = 0, desat_quiet = 0;                        // the chain's quiet state is re-established once per launch
     double charge = SD(F_E), shadow = SD(F_SHADOW);
-#if LEO_TUNE_A
-    mst(m, M_CHARGE, charge);
-#endif
     // clock of the first tick: CurrentSimNanos * NANO2SEC of this and of the previous tick (tick 0 integrates over an empty
     // interval); for the later ticks prevTime is the previous newTime
-    double newTime = t_mul(now_d, 1e-9);
+    double newTime = t_mul(now_d, LEO_NANO2SEC);
     double prevTime = j0 < 0 ? 0.0 : t_mul(now_d - dyn_d, 1e-9);
     double h = t_sub(newTime, prevTime);
     // Sun at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
-    double dtsm = t_mul((j0 < 0 ? 0.0 : now_d - dyn_d) - sun_d, 1e-9) + 0.5 * h;
-#if !LEO_TUNE_B
+    double dtsm = t_mul((j0 < 0 ? 0.0 : now_d - dyn_d) - sun_d, LEO_NANO2SEC) + 0.5 * h;
     if (!F32) a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
-#endif
 
 #pragma unroll 1
     for (int j = j0; j < ticks; j++) {
@@ -1298,9 +1298,6 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             x = rk4_step_mixed<(J2 != 0), DIAG>(PF, x, af, thr_on, thr_on ? tof(mld3(m, M_FM)) : mkf(0.f, 0.f, 0.f));
         } else {
             if (J2 == 2) a.dtp = dtsm;     // orientation held at the step's mid time, like the Sun
-#if LEO_TUNE_B
-            a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
-#endif
             x = rk4_step<J2, DIAG>(P, x, a, thr_active != 0, m);
         }
         // ================= everything else that runs every tick: one straight-line block =================
@@ -1314,14 +1311,10 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         // sigma.sigma > 1 + 2^-52 (sqrt(1 + 2^-52) rounds to 1).  A select, not a branch.
         {
             const double s2 = dot(x.s, x.s);
-#if LEO_TUNE_C
-            if (s2 > 1.0000000000000002) { x.s = x.s * (-frcp(s2)); nswitch++; }
-#else
             const bool sw = s2 > 1.0000000000000002;
             const double f = -frcp(sw ? s2 : 1.0);
             x.s = mk(sw ? x.s.x * f : x.s.x, sw ? x.s.y * f : x.s.y, sw ? x.s.z * f : x.s.z);
             nswitch += sw ? 1 : 0;
-#endif
         }
         // |r| of the new state: shared by the atmosphere, the eclipse model and the solar panel
         double r2 = 0., ir = 0., id = 0., rdh = 0., pgeo = 0.;
@@ -1374,12 +1367,10 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         now_d += dyn_d;
         phase = (phase + 1 == tpf) ? 0 : phase + 1;
         prevTime = newTime;
-        newTime = t_mul(now_d, 1e-9);
+        newTime = t_mul(now_d, LEO_NANO2SEC);
         h = t_sub(newTime, prevTime);
-        dtsm = t_mul((now_d - dyn_d) - sun_d, 1e-9) + 0.5 * h;
-#if !LEO_TUNE_B
+        dtsm = t_mul((now_d - dyn_d) - sun_d, LEO_NANO2SEC) + 0.5 * h;
         if (!F32) a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
-#endif
         // ================= rare, out of line =================
         // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
         if (rw_sat | lim | desat_ran) {
@@ -1410,23 +1401,12 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         // ================= battery (quirk Q2: the sink message does not exist at tick 0) =================
         {
             const double panel = F32 ? (double)(panel_f * shf) : pgeo * shadow;
-#if LEO_TUNE_A
-            const double c0 = mld(m, M_CHARGE);
-            double E = c0 + (panel + P.sink_power) * h_this;
-            if (E > P.capacity) E = P.capacity;
-            if (E < 0.) E = 0.;
-            mst(m, M_CHARGE, j >= 0 ? E : c0);
-#else
             double E = charge + (panel + P.sink_power) * h_this;
             if (E > P.capacity) E = P.capacity;
             if (E < 0.) E = 0.;
             charge = j >= 0 ? E : charge;
-#endif
         }
     }
-#if LEO_TUNE_A
-    charge = mld(m, M_CHARGE);
-#endif
     for (int f = 0; f < LEO_M_MIRROR; f++) SD(F_GUID + f) = mld(m, f);
     double W[NRW];
     wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);

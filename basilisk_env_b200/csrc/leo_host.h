@@ -118,6 +118,7 @@ static inline std::string build_params(const bskenv_config &c, LeoParams &p)
         }
         for (int ax = 0; ax < 3; ax++) {
             p.dragKa[ax] = 0.5 * (K[ax][0] + K[ax][1]) * p.inv_mass; p.dragKd[ax] = 0.5 * (K[ax][0] - K[ax][1]) * p.inv_mass;
+            if (p.dragKd[ax] != 0.0) p.diag = 0;        // the fast path drops the Kd terms (equal + / - facet areas)
             for (int j = 0; j < 3; j++) {
                 p.dragMa[ax][j] = 0.5 * (M[ax][0][j] + M[ax][1][j]); p.dragMd[ax][j] = 0.5 * (M[ax][0][j] - M[ax][1][j]);
                 if (ax != j && (p.dragMa[ax][j] != 0.0 || p.dragMd[ax][j] != 0.0)) p.diag = 0;
@@ -221,17 +222,17 @@ static inline void build_params_f(const LeoParams &p, LeoParamsF &f)
 // reference configuration, profiles/ncu_r01c.md; this formula gives 2.0736e6).  It is the work the kernel performs,
 // not the larger count of the un-fused Basilisk formulation (4.29e6), so the roofline fraction built
 // on it is the fraction of the FP64 pipe's flop rate actually delivered.
-//   per RK stage   gravity 22, MRP rotation set-up 17, [BN] v 30, collapsed drag 27, torque/gyro/inverse inertia 42,
-//                  MRP kinematics 31                                                               = 169 (diagonal path)
+//   per RK stage   gravity 22, MRP rotation set-up 17, [BN] v 30, collapsed drag 21 (equal + / - facet areas: no Kd terms), torque/gyro/inverse
+//                  inertia 42, MRP kinematics 31                                                   = 163 (diagonal path)
 //   RK4 per tick   stage inputs 96, weighted slope sums 96, final update 12                          = 204
 //   per tick       Sun third body 55, invariant/switch/|r| 30, atmosphere 40, wheel test 6, eclipse + panel + battery 105 = 236
 //   FSW pass       hillPoint 130, attTrackingError 146, MRP_Feedback 69, rwMotorTorque 15           = 360
 static inline double flops_per_step(const LeoParams &p)
 {
-    double F_eom = 169.0;
+    double F_eom = 163.0;
     const double F_rk4 = 204.0, F_tick = 236.0;
     double F_fsw = 360.0;
-    if (!p.diag) F_eom += 36.0 + 8.0 * (p.nrw - 3);        // full 3x3 D / Dinv / drag moment arms, wheel invariants
+    if (!p.diag) F_eom += 42.0 + 8.0 * (p.nrw - 3);        // full 3x3 D / Dinv / drag moment arms, wheel invariants
     if (p.grav_pfix) F_eom += 92.0;      // DCM Euler step 18, r_Pfix 15, |r|^-5/-7 9, M r + quadratic form 29, g_Pfix 9, back-rotation 15 (- point-mass share 3)
     else if (p.use_j2) F_eom += 14.0;
     if (p.nrw == 4) F_fsw += 5.0;

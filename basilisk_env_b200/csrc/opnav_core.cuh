@@ -73,9 +73,13 @@ __device__ __forceinline__ double neg2_log_u32(uint32_t x)
     int e = -1 - lz;
     if (m > ON_K[25]) { m *= 0.5; e += 1; }
     const double sq = (m - 1.0) * frcp(m + 1.0), s2 = sq * sq;
-    double p = fma(s2, ON_K[9], ON_K[8]);
-    p = fma(p, s2, ON_K[7]); p = fma(p, s2, ON_K[6]); p = fma(p, s2, ON_K[5]); p = fma(p, s2, ON_K[4]);
-    p = fma(p, s2, ON_K[3]); p = fma(p, s2, ON_K[2]); p = fma(p, s2, ON_K[1]); p = fma(p, s2, ON_K[0]);
+    // degree-9 polynomial in s^2, Estrin form: dependency depth 4 instead of 10 (the walk is a chain of short serial
+    // sections; with two warps per SM sub-partition the depth, not the operation count, is what costs)
+    const double z2 = s2 * s2, z4 = z2 * z2, z8 = z4 * z4;
+    const double a0 = fma(s2, ON_K[1], ON_K[0]), a1 = fma(s2, ON_K[3], ON_K[2]), a2 = fma(s2, ON_K[5], ON_K[4]);
+    const double a3 = fma(s2, ON_K[7], ON_K[6]), a4 = fma(s2, ON_K[9], ON_K[8]);
+    const double b0 = fma(a1, z2, a0), b1 = fma(a3, z2, a2);
+    const double p = fma(a4, z8, fma(b1, z4, b0));
     const double lnm = fma(sq * s2, p, sq);                  // atanh(s)
     return fma((double)e, ON_K[26], -4.0 * lnm);
 }
@@ -87,18 +91,19 @@ __device__ __forceinline__ void sincos_2pi_u32(uint32_t j, double &sn, double &c
     uint32_t fr = j & 0x1FFFFFFFu;
     if (oct & 1u) fr = 0x20000000u - fr;
     const double a = (double)fr * ON_K[27], a2 = a * a;
-    double ps = fma(a2, ON_K[16], ON_K[15]);
-    ps = fma(ps, a2, ON_K[14]); ps = fma(ps, a2, ON_K[13]); ps = fma(ps, a2, ON_K[12]);
-    ps = fma(ps, a2, ON_K[11]); ps = fma(ps, a2, ON_K[10]);
+    // Estrin form of both polynomials (degree 6 and 7 in a^2): depth 4 instead of 7 / 8
+    const double a4 = a2 * a2, a8 = a4 * a4;
+    const double s0 = fma(a2, ON_K[11], ON_K[10]), s1 = fma(a2, ON_K[13], ON_K[12]), s2_ = fma(a2, ON_K[15], ON_K[14]);
+    const double ps = fma(fma(ON_K[16], a4, s2_), a8, fma(s1, a4, s0));
     const double si = fma(a * a2, ps, a);
-    double pc = fma(a2, ON_K[24], ON_K[23]);
-    pc = fma(pc, a2, ON_K[22]); pc = fma(pc, a2, ON_K[21]); pc = fma(pc, a2, ON_K[20]);
-    pc = fma(pc, a2, ON_K[19]); pc = fma(pc, a2, ON_K[18]); pc = fma(pc, a2, ON_K[17]);
+    const double c0 = fma(a2, ON_K[18], ON_K[17]), c1 = fma(a2, ON_K[20], ON_K[19]), c2 = fma(a2, ON_K[22], ON_K[21]);
+    const double c3 = fma(a2, ON_K[24], ON_K[23]);
+    const double pc = fma(fma(c3, a4, c2), a8, fma(c1, a4, c0));
     const double co = fma(a2, pc, 1.0);
     const bool swap = ((oct + 1u) & 2u) != 0u;               // octants 1, 2, 5, 6
-    double s0 = swap ? co : si, c0 = swap ? si : co;
-    sn = (oct & 4u) ? -s0 : s0;                              // octants 4..7
-    cs = ((oct + 2u) & 4u) ? -c0 : c0;                       // octants 2..5
+    const double sv = swap ? co : si, cv = swap ? si : co;
+    sn = (oct & 4u) ? -sv : sv;                              // octants 4..7
+    cs = ((oct + 2u) & 4u) ? -cv : cv;                       // octants 2..5
 }
 #endif
 // Inline form (the caller's `out` stays in registers: used in the rolled loop of the noise walk, where the code exists once
@@ -259,10 +264,12 @@ __device__ __forceinline__ double exp_neg(double y)
     const double kd = t - 6755399441055744.0;
     double r = fma(kd, -6.93147180369123816490e-01, -y);
     r = fma(kd, -1.90821492927058770002e-10, r);
-    double p = fma(r, ON_K[39], ON_K[38]);
-    p = fma(p, r, ON_K[37]); p = fma(p, r, ON_K[36]); p = fma(p, r, ON_K[35]); p = fma(p, r, ON_K[34]); p = fma(p, r, ON_K[33]);
-    p = fma(p, r, ON_K[32]); p = fma(p, r, ON_K[31]); p = fma(p, r, ON_K[30]); p = fma(p, r, ON_K[29]); p = fma(p, r, ON_K[28]);
-    p = fma(p, r, 1.0); p = fma(p, r, 1.0);
+    // degree-13 Taylor polynomial in Estrin form (depth 5 instead of 14)
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a0 = r + 1.0, a1 = fma(r, ON_K[29], ON_K[28]), a2 = fma(r, ON_K[31], ON_K[30]), a3 = fma(r, ON_K[33], ON_K[32]);
+    const double a4 = fma(r, ON_K[35], ON_K[34]), a5 = fma(r, ON_K[37], ON_K[36]), a6 = fma(r, ON_K[39], ON_K[38]);
+    const double b0 = fma(a1, r2, a0), b1 = fma(a3, r2, a2), b2 = fma(a5, r2, a4);
+    const double p = fma(fma(a6, r4, b2), r8, fma(b1, r4, b0));
     return __hiloint2double(__double2hiint(p) + (kk << 20), __double2loint(p));
 }
 #endif
@@ -518,7 +525,7 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
 #pragma unroll 1
 #endif
 #ifndef ON_UKF_GROUP
-#define ON_UKF_GROUP 1
+#define ON_UKF_GROUP 4
 #endif
     for (int idx = 0; idx < 12; idx += ON_UKF_GROUP) {
         double Y[ON_UKF_GROUP][6];
@@ -739,8 +746,17 @@ struct NoiseRole {
         const double ndt = k > 0 ? P.dt : 0.0;
 #pragma unroll
         for (int i = 0; i < 3; i++) nerr[i] += ndt * nerr[3 + i];
+#ifndef ON_NZ_UNROLL
+#define ON_NZ_UNROLL 1
+#endif
 #if defined(__CUDA_ARCH__)
+#if ON_NZ_UNROLL == 1
 #pragma unroll 1
+#elif ON_NZ_UNROLL == 2
+#pragma unroll 2
+#else
+#pragma unroll
+#endif
 #endif
         for (int b = 0; b < 4; b++) {                                 // four normals per Philox block, 15 walk states
             double n4[4];

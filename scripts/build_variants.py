@@ -12,6 +12,7 @@ os.makedirs(os.path.join(ROOT, "variants"), exist_ok=True)
 b.build()                                                   # default objects (opnav.o is shared by every variant)
 objdir = os.path.join(b.HERE, "build", os.path.basename(b.LIB) + ".obj")
 KERNEL = os.environ.get("VARIANT_KERNEL", "leo_step_kernelILi3ELi0ELb1ELb0")
+VSRC = os.environ.get("VARIANT_SRC", "bskenv.cu")          # the translation unit that takes the flags; the others are shared
 
 
 def one(item):
@@ -22,8 +23,8 @@ def one(item):
     for src in b.SOURCES:
         if not os.path.exists(os.path.join(b.CSRC, src)):
             continue
-        if src == "opnav.cu":
-            objs.append(os.path.join(objdir, "opnav.o")); continue
+        if src != VSRC:
+            objs.append(os.path.join(objdir, src.replace(".cu", ".o"))); continue
         obj = os.path.join(ROOT, "variants", f"{name}_{src[:-3]}.o")
         r = subprocess.run([b.nvcc_path()] + b.NVCC_FLAGS + flags.split() + ["-Xptxas", "-v", "-c", "-o", obj, os.path.join(b.CSRC, src)],
                            cwd=b.CSRC, capture_output=True, text=True)
