@@ -74,5 +74,22 @@ def build(force=False, extra_flags=(), verbose=False, out=None):
     return out
 
 
+LITERAL_LIB = os.path.join(HERE, "libbskenv_literal.so")
+
+
+def build_literal(force=False):
+    """PARITY BUILD (tests only): the same library with -DLEO_LITERAL_ECLIPSE, i.e. the penumbra evaluated exactly as
+    Basilisk's eclipse.cpp writes it instead of the regrouped production form (deviation D7).
+    Loaded through BSKENV_LIB by tests/eclipse_probe.py; never by the product."""
+    stamp = LITERAL_LIB + ".stamp"
+    want = source_hash(("-DLEO_LITERAL_ECLIPSE",))
+    if not force and os.path.exists(LITERAL_LIB) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return LITERAL_LIB
+    build(extra_flags=("-DLEO_LITERAL_ECLIPSE",), out=LITERAL_LIB)
+    with open(stamp, "w") as f:
+        f.write(want)
+    return LITERAL_LIB
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))

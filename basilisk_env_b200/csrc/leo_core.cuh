@@ -557,6 +557,17 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double i
     const double area = a * a * clamp_acos(x / a) - x * y + (b * b) * (u * u2) * seg;
     return 1. - area / (PI * a * a);
 }
+// PARITY BUILD ONLY (-DLEO_LITERAL_ECLIPSE, libbskenv_literal.so; tests/test_gpu_round2.py): the disk overlap exactly as
+// eclipse.cpp writes it -- norms by sqrt, apparent radii and separation through asin / acos of quotients, the lens-area
+// formula in its original grouping -- so that the deviation of the regrouped production form above from the reference's
+// arithmetic is a MEASURED quantity (deviation D7), not an asserted one.
+LEO_HD_NOINLINE double penumbra_literal(const LeoParams &P, V3 sun_r, V3 r)
+{
+    const V3 r_HB = sun_r - r;
+    const double nh = sqrt(dot(r_HB, r_HB)), ns = sqrt(dot(r, r));
+    const double a = clamp_asin(P.R_sun / nh), b = clamp_asin(P.R_planet / ns), c = clamp_acos((-dot(r, r_HB)) / (ns * nh));
+    return percent_shadow_general(a, b, c);
+}
 // Shadow factor of the planet at the origin (zeroBase earth), eclipse.UpdateState + computePercentShadow.
 // Full sun / umbra are decided on squared cone radii (no sqrt, no transcendentals); a relative guard band of
 // ECL_BAND around both cone surfaces, and the penumbra itself, go through the disk-overlap formula.
@@ -961,7 +972,9 @@ LEO_HD Dyn rk4_step(const LeoParams &P, const Dyn &x, const StageIn &a, bool thr
     Dyn k, acc;
     k.r = k.v = k.s = k.w = acc.r = acc.v = acc.s = acc.w = mk(0., 0., 0.);
     double c = 0.;
-#if LEO_UNROLL_STAGES
+#if LEO_UNROLL_STAGES == 2
+#pragma unroll 2
+#elif LEO_UNROLL_STAGES
 #pragma unroll
 #else
 #pragma unroll 1
@@ -1400,7 +1413,11 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
                 shadow = eclipse_core(P, ec, sun_r, x.r, r2d, rsq(r2d), r_SB, d2, rsq(d2));
                 shf = (float)shadow;
             } else {
+#ifdef LEO_LITERAL_ECLIPSE
+                shadow = penumbra_literal(P, mld3(m, M_SUNR), x.r);
+#else
                 shadow = penumbra_fraction(P, ir, id, rdh);
+#endif
             }
         } else if (F32) {
             shadow = (double)shf;

@@ -89,8 +89,8 @@ __global__ void opnav_perm_identity_kernel(int32_t *__restrict__ perm, int64_t s
     if (e < stride) perm[e] = (int32_t)(e < n ? e : n - 1);
 }
 
-// per-thread scratch in shared memory: filter (49 doubles) + cold dynamics data (19) + walk states (15) = 83, an odd stride
-// (conflict-free); 83 x 8 B x 128 threads = 85 KB per block, two blocks per SM
+// per-thread scratch in shared memory: filter (33 doubles: the square-root factor is stored packed) + cold dynamics data (19) +
+// walk states (15) = 67, an odd stride (conflict-free); 67 x 8 B x 128 threads = 68.6 KB per block
 struct OnScratch { opnav::Ukf f; opnav::Cold c; opnav::Walk w; };
 
 // One thread runs the three roles of opnav_core.cuh (noise walk, dynamics + flight software, filter) of one env in sequence.

@@ -493,20 +493,21 @@ ON_HD bool chol_downdate6(double (&L)[21], double (&x)[6])
     }
     return ok;
 }
-// Filter state as the kernel holds it during a launch: estimate, square-root covariance as a full column-major 6 x 6 (column c
-// at C[6c .. 6c+5], zeros above the diagonal: a sigma-point column is six consecutive words), mean shift of the last time
-// update.  `Cold` is the cold per-env data of the dynamics side (four Sun nodes of the interval, Sun-heading / eclipse
-// latches, nav Sun heading).  Odd strides (49, 19 doubles) keep the per-thread copies in shared memory free of bank
-// conflicts; the cold fields are read through volatile accesses so that they are re-loaded at their (rare) points of use
+// Filter state as the kernel holds it during a launch: estimate, square-root covariance packed by columns (column c holds
+// rows c .. 5 at C[SC_COL(c) ..]: 21 words; a sigma-point column is read with one run-time base and immediate row offsets),
+// mean shift of the last time update.  `Cold` is the cold per-env data of the dynamics side (four Sun nodes of the interval,
+// Sun-heading / eclipse latches, nav Sun heading).  The per-thread scratch (Ukf + Cold + Walk = 67 doubles, an odd stride)
+// sits in shared memory free of bank conflicts and small enough for three 128-thread blocks per SM; the cold fields are read through volatile accesses so that they are re-loaded at their (rare) points of use
 // instead of being carried in registers through the tick loop.
-struct Ukf { double x[6]; double C[36]; double m[6]; double pad; };      // 49 doubles
+struct Ukf { double x[6]; double C[21]; double m[6]; };                  // 33 doubles
 struct Cold { double sun[12]; double cold[7]; };                         // 19 doubles: Sun nodes, cold per-env latches
 // simple_nav's 15 walk states: parked in the per-thread shared scratch as well.  The walk advances in a ROLLED loop (four
 // states per Philox block; the noise transform exists once in the instruction stream), i.e. the states are indexed at run
 // time -- in a per-thread array that means local memory (the kernel's former 752-byte stack: ~140 LDL / STL per tick and
 // 2.5x the algorithmic DRAM traffic from its write-backs); in shared memory it is an LDS / STS with an immediate stride.
 struct Walk { double e[15]; };
-#define SC(r, c) C[(c) * 6 + (r)]
+#define SC_COL(c) (6 * (c) - (c) * ((c) - 1) / 2)
+#define SC(r, c) C[SC_COL(c) + (r) - (c)]          /* r >= c */
 // relODuKFTimeUpdate over dt.  The twelve deviations are accumulated into the 21 independent entries of the Gram
 // matrix (no serial dependence between sigma points; propagating the +/- pair of a column side by side was measured and
 // is slower: 81 live doubles instead of 57), then one
@@ -534,7 +535,10 @@ ON_HD_NOINLINE bool ukf_time_update(const OpNavParams &P, Ukf &f, double dt)
             const int i = (idx + g) >> 1;
             const double gam = ((idx + g) & 1) ? -P.ukf_gamma : P.ukf_gamma;
 #pragma unroll
-            for (int r = 0; r < 6; r++) Y[g][r] = fmad(gam, f.C[i * 6 + r], f.x[r]);
+            for (int r = 0; r < 6; r++) {          // column i of the factor: rows r < i are zero (and not stored)
+                const double cr = f.C[SC_COL(i) - i + r];
+                Y[g][r] = fmad(gam, r >= i ? cr : 0.0, f.x[r]);
+            }
         }
         two_body_rk4_group<ON_UKF_GROUP>(Y, P.mu_fsw, dt);
 #pragma unroll
@@ -973,7 +977,7 @@ struct FilterRole {
 #define SI(f) I[(int64_t)(f) * stride + e]
         for (int i = 0; i < 6; i++) { f.x[i] = SD(OF_FSTATE + i); f.m[i] = 0.0; }
         for (int r = 0; r < 6; r++)
-            for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? SD(OF_FS + TRI(r, c)) : 0.0;
+            for (int c = 0; c <= r; c++) f.SC(r, c) = SD(OF_FS + TRI(r, c));
         ftick = SI(OI_FTICK); n_meas = SI(OI_NMEAS); n_bad = SI(OI_NBAD);
         const int64_t tick0 = SI(OI_TICK);
         k_first = tick0 + 1; k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;

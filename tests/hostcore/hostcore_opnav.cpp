@@ -92,7 +92,7 @@ void hco_ukf_time_update(HCO *h, double *x, double *S, double *m, double dt)
 {
     opnav::Ukf f;
     for (int i = 0; i < 6; i++) { f.x[i] = x[i]; f.m[i] = 0; }
-    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? S[k++] : 0.0;
+    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c <= r; c++) f.SC(r, c) = S[k++];
     (void)opnav::ukf_time_update(h->P, f, dt);
     for (int i = 0; i < 6; i++) { x[i] = f.x[i]; m[i] = f.m[i]; }
     for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c <= r; c++) S[k++] = f.SC(r, c);
@@ -101,7 +101,7 @@ int hco_ukf_meas_update(HCO *h, double *x, double *S, const double *m, double dt
 {
     opnav::Ukf f;
     for (int i = 0; i < 6; i++) { f.x[i] = x[i]; f.m[i] = m[i]; }
-    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c < 6; c++) f.SC(r, c) = c <= r ? S[k++] : 0.0;
+    for (int r = 0, k = 0; r < 6; r++) for (int c = 0; c <= r; c++) f.SC(r, c) = S[k++];
     double o[3] = {obs[0], obs[1], obs[2]}, R[6];
     for (int i = 0; i < 6; i++) R[i] = R6[i];
     bool ok = opnav::ukf_meas_update(h->P, f, dt, o, R);

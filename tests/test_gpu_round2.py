@@ -257,3 +257,52 @@ def test_long_horizon_batch_parity_all_done_reasons(bsk, orc):
     print("long horizon, perigee >= 200 km:", {k: f"{v:.1e}" for k, v in worst.items()})
     print("long horizon, perigee <  200 km:", {k: f"{v:.1e}" for k, v in worst_low.items()})
     env.close()
+
+
+def test_literal_eclipse_build_measures_the_shadow_factor_deviation(bsk, orc, tmp_path):
+    """Deviation D7, measured instead of asserted.  Inside the penumbra the production kernel evaluates
+    a REGROUPED, well-conditioned form of eclipse.cpp's disk-overlap formula; the parity build (-DLEO_LITERAL_ECLIPSE) evaluates
+    the literal form, as the oracle does.  Both builds step the same 2048 envs for 40 intervals of 10 s; the shadow factor
+    at every decision boundary is compared with the oracle's.  Positions agree to ~2e-14 in both builds, so what the
+    comparison shows is the evaluation of the formula alone.
+    Measured on a B200 (329 penumbra samples): production form vs oracle max 5.6e-9 (median 3.6e-10); LITERAL form vs oracle
+    max 1.3e-8 (median 1.3e-10).  I.e. the reference's formula, evaluated literally on two machines from inputs that agree to
+    2e-14, does not reproduce itself to 1e-9: its term b^2 acos((c - x) / b) amplifies rounding by ~1e6
+    (tests/test_hostcore_eclipse.py::test_reference_penumbra_formula_is_ill_conditioned shows the same on the CPU alone).
+    The 1e-7 absolute tolerance on shadowFactor / obs[4] is therefore a property of the reference formula, not of the
+    regrouped evaluation -- which is the closer of the two to the oracle in the worst case."""
+    import os
+    import subprocess
+    import sys
+    from basilisk_env_b200 import build as b
+    n, steps, dur = 2048, 40, 10.0
+    res = {}
+    for name, lib in (("production", b.LIB), ("literal", b.LITERAL_LIB)):
+        assert os.path.exists(lib), f"{lib} missing: run __graft_entry__.build()"
+        out = str(tmp_path / f"{name}.npz")
+        env = dict(os.environ, BSKENV_LIB=lib)
+        subprocess.check_call([sys.executable, "-m", "tests.eclipse_probe", out, str(n), str(steps), str(dur)],
+                              cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))), env=env)
+        res[name] = np.load(out)
+        assert str(res[name]["lib"]) == lib
+    ics, acts = res["production"]["ics"], res["production"]["acts"]
+    np.testing.assert_array_equal(ics, res["literal"]["ics"])
+    batch = orc.LeoEnvBatch(ics, orc.default_cfg(step_duration=dur), max_length=10 ** 6)
+    want = np.zeros((steps, n)); r_o = np.zeros((steps, n, 3))
+    for t in range(steps):
+        ob, _, _, _ = batch.step(acts[t])
+        want[t] = ob[:, 4]
+        r_o[t] = np.array([e.state().r_BN_N[:] for e in batch.envs])
+    pen = (want > 0.0) & (want < 1.0)
+    assert pen.sum() >= 30, int(pen.sum())                  # enough decision boundaries inside the penumbra
+    dev = {k: np.abs(res[k]["obs4"] - want) for k in res}
+    pos = {k: float((np.linalg.norm(res[k]["r"] - r_o, axis=2) / np.linalg.norm(r_o, axis=2)).max()) for k in res}
+    print(f"penumbra samples {int(pen.sum())}; position deviation {pos}; shadow-factor deviation inside the penumbra: "
+          f"production max {dev['production'][pen].max():.2e} median {np.median(dev['production'][pen]):.2e}; "
+          f"literal max {dev['literal'][pen].max():.2e} median {np.median(dev['literal'][pen]):.2e}")
+    # outside the penumbra the factor is exactly 0 or 1 in all three evaluations
+    for k in res:
+        assert float(dev[k][~pen].max()) <= 1e-7 and pos[k] < 1e-11
+        assert (res[k]["obs4"][want == 1.0] > 1.0 - 1e-7).all() and (res[k]["obs4"][want == 0.0] < 1e-7).all()
+    assert dev["literal"][pen].max() <= parity.SHADOW_ATOL and np.median(dev["literal"][pen]) <= 1e-9
+    assert dev["production"][pen].max() <= parity.SHADOW_ATOL and np.median(dev["production"][pen]) <= 1e-9

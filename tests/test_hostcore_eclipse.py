@@ -87,6 +87,35 @@ def test_penumbra_fraction_against_exact_arithmetic(orc, hostcore):
     assert err_ref <= 1e-7, err_ref
 
 
+def test_reference_penumbra_formula_is_ill_conditioned(orc, hostcore):
+    """Why shadowFactor / obs[4] carries an absolute tolerance of 1e-7 (tests/parity.py): inside the penumbra
+    the reference's computePercentShadow, evaluated literally in double precision (the oracle), changes by up to ~1e-8 when
+    the spacecraft position moves by ONE unit in the last place (1e-9 m) -- an amplification of ~1e7 -- while the regrouped
+    form of the step core moves by < 1e-13.  No evaluation of the literal formula can agree with another one to 1e-9."""
+    hc = hostcore.HostCore(1)
+    rng = np.random.RandomState(3)
+    Rp = 6378136.6
+    _, sun = hc.eclipse(0, np.array([[7e6, 0, 0.]]))
+    s_hat = sun / np.linalg.norm(sun)
+    m = 4000
+    depth = rng.uniform(1e5, 7.2e6, m); ang = rng.uniform(0, 2 * np.pi, m)
+    e1 = np.cross(s_hat, [0, 0, 1.0]); e1 /= np.linalg.norm(e1); e2 = np.cross(s_hat, e1)
+    rad = Rp + depth * 4.65e-3 * rng.uniform(-0.9, 0.9, m)
+    pts = -depth[:, None] * s_hat + rad[:, None] * (np.cos(ang)[:, None] * e1 + np.sin(ang)[:, None] * e2)
+    pts = np.ascontiguousarray(pts[np.linalg.norm(pts, axis=1) > Rp + 100e3])
+    pts2 = np.nextafter(pts, np.inf)                          # every coordinate one ulp up (~1e-9 m)
+    L = orc.lib()
+    planet = np.zeros(3)
+    ref = lambda q: np.array([L.orc_eclipse_shadow(sun.ctypes.data_as(P), planet.ctypes.data_as(P), p.ctypes.data_as(P), Rp) for p in q])   # noqa: E731
+    r1, r2 = ref(pts), ref(pts2)
+    f1, _ = hc.eclipse(0, pts); f2, _ = hc.eclipse(0, pts2)
+    pen = (r1 > 0) & (r1 < 1)
+    assert pen.sum() > 2000
+    d_ref, d_fast = np.abs(r1 - r2)[pen].max(), np.abs(f1 - f2)[pen].max()
+    print(f"one-ulp position change: literal formula moves by up to {d_ref:.2e}, regrouped form by {d_fast:.2e}")
+    assert 1e-10 < d_ref < 1e-6 and d_fast < 1e-12
+
+
 def test_general_eom_path_equals_fast_path(hostcore, orc):
     """DIAG fast path (structural zeros dropped, wheel speeds from the per-axis momentum invariant) == general
     3x3 path (per-wheel invariants) up to rounding: discrete outputs exact, continuous ones to 1e-10."""
