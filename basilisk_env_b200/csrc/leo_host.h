@@ -225,12 +225,13 @@ static inline void build_params_f(const LeoParams &p, LeoParamsF &f)
 //   per RK stage   gravity 22, MRP rotation set-up 17, [BN] v 30, collapsed drag 21 (equal + / - facet areas: no Kd terms), torque/gyro/inverse
 //                  inertia 42, MRP kinematics 31                                                   = 163 (diagonal path)
 //   RK4 per tick   stage inputs 96, weighted slope sums 96, final update 12                          = 204
-//   per tick       Sun third body 55, invariant/switch/|r| 30, atmosphere 40, wheel test 6, eclipse + panel + battery 105 = 236
+//   per tick       Sun third body 55, invariant/|r| 30, MRP switch as a select (reciprocal + 3 products, every tick) 10,
+//                  atmosphere 40, wheel test 6, eclipse + panel + battery 105                          = 246
 //   FSW pass       hillPoint 130, attTrackingError 146, MRP_Feedback 69, rwMotorTorque 15           = 360
 static inline double flops_per_step(const LeoParams &p)
 {
     double F_eom = 163.0;
-    const double F_rk4 = 204.0, F_tick = 236.0;
+    const double F_rk4 = 204.0, F_tick = 246.0;
     double F_fsw = 360.0;
     if (!p.diag) F_eom += 42.0 + 8.0 * (p.nrw - 3);        // full 3x3 D / Dinv / drag moment arms, wheel invariants
     if (p.grav_pfix) F_eom += 92.0;      // DCM Euler step 18, r_Pfix 15, |r|^-5/-7 9, M r + quadratic form 29, g_Pfix 9, back-rotation 15 (- point-mass share 3)

@@ -141,3 +141,35 @@ def test_mixed_precision_variant_tracks_fp64(hostcore, orc):
             np.testing.assert_array_equal(I64[parity.F("MRPSwitchCount")], I32[parity.F("MRPSwitchCount")])
     with pytest.raises(AssertionError):
         hostcore.HostCore(2, precision=2)
+
+
+def test_full_episodes_without_resynchronisation(orc, hostcore):
+    """CPU twin of tests/test_gpu_round2.py::test_long_horizon_batch_parity_all_done_reasons (reduced): 36 envs x complete
+    episodes of up to 25 decision intervals of 180 s, random actions, the host-compiled core never re-synchronised with the
+    oracle; every env is compared at every step until its episode ends.  All termination reasons occur and match."""
+    from tests.test_gpu_round2 import _failing_rows, _perigee_altitude, LOW_PERIGEE_ATT_TOL
+    n, L = 36, 24
+    rows = _failing_rows(orc, n, seed=41)
+    benign = _perigee_altitude(rows) >= 200e3
+    hc = hostcore.HostCore(n, max_length=L)
+    hc.reset_ics(rows)
+    batch = orc.LeoEnvBatch(rows, max_length=L)
+    acts = np.random.RandomState(43).randint(0, 3, size=(L + 1, n)).astype(np.int32)
+    live = np.ones(n, bool)
+    seen = 0
+    att = ("sigma", "omega", "Omega", "sigma_BR", "u")
+    for t in range(L + 1):
+        obs, rew, done, reason = hc.step(acts[t])
+        S, I = hc.state()
+        o_ob, o_rew, o_done, o_reason = batch.step(acts[t])
+        np.testing.assert_array_equal(np.asarray(done, bool)[live], o_done[live])
+        np.testing.assert_array_equal(np.asarray(reason)[live], o_reason[live])
+        for e in np.flatnonzero(live):
+            errs = parity.compare_state(batch.envs[e].state(), S[:, e], I[:, e], f"step {t} env {e}", check_continuous=False)
+            for k, v in errs.items():
+                tol = parity.SHADOW_ATOL if k == "shadow" else (parity.RTOL if (benign[e] or k not in att) else LOW_PERIGEE_ATT_TOL)
+                assert v <= tol, (t, e, k, v)
+            if o_done[e]:
+                seen |= int(o_reason[e])
+        live &= ~o_done
+    assert not live.any() and seen & 1 and seen & 2 and seen & 4, seen
