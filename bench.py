@@ -8,8 +8,9 @@ One "step" = one decision interval (180 s of simulated time = 1800 RK4 ticks + 1
 ticks + 180 flight-software ticks) of EVERY env of the batch = one launch of leo_step_kernel.
 Workload: BASELINE.json configs[2] -- 2^20 envs sharded over 8 GPUs, i.e. 131072 envs per GPU with
 weak scaling (per-GPU work fixed), random initial orbits, i.i.d. uniform actions, auto-reset so the
-batch stays in steady state.  The 4096-env case of configs[1] is measured as well and reported under
-"batch4096".  Prints ONE JSON line (rank 0)."""
+batch stays in steady state.  Side measurements in the same line: "batch4096" (configs[1], the small-batch organisation
+of the kernel), "stress" (configs[4]: J2 + four wheels + dumping, FP64 and mixed precision) and "opnav" (configs[3]).
+`e2e` goes through bskenv_step_host with host buffers (zero-copy page-locked memory).  Prints ONE JSON line (rank 0)."""
 import argparse
 import json
 import os
@@ -31,7 +32,7 @@ D2H_BYTES_PER_ENV = 5 * 8 + 8 + 1 + 1   # obs[5] f64, reward f64, done u8, done_
 # ALGORITHMIC bytes per env-step: persistent state read + written once, plus the step I/O
 STATE_BYTES_PER_ENV = (89 + 22) * 8
 # the ncu capture of the shipped build whose executed-flop count the roofline numerator is checked against
-FLOP_CAPTURE = "profiles/ncu_r01j.md: 2.082e6 per env-step"
+FLOP_CAPTURE = "profiles/ncu_leo_r02a.md: 2.0486e6 per env-step"
 
 
 def parse():
