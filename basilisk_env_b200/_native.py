@@ -43,7 +43,7 @@ OPNAV_EXPORTS = ["bskenv_opnav_default_config", "bskenv_opnav_create", "bskenv_o
                  "bskenv_opnav_get_ics", "bskenv_opnav_step", "bskenv_opnav_step_host", "bskenv_opnav_state_dims",
                  "bskenv_opnav_get_state", "bskenv_opnav_set_state", "bskenv_opnav_state_field",
                  "bskenv_opnav_episode_stats", "bskenv_opnav_launch_count", "bskenv_opnav_flops_per_step",
-                 "bskenv_opnav_set_ephemeris"]
+                 "bskenv_opnav_set_ephemeris", "bskenv_opnav_step_info"]
 
 EXPORTS = ["bskenv_abi_version", "bskenv_default_config", "bskenv_create", "bskenv_destroy", "bskenv_last_error",
            "bskenv_num_envs", "bskenv_reset_seeded", "bskenv_reset_ics", "bskenv_reset_init", "bskenv_get_ics",
@@ -113,6 +113,7 @@ def lib():
     L.bskenv_opnav_get_ics.argtypes = [vp, vp, vp]
     L.bskenv_opnav_step.argtypes = [vp] * 9
     L.bskenv_opnav_step_host.argtypes = [vp] * 7
+    L.bskenv_opnav_step_info.argtypes = [vp] * 11
     L.bskenv_opnav_state_dims.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.bskenv_opnav_get_state.argtypes = [vp, vp, vp, vp]
     L.bskenv_opnav_set_state.argtypes = [vp, vp, vp, vp]

@@ -102,7 +102,7 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
                   int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                   double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
                   double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc,
-                  const int32_t *__restrict__ perm)
+                  const int32_t *__restrict__ perm, double *__restrict__ ep_return, int64_t *__restrict__ ep_length)
 {
     extern __shared__ double on_smem[];
     OnScratch &scr = *reinterpret_cast<OnScratch *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratch) / sizeof(double)));
@@ -132,9 +132,15 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
             reason[e] = (uint8_t)o.reason;
             if (debug)
                 for (int k = 0; k < 12; k++) debug[e * 12 + k] = o.debug[k];
-            if (o.done) {
+            if (o.done || ep_return) {
                 ep_ret = S[(int64_t)OF_EPRET * stride + e];
                 ep_len = (double)I[(int64_t)OI_STEP * stride + e];
+            }
+            if (ep_return) {       // opNavEnvironment.py:106-109: info['episode'] = {'r': reward_total, 'l': curr_step (before its increment)}
+                ep_return[e] = ep_ret;
+                ep_length[e] = (int64_t)ep_len - 1;
+            }
+            if (o.done) {
                 if (term_obs)
                     for (int k = 0; k < 4; k++) term_obs[e * 4 + k] = o.ob[k];
                 if (P.auto_reset) {
@@ -246,7 +252,8 @@ struct bskenv_opnav_handle {
     } while (0)
 
 static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double *obs, double *rew, uint8_t *done,
-                             uint8_t *reason, double *debug, double *term_obs, cudaStream_t st)
+                             uint8_t *reason, double *debug, double *term_obs, cudaStream_t st, double *ep_return = nullptr,
+                             int64_t *ep_length = nullptr)
 {
     const int wpb = ON_BLOCK / 32;
     const int64_t groups = (h->n + 31) / 32;
@@ -271,7 +278,7 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
         attr_set[h->device & 63] = true;
     }
     opnav_step_kernel<<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
-                                                 term_obs, h->stats, sc, h->perm);
+                                                 term_obs, h->stats, sc, h->perm, ep_return, ep_length);
     ON_TRY(h, cudaGetLastError());
     h->launches++;
     if (st != h->own_stream || !st) { h->ev_valid = 1; ON_TRY(h, cudaEventRecord(h->ev_last, st)); }
@@ -407,6 +414,18 @@ int bskenv_opnav_step(bskenv_opnav_handle *h, const int32_t *actions_dev, double
     if (!actions_dev || !obs_dev || !reward_dev || !done_dev || !done_reason_dev) { h->err = "bskenv_opnav_step: null buffer"; return BSKENV_EINVAL; }
     ON_TRY(h, cudaSetDevice(h->device));
     return opnav_launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, done_reason_dev, debug_dev, term_obs_dev, (cudaStream_t)stream);
+}
+
+int bskenv_opnav_step_info(bskenv_opnav_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev, uint8_t *done_dev,
+                           uint8_t *done_reason_dev, double *debug_dev, double *term_obs_dev, double *ep_return_dev,
+                           int64_t *ep_length_dev, void *stream)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (!actions_dev || !obs_dev || !reward_dev || !done_dev || !done_reason_dev) { h->err = "bskenv_opnav_step_info: null buffer"; return BSKENV_EINVAL; }
+    if ((ep_return_dev == nullptr) != (ep_length_dev == nullptr)) { h->err = "bskenv_opnav_step_info: ep_return and ep_length go together"; return BSKENV_EINVAL; }
+    ON_TRY(h, cudaSetDevice(h->device));
+    return opnav_launch_step(h, actions_dev, obs_dev, reward_dev, done_dev, done_reason_dev, debug_dev, term_obs_dev, (cudaStream_t)stream,
+                             ep_return_dev, ep_length_dev);
 }
 
 // Host-buffer entry point: zero-copy, as bskenv_step_host (bskenv.cu) -- the kernel reads the actions from and writes its

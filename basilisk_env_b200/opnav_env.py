@@ -85,6 +85,8 @@ class OpNavVecEnv:
             self.reward = torch.zeros(n, dtype=torch.float64, device=self.device)
             self.done = torch.zeros(n, dtype=torch.uint8, device=self.device)
             self.done_reason = torch.zeros(n, dtype=torch.uint8, device=self.device)
+            self.episode_r = torch.zeros(n, dtype=torch.float64, device=self.device)
+            self.episode_l = torch.zeros(n, dtype=torch.int64, device=self.device)
         self.observation_space = spaces.Box(-1e16, 1e16, shape=(OBS_DIM, 1))
         self.action_space = spaces.Discrete(2)
         self.max_length = int(self.cfg.max_length)
@@ -173,12 +175,15 @@ class OpNavVecEnv:
         a = actions.to(device=self.device, dtype=torch.int32).contiguous()
         if a.numel() != self.num_envs:
             raise ValueError("one action per env")
-        self._check(self._L.bskenv_opnav_step(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(self.obs.data_ptr()),
-                                              C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
-                                              C.c_void_p(self.done_reason.data_ptr()), C.c_void_p(self.debug.data_ptr()),
-                                              C.c_void_p(self.term_obs.data_ptr()), self._stream()), "bskenv_opnav_step")
+        self._check(self._L.bskenv_opnav_step_info(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(self.obs.data_ptr()),
+                                                   C.c_void_p(self.reward.data_ptr()), C.c_void_p(self.done.data_ptr()),
+                                                   C.c_void_p(self.done_reason.data_ptr()), C.c_void_p(self.debug.data_ptr()),
+                                                   C.c_void_p(self.term_obs.data_ptr()), C.c_void_p(self.episode_r.data_ptr()),
+                                                   C.c_void_p(self.episode_l.data_ptr()), self._stream()), "bskenv_opnav_step_info")
         self._last_actions = a
-        info = {"done_reason": self.done_reason, "terminal_obs": self.term_obs, "full_states": self.debug}
+        # episode_r / episode_l: the reference's info['episode'] = {'r', 'l'} (opNavEnvironment.py:106-109) where done is set
+        info = {"done_reason": self.done_reason, "terminal_obs": self.term_obs, "full_states": self.debug,
+                "episode_r": self.episode_r, "episode_l": self.episode_l}
         return self.obs, self.reward, self.done, info
 
     def step_host(self, actions, out=None):

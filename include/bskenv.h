@@ -256,6 +256,11 @@ int bskenv_opnav_get_ics(bskenv_opnav_handle *h, double *ics_dev, void *stream);
  *   debug double[n*12] (may be NULL: info['full_states']); term_obs double[n*4] (may be NULL; auto_reset only). */
 int bskenv_opnav_step(bskenv_opnav_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
                       uint8_t *done_dev, uint8_t *done_reason_dev, double *debug_dev, double *term_obs_dev, void *stream);
+/* bskenv_opnav_step with the per-env episode record of `info['episode'] = {'r': self.reward_total, 'l': self.curr_step}`
+ * (envs/opNavEnvironment.py:106-109) as two more device outputs, written for every env at every step (as bskenv_step_info) */
+int bskenv_opnav_step_info(bskenv_opnav_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
+                           uint8_t *done_dev, uint8_t *done_reason_dev, double *debug_dev, double *term_obs_dev,
+                           double *ep_return_dev, int64_t *ep_length_dev, void *stream);
 /* same with HOST buffers (zero-copy for page-locked caller buffers, staging for pageable ones, as bskenv_step_host;
  * synchronous): what bench.py times as e2e */
 int bskenv_opnav_step_host(bskenv_opnav_handle *h, const int32_t *actions, double *obs, double *reward, uint8_t *done,

@@ -75,6 +75,8 @@ def lib(fast=False):
         L.orc_opnav_env_step.argtypes = [vp, C.c_int, C.POINTER(OpNavOut)]
         L.orc_opnav_env_sim.restype = vp
         L.orc_opnav_env_sim.argtypes = [vp]
+        L.orc_opnav_env_set_max_length.argtypes = [vp, C.c_int]
+        L.orc_opnav_env_episode.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]
         L.orc_opnav_env_step_batch.argtypes = [C.POINTER(vp), C.c_int, C.POINTER(C.c_int), C.POINTER(OpNavOut), C.c_int]
         L.orc_opnav_normals.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, dp]
         L.orc_opnav_project_circle.restype = C.c_int
@@ -165,10 +167,18 @@ class OpNavSim:
 class OpNavEnv:
     """Oracle restatement of opNavEnv.reset/step for one env."""
 
-    def __init__(self, cfg=None, L=None):
+    def __init__(self, cfg=None, L=None, max_length=None):
         self._L = L if L is not None else lib()
         self.cfg = cfg if cfg is not None else default_cfg()
         self._h = self._L.orc_opnav_env_create(C.byref(self.cfg))
+        if max_length is not None:
+            self._L.orc_opnav_env_set_max_length(self._h, int(max_length))
+
+    def episode(self):
+        """(reward_total, curr_step) as the reference puts them into info['episode'] (opNavEnvironment.py:106-109)."""
+        r, l = C.c_double(0.0), C.c_int(0)
+        self._L.orc_opnav_env_episode(self._h, C.byref(r), C.byref(l))
+        return r.value, l.value
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -195,11 +205,11 @@ class OpNavEnv:
 class OpNavEnvBatch:
     """n independent oracle envs stepped with OpenMP over envs (the CPU baseline)."""
 
-    def __init__(self, ic_rows, cfg=None, first_env_index=0, L=None):
+    def __init__(self, ic_rows, cfg=None, first_env_index=0, L=None, max_length=None):
         self._L = L if L is not None else lib()
         self.cfg = cfg if cfg is not None else default_cfg()
         self.n = len(ic_rows)
-        self.envs = [OpNavEnv(self.cfg, self._L) for _ in range(self.n)]
+        self.envs = [OpNavEnv(self.cfg, self._L, max_length) for _ in range(self.n)]
         self.obs0 = np.stack([e.reset(r, first_env_index + k, 0) for k, (e, r) in enumerate(zip(self.envs, ic_rows))])
         self._handles = (C.c_void_p * self.n)(*[e._h for e in self.envs])
         self._outs = (OpNavOut * self.n)()

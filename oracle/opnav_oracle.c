@@ -826,6 +826,9 @@ orc_opnav_env *orc_opnav_env_create(const orc_opnav_cfg *cfg)
 }
 void orc_opnav_env_destroy(orc_opnav_env *e) { if (e->sim) orc_opnav_destroy(e->sim); free(e); }
 orc_opnav_sim *orc_opnav_env_sim(orc_opnav_env *e) { return e->sim; }
+void orc_opnav_env_set_max_length(orc_opnav_env *e, int max_length) { e->max_length = max_length; }
+/* opNavEnvironment.py:106-109: info['episode'] = {'r': reward_total, 'l': curr_step}, assembled before curr_step += 1 (:122) */
+void orc_opnav_env_episode(const orc_opnav_env *e, double *r, int *l) { *r = e->reward_total; *l = e->curr_step - 1; }
 void orc_opnav_env_reset(orc_opnav_env *e, const orc_opnav_ic *ic, uint64_t env_index, uint64_t episode, double ob[4])
 { /* ONE:153-168: a fresh simulator; the initial observation is zeros (ONS:152) */
     if (e->sim) orc_opnav_destroy(e->sim);

@@ -78,6 +78,8 @@ void orc_opnav_env_destroy(orc_opnav_env *e);
 void orc_opnav_env_reset(orc_opnav_env *e, const orc_opnav_ic *ic, uint64_t env_index, uint64_t episode, double ob[4]);
 void orc_opnav_env_step(orc_opnav_env *e, int action, orc_opnav_out *out);
 orc_opnav_sim *orc_opnav_env_sim(orc_opnav_env *e);
+void orc_opnav_env_set_max_length(orc_opnav_env *e, int max_length);
+void orc_opnav_env_episode(const orc_opnav_env *e, double *reward_total, int *curr_step_at_info);
 void orc_opnav_env_step_batch(orc_opnav_env **envs, int n, const int *actions, orc_opnav_out *outs, int nthreads);
 
 /* helpers exposed for unit tests */

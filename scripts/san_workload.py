@@ -37,3 +37,20 @@ env.reset()
 for t in range(3):
     env.step(torch.full((60000,), t % 3, dtype=torch.int32, device="cuda"))
 print("leo queue+chunks", env.episode_stats()); env.close()
+# round 2: zero-copy host buffers (the kernel reads / writes page-locked host memory), per-env episode record, async / wait,
+# the stable-baselines adapter; batches of 200 envs run the small-batch organisation (MINB = 1), 60000 the throughput one
+env = LeoPowerAttVecEnv(200, device=0, auto_reset=True, step_duration=20.0, max_length=2, seed=6)
+env.reset()
+act, out = env.host_buffers(episode=True)
+for t in range(4):
+    act[:] = t % 3
+    env.step_host_async(act, out); env.step_host_wait()
+env.step(torch.zeros(200, dtype=torch.int32, device="cuda"))
+env.step_host(np.ones(200, np.int32))          # pageable buffers: staging path
+print("leo zero-copy", env.episode_stats(), float(out[4].sum()), int(out[5].sum())); env.close()
+from basilisk_env_b200.sb_vec_env import LeoPowerAttSBVecEnv
+sb = LeoPowerAttSBVecEnv(96, device=0, seed=7, step_duration=20.0, max_length=2)
+sb.reset()
+for t in range(4):
+    sb.step(np.full(96, t % 3))
+print("sb adapter ok"); sb.close()
