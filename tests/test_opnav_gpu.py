@@ -205,3 +205,26 @@ def test_opnav_sun_ephemeris_table(bsk):
         env.set_ephemeris(mars_sun_table(n_seg=1, seg_len=3600.0))       # does not cover an episode
     env.set_ephemeris(None)
     env.close()
+
+
+def test_opnav_per_env_episode_record_matches_oracle(bsk):
+    """`info['episode'] = {'r': reward_total, 'l': curr_step}` (opNavEnvironment.py:106-109) per env from the kernel
+    (bskenv_opnav_step_info, taken before the in-kernel auto-reset) against the oracle's restatement of the env."""
+    import torch
+    from oracle import opnav as on
+    n, L = 48, 3
+    rows = par.sample_rows(on, n, seed=31)
+    env = _vec(n, noise_seed=5, auto_reset=True, max_length=L, step_duration_min=2.0, camera_reenable=1)
+    batch = on.OpNavEnvBatch(rows, on.default_cfg(seed=5, step_duration_min=2.0, camera_reenable=1), max_length=L)
+    env.reset_ics(rows)
+    acts = np.random.RandomState(3).randint(0, 2, size=(L + 1, n)).astype(np.int32)
+    for t in range(L + 1):
+        o, r, d, info = env.step(torch.as_tensor(acts[t], device="cuda"))
+        _, o_rew, o_done, _, _ = batch.step(acts[t])
+        ep_r, ep_l = info["episode_r"].cpu().numpy(), info["episode_l"].cpu().numpy()
+        np.testing.assert_array_equal(d.cpu().numpy().astype(bool), o_done)
+        for e in range(n):
+            want_r, want_l = batch.envs[e].episode()
+            assert int(ep_l[e]) == want_l == t and abs(ep_r[e] - want_r) <= 1e-9 * max(1.0, abs(want_r)), (t, e, ep_r[e], want_r)
+    assert o_done.all()                                    # the (L + 1)-th call ends every episode (opNavEnvironment.py:91-92)
+    env.close()
