@@ -19,6 +19,7 @@
 
 #include "../../include/bskenv.h"
 #include "leo_core.cuh"
+#include "leo_duo.cuh"
 #include "leo_host.h"
 
 #ifndef LEO_LANES
@@ -28,6 +29,13 @@
 #define LEO_MIN_BLOCKS 3        // resident blocks per SM: 3 x 128 threads x 168 registers
 #endif
 #define LEO_BUS_BYTES ((size_t)leo::LEO_NM * LEO_BLOCK * sizeof(double))   // shared-memory message bus of one block
+#ifndef LEO_DUO_MAX_G
+#define LEO_DUO_MAX_G 4         // groups per block the two-warp organisation can be asked for (bskenv_set_organisation)
+#endif
+#ifndef LEO_DUO_AUTO_G
+#define LEO_DUO_AUTO_G 4        // ... and up to which it is selected automatically (groups <= SM count x this): measured on a
+                                // B200, one / two / four groups per block: 4096 envs 3.34 -> 2.36 ms, 8192 3.42 -> 2.49, 16384 3.76 -> 3.00
+#endif
 #define LEO_BUS_BYTES_PFIX ((size_t)leo::LEO_NM_PFIX * LEO_BLOCK * sizeof(double))   // ... of the planet-fixed gravity variant
 
 namespace {
@@ -73,6 +81,64 @@ __device__ __forceinline__ int chunk_peek(const int *p)
     return v;
 }
 
+// What follows the last chunk of a decision interval: results, per-env episode record, in-kernel auto-reset, episode statistics
+// (warp-shuffle reduction, one atomic per warp and statistic).  Called by all 32 lanes of the warp that stepped the group.
+__device__ __forceinline__ void step_finish(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+                                            int64_t stride, int64_t e, bool valid, int lane, leo::StepOut &o, double *__restrict__ obs,
+                                            double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
+                                            double *__restrict__ term_obs, double *__restrict__ stats, double *__restrict__ ep_return,
+                                            int64_t *__restrict__ ep_length)
+{
+    double ep_ret = 0., ep_len = 0.;
+    if (valid) {
+        reward[e] = o.reward;
+        done[e] = (uint8_t)o.done;
+        reason[e] = (uint8_t)o.reason;
+        if (o.done || ep_return) {
+            ep_ret = S[(int64_t)F_EPRET * stride + e];
+            ep_len = (double)I[(int64_t)I_STEP * stride + e];
+        }
+        if (ep_return) {       // ENV:130-136: info['episode'] = {'r': reward_total, 'l': curr_step (before its increment)}
+            ep_return[e] = ep_ret;
+            ep_length[e] = (int64_t)ep_len - 1;
+        }
+        if (o.done) {
+            if (term_obs)
+                for (int k = 0; k < 5; k++) term_obs[e * 5 + k] = o.ob[k];
+            if (P.auto_reset) {
+                // SB-VecEnv convention: the returned observation is the first one of the next episode
+                int64_t ep = I[(int64_t)I_EPISODE * stride + e] + 1;
+                I[(int64_t)I_EPISODE * stride + e] = ep;
+                double ic[19];
+                leo::sample_ic(P, P.first_env_index + e, ep, ic);
+                for (int k = 0; k < 19; k++) ics[(int64_t)k * stride + e] = ic[k];
+                leo::leo_reset_env(P, S, I, stride, e, ic, o.ob);
+            }
+        }
+        for (int k = 0; k < 5; k++) obs[e * 5 + k] = o.ob[k];
+    }
+    // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
+    if (stats) {
+        const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
+        if (any_done) {
+            double v_ret = warp_sum(o.done ? ep_ret : 0.), v_len = warp_sum(o.done ? ep_len : 0.);
+            int c_all = __popc(any_done);
+            int c_w = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
+            int c_p = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 4)));
+            int c_d = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 8)));
+            int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
+            if (lane == 0) {
+                atomicAdd(&stats[ST_RET], v_ret); atomicAdd(&stats[ST_LEN], v_len);
+                atomicAdd(&stats[ST_COUNT], (double)c_all); atomicAdd(&stats[ST_WHEEL], (double)c_w);
+                atomicAdd(&stats[ST_POWER], (double)c_p); atomicAdd(&stats[ST_DECAY], (double)c_d);
+                atomicAdd(&stats[ST_MAXLEN], (double)c_m);
+            }
+        }
+        const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
+        if (lane == 0 && c_valid) atomicAdd(&stats[ST_STEPS], (double)c_valid);
+    }
+}
+
 // MINB = resident blocks per SM the register allocation is made for.  LEO_MIN_BLOCKS (3 blocks x 128 threads x 168 registers,
 // a few spilled values) is the throughput organisation.  MINB = 1 is the SMALL-BATCH organisation (BASELINE configs[1], 4096
 // envs): when the whole batch fits one block per SM anyway, every warp runs alone on its SM sub-partition at its dependent-
@@ -112,7 +178,6 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
         const bool valid = lane < LEO_LANES && e < n;
         leo::StepOut o;
         o.done = 0; o.reason = 0; o.reward = 0.;
-        double ep_ret = 0., ep_len = 0.;
         for (int c = c_first; c < c_end; c++) {
         if (valid) leo::leo_step_env<NRW, J2, DIAG, F32>(P, S, I, stride, e, bus, actions[e], o, PF, c, sc.n_chunks);
         if (c + 1 < sc.n_chunks) {                              // chunk boundary inside the interval: publish and go on
@@ -123,56 +188,68 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
             }
             continue;
         }
-        if (valid) {
-            reward[e] = o.reward;
-            done[e] = (uint8_t)o.done;
-            reason[e] = (uint8_t)o.reason;
-            if (o.done || ep_return) {
-                ep_ret = S[(int64_t)F_EPRET * stride + e];
-                ep_len = (double)I[(int64_t)I_STEP * stride + e];
-            }
-            if (ep_return) {       // ENV:130-136: info['episode'] = {'r': reward_total, 'l': curr_step (before its increment)}
-                ep_return[e] = ep_ret;
-                ep_length[e] = (int64_t)ep_len - 1;
-            }
-            if (o.done) {
-                if (term_obs)
-                    for (int k = 0; k < 5; k++) term_obs[e * 5 + k] = o.ob[k];
-                if (P.auto_reset) {
-                    // SB-VecEnv convention: the returned observation is the first one of the next episode
-                    int64_t ep = I[(int64_t)I_EPISODE * stride + e] + 1;
-                    I[(int64_t)I_EPISODE * stride + e] = ep;
-                    double ic[19];
-                    leo::sample_ic(P, P.first_env_index + e, ep, ic);
-                    for (int k = 0; k < 19; k++) ics[(int64_t)k * stride + e] = ic[k];
-                    leo::leo_reset_env(P, S, I, stride, e, ic, o.ob);
-                }
-            }
-            for (int k = 0; k < 5; k++) obs[e * 5 + k] = o.ob[k];
-        }
-        // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
-        if (stats) {
-            const unsigned any_done = __ballot_sync(0xffffffffu, valid && o.done);
-            if (any_done) {
-                double v_ret = warp_sum(o.done ? ep_ret : 0.), v_len = warp_sum(o.done ? ep_len : 0.);
-                int c_all = __popc(any_done);
-                int c_w = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 2)));
-                int c_p = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 4)));
-                int c_d = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 8)));
-                int c_m = __popc(__ballot_sync(0xffffffffu, valid && o.done && (o.reason & 1)));
-                if (lane == 0) {
-                    atomicAdd(&stats[ST_RET], v_ret); atomicAdd(&stats[ST_LEN], v_len);
-                    atomicAdd(&stats[ST_COUNT], (double)c_all); atomicAdd(&stats[ST_WHEEL], (double)c_w);
-                    atomicAdd(&stats[ST_POWER], (double)c_p); atomicAdd(&stats[ST_DECAY], (double)c_d);
-                    atomicAdd(&stats[ST_MAXLEN], (double)c_m);
-                }
-            }
-            const int c_valid = __popc(__ballot_sync(0xffffffffu, valid));
-            if (lane == 0 && c_valid) atomicAdd(&stats[ST_STEPS], (double)c_valid);
-        }
+        step_finish(P, S, I, ics, stride, e, valid, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
         }   // chunks of this item
         __syncwarp();
     }
+}
+
+// SMALL-BATCH organisation (leo_duo.cuh): two warps per group of 32 envs -- a dynamics warp and a companion warp (flight
+// software + EnvTask) -- on different SM sub-partitions of one block, G groups per block (block = 64 G threads; the G
+// dynamics warps come first so that with G = 4 every sub-partition hosts one warp of each kind).  Every lane of a group is
+// a real env (the launcher only selects this organisation for batches that are a multiple of 32): all 64 threads of a pair
+// take every named barrier.  Chunks of the interval run back to back exactly as in the static path of leo_step_kernel.
+template <int NRW, int J2, bool DIAG>
+__global__ void __launch_bounds__(256, 1)
+leo_duo_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+               int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
+               double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
+               double *__restrict__ term_obs, double *__restrict__ stats, int n_groups, int n_chunks,
+               double *__restrict__ ep_return, int64_t *__restrict__ ep_length)
+{
+    extern __shared__ double bus_smem[];          // [LEO_NM][LEO_BLOCK] message bus, then [DUO_NF][LEO_BLOCK] mailbox
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 6;
+    const int role = warp / G, q = warp - role * G;             // 0 = dynamics, 1 = companion; pair index within the block
+    const int g = blockIdx.x * G + q;
+    if (g >= n_groups) return;                                  // both warps of the pair leave: their barriers are never used
+    const uint32_t col = (uint32_t)(q * 32 + lane) * (uint32_t)sizeof(double);
+    leo::MBus bus, box;
+    bus.p = box.p = nullptr;
+    bus.a = (uint32_t)__cvta_generic_to_shared(bus_smem) + col;
+    box.a = bus.a + (uint32_t)LEO_BUS_BYTES;
+    const int bar = 1 + 2 * q;                                  // named barriers bar (TICK) and bar + 1 (FSW) of this pair
+    const int64_t e = (int64_t)g * 32 + lane;
+    const int action = actions[e];
+    if (role == 1) {
+        for (int c = 0; c < n_chunks; c++) leo::duo_env<NRW>(P, S, I, stride, e, bus, box, bar, action, c, n_chunks);
+        return;
+    }
+#ifdef LEO_DUO_PROF
+    const long long prof_k0 = clock64();
+#endif
+    leo::StepOut o;
+    o.done = 0; o.reason = 0; o.reward = 0.;
+    for (int c = 0; c < n_chunks; c++) leo::duo_dyn<NRW, J2, DIAG>(P, S, I, stride, e, bus, box, bar, action, o, c, n_chunks);
+#ifdef LEO_DUO_PROF
+    const long long prof_fin0 = clock64();
+#endif
+    step_finish(P, S, I, ics, stride, e, true, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
+#ifdef LEO_DUO_PROF
+    if (lane == 0) {
+        printf("BLK %d cycles %lld general-ticks %d post-events %d penumbra-ticks %d thr-latches %d\n", blockIdx.x, clock64() - prof_k0, leo::duo_prof_cnt[4 * blockIdx.x],
+               leo::duo_prof_cnt[4 * blockIdx.x + 1], leo::duo_prof_cnt[4 * blockIdx.x + 2], leo::duo_prof_cnt[4 * blockIdx.x + 3]);
+        for (int k = 0; k < 4; k++) leo::duo_prof_cnt[4 * blockIdx.x + k] = 0;
+    }
+    if (blockIdx.x == 0 && lane == 0) {
+        const long long t_end = clock64();
+        for (int c = 0; c < n_chunks; c++) {
+            const long long *q = leo::duo_prof_log + 8 * c;
+            printf("chunk %d: load %lld latch %lld pre-loop %lld LOOP %lld final-wait %lld store+END %lld | gap to next entry %lld\n", c, q[1] - q[0], q[2] - q[1],
+                   q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5], (c + 1 < n_chunks ? q[8] : prof_fin0) - q[6]);
+        }
+        printf("step_finish %lld; whole kernel body %lld\n", t_end - prof_fin0, t_end - leo::duo_prof_log[0]);
+    }
+#endif
 }
 
 // mode 0: explicit ICs (row-major [n][19]); 1: stored ICs (reset_init); 2: device-sampled ICs
@@ -254,6 +331,7 @@ struct bskenv_handle {
     int ev_valid;
     int64_t launches;
     const char *kernel_name;    // the step-kernel instantiation of the last launch
+    int organisation;           // BSKENV_ORG_*: 0 auto, 1 one thread per env, 2 two warps per env group (small batches)
     std::string err;
 };
 
@@ -293,6 +371,40 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
         sc.dynamic = 1;
         grid = resident;
         CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int) * (size_t)(4 + groups), st));    // queue head + chunk progress per group
+    }
+    // two warps per env group: whole groups only, the two configurations the small-batch kernels are built for
+    const bool duo_cfg = !h->P.grav_pfix && !h->P.mixed && ((h->P.nrw == 3 && !h->cfg.use_j2 && h->P.diag) || (h->P.nrw == 4 && h->cfg.use_j2));
+    const bool duo_fit = duo_cfg && h->n % 32 == 0 && groups <= (int64_t)h->sm_count * LEO_DUO_MAX_G;
+    if (h->organisation == BSKENV_ORG_DUO && !duo_fit) {
+        h->err = "bskenv_step: the two-warp organisation needs a batch that is a multiple of 32, at most 32 * 4 * SM-count envs, "
+                 "FP64, and the reference or the stress configuration";
+        return BSKENV_EINVAL;
+    }
+    if (duo_fit && (h->organisation == BSKENV_ORG_DUO || (h->organisation == BSKENV_ORG_AUTO && groups <= (int64_t)h->sm_count * LEO_DUO_AUTO_G))) {
+        int G = (int)((groups + h->sm_count - 1) / h->sm_count);
+        G = G <= 1 ? 1 : (G == 2 ? 2 : 4);
+        const int dgrid = (int)((groups + G - 1) / G);
+        const size_t smem = LEO_BUS_BYTES + LEO_DUO_BOX_BYTES;
+        static bool duo_attr[64][2] = {{false}};
+        const int which = h->P.nrw == 3 ? 0 : 1;
+        if (!duo_attr[h->device & 63][which]) {
+            if (which == 0) CU_TRY(h, cudaFuncSetAttribute(leo_duo_kernel<3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CU_TRY(h, cudaFuncSetAttribute(leo_duo_kernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            duo_attr[h->device & 63][which] = true;
+        }
+        if (which == 0) {
+            h->kernel_name = "leo_duo_kernel<3,0,true>";
+            leo_duo_kernel<3, 0, true><<<dgrid, 64 * G, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs,
+                                                                 h->stats, (int)groups, sc.n_chunks, ep_return, ep_length);
+        } else {
+            h->kernel_name = "leo_duo_kernel<4,1,false>";
+            leo_duo_kernel<4, 1, false><<<dgrid, 64 * G, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs,
+                                                                  h->stats, (int)groups, sc.n_chunks, ep_return, ep_length);
+        }
+        CU_TRY(h, cudaGetLastError());
+        h->launches++;
+        if (st != h->own_stream || !st) CU_TRY(h, note_launch(h, st));
+        return BSKENV_OK;
     }
 #define LEO_STR_(x) #x
 #define LEO_STR(x) LEO_STR_(x)
@@ -343,6 +455,14 @@ int64_t bskenv_launch_count(const bskenv_handle *h) { return h ? h->launches : 0
 const char *bskenv_kernel_name(const bskenv_handle *h) { return (h && h->kernel_name) ? h->kernel_name : ""; }
 double bskenv_flops_per_step(const bskenv_handle *h) { return h ? leo_host::flops_per_step(h->P) : 0.0; }
 
+int bskenv_set_organisation(bskenv_handle *h, int organisation)
+{
+    if (!h) return BSKENV_EINVAL;
+    if (organisation < BSKENV_ORG_AUTO || organisation > BSKENV_ORG_DUO) { h->err = "bskenv_set_organisation: unknown organisation"; return BSKENV_EINVAL; }
+    h->organisation = organisation;
+    return BSKENV_OK;
+}
+
 int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t first_env_index, bskenv_handle **out)
 {
     if (!cfg || !out || n_envs <= 0) { g_create_error = "bskenv_create: bad arguments"; return BSKENV_EINVAL; }
@@ -363,7 +483,7 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     }
     leo_host::build_params_f(h->P, h->PF);
     h->P.first_env_index = first_env_index;
-    h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0; h->kernel_name = nullptr;
+    h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0; h->kernel_name = nullptr; h->organisation = BSKENV_ORG_AUTO;
     h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;
     h->d_eph[0] = h->d_eph[1] = nullptr;
     for (int k = 0; k < 8; k++) { h->h_stage[k] = nullptr; h->pend_user[k] = nullptr; h->pend_bytes[k] = 0; }

@@ -526,6 +526,48 @@ LEO_HD double asin_small(double t)
     p = fmad(p, t2, 35. / 1152.); p = fmad(p, t2, 5. / 112.); p = fmad(p, t2, 3. / 40.); p = fmad(p, t2, 1. / 6.);
     return fmad(t * t2, p, t);
 }
+#if defined(__CUDACC__)
+// R(z) ~ (asin(sqrt z) / sqrt z - 1) / z on [0, 1/4]: degree-12 Chebyshev interpolant (scripts/gen_asin_poly.py; the error of
+// s + s z R(z) against asin(s) on |s| <= 1/2 is 5.8e-17, i.e. the rounding of the result).  In constant memory: see LEO_K.
+__constant__ double LEO_ASIN_C[13] = {
+    0.16666666666666669, 0.07499999999998433, 0.04464285714635543, 0.030381944138531247, 0.02237217294214989,
+    0.017352392720869973, 0.013971212973552933, 0.011479177415184906, 0.01032281435018578, 0.005457506718640358,
+    0.01740087944269402, -0.014851887071247204, 0.028757851367421566};
+#endif
+#if defined(__CUDA_ARCH__)
+// Device-side inverse trigonometry of the penumbra evaluation.  The penumbra is a rare, divergent path, but a lone warp (small
+// batches) pays its full latency: libm's asin / acos / sqrt / divide cost ~2700 cycles per evaluation there, these ~1000.
+// No special operands: callers pass finite arguments inside the domain.
+LEO_HD double asin_poly(double s, double z)        // asin(s) for |s| <= 1/2, z = s^2 (Estrin form)
+{
+    const double *c = LEO_ASIN_C;
+    const double z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
+    const double p0 = fma(c[1], z, c[0]), p1 = fma(c[3], z, c[2]), p2 = fma(c[5], z, c[4]), p3 = fma(c[7], z, c[6]);
+    const double p4 = fma(c[9], z, c[8]), p5 = fma(c[11], z, c[10]);
+    const double q0 = fma(p1, z2, p0), q1 = fma(p3, z2, p2), q2 = fma(p5, z2, p4);
+    const double r0 = fma(q1, z4, q0), r1 = fma(c[12], z4, q2);
+    return fma(s * z, fma(r1, z8, r0), s);
+}
+LEO_HD double sqrt_pos(double x) { return x > 1e-290 ? x * rsq(x) : 0.0; }      // sqrt of a non-negative operand (~1 ulp)
+LEO_HD double acos_dev(double q)                   // acos with the argument clamped to [-1, 1] (clamp_acos)
+{
+    q = fmin(fmax(q, -1.0), 1.0);
+    const double aq = fabs(q);
+    const bool small = aq <= 0.5;
+    const double z = small ? q * q : fma(-0.5, aq, 0.5);       // |q| > 1/2: acos |q| = 2 asin sqrt((1 - |q|) / 2)
+    const double sv = small ? q : sqrt_pos(z);
+    const double r = asin_poly(sv, z);
+    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    if (small) return pio2_hi - (r - pio2_lo);
+    return q > 0. ? 2. * r : (2. * pio2_hi - 2. * r) + 2. * pio2_lo;
+}
+LEO_HD double asin_dev_hi(double x)                // asin for 1/2 <= x < 1
+{
+    const double z = fma(-0.5, x, 0.5);
+    const double r = asin_poly(sqrt_pos(z), z);
+    return (1.57079632679489655800e+00 - 2. * r) + 6.12323399573676603587e-17;
+}
+#endif
 // Fraction of the solar disk left visible inside the penumbra (eclipse.cpp computePercentShadow: overlap of two
 // disks of apparent radii a = asin(R_sun/|r_HB|), b = asin(R_p/|s_BP|) whose centres are c apart).
 // The Sun's disk is small (a = 4.65e-3 rad) and c is within a of b, so the reference's five inverse
@@ -540,9 +582,29 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double i
     const double ta = P.R_sun * id, tb = P.R_planet * ir;             // sin a, sin b
     const double cc = -rdh * ir * id;                                  // cos c
     const double sc2 = 1. - cc * cc, cb2 = 1. - tb * tb;
+#if defined(__CUDA_ARCH__) && !defined(LEO_LIBM_PENUMBRA)
+    const double sd = (sc2 > 0. && cb2 > 0.) ? sqrt_pos(sc2) * sqrt_pos(cb2) - cc * tb : 2.0;   // sin(c - b)
+#else
     const double sd = (sc2 > 0. && cb2 > 0.) ? sqrt(sc2) * sqrt(cb2) - cc * tb : 2.0;   // sin(c - b)
+#endif
     if (!(ta <= 0.05 && fabs(sd) <= 0.1 && tb >= 20. * ta && tb < 1.))                  // not a small Sun next to a big limb
         return percent_shadow_general(clamp_asin(ta), clamp_asin(tb), clamp_acos(cc));
+#if defined(__CUDA_ARCH__) && !defined(LEO_LIBM_PENUMBRA)
+    // same formula; reciprocals, square roots and the two inverse trigonometric calls without libm's special-operand paths
+    const double a = asin_small(ta), d = asin_small(sd), b = tb >= 0.5 ? asin_dev_hi(tb) : asin(tb);
+    if (d < -a) return 0.0;
+    if (!(d < a)) return 1.0;
+    const double c = b + d, a2 = a * a, ia = frcp(a);
+    const double x = (a2 + d * (2. * b + d)) * frcp(2. * c);
+    double y2 = a2 - x * x;
+    if (y2 < 0.) y2 = 0.;
+    const double y = sqrt_pos(y2);
+    const double u = y * frcp(b), u2 = u * u;
+    double seg = fmad(u2, 5. / 72., 3. / 28.);
+    seg = fmad(seg, u2, 1. / 5.); seg = fmad(seg, u2, 2. / 3.);
+    const double area = a2 * acos_dev(x * ia) - x * y + (b * b) * (u * u2) * seg;
+    return 1. - area * (ia * ia) * (1. / PI);
+#else
     const double a = asin_small(ta), d = asin_small(sd), b = asin(tb);
     if (d < -a) return 0.0;                                            // c < b - a: total
     if (!(d < a)) return 1.0;                                          // c >= a + b: clear   (c < a - b cannot occur: b > a)
@@ -556,6 +618,7 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double i
     seg = fmad(seg, u2, 1. / 5.); seg = fmad(seg, u2, 2. / 3.);
     const double area = a * a * clamp_acos(x / a) - x * y + (b * b) * (u * u2) * seg;
     return 1. - area / (PI * a * a);
+#endif
 }
 // PARITY BUILD ONLY (-DLEO_LITERAL_ECLIPSE, libbskenv_literal.so; tests/test_gpu_round2.py): the disk overlap exactly as
 // eclipse.cpp writes it -- norms by sqrt, apparent radii and separation through asin / acos of quotients, the lens-area
@@ -1275,8 +1338,10 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             const int64_t n = n_base + j;
             double W[NRW];
             wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
+#ifndef LEO_EXP_NOFSW
             desat_ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, W, (int64_t)sun_d, desat_quiet);
-            rw_sat |= 2;    // a (possibly) new wheel command: re-latch after this tick's integration
+            rw_sat |= 2;
+#endif    // a (possibly) new wheel command: re-latch after this tick's integration
             // SpiceTask was queued for this time long before DynTask -> runs first (scheduler FIFO rule); the
             // message is then newer than the start of this integration step (quirk Q18)
             if (n > 0 && n == n_end) {
@@ -1367,6 +1432,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
         int lim = 0;
 #pragma unroll
         for (int i = 0; i < NRW; i++) lim |= (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
+#ifndef LEO_EXP_NOENV
         if (!F32) {
             // EnvTask: eclipse cone tests and solar-panel geometry
             const V3 sun_r = mld3(m, M_SUNR);
@@ -1382,6 +1448,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             if (proj < 0.) proj = 0.;
             pgeo = P.panel_coef * proj * (id * id);
         }
+#endif
         // clock and Sun third body of the NEXT tick (its state is final: the rare events below do not touch x)
         const double h_this = h;
         now_d += dyn_d;

@@ -43,10 +43,11 @@ class LeoPowerAttVecEnv:
     seed : base seed of the device-side IC sampler.
     auto_reset : re-sample ICs inside the step launch for envs that finish (VecEnv convention: the
         returned obs is the first of the new episode, `info["terminal_obs"]` the last of the old).
+    organisation : "auto" | "thread" | "duo": work organisation of the step kernel (see `set_organisation`).
     **config : overrides of `bskenv_config` fields (include/bskenv.h), e.g. step_duration=60.
     """
 
-    def __init__(self, num_envs, device=0, first_env_index=0, seed=0, auto_reset=False, **config):
+    def __init__(self, num_envs, device=0, first_env_index=0, seed=0, auto_reset=False, organisation="auto", **config):
         if not torch.cuda.is_available():
             raise BskEnvError("LeoPowerAttVecEnv needs a CUDA device: the environment step has no CPU path")
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
@@ -81,6 +82,8 @@ class LeoPowerAttVecEnv:
         nd, ni = C.c_int32(), C.c_int32()
         self._L.bskenv_state_dims(self._h, C.byref(nd), C.byref(ni))
         self.n_double_fields, self.n_int_fields = nd.value, ni.value
+        if organisation != "auto":
+            self.set_organisation(organisation)
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -274,10 +277,17 @@ class LeoPowerAttVecEnv:
         """The step-kernel instantiation the last step launched (as ncu lists it)."""
         return self._L.bskenv_kernel_name(self._h).decode()
 
+    def set_organisation(self, organisation):
+        """Work organisation of the step kernel (include/bskenv.h: bskenv_set_organisation): "auto" (by batch size), "thread"
+        (one thread per env) or "duo" (two warps per group of 32 envs: the small-batch organisation).  Same arithmetic."""
+        org = ORGANISATIONS[organisation] if isinstance(organisation, str) else int(organisation)
+        self._check(self._L.bskenv_set_organisation(self._h, org), "bskenv_set_organisation")
+
     def flops_per_step(self):
         return float(self._L.bskenv_flops_per_step(self._h))
 
 
+ORGANISATIONS = {"auto": 0, "thread": 1, "duo": 2}
 _FIELD_WIDTH = {"r_BN_N": 3, "v_BN_N": 3, "sigma_BN": 3, "omega_BN_B": 3, "Omega": 4, "u_current": 4,
                 "extTorquePntB_B": 3, "att_guidance": 12, "att_reference": 9, "commandedControlTorque": 3,
                 "rwTorqueCommand": 4, "wheelDeltaH": 3, "ThrustOnCmd": 8, "thrOnTimeRemaining": 8, "OnTimeRequest": 8,

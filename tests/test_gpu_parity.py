@@ -46,7 +46,7 @@ def _run_against_oracle(bsk, orc, rows, action_seq, host_path=False, **cfg):
             parity.compare_obs(obs[e], o_ob[e], where)
             assert bool(done[e]) == bool(o_done[e]) and int(reason[e]) == int(o_reason[e]), where
             assert abs(rew[e] - o_rew[e]) <= 1e-12, where
-            parity.compare_state(batch.envs[e].state(), S[:, e], I[:, e], where)
+            parity.compare_state(batch.envs[e].state(), S[:, e], I[:, e], where, dyn_ns=int(round(cfg.get("dynRate", 0.1) * 1e9)))
     env.close()
 
 
