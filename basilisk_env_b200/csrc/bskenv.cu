@@ -19,7 +19,7 @@
 
 #include "../../include/bskenv.h"
 #include "leo_core.cuh"
-#include "leo_duo.cuh"
+#include "leo_split.cuh"
 #include "leo_host.h"
 
 #ifndef LEO_LANES
@@ -29,12 +29,12 @@
 #define LEO_MIN_BLOCKS 3        // resident blocks per SM: 3 x 128 threads x 168 registers
 #endif
 #define LEO_BUS_BYTES ((size_t)leo::LEO_NM * LEO_BLOCK * sizeof(double))   // shared-memory message bus of one block
-#ifndef LEO_DUO_MAX_G
-#define LEO_DUO_MAX_G 4         // groups per block the two-warp organisation can be asked for (bskenv_set_organisation)
+#ifndef LEO_SPLIT_MAX_G
+#define LEO_SPLIT_MAX_G 4       // groups per block of the two-warp organisation: 4 x 64 threads keep 255 registers per thread
 #endif
-#ifndef LEO_DUO_AUTO_G
-#define LEO_DUO_AUTO_G 4        // ... and up to which it is selected automatically (groups <= SM count x this): measured on a
-                                // B200, one / two / four groups per block: 4096 envs 3.34 -> 2.36 ms, 8192 3.42 -> 2.49, 16384 3.76 -> 3.00
+#ifndef LEO_SPLIT_AUTO_G
+#define LEO_SPLIT_AUTO_G 4      // ... and up to which it is selected automatically (groups <= SM count x this): measured on a
+                                // B200 with one / two / four groups per block: 4096 envs 3.34 -> 2.39 ms, 8192 3.42 -> 2.49, 16384 3.76 -> 3.00
 #endif
 #define LEO_BUS_BYTES_PFIX ((size_t)leo::LEO_NM_PFIX * LEO_BLOCK * sizeof(double))   // ... of the planet-fixed gravity variant
 
@@ -194,20 +194,20 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
     }
 }
 
-// SMALL-BATCH organisation (leo_duo.cuh): two warps per group of 32 envs -- a dynamics warp and a companion warp (flight
+// SMALL-BATCH organisation (leo_split.cuh): two warps per group of 32 envs -- a dynamics warp and a companion warp (flight
 // software + EnvTask) -- on different SM sub-partitions of one block, G groups per block (block = 64 G threads; the G
 // dynamics warps come first so that with G = 4 every sub-partition hosts one warp of each kind).  Every lane of a group is
 // a real env (the launcher only selects this organisation for batches that are a multiple of 32): all 64 threads of a pair
 // take every named barrier.  Chunks of the interval run back to back exactly as in the static path of leo_step_kernel.
 template <int NRW, int J2, bool DIAG>
 __global__ void __launch_bounds__(256, 1)
-leo_duo_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
-               int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
-               double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
-               double *__restrict__ term_obs, double *__restrict__ stats, int n_groups, int n_chunks,
-               double *__restrict__ ep_return, int64_t *__restrict__ ep_length)
+leo_split_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+                 int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
+                 double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
+                 double *__restrict__ term_obs, double *__restrict__ stats, int n_groups, int n_chunks,
+                 double *__restrict__ ep_return, int64_t *__restrict__ ep_length)
 {
-    extern __shared__ double bus_smem[];          // [LEO_NM][LEO_BLOCK] message bus, then [DUO_NF][LEO_BLOCK] mailbox
+    extern __shared__ double bus_smem[];          // [LEO_NM][LEO_BLOCK] message bus, then [SPLIT_NF][LEO_BLOCK] mailbox
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, G = blockDim.x >> 6;
     const int role = warp / G, q = warp - role * G;             // 0 = dynamics, 1 = companion; pair index within the block
     const int g = blockIdx.x * G + q;
@@ -221,35 +221,13 @@ leo_duo_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int6
     const int64_t e = (int64_t)g * 32 + lane;
     const int action = actions[e];
     if (role == 1) {
-        for (int c = 0; c < n_chunks; c++) leo::duo_env<NRW>(P, S, I, stride, e, bus, box, bar, action, c, n_chunks);
+        for (int c = 0; c < n_chunks; c++) leo::split_env<NRW>(P, S, I, stride, e, bus, box, bar, action, c, n_chunks);
         return;
     }
-#ifdef LEO_DUO_PROF
-    const long long prof_k0 = clock64();
-#endif
     leo::StepOut o;
     o.done = 0; o.reason = 0; o.reward = 0.;
-    for (int c = 0; c < n_chunks; c++) leo::duo_dyn<NRW, J2, DIAG>(P, S, I, stride, e, bus, box, bar, action, o, c, n_chunks);
-#ifdef LEO_DUO_PROF
-    const long long prof_fin0 = clock64();
-#endif
+    for (int c = 0; c < n_chunks; c++) leo::split_dyn<NRW, J2, DIAG>(P, S, I, stride, e, bus, box, bar, action, o, c, n_chunks);
     step_finish(P, S, I, ics, stride, e, true, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
-#ifdef LEO_DUO_PROF
-    if (lane == 0) {
-        printf("BLK %d cycles %lld general-ticks %d post-events %d penumbra-ticks %d thr-latches %d\n", blockIdx.x, clock64() - prof_k0, leo::duo_prof_cnt[4 * blockIdx.x],
-               leo::duo_prof_cnt[4 * blockIdx.x + 1], leo::duo_prof_cnt[4 * blockIdx.x + 2], leo::duo_prof_cnt[4 * blockIdx.x + 3]);
-        for (int k = 0; k < 4; k++) leo::duo_prof_cnt[4 * blockIdx.x + k] = 0;
-    }
-    if (blockIdx.x == 0 && lane == 0) {
-        const long long t_end = clock64();
-        for (int c = 0; c < n_chunks; c++) {
-            const long long *q = leo::duo_prof_log + 8 * c;
-            printf("chunk %d: load %lld latch %lld pre-loop %lld LOOP %lld final-wait %lld store+END %lld | gap to next entry %lld\n", c, q[1] - q[0], q[2] - q[1],
-                   q[3] - q[2], q[4] - q[3], q[5] - q[4], q[6] - q[5], (c + 1 < n_chunks ? q[8] : prof_fin0) - q[6]);
-        }
-        printf("step_finish %lld; whole kernel body %lld\n", t_end - prof_fin0, t_end - leo::duo_prof_log[0]);
-    }
-#endif
 }
 
 // mode 0: explicit ICs (row-major [n][19]); 1: stored ICs (reset_init); 2: device-sampled ICs
@@ -373,32 +351,32 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
         CU_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int) * (size_t)(4 + groups), st));    // queue head + chunk progress per group
     }
     // two warps per env group: whole groups only, the two configurations the small-batch kernels are built for
-    const bool duo_cfg = !h->P.grav_pfix && !h->P.mixed && ((h->P.nrw == 3 && !h->cfg.use_j2 && h->P.diag) || (h->P.nrw == 4 && h->cfg.use_j2));
-    const bool duo_fit = duo_cfg && h->n % 32 == 0 && groups <= (int64_t)h->sm_count * LEO_DUO_MAX_G;
-    if (h->organisation == BSKENV_ORG_DUO && !duo_fit) {
-        h->err = "bskenv_step: the two-warp organisation needs a batch that is a multiple of 32, at most 32 * 4 * SM-count envs, "
+    const bool split_cfg = !h->P.grav_pfix && !h->P.mixed && ((h->P.nrw == 3 && !h->cfg.use_j2 && h->P.diag) || (h->P.nrw == 4 && h->cfg.use_j2));
+    const bool split_fit = split_cfg && h->n % 32 == 0 && groups <= (int64_t)h->sm_count * LEO_SPLIT_MAX_G;
+    if (h->organisation == BSKENV_ORG_SPLIT && !split_fit) {
+        h->err = "bskenv_step: the split organisation needs a batch that is a multiple of 32, at most 128 * SM-count envs, "
                  "FP64, and the reference or the stress configuration";
         return BSKENV_EINVAL;
     }
-    if (duo_fit && (h->organisation == BSKENV_ORG_DUO || (h->organisation == BSKENV_ORG_AUTO && groups <= (int64_t)h->sm_count * LEO_DUO_AUTO_G))) {
+    if (split_fit && (h->organisation == BSKENV_ORG_SPLIT || (h->organisation == BSKENV_ORG_AUTO && groups <= (int64_t)h->sm_count * LEO_SPLIT_AUTO_G))) {
         int G = (int)((groups + h->sm_count - 1) / h->sm_count);
         G = G <= 1 ? 1 : (G == 2 ? 2 : 4);
         const int dgrid = (int)((groups + G - 1) / G);
-        const size_t smem = LEO_BUS_BYTES + LEO_DUO_BOX_BYTES;
-        static bool duo_attr[64][2] = {{false}};
+        const size_t smem = LEO_BUS_BYTES + LEO_SPLIT_BOX_BYTES;
+        static bool split_attr[64][2] = {{false}};
         const int which = h->P.nrw == 3 ? 0 : 1;
-        if (!duo_attr[h->device & 63][which]) {
-            if (which == 0) CU_TRY(h, cudaFuncSetAttribute(leo_duo_kernel<3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            else CU_TRY(h, cudaFuncSetAttribute(leo_duo_kernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            duo_attr[h->device & 63][which] = true;
+        if (!split_attr[h->device & 63][which]) {
+            if (which == 0) CU_TRY(h, cudaFuncSetAttribute(leo_split_kernel<3, 0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else CU_TRY(h, cudaFuncSetAttribute(leo_split_kernel<4, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            split_attr[h->device & 63][which] = true;
         }
         if (which == 0) {
-            h->kernel_name = "leo_duo_kernel<3,0,true>";
-            leo_duo_kernel<3, 0, true><<<dgrid, 64 * G, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs,
+            h->kernel_name = "leo_split_kernel<3,0,true>";
+            leo_split_kernel<3, 0, true><<<dgrid, 64 * G, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs,
                                                                  h->stats, (int)groups, sc.n_chunks, ep_return, ep_length);
         } else {
-            h->kernel_name = "leo_duo_kernel<4,1,false>";
-            leo_duo_kernel<4, 1, false><<<dgrid, 64 * G, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs,
+            h->kernel_name = "leo_split_kernel<4,1,false>";
+            leo_split_kernel<4, 1, false><<<dgrid, 64 * G, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, term_obs,
                                                                   h->stats, (int)groups, sc.n_chunks, ep_return, ep_length);
         }
         CU_TRY(h, cudaGetLastError());
@@ -458,7 +436,7 @@ double bskenv_flops_per_step(const bskenv_handle *h) { return h ? leo_host::flop
 int bskenv_set_organisation(bskenv_handle *h, int organisation)
 {
     if (!h) return BSKENV_EINVAL;
-    if (organisation < BSKENV_ORG_AUTO || organisation > BSKENV_ORG_DUO) { h->err = "bskenv_set_organisation: unknown organisation"; return BSKENV_EINVAL; }
+    if (organisation < BSKENV_ORG_AUTO || organisation > BSKENV_ORG_SPLIT) { h->err = "bskenv_set_organisation: unknown organisation"; return BSKENV_EINVAL; }
     h->organisation = organisation;
     return BSKENV_OK;
 }

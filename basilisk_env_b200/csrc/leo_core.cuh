@@ -1144,11 +1144,10 @@ LEO_HD_NOINLINE SunDt sun_dt_wrapped(double prev_ns_d, double sun_ns_d, double t
 // Rebuilds the held body torque.  Returns the new thr_active (or -1 when no thruster message arrived).
 template <int NRW>
 struct PostOut { double uJ[NRW]; V3 Lc, tau_u; int thr_active, quiet; };
+// reactionWheelStateEffector.UpdateState: torque saturation, dead band and speed limit of every wheel; rebuilds the held torque
 template <int NRW>
-LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m,
-                                              const double (&W)[NRW], V3 L_thr, int desat_ran, int64_t now_ns, int thr_factor)
+LEO_HD void wheel_latch(const LeoParams &P, MBus m, const double (&W)[NRW], V3 L_thr, double (&uJ)[NRW], V3 &Lc, V3 &tau_u_out)
 {
-    PostOut<NRW> o;
     V3 tau_u = mk(0., 0., 0.);
 #pragma unroll
     for (int i = 0; i < NRW; i++) {
@@ -1157,11 +1156,18 @@ LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int
         if (fabs(uc) < P.u_min[i]) uc = 0.0;
         if (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0 && W[i] * uc >= 0.0) uc = 0.0;
         mst(m, M_U + i, uc);
-        o.uJ[i] = uc * P.invJs[i];
+        uJ[i] = uc * P.invJs[i];
         tau_u = tau_u + arr(P.gs[i]) * uc;
     }
-    o.tau_u = tau_u;
-    o.Lc = (mld3(m, M_LEXT) + L_thr) - tau_u;
+    tau_u_out = tau_u;
+    Lc = (mld3(m, M_LEXT) + L_thr) - tau_u;
+}
+template <int NRW>
+LEO_HD_NOINLINE PostOut<NRW> post_tick_events(const LeoParams &P, double *S, int64_t *I, int64_t stride, int64_t e, MBus m,
+                                              const double (&W)[NRW], V3 L_thr, int desat_ran, int64_t now_ns, int thr_factor)
+{
+    PostOut<NRW> o;
+    wheel_latch<NRW>(P, m, W, L_thr, o.uJ, o.Lc, o.tau_u);
     o.thr_active = -1; o.quiet = 0;
     if (desat_ran & 1) {
         o.thr_active = thr_latch(P, S, I, stride, e, now_ns, thr_factor);

@@ -1,4 +1,4 @@
-// leo_duo.cuh -- the SMALL-BATCH organisation of the fused LEO decision step: TWO WARPS PER GROUP OF 32 SPACECRAFT.
+// leo_split.cuh -- the SMALL-BATCH organisation of the fused LEO decision step: TWO WARPS PER GROUP OF 32 SPACECRAFT.
 //
 // The same decision interval as leo_core.cuh: leo_step_env() (reference: LEOPowerAttitudeSimulator.run_sim,
 // /root/reference/basilisk_env/simulators/leoPowerAttitudeSimulator.py:535-644, + leoPowerAttEnv.step,
@@ -6,19 +6,21 @@
 // of one spacecraft is split over two threads that sit in different warps -- i.e. on different SM sub-partitions, each
 // with its own issue port and FP64 pipe -- of the same block:
 //
-//   dynamics thread  (duo_dyn)  everything the NEXT tick's integration depends on: spacecraftPlus RK4 (DynTask, SIM:101),
+//   dynamics thread  (split_dyn)  everything the NEXT tick's integration depends on: spacecraftPlus RK4 (DynTask, SIM:101),
 //                               wheel invariant, MRP switch, atmosphere, wheel-limit flags, Sun third body, the command
 //                               latches of the wheels and thrusters, the per-stage thruster path;
-//   companion thread (duo_env)  everything that only OBSERVES the state: EnvTask (eclipse, solar panel, battery:
+//   companion thread (split_env)  everything that only OBSERVES the state: EnvTask (eclipse, solar panel, battery:
 //                               SIM:102-103, 311-345) one tick behind, and the flight-software pass (SIM:383-386,
 //                               hillPoint / attTrackingError / MRP_Feedback / rwMotorTorque / desat chain) -- its wheel
 //                               command is only latched AFTER the integration of the tick it runs in, so it has a whole
 //                               tick to get there.
 //
 // Why: with 4096 envs (BASELINE configs[1]) there are 128 warps for 592 sub-partitions; one warp per group runs its 1800
-// serial ticks alone at its dependent-issue latency (3.7 ms per interval).  Measured by compiling the two companion
+// serial ticks alone at its dependent-issue latency (3.3 ms per interval).  Measured by compiling the two companion
 // blocks out of the one-thread kernel: 3.78 ms -> 1.97 ms; they are 48 % of the chain and none of it feeds the next
-// tick.  (Splitting one RK4 stage over lanes or warps does not pay: DESIGN.md section 5b.)
+// tick.  (Splitting one RK4 stage over lanes or warps does not pay, and a THIRD warp that takes the flight software off
+// the companion -- control half handed over first, guidance half at leisure -- was built and measured 4 % slower than
+// this form, 2.50 against 2.39 ms at 4096 envs: what it saves in waiting it pays in barrier operations.  DESIGN.md 5b.)
 //
 // Hand-off: a per-lane mailbox in shared memory, double-buffered by tick parity, and two named barriers per group
 // (PTX barrier.sync / barrier.arrive with 64 threads): TICK, by both warps once per tick (the state after tick j is in
@@ -35,26 +37,17 @@
 #if defined(__CUDACC__)
 namespace leo {
 
-enum DuoField : int {
-    DX_R = 0, DX_V = 3, DX_S = 6, DX_W = 9, DX_WHL = 12, DX_R2 = 16, DX_IR = 17, DX_H = 18, DUO_SLOT = 19,   // per tick, two slots
-    DB_RAN = 2 * DUO_SLOT,    // companion -> dynamics: return value of fsw_pass
+enum SplitField : int {
+    DX_R = 0, DX_V = 3, DX_S = 6, DX_W = 9, DX_WHL = 12, DX_R2 = 16, DX_IR = 17, DX_H = 18, SPLIT_SLOT = 19,   // per tick, two slots
+    DB_RAN = 2 * SPLIT_SLOT,    // companion -> dynamics: return value of fsw_pass
     DB_QUIET,                 // dynamics -> companion: desat chain confirmed quiet by the thruster latch
     DB_CHARGE, DB_SHADOW,     // companion -> dynamics at the end of the call
-    DUO_NF
+    SPLIT_NF
 };
-#define LEO_DUO_BOX_BYTES ((size_t)leo::DUO_NF * LEO_BLOCK * sizeof(double))
+#define LEO_SPLIT_BOX_BYTES ((size_t)leo::SPLIT_NF * LEO_BLOCK * sizeof(double))
 
-#ifdef LEO_DUO_PROF
-__device__ long long duo_prof_log[64];
-__device__ int duo_prof_cnt[4 * 1024];
-#define DUO_T0() const long long _t0 = clock64()
-#define DUO_ACC(v) v += clock64() - _t0
-#else
-#define DUO_T0()
-#define DUO_ACC(v)
-#endif
-__device__ __forceinline__ void duo_sync(int id) { asm volatile("barrier.sync %0, 64;" : : "r"(id) : "memory"); }
-__device__ __forceinline__ void duo_arrive(int id)
+__device__ __forceinline__ void split_sync(int id) { asm volatile("barrier.sync %0, 64;" : : "r"(id) : "memory"); }
+__device__ __forceinline__ void split_arrive(int id)
 {
     __threadfence_block();
     asm volatile("barrier.arrive %0, 64;" : : "r"(id) : "memory");
@@ -64,15 +57,12 @@ __device__ __forceinline__ void duo_arrive(int id)
 // dynamics thread
 // ------------------------------------------------------------------------------------------------------------------
 template <int NRW, int J2, bool DIAG>
-__device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
+__device__ __forceinline__ void split_dyn(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
                                         MBus m, MBus box, int bar, int action, StepOut &out, int chunk, int n_chunks)
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
     // ---------------- load (as leo_step_env) ----------------
-#ifdef LEO_DUO_PROF
-    const long long prof_entry = clock64();
-#endif
     Dyn x;
     StageIn a;
     x.r = mk(SD(F_R), SD(F_R + 1), SD(F_R + 2));
@@ -118,14 +108,8 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
     const int64_t n_end = n_step0 + ticks_step;
     const double dyn_d = (double)P.dyn_ns;
     double sun_d = (double)(n_step0 * P.dyn_ns);
-#ifdef LEO_DUO_PROF
-    const long long prof_latch0 = clock64();
-#endif
     sun_latch_to_bus(P, m, n_step0 * P.dyn_ns);
     if (J2 == 2) pfix_latch_to_bus(P, m, n_step0 * P.dyn_ns);
-#ifdef LEO_DUO_PROF
-    const long long prof_latch1 = clock64();
-#endif
     a.dtp = 0.;
     const int j0 = first ? -1 : 0;
     const int jlo = __any_sync(0xffffffffu, first) ? -1 : 0;   // warp-uniform loop start: every lane takes every barrier
@@ -134,7 +118,7 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
     const int ph0 = (int)((n_base) % tpf);
     const bool ph_uniform = __all_sync(0xffffffffu, ph0 == __shfl_sync(0xffffffffu, ph0, 0));
     double now_d = (double)((n_base + j0) * P.dyn_ns);
-    int desat_ran = 0, desat_quiet = 0;
+    int desat_ran = 0;
     double newTime = t_mul(now_d, LEO_NANO2SEC);
     double prevTime = j0 < 0 ? 0.0 : t_mul(now_d - dyn_d, 1e-9);
     double h = t_sub(newTime, prevTime);
@@ -145,7 +129,7 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
     {
         double W[NRW];
         wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
-        for (int sl = 0; sl <= DUO_SLOT; sl += DUO_SLOT) {        // both slots: a lane that sits out tick -1 publishes nothing in it
+        for (int sl = 0; sl <= SPLIT_SLOT; sl += SPLIT_SLOT) {        // both slots: a lane that sits out tick -1 publishes nothing in it
             mst3(box, sl + DX_R, x.r); mst3(box, sl + DX_V, x.v); mst3(box, sl + DX_S, x.s); mst3(box, sl + DX_W, x.w);
 #pragma unroll
             for (int i = 0; i < NRW; i++) mst(box, sl + DX_WHL + i, W[i]);
@@ -153,11 +137,8 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
         mst(box, DB_QUIET, 0.0);
     }
     __syncwarp();
-    duo_sync(bar);                                             // START: bus mirror, Sun latch and mailbox are in place
+    split_sync(bar);                                             // START: bus mirror, Sun latch and mailbox are in place
 
-#ifdef LEO_DUO_PROF
-    long long prof_tick = 0, prof_fsw = 0; const long long prof_start = clock64();
-#endif
 #pragma unroll 1
     for (int j = jlo; j < ticks; j++) {
         const bool on = j >= j0;
@@ -189,9 +170,6 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
                     const double ph = t_sub(prevTime, ppT);
                     tauPrev = t_add(t_sub(prevTime, ph), ph);
                 }
-#ifdef LEO_DUO_PROF
-                if (__activemask() == (1u << (31 - __clz(__activemask()))) || (threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&duo_prof_cnt[4 * blockIdx.x + 0], 1);
-#endif
                 ThrEventOut o = rk4_general<J2, DIAG>(P, S, stride, e, m, x, a, dts, tBefore, tauPrev, thr_factor, thr_active);
                 x = o.x; thr_factor = o.factor; thr_active = o.active;
                 ThrRefresh th = thr_refresh(P, S, stride, e, m, thr_active ? thr_factor : 0, a.tau_u);
@@ -221,7 +199,7 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
             for (int i = 0; i < NRW; i++) lim |= (fabs(W[i]) >= P.Om_max[i] && P.Om_max[i] > 0.0) ? 1 : 0;
             // publish the state after this tick
             {
-                const int sl = (j & 1) * DUO_SLOT;
+                const int sl = (j & 1) * SPLIT_SLOT;
                 mst3(box, sl + DX_R, x.r); mst3(box, sl + DX_V, x.v); mst3(box, sl + DX_S, x.s); mst3(box, sl + DX_W, x.w);
 #pragma unroll
                 for (int i = 0; i < NRW; i++) mst(box, sl + DX_WHL + i, W[i]);
@@ -238,38 +216,27 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
         // ================= flight-software outputs of this tick (written by the companion while we integrated) =================
         if (fsw_any) {
             __syncwarp();
-            { DUO_T0(); duo_sync(bar + 1); DUO_ACC(prof_fsw); }
+            split_sync(bar + 1);
             if (fsw_now) desat_ran = (int)mld(box, DB_RAN);
         }
         if (on && LEO_RARE(rw_sat | lim | desat_ran)) {
-#ifdef LEO_DUO_PROF
-            if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&duo_prof_cnt[4 * blockIdx.x + 1], 1);
-#endif
+            // (out of line even for the plain wheel latch of every pass: inlining it here measured 2 % slower)
             PostOut<NRW> po = post_tick_events<NRW>(P, S, I, stride, e, m, W, mld3(m, M_LTHR), desat_ran, (int64_t)(now_d - dyn_d), thr_factor);
 #pragma unroll
             for (int i = 0; i < NRW; i++) uJ[i] = po.uJ[i];
             a.Lc = po.Lc; a.tau_u = po.tau_u;
             rw_sat = lim;
             if (po.thr_active >= 0) { thr_active = po.thr_active; mst(m, M_TNEXT, -1.0); }
-            if (desat_ran) { desat_quiet = po.quiet; mst(box, DB_QUIET, (double)desat_quiet); }
+            if (desat_ran) mst(box, DB_QUIET, (double)po.quiet);
             desat_ran = 0;
         }
         __syncwarp();
-        { DUO_T0(); duo_sync(bar); DUO_ACC(prof_tick); }       // TICK
+        split_sync(bar);                                     // TICK
     }
-#ifdef LEO_DUO_PROF
-    const long long prof_loop_end = clock64();
-#endif
     double W[NRW];
     wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
-    duo_sync(bar);                                             // FINAL: battery charge and shadow factor of the last tick
+    split_sync(bar);                                             // FINAL: battery charge and shadow factor of the last tick
     const double charge = mld(box, DB_CHARGE), shadow = mld(box, DB_SHADOW);
-#ifdef LEO_DUO_PROF
-    const long long prof_final = clock64();
-#define DUO_PROF_DUMP() if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) { long long *q = duo_prof_log + 8 * chunk; q[0] = prof_entry; q[1] = prof_latch0; q[2] = prof_latch1; q[3] = prof_start; q[4] = prof_loop_end; q[5] = prof_final; q[6] = clock64(); }
-#else
-#define DUO_PROF_DUMP()
-#endif
     for (int f = 0; f < LEO_M_MIRROR; f++) SD(F_GUID + f) = mld(m, f);
     if (chunk + 1 < n_chunks) {
         SD(F_R) = x.r.x; SD(F_R + 1) = x.r.y; SD(F_R + 2) = x.r.z;
@@ -283,8 +250,7 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
         SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_RWSAT) = rw_sat;
         out.done = 0; out.reason = 0; out.reward = 0.;
         __syncwarp();
-        duo_sync(bar);                                         // END: the state is in memory for the next chunk's companion
-        DUO_PROF_DUMP();
+        split_sync(bar);                                         // END: the state is in memory for the next chunk's companion
         return;
     }
     // ---------------- observation sampling (SIM:598-642) + gym bookkeeping (ENV:98-145) ----------------
@@ -321,8 +287,7 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
     SI(I_TICK) = n_end; SI(I_STEP) = curr_step + 1; SI(I_MASK) = mask; SI(I_SWITCH) = SI(I_SWITCH) + nswitch;
     SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_OVER) = over; SI(I_RWSAT) = rw_sat;
     __syncwarp();
-    duo_sync(bar);                                             // END
-    DUO_PROF_DUMP();
+    split_sync(bar);                                             // END
 #undef SD
 #undef SI
 }
@@ -331,7 +296,7 @@ __device__ __forceinline__ void duo_dyn(const LeoParams &P, double *__restrict__
 // companion thread: flight software + EnvTask
 // ------------------------------------------------------------------------------------------------------------------
 template <int NRW>
-__device__ __forceinline__ void duo_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
+__device__ __forceinline__ void split_env(const LeoParams &P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t e,
                                         MBus m, MBus box, int bar, int action, int chunk, int n_chunks)
 {
 #define SD(f) S[(int64_t)(f) * stride + e]
@@ -361,49 +326,36 @@ __device__ __forceinline__ void duo_env(const LeoParams &P, double *__restrict__
     const int ph0 = (int)((n_base) % tpf);
     const bool ph_uniform = __all_sync(0xffffffffu, ph0 == __shfl_sync(0xffffffffu, ph0, 0));
 
-    duo_sync(bar);                                             // START
+    split_sync(bar);                                             // START
     V3 sun_r = mld3(m, M_SUNR);
     double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
 
     // flight-software pass of tick jj, from the state after tick jj - 1 (slot (jj - 1) & 1)
-#ifdef LEO_DUO_PROF
-    long long prof_tick = 0, prof_fsw = 0, prof_env = 0; const long long prof_start = clock64();
-#endif
     auto fsw_if_due = [&](int jj) {
-        DUO_T0();
         const bool due = jj >= j0 && (int)((n_base + jj) % tpf) == 0;
         if (!((ph_uniform && jj >= 0) ? due : __any_sync(0xffffffffu, due))) return;
         if (due) {
             const int64_t n = n_base + jj;
-            const int sl = ((jj - 1) & 1) * DUO_SLOT;
+            const int sl = ((jj - 1) & 1) * SPLIT_SLOT;
             Dyn x;
             x.r = mld3(box, sl + DX_R); x.v = mld3(box, sl + DX_V); x.s = mld3(box, sl + DX_S); x.w = mld3(box, sl + DX_W);
             double W[NRW];
 #pragma unroll
             for (int i = 0; i < NRW; i++) W[i] = mld(box, sl + DX_WHL + i);
             const int quiet = (int)mld(box, DB_QUIET);
-#ifdef LEO_EXP_NOFSW
-            const int ran = 0;
-#else
             const int ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, W, sun_ns, quiet);
-#endif
             mst(box, DB_RAN, (double)ran);
         }
         __syncwarp();
-        duo_arrive(bar + 1);
-        DUO_ACC(prof_fsw);
+        split_arrive(bar + 1);
     };
     fsw_if_due(jlo);
 
 #pragma unroll 1
     for (int j = jlo; j < ticks; j++) {
-        { DUO_T0(); duo_sync(bar); DUO_ACC(prof_tick); }       // TICK j: slot j & 1 holds the state after tick j
+        split_sync(bar);                                     // TICK j: slot j & 1 holds the state after tick j
         if (j + 1 < ticks) fsw_if_due(j + 1);                  // first: the dynamics warp waits for this one
         if (j < j0) continue;
-        DUO_T0();
-#ifdef LEO_EXP_NOENV
-        continue;
-#endif
         const int64_t n = n_base + j;
         if (n > 0 && n == n_end) {                             // the tick ran under the NEXT interval's Sun message (quirk Q18)
             sun_r = mld3(m, M_SUNR);
@@ -411,7 +363,7 @@ __device__ __forceinline__ void duo_env(const LeoParams &P, double *__restrict__
             for (int q = 0; q < 6; q++) ec[q] = mld(m, M_ECL + q);
         }
         // ================= EnvTask: eclipse cone tests, solar-panel geometry, battery =================
-        const int sl = (j & 1) * DUO_SLOT;
+        const int sl = (j & 1) * SPLIT_SLOT;
         const V3 xr = mld3(box, sl + DX_R), xs = mld3(box, sl + DX_S);
         const double r2 = mld(box, sl + DX_R2), ir = mld(box, sl + DX_IR), h_this = mld(box, sl + DX_H);
         const V3 r_SB = sun_r - xr;
@@ -426,19 +378,10 @@ __device__ __forceinline__ void duo_env(const LeoParams &P, double *__restrict__
         if (proj < 0.) proj = 0.;
         const double pgeo = P.panel_coef * proj * (id * id);
         if (LEO_RARE(penumbra)) {
-#ifdef LEO_DUO_PROF
-            if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&duo_prof_cnt[4 * blockIdx.x + 2], 1);
-#endif
-#ifdef LEO_DUO_PROF
-            const long long tp0 = clock64();
-#endif
 #ifdef LEO_LITERAL_ECLIPSE
             shadow = penumbra_literal(P, sun_r, xr);
 #else
             shadow = penumbra_fraction(P, ir, id, rdh);
-#endif
-#ifdef LEO_DUO_PROF
-            if ((threadIdx.x & 31) == (__ffs(__activemask()) - 1)) atomicAdd(&duo_prof_cnt[4 * blockIdx.x + 3], (int)((clock64() - tp0 + (shadow > 2. ? 1 : 0)) >> 4));
 #endif
         }
         {
@@ -448,12 +391,11 @@ __device__ __forceinline__ void duo_env(const LeoParams &P, double *__restrict__
             if (E < 0.) E = 0.;
             charge = j >= 0 ? E : charge;
         }
-        DUO_ACC(prof_env);
     }
     mst(box, DB_CHARGE, charge); mst(box, DB_SHADOW, shadow);
     __syncwarp();
-    duo_sync(bar);                                             // FINAL
-    duo_sync(bar);                                             // END
+    split_sync(bar);                                             // FINAL
+    split_sync(bar);                                             // END
 #undef SD
 #undef SI
 }

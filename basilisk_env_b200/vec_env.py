@@ -43,7 +43,7 @@ class LeoPowerAttVecEnv:
     seed : base seed of the device-side IC sampler.
     auto_reset : re-sample ICs inside the step launch for envs that finish (VecEnv convention: the
         returned obs is the first of the new episode, `info["terminal_obs"]` the last of the old).
-    organisation : "auto" | "thread" | "duo": work organisation of the step kernel (see `set_organisation`).
+    organisation : "auto" | "thread" | "split": work organisation of the step kernel (see `set_organisation`).
     **config : overrides of `bskenv_config` fields (include/bskenv.h), e.g. step_duration=60.
     """
 
@@ -279,7 +279,7 @@ class LeoPowerAttVecEnv:
 
     def set_organisation(self, organisation):
         """Work organisation of the step kernel (include/bskenv.h: bskenv_set_organisation): "auto" (by batch size), "thread"
-        (one thread per env) or "duo" (two warps per group of 32 envs: the small-batch organisation).  Same arithmetic."""
+        (one thread per env) or "split" (two warps per group of 32 envs: the small-batch organisation).  Same arithmetic."""
         org = ORGANISATIONS[organisation] if isinstance(organisation, str) else int(organisation)
         self._check(self._L.bskenv_set_organisation(self._h, org), "bskenv_set_organisation")
 
@@ -287,7 +287,7 @@ class LeoPowerAttVecEnv:
         return float(self._L.bskenv_flops_per_step(self._h))
 
 
-ORGANISATIONS = {"auto": 0, "thread": 1, "duo": 2}
+ORGANISATIONS = {"auto": 0, "thread": 1, "split": 2}
 _FIELD_WIDTH = {"r_BN_N": 3, "v_BN_N": 3, "sigma_BN": 3, "omega_BN_B": 3, "Omega": 4, "u_current": 4,
                 "extTorquePntB_B": 3, "att_guidance": 12, "att_reference": 9, "commandedControlTorque": 3,
                 "rwTorqueCommand": 4, "wheelDeltaH": 3, "ThrustOnCmd": 8, "thrOnTimeRemaining": 8, "OnTimeRequest": 8,

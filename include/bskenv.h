@@ -193,7 +193,7 @@ const char *bskenv_kernel_name(const bskenv_handle *h);
  *   BSKENV_ORG_AUTO    pick by batch size (default)
  *   BSKENV_ORG_THREAD  one thread per env, one warp per 32 envs (throughput organisation; `north_star`: "thread ... owns
  *                      one spacecraft")
- *   BSKENV_ORG_DUO     two warps per group of 32 envs: a dynamics warp (RK4 and everything the next tick depends on) and a
+ *   BSKENV_ORG_SPLIT   two warps per group of 32 envs: a dynamics warp (RK4 and everything the next tick depends on) and a
  *                      companion warp (flight software, eclipse / panel / battery) on another SM sub-partition, handing
  *                      state over in shared memory once per tick -- the small-batch organisation (BASELINE configs[1]:
  *                      4096 envs), where one warp per group is bound by its own dependent-issue latency.  Needs a batch
@@ -201,7 +201,7 @@ const char *bskenv_kernel_name(const bskenv_handle *h);
  * Replaces nothing in the reference (one Basilisk sim per Python process there, leoPowerAttitudeSimulator.py:75). */
 #define BSKENV_ORG_AUTO 0
 #define BSKENV_ORG_THREAD 1
-#define BSKENV_ORG_DUO 2
+#define BSKENV_ORG_SPLIT 2
 int bskenv_set_organisation(bskenv_handle *h, int organisation);
 
 /* FP64 FMA-pipe microbenchmark used as the roofline denominator (MEASURED_PEAKS.json has none):

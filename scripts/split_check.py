@@ -1,7 +1,7 @@
 #!/usr/bin/env python
-"""Two-warp (duo) organisation against the one-thread organisation: bitwise comparison of obs / reward / done / state over
+"""Two-warp (split) organisation against the one-thread organisation: bitwise comparison of obs / reward / done / state over
 several decision steps with random actions (incl. mode 2) and auto-reset, then device-timed ms per step of both.
-    python scripts/duo_check.py [--envs 4096,8192] [--steps 6] [--stress]"""
+    python scripts/split_check.py [--envs 4096,8192] [--steps 6] [--stress]"""
 import argparse, json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -17,7 +17,7 @@ a = ap.parse_args()
 kw = dict(use_j2=1, rw_set=1) if a.stress else {}
 for n in [int(x) for x in a.envs.split(",")]:
     res = {}
-    for org in ("thread", "duo"):
+    for org in ("thread", "split"):
         env = LeoPowerAttVecEnv(n, device=0, seed=7, auto_reset=True, max_length=4, **kw)
         env.set_organisation(org)
         env.reset()
@@ -40,7 +40,7 @@ for n in [int(x) for x in a.envs.split(",")]:
         ms = float(np.median([ev[t].elapsed_time(ev[t + 1]) for t in range(a.time_steps)]))
         res[org] = (outs, S.clone(), I.clone(), name, ms)
         env.close()
-    (o1, S1, I1, k1, ms1), (o2, S2, I2, k2, ms2) = res["thread"], res["duo"]
+    (o1, S1, I1, k1, ms1), (o2, S2, I2, k2, ms2) = res["thread"], res["split"]
     worst = 0.0
     equal = True
     for t in range(a.steps):
@@ -54,6 +54,6 @@ for n in [int(x) for x in a.envs.split(",")]:
     st_equal = bool((S1 == S2).all()) and bool((I1 == I2).all())
     rel = float((sd / (S1.abs() + 1e-30)).max())
     dones = int(sum(int(o[2].sum()) for o in o1))
-    print(json.dumps({"envs": n, "thread": k1, "duo": k2, "outputs_bit_equal": equal, "worst_rel_output": worst, "state_bit_equal": st_equal,
+    print(json.dumps({"envs": n, "thread": k1, "split": k2, "outputs_bit_equal": equal, "worst_rel_output": worst, "state_bit_equal": st_equal,
                       "state_worst_rel": rel, "int_state_equal": bool((I1 == I2).all()), "episodes_ended": dones,
-                      "ms_thread": ms1, "ms_duo": ms2, "M_env_steps_s_duo": n / ms2 / 1e3}))
+                      "ms_thread": ms1, "ms_split": ms2, "M_env_steps_s_split": n / ms2 / 1e3}))

@@ -1,9 +1,9 @@
-"""GPU suite for the two-warp ("duo") organisation of the LEO step kernel (csrc/leo_duo.cuh; include/bskenv.h:
+"""GPU suite for the two-warp ("split") organisation of the LEO step kernel (csrc/leo_split.cuh; include/bskenv.h:
 bskenv_set_organisation): a dynamics warp and a companion warp (flight software + EnvTask) per group of 32 envs, the
 small-batch organisation behind BASELINE configs[1] (4096 envs on one B200).
 
 Both organisations run the same arithmetic, so the bar is (i) the oracle, at the same tolerances as tests/test_gpu_parity.py
-(discrete exact, continuous <= 1e-9), for BOTH organisations explicitly -- batches of a few groups are routed to the duo
+(discrete exact, continuous <= 1e-9), for BOTH organisations explicitly -- batches of a few groups are routed to the split
 kernel automatically, so the one-thread kernel is pinned here as well -- and (ii) each other, BIT FOR BIT, at 4096 / 8192 /
 16384 envs (one, two and four groups per block) with every mode, in-kernel auto-reset and the per-env episode record.
 Reference for what a step is: LEOPowerAttitudeSimulator.run_sim (leoPowerAttitudeSimulator.py:535-644) +
@@ -15,7 +15,7 @@ from tests import parity
 from tests.test_gpu_parity import _run_against_oracle, _state_np, _vec
 
 pytestmark = pytest.mark.gpu
-ORGS = ("thread", "duo")
+ORGS = ("thread", "split")
 
 
 @pytest.mark.parametrize("org", ORGS)
@@ -65,13 +65,13 @@ def _rollout(bsk, n, org, steps, **kw):
 
 
 @pytest.mark.parametrize("n,kw", [(4096, {}), (8192, {}), (16384, {}), (4096, dict(use_j2=1, rw_set=1)), (2048, dict(step_duration=10.0))])
-def test_duo_equals_thread_bit_for_bit(bsk, n, kw):
+def test_split_equals_thread_bit_for_bit(bsk, n, kw):
     """BASELINE configs[1] size and its multiples (1, 2, 4 groups per block): random actions over all modes, episodes of at
     most four steps so that freshly reset envs (tick 0 runs) and running ones share warps, auto-reset inside the launch."""
     import torch
     a, Sa, Ia, ka, sta = _rollout(bsk, n, "thread", 6, **kw)
-    b, Sb, Ib, kb, stb = _rollout(bsk, n, "duo", 6, **kw)
-    assert ka.startswith("leo_step_kernel") and kb.startswith("leo_duo_kernel"), (ka, kb)
+    b, Sb, Ib, kb, stb = _rollout(bsk, n, "split", 6, **kw)
+    assert ka.startswith("leo_step_kernel") and kb.startswith("leo_split_kernel"), (ka, kb)
     ended = 0
     for t, (x, y) in enumerate(zip(a, b)):
         for k, (p, q) in enumerate(zip(x, y)):
@@ -84,18 +84,18 @@ def test_duo_equals_thread_bit_for_bit(bsk, n, kw):
 
 
 def test_automatic_selection_and_ragged_batches(bsk):
-    """`auto` picks the duo kernel for whole groups that fit four groups per SM, the one-thread kernel otherwise; asking for
-    `duo` on a batch that is not a multiple of 32 is an error of the step call (no silent fallback)."""
+    """`auto` picks the split kernel for whole groups that fit four groups per SM, the one-thread kernel otherwise; asking for
+    `split` on a batch that is not a multiple of 32 is an error of the step call (no silent fallback)."""
     import torch
     from basilisk_env_b200.vec_env import BskEnvError
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    for n, want in ((4096, "leo_duo_kernel"), (64, "leo_duo_kernel"), (33, "leo_step_kernel"), (32 * (4 * sms + 1), "leo_step_kernel")):
+    for n, want in ((4096, "leo_split_kernel"), (64, "leo_split_kernel"), (33, "leo_step_kernel"), (32 * (4 * sms + 1), "leo_step_kernel")):
         env = _vec(bsk, n, seed=1, step_duration=10.0)
         env.reset()
         env.step(torch.zeros(n, dtype=torch.int32, device="cuda"))
         assert env.kernel_name().startswith(want), (n, env.kernel_name())
         env.close()
-    env = _vec(bsk, 33, seed=1, step_duration=10.0, organisation="duo")
+    env = _vec(bsk, 33, seed=1, step_duration=10.0, organisation="split")
     env.reset()
     with pytest.raises(BskEnvError, match="multiple of 32"):
         env.step(torch.zeros(33, dtype=torch.int32, device="cuda"))
@@ -113,7 +113,7 @@ def test_checkpoint_crosses_organisations(bsk):
     acts = torch.randint(0, 3, (4, n), dtype=torch.int32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5))
     ref = _vec(bsk, n, seed=9, step_duration=30.0, organisation="thread")
     ref.reset()
-    a = _vec(bsk, n, seed=9, step_duration=30.0, organisation="duo")
+    a = _vec(bsk, n, seed=9, step_duration=30.0, organisation="split")
     a.reset()
     for t in range(2):
         ref.step(acts[t]); a.step(acts[t])
