@@ -533,6 +533,11 @@ __constant__ double LEO_ASIN_C[13] = {
     0.16666666666666669, 0.07499999999998433, 0.04464285714635543, 0.030381944138531247, 0.02237217294214989,
     0.017352392720869973, 0.013971212973552933, 0.011479177415184906, 0.01032281435018578, 0.005457506718640358,
     0.01740087944269402, -0.014851887071247204, 0.028757851367421566};
+// asin_small() in Estrin form with its coefficients, the planet-segment series, pi/2 (hi, lo) and 1/pi as constant-bank operands
+// (a 64-bit literal costs two uniform-register moves per use: the libm-free penumbra was 240 UMOV of 830 instructions)
+__constant__ double LEO_PEN_K[14] = {1. / 6., 3. / 40., 5. / 112., 35. / 1152., 63. / 2816., 231. / 13312.,
+                                     2. / 3., 1. / 5., 3. / 28., 5. / 72.,
+                                     1.57079632679489655800e+00, 6.12323399573676603587e-17, 0.31830988618379067154, 3.14159265358979323846};
 #endif
 #if defined(__CUDA_ARCH__)
 // Device-side inverse trigonometry of the penumbra evaluation.  The penumbra is a rare, divergent path, but a lone warp (small
@@ -549,6 +554,13 @@ LEO_HD double asin_poly(double s, double z)        // asin(s) for |s| <= 1/2, z 
     return fma(s * z, fma(r1, z8, r0), s);
 }
 LEO_HD double sqrt_pos(double x) { return x > 1e-290 ? x * rsq(x) : 0.0; }      // sqrt of a non-negative operand (~1 ulp)
+LEO_HD double asin_small_dev(double t)
+{
+    const double *k = LEO_PEN_K;
+    const double z = t * t, z2 = z * z, z4 = z2 * z2;
+    const double p0 = fma(k[1], z, k[0]), p1 = fma(k[3], z, k[2]), p2 = fma(k[5], z, k[4]);
+    return fma(t * z, fma(p2, z4, fma(p1, z2, p0)), t);
+}
 LEO_HD double acos_dev(double q)                   // acos with the argument clamped to [-1, 1] (clamp_acos)
 {
     q = fmin(fmax(q, -1.0), 1.0);
@@ -557,7 +569,7 @@ LEO_HD double acos_dev(double q)                   // acos with the argument cla
     const double z = small ? q * q : fma(-0.5, aq, 0.5);       // |q| > 1/2: acos |q| = 2 asin sqrt((1 - |q|) / 2)
     const double sv = small ? q : sqrt_pos(z);
     const double r = asin_poly(sv, z);
-    const double pio2_hi = 1.57079632679489655800e+00, pio2_lo = 6.12323399573676603587e-17;
+    const double pio2_hi = LEO_PEN_K[10], pio2_lo = LEO_PEN_K[11];
     if (small) return pio2_hi - (r - pio2_lo);
     return q > 0. ? 2. * r : (2. * pio2_hi - 2. * r) + 2. * pio2_lo;
 }
@@ -565,7 +577,7 @@ LEO_HD double asin_dev_hi(double x)                // asin for 1/2 <= x < 1
 {
     const double z = fma(-0.5, x, 0.5);
     const double r = asin_poly(sqrt_pos(z), z);
-    return (1.57079632679489655800e+00 - 2. * r) + 6.12323399573676603587e-17;
+    return (LEO_PEN_K[10] - 2. * r) + LEO_PEN_K[11];
 }
 #endif
 // Fraction of the solar disk left visible inside the penumbra (eclipse.cpp computePercentShadow: overlap of two
@@ -576,35 +588,46 @@ LEO_HD double asin_dev_hi(double x)                // asin for 1/2 <= x < 1
 // planet's circular segment b^2 (phi - sin phi cos phi), sin phi = y/b <= a/b, is a short series.  The same
 // lens-area formula, regrouped as (Sun segment) + (planet segment); agreement with the literal form is ~1e-13.
 //   ir = 1/|s_BP|, id = 1/|r_HB|, rdh = s_BP . r_HB
+#if defined(__CUDA_ARCH__) && !defined(LEO_LIBM_PENUMBRA)
+// Device form: the same formula; reciprocals, square roots and the inverse trigonometric functions without libm's special-operand
+// paths, polynomial coefficients as constant-bank operands, Estrin forms (this rare, divergent path sits on a lone warp's chain
+// in the small-batch organisations: 2700 cycles per evaluation with libm, 2000 with the first libm-free form).
+LEO_HD_NOINLINE double penumbra_cold(const LeoParams &P, double ta, double tb, double cc)
+{
+    return percent_shadow_general(clamp_asin(ta), clamp_asin(tb), clamp_acos(cc));
+}
+LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double id, double rdh)
+{
+    const double *k = LEO_PEN_K;
+    const double ta = P.R_sun * id, tb = P.R_planet * ir;             // sin a, sin b
+    const double cc = -rdh * ir * id;                                  // cos c
+    const double sc2 = 1. - cc * cc, cb2 = 1. - tb * tb;
+    const double sd = (sc2 > 0. && cb2 > 0.) ? sqrt_pos(sc2) * sqrt_pos(cb2) - cc * tb : 2.0;   // sin(c - b)
+    if (!(ta <= 0.05 && fabs(sd) <= 0.1 && tb >= 20. * ta && tb < 1. && tb >= 0.5))    // not a small Sun next to a big, near limb
+        return penumbra_cold(P, ta, tb, cc);
+    const double a = asin_small_dev(ta), d = asin_small_dev(sd), b = asin_dev_hi(tb);
+    if (d < -a) return 0.0;                                            // c < b - a: total
+    if (!(d < a)) return 1.0;                                          // c >= a + b: clear   (c < a - b cannot occur: b > a)
+    const double c = b + d, a2 = a * a, ia = frcp(a), ib = frcp(b);
+    const double x = (a2 + d * (2. * b + d)) * frcp(2. * c);
+    double y2 = a2 - x * x;
+    if (y2 < 0.) y2 = 0.;
+    const double y = sqrt_pos(y2);
+    const double u = y * ib, u2 = u * u;
+    const double seg = fma(fma(k[9], u2, k[8]), u2 * u2, fma(k[7], u2, k[6]));
+    const double area = a2 * acos_dev(x * ia) - x * y + (b * b) * (u * u2) * seg;
+    return 1. - area * (ia * ia) * k[12];
+}
+#else
 LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double id, double rdh)
 {
     const double PI = 3.14159265358979323846;
     const double ta = P.R_sun * id, tb = P.R_planet * ir;             // sin a, sin b
     const double cc = -rdh * ir * id;                                  // cos c
     const double sc2 = 1. - cc * cc, cb2 = 1. - tb * tb;
-#if defined(__CUDA_ARCH__) && !defined(LEO_LIBM_PENUMBRA)
-    const double sd = (sc2 > 0. && cb2 > 0.) ? sqrt_pos(sc2) * sqrt_pos(cb2) - cc * tb : 2.0;   // sin(c - b)
-#else
     const double sd = (sc2 > 0. && cb2 > 0.) ? sqrt(sc2) * sqrt(cb2) - cc * tb : 2.0;   // sin(c - b)
-#endif
     if (!(ta <= 0.05 && fabs(sd) <= 0.1 && tb >= 20. * ta && tb < 1.))                  // not a small Sun next to a big limb
         return percent_shadow_general(clamp_asin(ta), clamp_asin(tb), clamp_acos(cc));
-#if defined(__CUDA_ARCH__) && !defined(LEO_LIBM_PENUMBRA)
-    // same formula; reciprocals, square roots and the two inverse trigonometric calls without libm's special-operand paths
-    const double a = asin_small(ta), d = asin_small(sd), b = tb >= 0.5 ? asin_dev_hi(tb) : asin(tb);
-    if (d < -a) return 0.0;
-    if (!(d < a)) return 1.0;
-    const double c = b + d, a2 = a * a, ia = frcp(a);
-    const double x = (a2 + d * (2. * b + d)) * frcp(2. * c);
-    double y2 = a2 - x * x;
-    if (y2 < 0.) y2 = 0.;
-    const double y = sqrt_pos(y2);
-    const double u = y * frcp(b), u2 = u * u;
-    double seg = fmad(u2, 5. / 72., 3. / 28.);
-    seg = fmad(seg, u2, 1. / 5.); seg = fmad(seg, u2, 2. / 3.);
-    const double area = a2 * acos_dev(x * ia) - x * y + (b * b) * (u * u2) * seg;
-    return 1. - area * (ia * ia) * (1. / PI);
-#else
     const double a = asin_small(ta), d = asin_small(sd), b = asin(tb);
     if (d < -a) return 0.0;                                            // c < b - a: total
     if (!(d < a)) return 1.0;                                          // c >= a + b: clear   (c < a - b cannot occur: b > a)
@@ -618,8 +641,8 @@ LEO_HD_NOINLINE double penumbra_fraction(const LeoParams &P, double ir, double i
     seg = fmad(seg, u2, 1. / 5.); seg = fmad(seg, u2, 2. / 3.);
     const double area = a * a * clamp_acos(x / a) - x * y + (b * b) * (u * u2) * seg;
     return 1. - area / (PI * a * a);
-#endif
 }
+#endif
 // PARITY BUILD ONLY (-DLEO_LITERAL_ECLIPSE, libbskenv_literal.so; tests/test_gpu_round2.py): the disk overlap exactly as
 // eclipse.cpp writes it -- norms by sqrt, apparent radii and separation through asin / acos of quotients, the lens-area
 // formula in its original grouping -- so that the deviation of the regrouped production form above from the reference's
