@@ -54,3 +54,11 @@ sb.reset()
 for t in range(4):
     sb.step(np.full(96, t % 3))
 print("sb adapter ok"); sb.close()
+# round 2: the split (two warps per env group) organisation: named barriers + shared-memory mailbox; one group per
+# block (several groups per block need more than 148 groups: tests/test_gpu_split.py), both configurations, mode 2 (desat chain crosses the FSW barrier), fresh and running envs in one warp
+for n, kw in ((64, {}), (64 * 6, {}), (64, dict(use_j2=1, rw_set=1))):
+    env = LeoPowerAttVecEnv(n, device=0, auto_reset=True, step_duration=20.0, max_length=2, seed=8, organisation="split", **kw)
+    env.reset()
+    for t in range(4):
+        env.step(torch.randint(0, 3, (n,), dtype=torch.int32, device="cuda"))
+    print("leo split", n, env.kernel_name(), env.episode_stats()["episodes"]); env.close()
