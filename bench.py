@@ -8,8 +8,8 @@ One "step" = one decision interval (180 s of simulated time = 1800 RK4 ticks + 1
 ticks + 180 flight-software ticks) of EVERY env of the batch = one launch of leo_step_kernel.
 Workload: BASELINE.json configs[2] -- 2^20 envs sharded over 8 GPUs, i.e. 131072 envs per GPU with
 weak scaling (per-GPU work fixed), random initial orbits, i.i.d. uniform actions, auto-reset so the
-batch stays in steady state.  Side measurements in the same line: "batch4096" (configs[1], the small-batch organisation
-of the kernel), "stress" (configs[4]: J2 + four wheels + dumping, FP64 and mixed precision) and "opnav" (configs[3]).
+batch stays in steady state.  Side measurements in the same line: "batch4096" (configs[1]: the split organisation of the
+kernel, with the one-thread organisation beside it), "stress" (configs[4]: J2 + four wheels + dumping, FP64 and mixed precision) and "opnav" (configs[3]).
 `e2e` goes through bskenv_step_host with host buffers (zero-copy page-locked memory).  Prints ONE JSON line (rank 0)."""
 import argparse
 import json
@@ -335,19 +335,40 @@ def main():
 
 
 def side_batch(n, torch, dev, peak_tf):
-    """BASELINE configs[1]: 4096 envs on one GPU (fewer env groups than SM sub-partitions: the small-batch organisation
-    of the step kernel)."""
+    """BASELINE configs[1]: 4096 envs on one GPU -- fewer env groups than SM sub-partitions.  The library picks the split
+    organisation (two warps per group of 32 envs: csrc/leo_split.cuh); the one-thread organisation
+    (bskenv_set_organisation) is timed beside it on the same actions, and the split one also end to end through
+    bskenv_step_host with host buffers."""
     from basilisk_env_b200.vec_env import LeoPowerAttVecEnv
-    env = LeoPowerAttVecEnv(n, device=dev.index, seed=5, auto_reset=True)
-    env.reset()
     acts = torch.randint(0, 3, (13, n), dtype=torch.int32, device=dev)
-    total_ms, per = time_device_steps(env, acts, 10, 3, torch, None, 1)
-    flops, name = env.flops_per_step(), env.kernel_name()
-    env.close()
-    ms = total_ms / 10
-    tf = flops * n / (ms * 1e-3) / 1e12
-    return {"envs": n, "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "fp64_tflops": tf,
-            "frac": tf / peak_tf if peak_tf else None, "kernel": name}
+    acts_host = acts.cpu().numpy()
+    out = {}
+    for org in ("auto", "thread"):
+        env = LeoPowerAttVecEnv(n, device=dev.index, seed=5, auto_reset=True, organisation=org)
+        env.reset()
+        total_ms, per = time_device_steps(env, acts, 10, 3, torch, None, 1)
+        flops, name = env.flops_per_step(), env.kernel_name()
+        ms = total_ms / 10
+        tf = flops * n / (ms * 1e-3) / 1e12
+        res = {"envs": n, "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "fp64_tflops": tf,
+               "frac": tf / peak_tf if peak_tf else None, "kernel": name}
+        if org == "auto":
+            act_pinned, outs = env.host_buffers()
+            for t in range(3):
+                act_pinned[:] = acts_host[t]; env.step_host(act_pinned, outs)
+            torch.cuda.synchronize()
+            e0 = time.perf_counter()
+            for t in range(10):
+                act_pinned[:] = acts_host[3 + t]; env.step_host(act_pinned, outs)
+            torch.cuda.synchronize()
+            e_ms = (time.perf_counter() - e0) * 1e3 / 10
+            res["e2e"] = {"value": n / (e_ms * 1e-3), "unit": UNIT, "ms_per_step": e_ms, "h2d_bytes_per_step": H2D_BYTES_PER_ENV * n,
+                          "d2h_bytes_per_step": D2H_BYTES_PER_ENV * n, "api": "bskenv_step_host, page-locked host buffers"}
+            out = res
+        else:
+            out["one_thread_per_env"] = {k: res[k] for k in ("value", "ms_per_step", "frac", "kernel")}
+        env.close()
+    return out
 
 
 def side_stress(n, torch, dev, peak_tf, steps=5, warmup=3):

@@ -126,3 +126,35 @@ def test_checkpoint_crosses_organisations(bsk):
     np.testing.assert_array_equal(S0, S1); np.testing.assert_array_equal(I0, I1)
     for e in (ref, a, b):
         e.close()
+
+
+def test_foreign_tick_counts_take_the_voted_schedule(bsk):
+    """Envs of one warp whose tick counts are NOT congruent modulo the flight-software period (only reachable by injecting a
+    foreign state with bskenv_set_state): the flight-software passes of a group then fall on different ticks per lane, the
+    split kernel's barrier schedule switches from the uniform rule to warp votes, and the result is still what the
+    one-thread kernel computes, bit for bit."""
+    import torch
+    from basilisk_env_b200 import _native
+    n = 96
+    acts = torch.randint(0, 3, (3, n), dtype=torch.int32, device="cuda", generator=torch.Generator(device="cuda").manual_seed(8))
+    src = _vec(bsk, n, seed=13, step_duration=30.0, organisation="thread")
+    src.reset()
+    src.step(acts[0])
+    S, I = src.get_state()
+    I = I.clone()
+    I[_native.state_field("tick")[0]] += torch.arange(n, device=I.device, dtype=I.dtype) % 7      # 0 .. 6 ticks ahead, per lane
+    out = {}
+    for org in ORGS:
+        env = _vec(bsk, n, seed=13, step_duration=30.0, organisation=org)
+        env.reset()
+        env.set_state(S, I)
+        res = []
+        for t in (1, 2):
+            o, r, d, info = env.step(acts[t])
+            res += [o.clone(), r.clone(), d.clone(), info["done_reason"].clone()]
+        out[org] = res + list(env.get_state()) + [env.kernel_name()]
+        env.close()
+    assert out["thread"][-1].startswith("leo_step_kernel") and out["split"][-1].startswith("leo_split_kernel")
+    for k, (p, q) in enumerate(zip(out["thread"][:-1], out["split"][:-1])):
+        assert torch.equal(p, q) or bool((torch.isnan(p.double()) == torch.isnan(q.double())).all() and torch.equal(torch.nan_to_num(p.double()), torch.nan_to_num(q.double()))), f"output {k}"
+    src.close()
