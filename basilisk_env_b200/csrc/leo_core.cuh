@@ -955,6 +955,22 @@ LEO_HD V3 sun_accel(const LeoParams &P, V3 rs, V3 r)
     return rs * (-P.mu_sun * (is * is * is)) + d * (-P.mu_sun * (id * id * id));
 }
 
+// The Sun third-body acceleration HELD over a window of w dynamics ticks (one flight-software period): evaluated once, at the
+// window's mid time and the position predicted for it from the state at the window's start (time offset dt0 from the Sun
+// message in force; the first tick of the window has length h_first, the others dyn_s).  The term is a tide of 2.8e-7 m/s^2
+// that turns with the orbit (rate of change ~5e-10 m/s^3): held at the midpoint of a 1 s window the first-order error
+// cancels over the window and the second-order one leaves ~5e-14 m/s of velocity per window.  MEASURED against the oracle,
+// which evaluates the Sun at every RK stage (tests/test_gpu_round2.py, long-horizon test, up to 61 intervals = 3 h without
+// re-synchronisation): position / velocity 9.6e-12 relative (2.2e-12 with the term evaluated every tick; a second-order
+// position prediction changes nothing), growing quadratically -- 2e-10 after a full 270-interval episode; per decision
+// interval < 1e-13.  Steps in which a thruster may switch, and the step whose Sun clock wraps, evaluate the Sun at every
+// stage (rk4_general).  DESIGN.md section 9b, D14.
+LEO_HD V3 sun_window(const LeoParams &P, MBus m, const Dyn &x, double dt0, double h_first, int w, double dyn_s)
+{
+    const double half = 0.5 * (h_first + (double)(w - 1) * dyn_s);
+    return sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * (dt0 + half), x.r + x.v * half);
+}
+
 // What one RK4 step needs besides the parameter block and the integrated state.
 struct StageIn {
     V3 Lc;                         // held body torque: extForceTorque (+ thrusters) - wheel motor torque on the hub
@@ -1046,11 +1062,9 @@ LEO_HD void eom(const LeoParams &P, const Dyn &x, Dyn &k, const StageIn &a, doub
 // stall_no_instruction, profiles/).  No register copies cross the back edge: the stage input is rebuilt from
 // the tick-start state and the previous slope (xs = x + c k, with k = 0 before the first stage), and the
 // weighted slopes are summed separately and added once.
-// The Sun's third-body acceleration is held over the step (evaluated by the caller at the step's mid time and
-// the predicted mid position r + v h/2): its gradient is 2 mu_sun/d^3 = 8e-14 s^-2, the stage positions are
-// within 0.4 km of that point and the deviations of the first and last stage cancel in the RK4 weights -- the
-// net effect is < 1e-10 m of position per decision interval (1e-17 relative); the thrust is constant over the
-// step.  Steps in which a thruster may switch, and the step whose Sun clock wraps, go through rk4_general().
+// The Sun's third-body acceleration is held (evaluated by the caller once per flight-software period at the period's mid
+// time and predicted mid position, see sun_window()); the thrust is constant over the step.  Steps in which a thruster may
+// switch, and the step whose Sun clock wraps, go through rk4_general().
 template <int J2, bool DIAG>
 LEO_HD Dyn rk4_step(const LeoParams &P, const Dyn &x, const StageIn &a, bool thr_on, MBus m)
 {
@@ -1357,7 +1371,9 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
     double h = t_sub(newTime, prevTime);
     // Sun at the step's mid time: dt = (systemClock - WriteClockNanos) * 1e-9 at the second/third stage
     double dtsm = t_mul((j0 < 0 ? 0.0 : now_d - dyn_d) - sun_d, LEO_NANO2SEC) + 0.5 * h;
-    if (!F32) a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+    // Sun third body: held per flight-software period (sun_window); here for the ticks up to the next pass
+    const double dyn_s = t_mul(dyn_d, LEO_NANO2SEC);
+    if (!F32) a.gsun = sun_window(P, m, x, dtsm - 0.5 * h, h, tpf - phase, dyn_s);
 
 #pragma unroll 1
     for (int j = j0; j < ticks; j++) {
@@ -1382,6 +1398,8 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
                     for (int q = 0; q < 6; q++) ecf[q] = (float)mld(m, M_ECL + q);
                 }
             }
+            // Sun third body of the ticks up to the next pass
+            if (!F32) a.gsun = sun_window(P, m, x, t_mul((j < 0 ? 0.0 : now_d - dyn_d) - sun_d, LEO_NANO2SEC), h, tpf, dyn_s);
         }
         // ================= DynTask: spacecraftPlus.UpdateState (RK4 over [t-h, t]) =================
         a.h = h;
@@ -1478,15 +1496,14 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             pgeo = P.panel_coef * proj * (id * id);
         }
 #endif
-        // clock and Sun third body of the NEXT tick (its state is final: the rare events below do not touch x)
+        // clock of the NEXT tick
         const double h_this = h;
         now_d += dyn_d;
         phase = (phase + 1 == tpf) ? 0 : phase + 1;
         prevTime = newTime;
         newTime = t_mul(now_d, LEO_NANO2SEC);
         h = t_sub(newTime, prevTime);
-        dtsm = t_mul((now_d - dyn_d) - sun_d, LEO_NANO2SEC) + 0.5 * h;
-        if (!F32) a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+        dtsm = t_mul((now_d - dyn_d) - sun_d, LEO_NANO2SEC) + 0.5 * h;      // (mixed precision / planet-fixed gravity only)
         // ================= rare, out of line =================
         // wheel command latch (new command, or a wheel at its speed limit) and thruster command latch
         if (LEO_RARE(rw_sat | lim | desat_ran)) {

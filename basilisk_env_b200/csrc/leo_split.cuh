@@ -123,7 +123,8 @@ __device__ __forceinline__ void split_dyn(const LeoParams &P, double *__restrict
     double prevTime = j0 < 0 ? 0.0 : t_mul(now_d - dyn_d, 1e-9);
     double h = t_sub(newTime, prevTime);
     double dtsm = t_mul((j0 < 0 ? 0.0 : now_d - dyn_d) - sun_d, LEO_NANO2SEC) + 0.5 * h;
-    a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
+    const double dyn_s = t_mul(dyn_d, LEO_NANO2SEC);
+    a.gsun = sun_window(P, m, x, dtsm - 0.5 * h, h, tpf - phase, dyn_s);        // held per flight-software period, as leo_step_env
 
     // the state before the first tick, for a flight-software pass that is due in it
     {
@@ -155,6 +156,8 @@ __device__ __forceinline__ void split_dyn(const LeoParams &P, double *__restrict
                     sun_d = now_d; sun_latch_to_bus(P, m, n * P.dyn_ns); wrapped = true;
                     if (J2 == 2) pfix_latch_to_bus(P, m, n * P.dyn_ns);
                 }
+                // Sun third body of the ticks up to the next pass (as leo_step_env)
+                a.gsun = sun_window(P, m, x, t_mul((j < 0 ? 0.0 : now_d - dyn_d) - sun_d, LEO_NANO2SEC), h, tpf, dyn_s);
             }
             // ================= DynTask =================
             a.h = h;
@@ -211,7 +214,6 @@ __device__ __forceinline__ void split_dyn(const LeoParams &P, double *__restrict
             newTime = t_mul(now_d, LEO_NANO2SEC);
             h = t_sub(newTime, prevTime);
             dtsm = t_mul((now_d - dyn_d) - sun_d, LEO_NANO2SEC) + 0.5 * h;
-            a.gsun = sun_accel(P, mld3(m, M_SUNR) + mld3(m, M_SUNV) * dtsm, x.r + x.v * (0.5 * h));
         }
         // ================= flight-software outputs of this tick (written by the companion while we integrated) =================
         if (fsw_any) {
