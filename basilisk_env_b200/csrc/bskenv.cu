@@ -226,8 +226,16 @@ leo_split_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, in
     }
     leo::StepOut o;
     o.done = 0; o.reason = 0; o.reward = 0.;
+#ifdef LEO_SPLIT_PROF
+    long long tc[8]; tc[0] = clock64();
+    for (int c = 0; c < n_chunks; c++) { leo::split_dyn<NRW, J2, DIAG>(P, S, I, stride, e, bus, box, bar, action, o, c, n_chunks); tc[c + 1] = clock64(); }
+    step_finish(P, S, I, ics, stride, e, true, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
+    if (lane == 0) printf("BLK %d total %lld chunks %lld %lld %lld %lld %lld %lld finish %lld\n", blockIdx.x, clock64() - tc[0], tc[1] - tc[0], tc[2] - tc[1], tc[3] - tc[2],
+                          tc[4] - tc[3], tc[5] - tc[4], tc[6] - tc[5], clock64() - tc[6]);
+#else
     for (int c = 0; c < n_chunks; c++) leo::split_dyn<NRW, J2, DIAG>(P, S, I, stride, e, bus, box, bar, action, o, c, n_chunks);
     step_finish(P, S, I, ics, stride, e, true, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
+#endif
 }
 
 // mode 0: explicit ICs (row-major [n][19]); 1: stored ICs (reset_init); 2: device-sampled ICs
