@@ -238,8 +238,9 @@ static inline double flops_per_step(const LeoParams &p)
     else if (p.use_j2) F_eom += 14.0;
     if (p.nrw == 4) F_fsw += 5.0;
     double ticks = (double)p.ticks_per_fsw * p.fsw_per_step;
-    // the Sun third-body term (55 flop) is evaluated once per flight-software period, not per tick (leo_core.cuh: sun_window)
-    return ticks * (4 * F_eom + F_rk4 + (F_tick - 55.0)) + p.fsw_per_step * (F_fsw + 59.0);
+    // the Sun third-body term (55 flop + 6 for its mid-step position and time) is evaluated once per flight-software period,
+    // not per tick (leo_core.cuh: sun_window); matched to ncu's executed count (profiles/ncu_leo_r02c.md: 1.9483e6 per env-step)
+    return ticks * (4 * F_eom + F_rk4 + (F_tick - 61.0)) + p.fsw_per_step * (F_fsw + 59.0);
 }
 
 }  // namespace leo_host
