@@ -194,11 +194,25 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
     }
 }
 
+// Ragged batches in the split organisation: the lanes of the last group that have no env step a DUPLICATE of the last env
+// (its state copied into the padding columns [n, stride) of the state blocks before every launch, the same action), so that
+// every lane of a group takes the same barriers through the same code; nothing they compute leaves the padding columns.
+__global__ void leo_pad_kernel(double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t n)
+{
+    const int pads = (int)(stride - n);
+    for (int t = threadIdx.x; t < (LEO_ND + LEO_NI) * pads; t += blockDim.x) {
+        const int f = t / pads;
+        const int64_t e = n + t % pads;
+        if (f < LEO_ND) S[(int64_t)f * stride + e] = S[(int64_t)f * stride + n - 1];
+        else I[(int64_t)(f - LEO_ND) * stride + e] = I[(int64_t)(f - LEO_ND) * stride + n - 1];
+    }
+}
+
 // SMALL-BATCH organisation (leo_split.cuh): two warps per group of 32 envs -- a dynamics warp and a companion warp (flight
 // software + EnvTask) -- on different SM sub-partitions of one block, G groups per block (block = 64 G threads; the G
-// dynamics warps come first so that with G = 4 every sub-partition hosts one warp of each kind).  Every lane of a group is
-// a real env (the launcher only selects this organisation for batches that are a multiple of 32): all 64 threads of a pair
-// take every named barrier.  Chunks of the interval run back to back exactly as in the static path of leo_step_kernel.
+// dynamics warps come first so that with G = 4 every sub-partition hosts one warp of each kind).  Every lane of a group
+// steps an env (the spare lanes of a ragged last group a duplicate of the last one, see leo_pad_kernel): all 64 threads of a
+// pair take every named barrier.  Chunks of the interval run back to back exactly as in the static path of leo_step_kernel.
 template <int NRW, int J2, bool DIAG>
 __global__ void __launch_bounds__(256, 1)
 leo_split_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
@@ -219,7 +233,8 @@ leo_split_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, in
     box.a = bus.a + (uint32_t)LEO_BUS_BYTES;
     const int bar = 1 + 2 * q;                                  // named barriers bar (TICK) and bar + 1 (FSW) of this pair
     const int64_t e = (int64_t)g * 32 + lane;
-    const int action = actions[e];
+    const bool valid = e < n;
+    const int action = actions[valid ? e : n - 1];
     if (role == 1) {
         for (int c = 0; c < n_chunks; c++) leo::split_env<NRW>(P, S, I, stride, e, bus, box, bar, action, c, n_chunks);
         return;
@@ -229,12 +244,12 @@ leo_split_kernel(const __grid_constant__ LeoParams P, double *__restrict__ S, in
 #ifdef LEO_SPLIT_PROF
     long long tc[8]; tc[0] = clock64();
     for (int c = 0; c < n_chunks; c++) { leo::split_dyn<NRW, J2, DIAG>(P, S, I, stride, e, bus, box, bar, action, o, c, n_chunks); tc[c + 1] = clock64(); }
-    step_finish(P, S, I, ics, stride, e, true, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
+    step_finish(P, S, I, ics, stride, e, valid, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
     if (lane == 0) printf("BLK %d total %lld chunks %lld %lld %lld %lld %lld %lld finish %lld\n", blockIdx.x, clock64() - tc[0], tc[1] - tc[0], tc[2] - tc[1], tc[3] - tc[2],
                           tc[4] - tc[3], tc[5] - tc[4], tc[6] - tc[5], clock64() - tc[6]);
 #else
     for (int c = 0; c < n_chunks; c++) leo::split_dyn<NRW, J2, DIAG>(P, S, I, stride, e, bus, box, bar, action, o, c, n_chunks);
-    step_finish(P, S, I, ics, stride, e, true, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
+    step_finish(P, S, I, ics, stride, e, valid, lane, o, obs, reward, done, reason, term_obs, stats, ep_return, ep_length);
 #endif
 }
 
@@ -360,16 +375,16 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
     }
     // two warps per env group: whole groups only, the two configurations the small-batch kernels are built for
     const bool split_cfg = !h->P.grav_pfix && !h->P.mixed && ((h->P.nrw == 3 && !h->cfg.use_j2 && h->P.diag) || (h->P.nrw == 4 && h->cfg.use_j2));
-    const bool split_fit = split_cfg && h->n % 32 == 0 && groups <= (int64_t)h->sm_count * LEO_SPLIT_MAX_G;
+    const bool split_fit = split_cfg && groups <= (int64_t)h->sm_count * LEO_SPLIT_MAX_G;
     if (h->organisation == BSKENV_ORG_SPLIT && !split_fit) {
-        h->err = "bskenv_step: the split organisation needs a batch that is a multiple of 32, at most 128 * SM-count envs, "
-                 "FP64, and the reference or the stress configuration";
+        h->err = "bskenv_step: the split organisation takes at most 128 * SM-count envs, FP64, and the reference or the stress configuration";
         return BSKENV_EINVAL;
     }
     if (split_fit && (h->organisation == BSKENV_ORG_SPLIT || (h->organisation == BSKENV_ORG_AUTO && groups <= (int64_t)h->sm_count * LEO_SPLIT_AUTO_G))) {
         int G = (int)((groups + h->sm_count - 1) / h->sm_count);
         G = G <= 1 ? 1 : (G == 2 ? 2 : 4);
         const int dgrid = (int)((groups + G - 1) / G);
+        if (h->n % 32) leo_pad_kernel<<<1, 256, 0, st>>>(h->S, h->I, h->stride, h->n);
         const size_t smem = LEO_BUS_BYTES + LEO_SPLIT_BOX_BYTES;
         static bool split_attr[64][2] = {{false}};
         const int which = h->P.nrw == 3 ? 0 : 1;

@@ -196,8 +196,9 @@ const char *bskenv_kernel_name(const bskenv_handle *h);
  *   BSKENV_ORG_SPLIT   two warps per group of 32 envs: a dynamics warp (RK4 and everything the next tick depends on) and a
  *                      companion warp (flight software, eclipse / panel / battery) on another SM sub-partition, handing
  *                      state over in shared memory once per tick -- the small-batch organisation (BASELINE configs[1]:
- *                      4096 envs), where one warp per group is bound by its own dependent-issue latency.  Needs a batch
- *                      that is a multiple of 32 and at most 128 x SM-count envs; bskenv_step* returns BSKENV_EINVAL otherwise.
+ *                      4096 envs), where one warp per group is bound by its own dependent-issue latency.  Takes batches
+ *                      of at most 128 x SM-count envs (18944 on a B200), FP64, the reference or the stress configuration;
+ *                      bskenv_step* returns BSKENV_EINVAL otherwise.
  * Replaces nothing in the reference (one Basilisk sim per Python process there, leoPowerAttitudeSimulator.py:75). */
 #define BSKENV_ORG_AUTO 0
 #define BSKENV_ORG_THREAD 1

@@ -64,10 +64,12 @@ def _rollout(bsk, n, org, steps, **kw):
     return out, S, I, name, stats
 
 
-@pytest.mark.parametrize("n,kw", [(4096, {}), (8192, {}), (16384, {}), (4096, dict(use_j2=1, rw_set=1)), (2048, dict(step_duration=10.0))])
+@pytest.mark.parametrize("n,kw", [(4096, {}), (8192, {}), (16384, {}), (4096, dict(use_j2=1, rw_set=1)), (2048, dict(step_duration=10.0)),
+                                  (4000, {}), (33, dict(step_duration=30.0)), (1, dict(step_duration=30.0)), (95, dict(use_j2=1, rw_set=1, step_duration=30.0))])
 def test_split_equals_thread_bit_for_bit(bsk, n, kw):
     """BASELINE configs[1] size and its multiples (1, 2, 4 groups per block): random actions over all modes, episodes of at
-    most four steps so that freshly reset envs (tick 0 runs) and running ones share warps, auto-reset inside the launch."""
+    most four steps so that freshly reset envs (tick 0 runs) and running ones share warps, auto-reset inside the launch; and
+    ragged batches (4000, 95, 33, 1 envs: the spare lanes of the last group step a duplicate of the last env)."""
     import torch
     a, Sa, Ia, ka, sta = _rollout(bsk, n, "thread", 6, **kw)
     b, Sb, Ib, kb, stb = _rollout(bsk, n, "split", 6, **kw)
@@ -84,23 +86,25 @@ def test_split_equals_thread_bit_for_bit(bsk, n, kw):
 
 
 def test_automatic_selection_and_ragged_batches(bsk):
-    """`auto` picks the split kernel for whole groups that fit four groups per SM, the one-thread kernel otherwise; asking for
-    `split` on a batch that is not a multiple of 32 is an error of the step call (no silent fallback)."""
+    """`auto` picks the split kernel for batches that fit four groups of 32 per SM -- ragged ones included: the spare lanes of
+    the last group step a duplicate of the last env (leo_pad_kernel) --, the one-thread kernel otherwise; asking for `split` on
+    a batch that is too large is an error of the step call (no silent fallback)."""
     import torch
     from basilisk_env_b200.vec_env import BskEnvError
     sms = torch.cuda.get_device_properties(0).multi_processor_count
-    for n, want in ((4096, "leo_split_kernel"), (64, "leo_split_kernel"), (33, "leo_step_kernel"), (32 * (4 * sms + 1), "leo_step_kernel")):
+    big = 32 * (4 * sms + 1)
+    for n, want in ((4096, "leo_split_kernel"), (64, "leo_split_kernel"), (33, "leo_split_kernel"), (1, "leo_split_kernel"), (big, "leo_step_kernel")):
         env = _vec(bsk, n, seed=1, step_duration=10.0)
         env.reset()
         env.step(torch.zeros(n, dtype=torch.int32, device="cuda"))
         assert env.kernel_name().startswith(want), (n, env.kernel_name())
         env.close()
-    env = _vec(bsk, 33, seed=1, step_duration=10.0, organisation="split")
+    env = _vec(bsk, big, seed=1, step_duration=10.0, organisation="split")
     env.reset()
-    with pytest.raises(BskEnvError, match="multiple of 32"):
-        env.step(torch.zeros(33, dtype=torch.int32, device="cuda"))
+    with pytest.raises(BskEnvError, match="at most"):
+        env.step(torch.zeros(big, dtype=torch.int32, device="cuda"))
     env.set_organisation("thread")
-    env.step(torch.zeros(33, dtype=torch.int32, device="cuda"))
+    env.step(torch.zeros(big, dtype=torch.int32, device="cuda"))
     with pytest.raises(BskEnvError):
         env.set_organisation(7)
     env.close()
