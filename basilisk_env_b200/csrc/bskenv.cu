@@ -364,7 +364,10 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
     const int64_t groups = (h->n + LEO_LANES - 1) / LEO_LANES;
     const int resident = h->sm_count * LEO_MIN_BLOCKS;          // blocks of one full resident set
     int grid = (int)((groups + wpb - 1) / wpb);
-    const bool small = grid <= h->sm_count;                     // at most one block per SM: the small-batch organisation
+#ifndef LEO_SMALL_BLOCKS
+#define LEO_SMALL_BLOCKS 2      // two 128-thread blocks of the 255-register build fit one SM; measured against the 168-register
+#endif                          // build: 18976 envs 4.35 -> 4.12 ms, 32768 envs 5.31 -> 5.02 ms (one block per SM before r02c)
+    const bool small = grid <= h->sm_count * LEO_SMALL_BLOCKS;  // at most LEO_SMALL_BLOCKS blocks per SM: the 255-register build
     LeoSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
     sc.n_chunks = leo_host::step_chunks(h->P); sc.progress = h->sched + 4;
