@@ -7,13 +7,13 @@
 // with its own issue port and FP64 pipe -- of the same block:
 //
 //   dynamics thread  (split_dyn)  everything the NEXT tick's integration depends on: spacecraftPlus RK4 (DynTask, SIM:101),
-//                               wheel invariant, MRP switch, atmosphere, wheel-limit flags, Sun third body, the command
-//                               latches of the wheels and thrusters, the per-stage thruster path;
+//                                 wheel invariant, MRP switch, atmosphere, wheel-limit flags, Sun third body, the command
+//                                 latches of the wheels and thrusters, the per-stage thruster path;
 //   companion thread (split_env)  everything that only OBSERVES the state: EnvTask (eclipse, solar panel, battery:
-//                               SIM:102-103, 311-345) one tick behind, and the flight-software pass (SIM:383-386,
-//                               hillPoint / attTrackingError / MRP_Feedback / rwMotorTorque / desat chain) -- its wheel
-//                               command is only latched AFTER the integration of the tick it runs in, so it has a whole
-//                               tick to get there.
+//                                 SIM:102-103, 311-345) one tick behind, and the flight-software pass (SIM:383-386,
+//                                 hillPoint / attTrackingError / MRP_Feedback / rwMotorTorque / desat chain) -- its wheel
+//                                 command is only latched AFTER the integration of the tick it runs in, so it has a whole
+//                                 tick to get there.
 //
 // Why: with 4096 envs (BASELINE configs[1]) there are 128 warps for 592 sub-partitions; one warp per group runs its 1800
 // serial ticks alone at its dependent-issue latency (3.3 ms per interval).  Measured by compiling the two companion
@@ -39,7 +39,7 @@ namespace leo {
 
 enum SplitField : int {
     DX_R = 0, DX_V = 3, DX_S = 6, DX_W = 9, DX_WHL = 12, DX_R2 = 16, DX_IR = 17, DX_H = 18, SPLIT_SLOT = 19,   // per tick, two slots
-    DB_RAN = 2 * SPLIT_SLOT,    // companion -> dynamics: return value of fsw_pass
+    DB_RAN = 2 * SPLIT_SLOT,  // companion -> dynamics: return value of fsw_pass
     DB_QUIET,                 // dynamics -> companion: desat chain confirmed quiet by the thruster latch
     DB_CHARGE, DB_SHADOW,     // companion -> dynamics at the end of the call
     SPLIT_NF
@@ -138,7 +138,7 @@ __device__ __forceinline__ void split_dyn(const LeoParams &P, double *__restrict
         mst(box, DB_QUIET, 0.0);
     }
     __syncwarp();
-    split_sync(bar);                                             // START: bus mirror, Sun latch and mailbox are in place
+    split_sync(bar);                                           // START: bus mirror, Sun latch and mailbox are in place
 
 #pragma unroll 1
     for (int j = jlo; j < ticks; j++) {
@@ -237,7 +237,7 @@ __device__ __forceinline__ void split_dyn(const LeoParams &P, double *__restrict
     }
     double W[NRW];
     wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
-    split_sync(bar);                                             // FINAL: battery charge and shadow factor of the last tick
+    split_sync(bar);                                           // FINAL: battery charge and shadow factor of the last tick
     const double charge = mld(box, DB_CHARGE), shadow = mld(box, DB_SHADOW);
     for (int f = 0; f < LEO_M_MIRROR; f++) SD(F_GUID + f) = mld(m, f);
     if (chunk + 1 < n_chunks) {
@@ -289,7 +289,7 @@ __device__ __forceinline__ void split_dyn(const LeoParams &P, double *__restrict
     SI(I_TICK) = n_end; SI(I_STEP) = curr_step + 1; SI(I_MASK) = mask; SI(I_SWITCH) = SI(I_SWITCH) + nswitch;
     SI(I_THRFACTOR) = thr_factor; SI(I_THRACTIVE) = thr_active; SI(I_OVER) = over; SI(I_RWSAT) = rw_sat;
     __syncwarp();
-    split_sync(bar);                                             // END
+    split_sync(bar);                                           // END
 #undef SD
 #undef SI
 }
@@ -328,7 +328,7 @@ __device__ __forceinline__ void split_env(const LeoParams &P, double *__restrict
     const int ph0 = (int)((n_base) % tpf);
     const bool ph_uniform = __all_sync(0xffffffffu, ph0 == __shfl_sync(0xffffffffu, ph0, 0));
 
-    split_sync(bar);                                             // START
+    split_sync(bar);                                           // START
     V3 sun_r = mld3(m, M_SUNR);
     double ec[6] = {mld(m, M_ECL), mld(m, M_ECL + 1), mld(m, M_ECL + 2), mld(m, M_ECL + 3), mld(m, M_ECL + 4), mld(m, M_ECL + 5)};
 
@@ -396,8 +396,8 @@ __device__ __forceinline__ void split_env(const LeoParams &P, double *__restrict
     }
     mst(box, DB_CHARGE, charge); mst(box, DB_SHADOW, shadow);
     __syncwarp();
-    split_sync(bar);                                             // FINAL
-    split_sync(bar);                                             // END
+    split_sync(bar);                                           // FINAL
+    split_sync(bar);                                           // END
 #undef SD
 #undef SI
 }
