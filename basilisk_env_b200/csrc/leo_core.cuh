@@ -279,15 +279,27 @@ struct Dyn { V3 r, v, s, w; };
 // Thruster force/torque at one RK stage (thrusterDynamicEffector::computeForceTorque without ramps).
 // Rare path (only while a desat pulse may still burn): state stays in global memory.
 struct ThrOut { V3 F, L; int factor, active; };
-LEO_HD_NOINLINE ThrOut thr_stage(const LeoParams &P, const double *S, int64_t stride, int64_t e, double tau, double dtFire, int factor)
+// The thruster command in force (start time + on-times): constant over a dynamics tick, so the four stages of a step read
+// it from registers -- one global-memory round trip per step instead of four (the path is latency-bound: DESIGN.md 6)
+struct ThrCmd { double start, on[LEO_NTHR]; };
+LEO_HD ThrCmd thr_cmd_load(const double *S, int64_t stride, int64_t e)
 {
-    double start = S[(int64_t)F_THRSTART * stride + e];
+    ThrCmd c;
+    c.start = S[(int64_t)F_THRSTART * stride + e];
+#pragma unroll
+    for (int k = 0; k < LEO_NTHR; k++) c.on[k] = S[(int64_t)(F_THRON + k) * stride + e];
+    return c;
+}
+LEO_HD_NOINLINE ThrOut thr_stage(const LeoParams &P, const ThrCmd &c, double tau, double dtFire, int factor)
+{
+    double start = c.start;
     double tol = t_mul(-dtFire, 10E-10);
     ThrOut o;
     o.F = mk(0., 0., 0.); o.L = mk(0., 0., 0.);
     int any = 0;
+#pragma unroll
     for (int k = 0; k < LEO_NTHR; k++) {
-        double on = S[(int64_t)(F_THRON + k) * stride + e];
+        double on = c.on[k];
         bool fire = (t_sub(t_add(on, start), tau) >= tol) && (on > 0.0);
         if (fire) {
             factor |= (1 << k);
@@ -1107,6 +1119,8 @@ LEO_HD_NOINLINE ThrEventOut rk4_general(const LeoParams &P, const double *S, int
     const double h = a.h, hh = 0.5 * h, h6 = h * (1.0 / 6.0), h3 = h * (1.0 / 3.0);
     const V3 sun_r = mld3(m, M_SUNR), sun_v = mld3(m, M_SUNV), L_ext = mld3(m, M_LEXT);
     Dyn xs = x, xo = x, k;
+    ThrCmd tc = {};
+    if (thr_active) tc = thr_cmd_load(S, stride, e);
 #pragma unroll 1
     for (int st = 0; st < 4; st++) {
         const double dt = (st == 0) ? dts.d0 : (st == 3 ? dts.d1 : dts.dm);
@@ -1117,7 +1131,7 @@ LEO_HD_NOINLINE ThrEventOut rk4_general(const LeoParams &P, const double *S, int
         const bool thr_on = thr_active != 0;
         if (thr_on) {
             const double tau = t_add(tBefore, (st == 0) ? 0.0 : (st == 3 ? h : t_mul(h, 0.5)));
-            ThrOut to = thr_stage(P, S, stride, e, tau, t_sub(tau, tauPrev), thr_factor);
+            ThrOut to = thr_stage(P, tc, tau, t_sub(tau, tauPrev), thr_factor);
             thr_factor = to.factor; thr_active = to.active;
             Fm = to.F * P.inv_mass; Lx = Lx + to.L;
             tauPrev = tau;
