@@ -1397,7 +1397,7 @@ LEO_HD void leo_step_env(const LeoParams &P, double *__restrict__ S, int64_t *__
             const int64_t n = n_base + j;
             double W[NRW];
             wheel_speeds<NRW, DIAG>(P, a.HB, C, x.w, W);
-#ifndef LEO_EXP_NOFSW
+#ifndef LEO_EXP_NOFSW       // (LEO_EXP_*: measurement switches -- compile a block out to read its cost off the clock)
             desat_ran = fsw_pass<NRW>(P, S, I, stride, e, m, mask, n, n * P.dyn_ns, x, W, (int64_t)sun_d, desat_quiet);
             rw_sat |= 2;
 #endif    // a (possibly) new wheel command: re-latch after this tick's integration

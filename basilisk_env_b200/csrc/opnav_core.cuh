@@ -1029,9 +1029,19 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
 #endif
     for (int64_t k = d.k_first; k <= d.k_last; k++) {
         Meas m;
+        // (ON_EXP_*: measurement switches -- compile one role out to read its cost off the clock; never in the product)
+#ifdef ON_EXP_NODYN
+        m.valid = false;
+#endif
+#ifndef ON_EXP_NONOISE
         nz.tick(P, k);
+#endif
+#ifndef ON_EXP_NODYN
         d.tick(P, k, c, nz.nerr, m);
+#endif
+#ifndef ON_EXP_NOFILTER
         fr.tick(P, f, k, m.valid, m.obs, m.R);
+#endif
     }
     double fx[3], psig[3];
     nz.finish(S, stride, e);
