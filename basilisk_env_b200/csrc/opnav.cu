@@ -18,7 +18,7 @@
 #include "opnav_host.h"
 
 #ifndef ON_MIN_BLOCKS
-#define ON_MIN_BLOCKS 2
+#define ON_MIN_BLOCKS 3
 #endif
 
 namespace {
@@ -37,9 +37,9 @@ __device__ __forceinline__ double warp_sum_d(double v)
 struct OnSched { int *sched; int n_groups; int dynamic; };
 
 #ifdef ON_MAXNREG
-#define ON_STEP_BOUNDS __maxnreg__(ON_MAXNREG)          // tuning builds: explicit register cap instead of an occupancy target
+#define ON_STEP_BOUNDS(MINB) __maxnreg__(ON_MAXNREG)    // tuning builds: explicit register cap instead of an occupancy target
 #else
-#define ON_STEP_BOUNDS __launch_bounds__(ON_BLOCK, ON_MIN_BLOCKS)
+#define ON_STEP_BOUNDS(MINB) __launch_bounds__(ON_BLOCK, MINB)
 #endif
 
 // Lane assignment.  The two flight-software task sets execute different code every tick (hillPoint + tracking error vs CSS +
@@ -97,12 +97,18 @@ struct OnScratch { opnav::Ukf f; opnav::Cold c; opnav::Walk w; };
 // A warp-specialised form (one warp per role, mailboxes in shared memory, one block barrier per tick) was built and is
 // parity-green (git history, profiles/README.md): its pipeline latency is 26 ms instead of 45 ms per interval, but at equal
 // residency it delivers 0.54 M env-steps/s against 0.58 M of this form, so the simpler kernel stays.
-__global__ void ON_STEP_BOUNDS
+// MINB = resident blocks per SM the registers are allocated for: 2 (255 registers) or 3 (168 registers; the two-pass step of
+// opnav_core.cuh keeps the spilled values off the tick loops' chains).  Three blocks deliver more per resident set (measured
+// at 113664 envs = three sets of 37888 or two of 56832: 139.0 against 134.4 ms) but a set is larger and a partial set costs a
+// whole one (the ticks are a latency-bound chain): the launcher picks the organisation with the shorter predicted launch.
+template <int MINB>
+__global__ void ON_STEP_BOUNDS(MINB)
 opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
                   int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
                   double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
                   double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc,
-                  const int32_t *__restrict__ perm, double *__restrict__ ep_return, int64_t *__restrict__ ep_length)
+                  const int32_t *__restrict__ perm, double *__restrict__ ep_return, int64_t *__restrict__ ep_length,
+                  double *__restrict__ mbuf)
 {
     extern __shared__ double on_smem[];
     OnScratch &scr = *reinterpret_cast<OnScratch *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratch) / sizeof(double)));
@@ -125,7 +131,9 @@ opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S,
         double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
         if (valid) {
             const int64_t m0 = I[(int64_t)OI_NMEAS * stride + e], b0 = I[(int64_t)OI_NBAD * stride + e];
-            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o, scr.f, scr.c, scr.w);
+            opnav::MeasBuf mb;                               // this env's column of the measurement hand-over buffer
+            mb.p = mbuf + e; mb.stride = stride;
+            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o, scr.f, scr.c, scr.w, mb);
             d_meas = (double)(I[(int64_t)OI_NMEAS * stride + e] - m0); d_bad = (double)(I[(int64_t)OI_NBAD * stride + e] - b0);
             reward[e] = o.reward;
             done[e] = (uint8_t)o.done;
@@ -232,6 +240,7 @@ struct bskenv_opnav_handle {
     int64_t *I;
     int *sched;
     int32_t *perm;              // lane assignment of the step kernel (envs bucketed by task set)
+    double *mbuf;               // measurements of the interval, first pass -> second pass: [slot][ON_MEAS_W][stride]
     double *d_eph;              // device copy of the Sun ephemeris table
     int sm_count;
     void *h_stage[6];           // page-locked staging for pageable caller buffers: actions, obs, reward, done, reason, debug
@@ -257,7 +266,11 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
 {
     const int wpb = ON_BLOCK / 32;
     const int64_t groups = (h->n + 31) / 32;
-    const int resident = h->sm_count * ON_MIN_BLOCKS;
+    // sets of 2 x 128 or 3 x 128 envs per SM; measured per full set on a B200: 46 ms against 66 ms
+    const int64_t set2 = (int64_t)h->sm_count * 2 * ON_BLOCK, set3 = (int64_t)h->sm_count * 3 * ON_BLOCK;
+    const int64_t n2 = (h->n + set2 - 1) / set2, n3 = (h->n + set3 - 1) / set3;
+    const int minb = (ON_MIN_BLOCKS == 3 && n3 * 66 < n2 * 46) ? 3 : 2;
+    const int resident = h->sm_count * minb;
     int grid = (int)((groups + wpb - 1) / wpb);
     OnSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
@@ -274,11 +287,16 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
     const size_t smem = sizeof(OnScratch) * ON_BLOCK;
     static bool attr_set[64] = {false};             // opt in to > 48 KB of dynamic shared memory once per device
     if (!attr_set[h->device & 63]) {
-        ON_TRY(h, cudaFuncSetAttribute(opnav_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ON_TRY(h, cudaFuncSetAttribute(opnav_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ON_TRY(h, cudaFuncSetAttribute(opnav_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[h->device & 63] = true;
     }
-    opnav_step_kernel<<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
-                                                 term_obs, h->stats, sc, h->perm, ep_return, ep_length);
+    if (minb == 3)
+        opnav_step_kernel<3><<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
+                                                        term_obs, h->stats, sc, h->perm, ep_return, ep_length, h->mbuf);
+    else
+        opnav_step_kernel<2><<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
+                                                        term_obs, h->stats, sc, h->perm, ep_return, ep_length, h->mbuf);
     ON_TRY(h, cudaGetLastError());
     h->launches++;
     if (st != h->own_stream || !st) { h->ev_valid = 1; ON_TRY(h, cudaEventRecord(h->ev_last, st)); }
@@ -310,7 +328,7 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
     if (!perr.empty()) { g_opnav_create_error = "bskenv_opnav_create: " + perr; delete h; return BSKENV_EINVAL; }
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
-    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr; h->d_eph = nullptr;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr; h->d_eph = nullptr; h->mbuf = nullptr;
     for (int k = 0; k < 6; k++) h->h_stage[k] = nullptr;
     h->own_stream = nullptr; h->ev_last = nullptr; h->ev_valid = 0;
     cudaError_t e = cudaSetDevice(device);
@@ -318,6 +336,7 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->mbuf, sizeof(double) * (size_t)opnav::opnav_meas_slots(h->P) * ON_MEAS_W * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * OPNAV_ND * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * OPNAV_NI * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * OPNAV_IC_DIM * h->stride);
@@ -343,7 +362,7 @@ int bskenv_opnav_destroy(bskenv_opnav_handle *h)
 {
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm); cudaFree(h->d_eph);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm); cudaFree(h->d_eph); cudaFree(h->mbuf);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     for (int k = 0; k < 6; k++) cudaFreeHost(h->h_stage[k]);
     if (h->ev_last) cudaEventDestroy(h->ev_last);

@@ -1015,15 +1015,26 @@ struct FilterRole {
 };
 
 // Both roles in one thread (host-compiled core; single-role kernel).  `f` and `c` are scratch storage for the call.
+// Hand-over of the measurements between the two passes of a decision interval: slot-major [slot][ON_MEAS_W][env] doubles
+// (tick, obs[3], R[6]); a slot per camera frame of the interval (opnav_meas_slots).
+#define ON_MEAS_W 10
+struct MeasBuf { double *p; int64_t stride; };
+ON_HD int opnav_meas_slots(const OpNavParams &P) { return P.ticks_per_step / (P.cam_ticks > 0 ? P.cam_ticks : 1) + 2; }
+
+// One decision interval of one env in TWO PASSES over its ticks: first the noise walk and the dynamics / flight-software role,
+// which leave the interval's measurements (one per valid camera frame, at most opnav_meas_slots) in `mb`; then the filter,
+// which between frames needs nothing from the other two (FilterRole).  Same arithmetic, same order per role, as a single
+// interleaved loop; but the working sets of the two passes are never live together, which is what lets the kernel run three
+// blocks per SM (168 registers) without spilling onto the dependency chain: measured 140.1 ms (two blocks, 255 registers,
+// interleaved) -> passes at three blocks 75.7 + 49.0 ms at 113664 envs.
 ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out,
-                          Ukf &f, Cold &c, Walk &w)
+                          Ukf &f, Cold &c, Walk &w, MeasBuf mb)
 {
     DynRole d;
-    FilterRole fr;
     NoiseRole nz;
     d.load(P, S, I, stride, e, action, c);
-    fr.load(P, S, I, stride, e, f);
     nz.load(P, S, I, stride, e, w);
+    int n_m = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
@@ -1039,12 +1050,37 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
 #ifndef ON_EXP_NODYN
         d.tick(P, k, c, nz.nerr, m);
 #endif
-#ifndef ON_EXP_NOFILTER
-        fr.tick(P, f, k, m.valid, m.obs, m.R);
-#endif
+        if (m.valid) {
+            double *q = mb.p + (int64_t)n_m * ON_MEAS_W * mb.stride;
+            q[0] = (double)k;
+            for (int i = 0; i < 3; i++) q[(1 + i) * mb.stride] = m.obs[i];
+            for (int i = 0; i < 6; i++) q[(4 + i) * mb.stride] = m.R[i];
+            n_m++;
+        }
     }
-    double fx[3], psig[3];
     nz.finish(S, stride, e);
+    FilterRole fr;
+    fr.load(P, S, I, stride, e, f);
+#ifndef ON_EXP_NOFILTER
+    int next = 0;
+    double k_next = n_m > 0 ? mb.p[0] : -1.0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int64_t k = fr.k_first; k <= fr.k_last; k++) {
+        double obs[3] = {0., 0., 0.}, R[6] = {0., 0., 0., 0., 0., 0.};
+        const bool meas = next < n_m && k_next == (double)k;
+        if (meas) {
+            const double *q = mb.p + (int64_t)next * ON_MEAS_W * mb.stride;
+            for (int i = 0; i < 3; i++) obs[i] = q[(1 + i) * mb.stride];
+            for (int i = 0; i < 6; i++) R[i] = q[(4 + i) * mb.stride];
+            next++;
+            k_next = next < n_m ? mb.p[(int64_t)next * ON_MEAS_W * mb.stride] : -1.0;
+        }
+        fr.tick(P, f, k, meas, obs, R);
+    }
+#endif
+    double fx[3], psig[3];
     fr.finish(S, I, stride, e, f, fx, psig);
     d.finish(P, S, I, stride, e, action, fx, psig, c, out);
 }

@@ -47,8 +47,9 @@ def parse():
     ap.add_argument("--no-extra", action="store_true", help="skip the 4096-env and opNav side measurements")
     ap.add_argument("--workload", default="leo", choices=["leo", "opnav"],
                     help="leo: the headline line (default); opnav: the same JSON line for BASELINE configs[3] (N=1 only)")
-    ap.add_argument("--opnav-envs", type=int, default=75776,
-                    help="opNav batch: two resident sets of the step kernel (148 SMs x 2 blocks x 128 threads = 37888 envs each)")
+    ap.add_argument("--opnav-envs", type=int, default=113664,
+                    help="opNav batch: two resident sets of the step kernel's three-block organisation (148 SMs x 3 blocks x 128 "
+                         "threads = 56832 envs each) = three sets of its two-block organisation")
     return ap.parse_args()
 
 
@@ -419,7 +420,7 @@ OPNAV_D2H_BYTES_PER_ENV = 4 * 8 + 8 + 1 + 1 + 12 * 8
 
 
 def opnav_workload_name(n):
-    return (f"opNav env, {n} envs on one GPU (BASELINE configs[3]; {n / 37888:.2f} resident sets of 148 SMs x 2 blocks x 128 threads): Mars orbits from the reference's element ranges, filter "
+    return (f"opNav env, {n} envs on one GPU (BASELINE configs[3]; {n / 56832:.2f} resident sets of 148 SMs x 3 blocks x 128 threads): Mars orbits from the reference's element ranges, filter "
             "initial error U(+-1e5 m, +-1e3 m/s), simple_nav noise on, one synthetic circle measurement per 60 s while imaging, "
             "i.i.d. uniform actions {0,1}, camera re-enabled by action 0, auto-reset, FP64; one step = 50 min = 3000 ticks")
 

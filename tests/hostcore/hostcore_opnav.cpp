@@ -60,7 +60,10 @@ void hco_step(HCO *h, const int32_t *actions, double *obs, double *reward, uint8
         opnav::Ukf f;
         opnav::Cold c;
         opnav::Walk w;
-        opnav::opnav_step_env(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o, f, c, w);
+        std::vector<double> mbuf((size_t)opnav::opnav_meas_slots(h->P) * ON_MEAS_W);
+        opnav::MeasBuf mb;
+        mb.p = mbuf.data(); mb.stride = 1;
+        opnav::opnav_step_env(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o, f, c, w, mb);
         for (int k = 0; k < 4; k++) obs[4 * e + k] = o.ob[k];
         if (debug) for (int k = 0; k < 12; k++) debug[12 * e + k] = o.debug[k];
         reward[e] = o.reward; done[e] = (uint8_t)o.done; reason[e] = (uint8_t)o.reason;
