@@ -1,10 +1,12 @@
 // opnav.cu -- sm_100a kernels and the C ABI (include/bskenv.h, bskenv_opnav_*) of the batched opNav environment step.
 //
 // Kernels:
-//   opnav_step_kernel   one thread = one spacecraft; ONE launch = one 50-minute decision interval (3000 ticks) for all
-//                       envs (replaces Basilisk ExecuteSimulation(), reference simulators/opNavSimulator.py:256-261,
-//                       and the gym bookkeeping of envs/opNavEnvironment.py:55-125); warp-shuffle reduction of the
-//                       episode statistics; optional in-kernel auto-reset.
+//   opnav_pass1_kernel, opnav_pass2_kernel
+//                       one thread = one spacecraft; the two launches are one 50-minute decision interval (3000 ticks) for
+//                       all envs (replace Basilisk ExecuteSimulation(), reference simulators/opNavSimulator.py:256-261,
+//                       and the gym bookkeeping of envs/opNavEnvironment.py:55-125): noise walk + dynamics / flight
+//                       software, then the filter + observation / reward; warp-shuffle reduction of the episode
+//                       statistics; optional in-kernel auto-reset.
 //   opnav_reset_kernel  simulator construction + initial observation from explicit, stored or device-sampled ICs.
 // There is no CPU path in this library.
 #include <cuda_runtime.h>
@@ -89,51 +91,79 @@ __global__ void opnav_perm_identity_kernel(int32_t *__restrict__ perm, int64_t s
     if (e < stride) perm[e] = (int32_t)(e < n ? e : n - 1);
 }
 
-// per-thread scratch in shared memory: filter (33 doubles: the square-root factor is stored packed) + cold dynamics data (19) +
-// walk states (15) = 67, an odd stride (conflict-free); 67 x 8 B x 128 threads = 68.6 KB per block
-struct OnScratch { opnav::Ukf f; opnav::Cold c; opnav::Walk w; };
+// Per-thread scratch in shared memory, one struct per pass, odd strides in doubles (conflict-free): first pass cold dynamics
+// data (19) + walk states (15) + pad = 35, second pass the filter (33: the square-root factor is stored packed).
+struct OnScratchA { opnav::Cold c; opnav::Walk w; double pad; };
+struct OnScratchB { opnav::Ukf f; };
 
-// One thread runs the three roles of opnav_core.cuh (noise walk, dynamics + flight software, filter) of one env in sequence.
-// A warp-specialised form (one warp per role, mailboxes in shared memory, one block barrier per tick) was built and is
-// parity-green (git history, profiles/README.md): its pipeline latency is 26 ms instead of 45 ms per interval, but at equal
-// residency it delivers 0.54 M env-steps/s against 0.58 M of this form, so the simpler kernel stays.
-// MINB = resident blocks per SM the registers are allocated for: 2 (255 registers) or 3 (168 registers; the two-pass step of
-// opnav_core.cuh keeps the spilled values off the tick loops' chains).  Three blocks deliver more per resident set (measured
-// at 113664 envs = three sets of 37888 or two of 56832: 139.0 against 134.4 ms) but a set is larger and a partial set costs a
-// whole one (the ticks are a latency-bound chain): the launcher picks the organisation with the shorter predicted launch.
+// One decision interval = two kernels (opnav_core.cuh: opnav_pass1 / opnav_pass2): noise walk + dynamics / flight software, then
+// filter + observation / reward / termination, auto-reset and statistics.  One thread per env in both; the measurements of the
+// interval cross in a global buffer.  Separate kernels give each pass its own register allocation: three blocks per SM (168
+// registers) without the spills that the single interleaved loop had at that occupancy (and a warp-specialised form -- one
+// warp per role, mailboxes in shared memory, git history -- could not have: one kernel, one allocation).
+// MINB = resident blocks per SM the registers are allocated for: 2 (255 registers) or 3 (168 registers).  Three blocks deliver
+// more per resident set but a set is larger and a partial set costs a whole one (the ticks are a latency-bound chain): the
+// launcher picks the organisation with the shorter predicted launch.
+__device__ __forceinline__ bool on_next_group(const OnSched &sc, int *head, int lane, int warp, int &g)
+{
+    if (sc.dynamic) {
+        g = 0;
+        if (lane == 0) g = atomicAdd(head, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        return g < sc.n_groups;
+    }
+    g = blockIdx.x * (ON_BLOCK / 32) + warp;
+    return true;
+}
+
 template <int MINB>
 __global__ void ON_STEP_BOUNDS(MINB)
-opnav_step_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
-                  int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
-                  double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
-                  double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc,
-                  const int32_t *__restrict__ perm, double *__restrict__ ep_return, int64_t *__restrict__ ep_length,
-                  double *__restrict__ mbuf)
+opnav_pass1_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t n,
+                   const int32_t *__restrict__ actions, const OnSched sc, const int32_t *__restrict__ perm, double *__restrict__ mbuf)
 {
     extern __shared__ double on_smem[];
-    OnScratch &scr = *reinterpret_cast<OnScratch *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratch) / sizeof(double)));
+    OnScratchA &scr = *reinterpret_cast<OnScratchA *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratchA) / sizeof(double)));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (bool more = true; more; more = sc.dynamic != 0) {
         int g;
-        if (sc.dynamic) {
-            g = 0;
-            if (lane == 0) g = atomicAdd(&sc.sched[0], 1);
-            g = __shfl_sync(0xffffffffu, g, 0);
-            if (g >= sc.n_groups) break;
-        } else {
-            g = blockIdx.x * (ON_BLOCK / 32) + warp;
+        if (!on_next_group(sc, &sc.sched[0], lane, warp, g)) break;
+        const int64_t slot = (int64_t)g * 32 + lane;
+        if (slot < n) {
+            const int64_t e = (int64_t)perm[slot];              // envs of one flight-software task set per warp
+            opnav::MeasBuf mb;                                  // this env's column of the hand-over buffer
+            mb.p = mbuf + e; mb.stride = stride;
+            opnav::opnav_pass1(P, S, I, stride, e, actions[e], scr.c, scr.w, mb);
         }
+        __syncwarp();
+    }
+}
+
+template <int MINB>
+__global__ void ON_STEP_BOUNDS(MINB)
+opnav_pass2_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, double *__restrict__ ics,
+                   int64_t stride, int64_t n, const int32_t *__restrict__ actions, double *__restrict__ obs,
+                   double *__restrict__ reward, uint8_t *__restrict__ done, uint8_t *__restrict__ reason,
+                   double *__restrict__ debug, double *__restrict__ term_obs, double *__restrict__ stats, const OnSched sc,
+                   const int32_t *__restrict__ perm, double *__restrict__ ep_return, int64_t *__restrict__ ep_length,
+                   double *__restrict__ mbuf)
+{
+    extern __shared__ double on_smem[];
+    OnScratchB &scr = *reinterpret_cast<OnScratchB *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratchB) / sizeof(double)));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (bool more = true; more; more = sc.dynamic != 0) {
+        int g;
+        if (!on_next_group(sc, &sc.sched[5], lane, warp, g)) break;
         const int64_t slot = (int64_t)g * 32 + lane;
         const bool valid = slot < n;
-        const int64_t e = valid ? (int64_t)perm[slot] : 0;      // envs of one flight-software task set per warp
+        const int64_t e = valid ? (int64_t)perm[slot] : 0;
         opnav::StepOut o;
         o.done = 0; o.reason = 0; o.reward = 0.;
         double ep_ret = 0., ep_len = 0., d_meas = 0., d_bad = 0.;
         if (valid) {
             const int64_t m0 = I[(int64_t)OI_NMEAS * stride + e], b0 = I[(int64_t)OI_NBAD * stride + e];
-            opnav::MeasBuf mb;                               // this env's column of the measurement hand-over buffer
+            opnav::MeasBuf mb;
             mb.p = mbuf + e; mb.stride = stride;
-            opnav::opnav_step_env(P, S, I, stride, e, actions[e], o, scr.f, scr.c, scr.w, mb);
+            opnav::opnav_pass2(P, S, I, stride, e, actions[e], o, scr.f, mb);
             d_meas = (double)(I[(int64_t)OI_NMEAS * stride + e] - m0); d_bad = (double)(I[(int64_t)OI_NBAD * stride + e] - b0);
             reward[e] = o.reward;
             done[e] = (uint8_t)o.done;
@@ -266,12 +296,13 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
 {
     const int wpb = ON_BLOCK / 32;
     const int64_t groups = (h->n + 31) / 32;
-    // sets of 2 x 128 or 3 x 128 envs per SM; measured per full set on a B200: 46 ms against 66 ms
+    // First pass (noise + dynamics): 255 registers / two blocks per SM or 168 registers (with spills) / three; measured per full
+    // resident set on a B200: 30.2 ms per 37888 envs against 37.9 ms per 56832, and a partial set costs a whole one (latency-
+    // bound ticks) -> the shorter predicted launch wins.  Second pass (filter): 168 registers without spills, always three.
     const int64_t set2 = (int64_t)h->sm_count * 2 * ON_BLOCK, set3 = (int64_t)h->sm_count * 3 * ON_BLOCK;
     const int64_t n2 = (h->n + set2 - 1) / set2, n3 = (h->n + set3 - 1) / set3;
-    const int minb = (ON_MIN_BLOCKS == 3 && n3 * 66 < n2 * 46) ? 3 : 2;
-    const int resident = h->sm_count * minb;
-    int grid = (int)((groups + wpb - 1) / wpb);
+    const int minb1 = (ON_MIN_BLOCKS == 3 && n3 * 379 < n2 * 302) ? 3 : 2, minb2 = ON_MIN_BLOCKS == 3 ? 3 : 2;
+    const int full = (int)((groups + wpb - 1) / wpb);
     OnSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
     ON_TRY(h, cudaMemsetAsync(h->sched, 0, sizeof(int) * 8, st));
@@ -280,25 +311,29 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
         opnav_bucket_count_kernel<<<bgrid, 256, 0, st>>>(h->I, h->stride, h->n, act, h->sched);
         opnav_bucket_fill_kernel<<<bgrid, 256, 0, st>>>(h->I, h->stride, h->n, act, h->sched, h->perm);
     }
-    if (grid > resident) {
-        sc.dynamic = 1;
-        grid = resident;
-    }
-    const size_t smem = sizeof(OnScratch) * ON_BLOCK;
-    static bool attr_set[64] = {false};             // opt in to > 48 KB of dynamic shared memory once per device
+    OnSched s1 = sc, s2 = sc;
+    const int r1 = h->sm_count * minb1, r2 = h->sm_count * minb2;
+    s1.dynamic = full > r1; s2.dynamic = full > r2;
+    const int grid1 = full > r1 ? r1 : full, grid2 = full > r2 ? r2 : full;
+    const size_t smem_a = sizeof(OnScratchA) * ON_BLOCK, smem_b = sizeof(OnScratchB) * ON_BLOCK;
+    static bool attr_set[64] = {false};             // opt in to the dynamic shared memory once per device
     if (!attr_set[h->device & 63]) {
-        ON_TRY(h, cudaFuncSetAttribute(opnav_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ON_TRY(h, cudaFuncSetAttribute(opnav_step_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ON_TRY(h, cudaFuncSetAttribute(opnav_pass1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+        ON_TRY(h, cudaFuncSetAttribute(opnav_pass1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+        ON_TRY(h, cudaFuncSetAttribute(opnav_pass2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
+        ON_TRY(h, cudaFuncSetAttribute(opnav_pass2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         attr_set[h->device & 63] = true;
     }
-    if (minb == 3)
-        opnav_step_kernel<3><<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
-                                                        term_obs, h->stats, sc, h->perm, ep_return, ep_length, h->mbuf);
+    if (minb1 == 3) opnav_pass1_kernel<3><<<grid1, ON_BLOCK, smem_a, st>>>(h->P, h->S, h->I, h->stride, h->n, act, s1, h->perm, h->mbuf);
+    else opnav_pass1_kernel<2><<<grid1, ON_BLOCK, smem_a, st>>>(h->P, h->S, h->I, h->stride, h->n, act, s1, h->perm, h->mbuf);
+    if (minb2 == 3)
+        opnav_pass2_kernel<3><<<grid2, ON_BLOCK, smem_b, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
+                                                          term_obs, h->stats, s2, h->perm, ep_return, ep_length, h->mbuf);
     else
-        opnav_step_kernel<2><<<grid, ON_BLOCK, smem, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
-                                                        term_obs, h->stats, sc, h->perm, ep_return, ep_length, h->mbuf);
+        opnav_pass2_kernel<2><<<grid2, ON_BLOCK, smem_b, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
+                                                          term_obs, h->stats, s2, h->perm, ep_return, ep_length, h->mbuf);
     ON_TRY(h, cudaGetLastError());
-    h->launches++;
+    h->launches += 2;
     if (st != h->own_stream || !st) { h->ev_valid = 1; ON_TRY(h, cudaEventRecord(h->ev_last, st)); }
     return BSKENV_OK;
 }

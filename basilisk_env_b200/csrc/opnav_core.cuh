@@ -730,6 +730,12 @@ struct StepOut { double ob[4]; double debug[12]; double reward; int done; int re
 // opnav_step_env() runs them in sequence in one thread (host-compiled core); the warp-specialised kernel of opnav.cu gives
 // them to three warps of a block, each one tick behind the previous, with the messages in shared mailboxes.
 struct Meas { bool valid; double obs[3]; double R[6]; };
+// Hand-over between the two passes of a decision interval: slot-major [slot][ON_MEAS_W][env] doubles.  Slot 0 is a header
+// (number of measurements, nav Sun heading of the last tick, episode flags, tick range), slots 1.. hold the measurements
+// (tick, obs[3], R[6]) of the interval's valid camera frames.
+#define ON_MEAS_W 10
+enum OnHdr : int { OH_NM = 0, OH_SUN = 1, OH_OVER = 4, OH_REASON = 5, OH_KFIRST = 6, OH_KLAST = 7 };
+struct MeasBuf { double *p; int64_t stride; };
 
 // simple_nav's Gauss-Markov error states: a bounded random walk driven by the per-env Philox stream, independent of the
 // dynamics (SimpleNav::computeErrors, OND:236-258).  tick(k) advances the 15 states to tick k.
@@ -925,44 +931,24 @@ struct DynRole {
         }
     }
 
-    // observation (ONS:263-293), opNavEnv.step epilogue (ONE:100-125, :139-152) and the dynamics side of the state;
-    // fx = filter position estimate, psig = sqrt of the first three covariance diagonal entries
-    ON_HD void finish(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, const double (&fx)[3],
-                      const double (&psig)[3], Cold &c, StepOut &out)
+    // The dynamics side of the persistent state at the end of the first pass; what the end of the interval needs besides it
+    // (nav Sun heading, episode flags, the tick range) goes into the header slot of the measurement buffer (opnav_finish_obs).
+    ON_HD void finish_state(double *S, int64_t *I, int64_t stride, int64_t e, Cold &c, double *hdr, int64_t hs, int n_m)
     {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
         volatile double *cold = c.cold;
-        const double nr2 = fx[0] * fx[0] + fx[1] * fx[1] + fx[2] * fx[2], inr = 1.0 / sqrt(nr2);
-        {
-            MrpRot BN = mrp_rot(x.s);
-            V3 pos_B = -rot_BN(BN, x.s, mk(fx[0], fx[1], fx[2]) * inr);
-            V3 nav_sun_B = mk(cold[4], cold[5], cold[6]);
-            V3 sh = nav_sun_B * (1.0 / norm(nav_sun_B));
-            out.ob[0] = dot(pos_B, sh);
-            out.ob[1] = psig[0] * inr; out.ob[2] = psig[1] * inr; out.ob[3] = psig[2] * inr;
-        }
-        out.debug[0] = fx[0]; out.debug[1] = fx[1]; out.debug[2] = fx[2];
-        out.debug[3] = x.r.x; out.debug[4] = x.r.y; out.debug[5] = x.r.z;
-        out.debug[6] = x.v.x; out.debug[7] = x.v.y; out.debug[8] = x.v.z;
-        out.debug[9] = x.s.x; out.debug[10] = x.s.y; out.debug[11] = x.s.z;
-        double reward = 0.0;
-        if (action == 1) {
-            V3 real = x.r, nav = (mk(fx[0], fx[1], fx[2]) - real) * (1.0 / norm(real));
-            reward = fabs(P.reward_mult / (1.0 + dot(nav, nav)));
-        }
-        if (modeCounter >= P.numModes) { over = 1; reason |= 2; }
-        out.reward = reward; out.done = over; out.reason = reason;
         SD(OF_R) = x.r.x; SD(OF_R + 1) = x.r.y; SD(OF_R + 2) = x.r.z; SD(OF_V) = x.v.x; SD(OF_V + 1) = x.v.y; SD(OF_V + 2) = x.v.z;
         SD(OF_SIG) = x.s.x; SD(OF_SIG + 1) = x.s.y; SD(OF_SIG + 2) = x.s.z; SD(OF_OMG) = x.w.x; SD(OF_OMG + 1) = x.w.y; SD(OF_OMG + 2) = x.w.z;
         for (int i = 0; i < ON_NRW; i++) { SD(OF_WHL + i) = x.Om[i]; SD(OF_RWCMD + i) = rwcmd[i]; }
         SD(OF_SUNPT) = cold[0]; SD(OF_SUNPT + 1) = cold[1]; SD(OF_SUNPT + 2) = cold[2];
         SD(OF_SHADOW) = cold[3];
-        SD(OF_EPRET) = SD(OF_EPRET) + reward;
-        for (int i = 0; i < 4; i++) SD(OF_OBS + i) = out.ob[i];
-        for (int i = 0; i < 12; i++) SD(OF_DEBUG + i) = out.debug[i];
         SI(OI_TICK) = k_last; SI(OI_STEP) = curr_step + 1; SI(OI_MODE) = mode; SI(OI_CAMERA) = camera; SI(OI_MODECNT) = modeCounter;
-        SI(OI_FIRST) = 0; SI(OI_SWITCH) = n_switch; SI(OI_OVER) = over; SI(OI_SUNPT_W) = sunpt_w; SI(OI_NIMG) = n_img;
+        SI(OI_FIRST) = 0; SI(OI_SWITCH) = n_switch; SI(OI_SUNPT_W) = sunpt_w; SI(OI_NIMG) = n_img;
+        hdr[OH_NM * hs] = (double)n_m;
+        hdr[(OH_SUN + 0) * hs] = cold[4]; hdr[(OH_SUN + 1) * hs] = cold[5]; hdr[(OH_SUN + 2) * hs] = cold[6];
+        hdr[OH_OVER * hs] = (double)over; hdr[OH_REASON * hs] = (double)reason;
+        hdr[OH_KFIRST * hs] = (double)k_first; hdr[OH_KLAST * hs] = (double)k_last;
 #undef SD
 #undef SI
     }
@@ -971,7 +957,7 @@ struct DynRole {
 struct FilterRole {
     int64_t ftick, n_meas, n_bad, k_first, k_last;
 
-    ON_HD void load(const OpNavParams &P, const double *S, const int64_t *I, int64_t stride, int64_t e, Ukf &f)
+    ON_HD void load(const OpNavParams &P, const double *S, const int64_t *I, int64_t stride, int64_t e, Ukf &f, int64_t kf, int64_t kl)
     {
 #define SD(f) S[(int64_t)(f) * stride + e]
 #define SI(f) I[(int64_t)(f) * stride + e]
@@ -979,8 +965,7 @@ struct FilterRole {
         for (int r = 0; r < 6; r++)
             for (int c = 0; c <= r; c++) f.SC(r, c) = SD(OF_FS + TRI(r, c));
         ftick = SI(OI_FTICK); n_meas = SI(OI_NMEAS); n_bad = SI(OI_NBAD);
-        const int64_t tick0 = SI(OI_TICK);
-        k_first = tick0 + 1; k_last = (tick0 < 0 ? 0 : tick0) + P.ticks_per_step;
+        k_first = kf; k_last = kl;       // from the first pass (which has already advanced OI_TICK)
 #undef SD
 #undef SI
     }
@@ -1015,20 +1000,15 @@ struct FilterRole {
 };
 
 // Both roles in one thread (host-compiled core; single-role kernel).  `f` and `c` are scratch storage for the call.
-// Hand-over of the measurements between the two passes of a decision interval: slot-major [slot][ON_MEAS_W][env] doubles
-// (tick, obs[3], R[6]); a slot per camera frame of the interval (opnav_meas_slots).
-#define ON_MEAS_W 10
-struct MeasBuf { double *p; int64_t stride; };
-ON_HD int opnav_meas_slots(const OpNavParams &P) { return P.ticks_per_step / (P.cam_ticks > 0 ? P.cam_ticks : 1) + 2; }
+ON_HD int opnav_meas_slots(const OpNavParams &P) { return P.ticks_per_step / (P.cam_ticks > 0 ? P.cam_ticks : 1) + 3; }   // + header
 
-// One decision interval of one env in TWO PASSES over its ticks: first the noise walk and the dynamics / flight-software role,
-// which leave the interval's measurements (one per valid camera frame, at most opnav_meas_slots) in `mb`; then the filter,
-// which between frames needs nothing from the other two (FilterRole).  Same arithmetic, same order per role, as a single
-// interleaved loop; but the working sets of the two passes are never live together, which is what lets the kernel run three
-// blocks per SM (168 registers) without spilling onto the dependency chain: measured 140.1 ms (two blocks, 255 registers,
-// interleaved) -> passes at three blocks 75.7 + 49.0 ms at 113664 envs.
-ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out,
-                          Ukf &f, Cold &c, Walk &w, MeasBuf mb)
+// One decision interval of one env runs in TWO PASSES over its ticks: first the noise walk and the dynamics / flight-software
+// role, which leave the interval's measurements (one per valid camera frame) and a header in `mb`; then the filter, which
+// between frames needs nothing from the other two (FilterRole), and the observation / reward / termination of the step.  Same
+// arithmetic, same order per role, as a single interleaved loop; but the working sets of the two passes are never live
+// together: they are separate kernels (opnav.cu: opnav_pass1_kernel, opnav_pass2_kernel), each with its own register
+// allocation and shared-memory scratch, three blocks per SM.  DESIGN.md 6b.
+ON_HD void opnav_pass1(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, Cold &c, Walk &w, MeasBuf mb)
 {
     DynRole d;
     NoiseRole nz;
@@ -1051,38 +1031,92 @@ ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t s
         d.tick(P, k, c, nz.nerr, m);
 #endif
         if (m.valid) {
+            n_m++;
             double *q = mb.p + (int64_t)n_m * ON_MEAS_W * mb.stride;
             q[0] = (double)k;
             for (int i = 0; i < 3; i++) q[(1 + i) * mb.stride] = m.obs[i];
             for (int i = 0; i < 6; i++) q[(4 + i) * mb.stride] = m.R[i];
-            n_m++;
         }
     }
     nz.finish(S, stride, e);
+    d.finish_state(S, I, stride, e, c, mb.p, mb.stride, n_m);
+}
+
+// observation (ONS:263-293) and opNavEnv.step epilogue (ONE:100-125, :139-152); fx = filter position estimate, psig = sqrt of the
+// first three covariance diagonal entries; the truth comes back from the state the first pass stored
+ON_HD void opnav_finish_obs(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, const double (&fx)[3],
+                            const double (&psig)[3], MeasBuf mb, StepOut &out)
+{
+#define SD(f) S[(int64_t)(f) * stride + e]
+#define SI(f) I[(int64_t)(f) * stride + e]
+    Truth x;
+    x.r = mk(SD(OF_R), SD(OF_R + 1), SD(OF_R + 2)); x.v = mk(SD(OF_V), SD(OF_V + 1), SD(OF_V + 2));
+    x.s = mk(SD(OF_SIG), SD(OF_SIG + 1), SD(OF_SIG + 2));
+    int over = (int)mb.p[OH_OVER * mb.stride], reason = (int)mb.p[OH_REASON * mb.stride];
+    const int modeCounter = (int)SI(OI_MODECNT);
+    const double nr2 = fx[0] * fx[0] + fx[1] * fx[1] + fx[2] * fx[2], inr = 1.0 / sqrt(nr2);
+    {
+        MrpRot BN = mrp_rot(x.s);
+        V3 pos_B = -rot_BN(BN, x.s, mk(fx[0], fx[1], fx[2]) * inr);
+        V3 nav_sun_B = mk(mb.p[(OH_SUN + 0) * mb.stride], mb.p[(OH_SUN + 1) * mb.stride], mb.p[(OH_SUN + 2) * mb.stride]);
+        V3 sh = nav_sun_B * (1.0 / norm(nav_sun_B));
+        out.ob[0] = dot(pos_B, sh);
+        out.ob[1] = psig[0] * inr; out.ob[2] = psig[1] * inr; out.ob[3] = psig[2] * inr;
+    }
+    out.debug[0] = fx[0]; out.debug[1] = fx[1]; out.debug[2] = fx[2];
+    out.debug[3] = x.r.x; out.debug[4] = x.r.y; out.debug[5] = x.r.z;
+    out.debug[6] = x.v.x; out.debug[7] = x.v.y; out.debug[8] = x.v.z;
+    out.debug[9] = x.s.x; out.debug[10] = x.s.y; out.debug[11] = x.s.z;
+    double reward = 0.0;
+    if (action == 1) {
+        V3 real = x.r, nav = (mk(fx[0], fx[1], fx[2]) - real) * (1.0 / norm(real));
+        reward = fabs(P.reward_mult / (1.0 + dot(nav, nav)));
+    }
+    if (modeCounter >= P.numModes) { over = 1; reason |= 2; }
+    out.reward = reward; out.done = over; out.reason = reason;
+    SD(OF_EPRET) = SD(OF_EPRET) + reward;
+    for (int i = 0; i < 4; i++) SD(OF_OBS + i) = out.ob[i];
+    for (int i = 0; i < 12; i++) SD(OF_DEBUG + i) = out.debug[i];
+    SI(OI_OVER) = over;
+#undef SD
+#undef SI
+}
+
+ON_HD void opnav_pass2(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out, Ukf &f, MeasBuf mb)
+{
     FilterRole fr;
-    fr.load(P, S, I, stride, e, f);
+    fr.load(P, S, I, stride, e, f, (int64_t)mb.p[OH_KFIRST * mb.stride], (int64_t)mb.p[OH_KLAST * mb.stride]);
 #ifndef ON_EXP_NOFILTER
-    int next = 0;
-    double k_next = n_m > 0 ? mb.p[0] : -1.0;
+    const int n_m = (int)mb.p[OH_NM * mb.stride];
+    int next = 1;
+    double k_next = n_m > 0 ? mb.p[(int64_t)ON_MEAS_W * mb.stride] : -1.0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
     for (int64_t k = fr.k_first; k <= fr.k_last; k++) {
         double obs[3] = {0., 0., 0.}, R[6] = {0., 0., 0., 0., 0., 0.};
-        const bool meas = next < n_m && k_next == (double)k;
+        const bool meas = next <= n_m && k_next == (double)k;
         if (meas) {
             const double *q = mb.p + (int64_t)next * ON_MEAS_W * mb.stride;
             for (int i = 0; i < 3; i++) obs[i] = q[(1 + i) * mb.stride];
             for (int i = 0; i < 6; i++) R[i] = q[(4 + i) * mb.stride];
             next++;
-            k_next = next < n_m ? mb.p[(int64_t)next * ON_MEAS_W * mb.stride] : -1.0;
+            k_next = next <= n_m ? mb.p[(int64_t)next * ON_MEAS_W * mb.stride] : -1.0;
         }
         fr.tick(P, f, k, meas, obs, R);
     }
 #endif
     double fx[3], psig[3];
     fr.finish(S, I, stride, e, f, fx, psig);
-    d.finish(P, S, I, stride, e, action, fx, psig, c, out);
+    opnav_finish_obs(P, S, I, stride, e, action, fx, psig, mb, out);
+}
+
+// both passes in one thread (the host-compiled core of the tests)
+ON_HD void opnav_step_env(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, StepOut &out,
+                          Ukf &f, Cold &c, Walk &w, MeasBuf mb)
+{
+    opnav_pass1(P, S, I, stride, e, action, c, w, mb);
+    opnav_pass2(P, S, I, stride, e, action, out, f, mb);
 }
 
 }  // namespace opnav

@@ -472,7 +472,8 @@ def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
     for t in range(steps):
         env.step_host(acts_host[warmup + t], outs)
     e2e_ms = (time.perf_counter() - e0) * 1e3 / steps
-    launches = env.launch_count() - l0 - warmup - 1
+    per_step = (env.launch_count() - l0) // (warmup + steps + 1 + steps)    # kernels per decision step (two passes: two launches)
+    launches = per_step * 2 * steps                                          # device-timed + host-buffer steps of the timed regions
     stats = env.episode_stats()
     flops = env.flops_per_step()
     env.close()

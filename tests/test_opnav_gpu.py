@@ -51,7 +51,7 @@ def _run_against_oracle(bsk, rows, action_seq, host_path=False, first_env=0, see
             assert bool(done[e]) == bool(o_done[e]) and int(reason[e]) == int(o_reason[e]), where
             assert abs(rew[e] - o_rew[e]) <= 1e-12, where
             par.compare_state(st, S[:, e], I[:, e], where)
-    assert env.launch_count() == len(action_seq)
+    assert env.launch_count() == 2 * len(action_seq)        # two kernels per decision interval (pass 1, pass 2), nothing else
     env.close()
 
 
