@@ -479,12 +479,17 @@ def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
     env.close()
     ms = float(np.mean(per))
     tf = flops * n / (ms * 1e-3) / 1e12
-    alg_bytes = (2 * OPNAV_STATE_BYTES_PER_ENV + OPNAV_H2D_BYTES_PER_ENV + OPNAV_D2H_BYTES_PER_ENV) * n
+    # the decision interval is two kernels (noise + dynamics, then the filter): the interval's measurements (one per camera frame:
+    # tick, obs[3], R[6]) and an 8-double header cross in a global buffer, written once and read once; the dynamics side of the
+    # state is read by both (the second pass needs position / velocity / attitude for the observation)
+    meas_bytes = (8 + 10 * (3000 // 60 + 1)) * 8
+    alg_bytes = (2 * OPNAV_STATE_BYTES_PER_ENV + 2 * meas_bytes + OPNAV_H2D_BYTES_PER_ENV + OPNAV_D2H_BYTES_PER_ENV) * n
     out = {"workload": opnav_workload_name(n), "envs": n, "value": n * steps / (total_ms * 1e-3), "unit": UNIT,
            "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup, "ticks_per_step": 3000,
            "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None,
-                        "kernel": "opnav_step_kernel", "kernel_ms": ms, "flop_per_env_step": flops,
-                        "flop_source": "operation list of opnav_core.cuh (bskenv_opnav_flops_per_step; DESIGN.md)",
+                        "kernel": "opnav_pass1_kernel + opnav_pass2_kernel (one decision interval)", "kernel_ms": ms, "flop_per_env_step": flops,
+                        "flop_source": "operation list of opnav_core.cuh (bskenv_opnav_flops_per_step; DESIGN.md), within 1 % of the executed "
+                                       "2*DFMA+DMUL+DADD count of ncu (profiles/ncu_opnav_p1_r02c.md + ncu_opnav_p2_r02c.md: 17.71e6 per env-step)",
                         "algorithmic_bytes_per_launch": alg_bytes},
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": OPNAV_H2D_BYTES_PER_ENV * n,
                    "d2h_bytes_per_step": OPNAV_D2H_BYTES_PER_ENV * n, "api": "bskenv_opnav_step_host"},
