@@ -448,7 +448,7 @@ def opnav_cpu_arm(envs_per_core, seconds, threads=None, fixed_steps=None, build=
 
 
 def opnav_traffic(n):
-    """DRAM bytes per launch of opnav_step_kernel from the latest `ncu --set full` capture (profiles/traffic_opnav.json,
+    """DRAM bytes per decision interval (both opNav kernels) from the latest `ncu --set full` captures (profiles/traffic_opnav.json,
     of a launch with the same env count); None for any other size."""
     try:
         j = json.load(open(os.path.join(ROOT, "profiles", "traffic_opnav.json")))
