@@ -186,9 +186,19 @@ class OpNavVecEnv:
                 "episode_r": self.episode_r, "episode_l": self.episode_l}
         return self.obs, self.reward, self.done, info
 
+    def host_buffers(self):
+        """Page-locked, device-mapped numpy buffers for `step_host`: (actions int32 [N], (obs [N,4], reward [N], done u8 [N],
+        done_reason u8 [N], full_states [N,12])).  The second kernel of the step writes them in place (zero-copy over PCIe);
+        ordinary numpy arrays work too, through staging and one memcpy each."""
+        n = self.num_envs
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory().numpy()     # noqa: E731
+        return pin(n, torch.int32), (pin((n, OBS_DIM), torch.float64), pin(n, torch.float64), pin(n, torch.uint8),
+                                     pin(n, torch.uint8), pin((n, DEBUG_DIM), torch.float64))
+
     def step_host(self, actions, out=None):
         """Host-buffer step: numpy int32 [N] in, numpy (obs, reward, done, done_reason, full_states) out."""
-        a = np.ascontiguousarray(actions, dtype=np.int32)
+        a = actions if (isinstance(actions, np.ndarray) and actions.dtype == np.int32 and actions.flags.c_contiguous) \
+            else np.ascontiguousarray(actions, dtype=np.int32)
         if a.size != self.num_envs:
             raise ValueError("one action per env")
         if out is None:

@@ -465,12 +465,14 @@ def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
     acts_host = acts.cpu().numpy()
     l0 = env.launch_count()
     total_ms, per = time_device_steps(env, acts, steps, warmup, torch, None, 1)
-    outs = (np.empty((n, 4)), np.empty(n), np.empty(n, np.uint8), np.empty(n, np.uint8), np.empty((n, 12)))
-    env.step_host(acts_host[0], outs)
+    act_pinned, outs = env.host_buffers()             # page-locked, device-mapped: the kernels read / write them in place
+    act_pinned[:] = acts_host[0]
+    env.step_host(act_pinned, outs)
     torch.cuda.synchronize()
     e0 = time.perf_counter()
     for t in range(steps):
-        env.step_host(acts_host[warmup + t], outs)
+        act_pinned[:] = acts_host[warmup + t]         # the trainer's actions of this step (host memory)
+        env.step_host(act_pinned, outs)
     e2e_ms = (time.perf_counter() - e0) * 1e3 / steps
     per_step = (env.launch_count() - l0) // (warmup + steps + 1 + steps)    # kernels per decision step (two passes: two launches)
     launches = per_step * 2 * steps                                          # device-timed + host-buffer steps of the timed regions
@@ -492,7 +494,8 @@ def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
                                        "2*DFMA+DMUL+DADD count of ncu (profiles/ncu_opnav_p1_r02c.md + ncu_opnav_p2_r02c.md: 17.71e6 per env-step)",
                         "algorithmic_bytes_per_launch": alg_bytes},
            "e2e": {"value": n / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": OPNAV_H2D_BYTES_PER_ENV * n,
-                   "d2h_bytes_per_step": OPNAV_D2H_BYTES_PER_ENV * n, "api": "bskenv_opnav_step_host"},
+                   "d2h_bytes_per_step": OPNAV_D2H_BYTES_PER_ENV * n,
+                   "api": "bskenv_opnav_step_host with page-locked host buffers (env.host_buffers)"},
            "gpu_launches": int(launches), "episode_stats": stats, "checksum": float(outs[0].sum())}
     if cpu_seconds > 0:
         cb = opnav_cpu_arm(2, cpu_seconds)

@@ -228,3 +228,22 @@ def test_opnav_per_env_episode_record_matches_oracle(bsk):
             assert int(ep_l[e]) == want_l == t and abs(ep_r[e] - want_r) <= 1e-9 * max(1.0, abs(want_r)), (t, e, ep_r[e], want_r)
     assert o_done.all()                                    # the (L + 1)-th call ends every episode (opNavEnvironment.py:91-92)
     env.close()
+
+
+def test_opnav_pinned_host_buffers_equal_device_step(bsk):
+    """`OpNavVecEnv.host_buffers()`: page-locked, device-mapped buffers that the second kernel of the step writes in place
+    (zero-copy); same bytes as the device-buffer entry point on a twin env."""
+    import torch
+    n = 96
+    a, b = _vec(n, noise_seed=9, camera_reenable=1, step_duration_min=2.0), _vec(n, noise_seed=9, camera_reenable=1, step_duration_min=2.0)
+    a.reset(seed=4); b.reset(seed=4)
+    act_pinned, outs = b.host_buffers()
+    acts = np.random.RandomState(6).randint(0, 2, size=(3, n)).astype(np.int32)
+    for t in range(3):
+        o, r, d, info = a.step(torch.as_tensor(acts[t], device="cuda"))
+        act_pinned[:] = acts[t]
+        ob, rw, dn, rs, dbg = b.step_host(act_pinned, outs)
+        np.testing.assert_array_equal(o.cpu().numpy(), ob); np.testing.assert_array_equal(r.cpu().numpy(), rw)
+        np.testing.assert_array_equal(d.cpu().numpy(), dn); np.testing.assert_array_equal(info["done_reason"].cpu().numpy(), rs)
+        np.testing.assert_array_equal(info["full_states"].cpu().numpy(), dbg)
+    a.close(); b.close()
