@@ -203,8 +203,10 @@ def _perigee_altitude(rows):
 LOW_PERIGEE_ATT_TOL = 1e-5
 
 
-def test_long_horizon_batch_parity_all_done_reasons(bsk, orc):
-    """264 envs x full episodes of up to 61 decision intervals of 180 s (max_length = 60), random actions, NO
+@pytest.mark.parametrize("org", ("thread", "split"))
+def test_long_horizon_batch_parity_all_done_reasons(bsk, orc, org):
+    """(Both organisations of the step kernel: 264 envs are a ragged batch of nine groups, the split kernel's automatic range.)
+    264 envs x full episodes of up to 61 decision intervals of 180 s (max_length = 60), random actions, NO
     re-synchronisation: the GPU state is never touched between steps and every env is compared at every step until its
     episode ends.  All termination reasons the scenario reaches -- max_length (1), wheel speed (2), power (4) -- occur
     and match; discrete quantities are exact throughout.  Continuous tolerances over the whole episode:
@@ -219,7 +221,7 @@ def test_long_horizon_batch_parity_all_done_reasons(bsk, orc):
     rows = _failing_rows(orc, n, seed=41)
     benign = _perigee_altitude(rows) >= 200e3
     assert benign.sum() >= 200 and (~benign).sum() >= 8
-    env = _vec(n, max_length=L)
+    env = _vec(n, max_length=L, organisation=org)
     batch = orc.LeoEnvBatch(rows, max_length=L)
     env.reset_ics(rows)
     acts = np.random.RandomState(43).randint(0, 3, size=(steps, n)).astype(np.int32)
