@@ -247,3 +247,45 @@ def test_opnav_pinned_host_buffers_equal_device_step(bsk):
         np.testing.assert_array_equal(d.cpu().numpy(), dn); np.testing.assert_array_equal(info["done_reason"].cpu().numpy(), rs)
         np.testing.assert_array_equal(info["full_states"].cpu().numpy(), dbg)
     a.close(); b.close()
+
+
+def test_opnav_queued_three_block_builds_equal_static_two_block_shards(bsk):
+    """113664 envs on one handle take the three-blocks-per-SM build of the first pass and the atomic work queues of both
+    passes (two resident sets of 56832 envs); three shards of 37888 envs take its two-block build on the static path (each
+    warp its own group).  Same global env indices, same actions: obs, reward, done, the per-env episode record and the whole
+    state have to agree bit for bit over three decision steps with auto-reset (short intervals: 2 min = 120 ticks, two camera
+    frames each), and the measurement counters have to add up."""
+    import torch
+    n, shards = 113664, 3
+    per = n // shards
+    kw = dict(noise_seed=21, sample_orbit=1, camera_reenable=1, step_duration_min=2.0, auto_reset=True, max_length=2)
+    big = _vec(n, first_env_index=0, **kw)
+    parts = [_vec(per, first_env_index=k * per, **kw) for k in range(shards)]
+    big.reset(seed=5)
+    for p in parts:
+        p.reset(seed=5)
+    g = torch.Generator(device="cuda"); g.manual_seed(8)
+    ended = 0
+    for t in range(3):
+        a = torch.randint(0, 2, (n,), dtype=torch.int32, device="cuda", generator=g)
+        o, r, d, info = big.step(a)
+        ob = [x.clone() for x in (o, r, d, info["done_reason"], info["episode_r"], info["episode_l"])]
+        outs = [p.step(a[k * per:(k + 1) * per]) for k, p in enumerate(parts)]
+        cat = [torch.cat([x[0] for x in outs]), torch.cat([x[1] for x in outs]), torch.cat([x[2] for x in outs]),
+               torch.cat([x[3]["done_reason"] for x in outs]), torch.cat([x[3]["episode_r"] for x in outs]),
+               torch.cat([x[3]["episode_l"] for x in outs])]
+        for j, (p, q) in enumerate(zip(ob, cat)):
+            assert torch.equal(p, q), f"step {t} output {j}"
+        ended += int(d.sum())
+    Sb, Ib = big.get_state()
+    Sp = torch.cat([p.get_state()[0] for p in parts], dim=1); Ip = torch.cat([p.get_state()[1] for p in parts], dim=1)
+    assert torch.equal(Sb, Sp) and torch.equal(Ib, Ip)
+    assert ended >= n                                          # max_length = 2: every env finished an episode and was re-sampled
+    sb = big.episode_stats()
+    sp = [p.episode_stats() for p in parts]
+    for k in ("episodes", "env_steps", "measurements"):
+        if k in sb:
+            assert sb[k] == sum(s[k] for s in sp), (k, sb[k], [s[k] for s in sp])
+    big.close()
+    for p in parts:
+        p.close()
