@@ -62,3 +62,10 @@ for n, kw in ((64, {}), (64 * 6, {}), (64, dict(use_j2=1, rw_set=1))):
     for t in range(4):
         env.step(torch.randint(0, 3, (n,), dtype=torch.int32, device="cuda"))
     print("leo split", n, env.kernel_name(), env.episode_stats()["episodes"]); env.close()
+# round 2: the opNav decision interval as two kernels with the work queues of both (more groups than one resident set of the
+# three-block builds: 60000 envs), measurement hand-over buffer, auto-reset in the second kernel; 0.5 min intervals = 30 ticks
+on = OpNavVecEnv(60000, device=0, auto_reset=True, step_duration_min=0.5, max_length=2, camera_reenable=1, sample_orbit=1, noise_seed=9)
+on.reset(seed=9)
+for t in range(3):
+    on.step(torch.randint(0, 2, (60000,), dtype=torch.int32, device="cuda"))
+print("opnav two kernels + queues", on.episode_stats()["episodes"]); on.close()
