@@ -68,7 +68,48 @@ __device__ __forceinline__ double warp_sum(double v)
 // for 4.6 ms).  Chunk c of a group may start when chunk c - 1 has been published in progress[group] (release / acquire at
 // GPU scope); its predecessor was handed out n_groups items earlier, so in practice nobody waits.  Without the queue
 // (grid covers all groups) each warp runs the chunks of its own group back to back.
-struct LeoSched { int *sched; int n_groups; int dynamic; int n_chunks; int *progress; };
+struct LeoSched { int *sched; int n_groups; int dynamic; int n_chunks; int *progress; const int32_t *perm; };
+
+// Lane assignment of the throughput organisation.  The three modes run different flight software (hillPoint vs inertial3D;
+// the desat chain, the thruster latch and the exact thruster steps only after action 2): a warp of mixed actions executes
+// all of it, 180 times per interval.  Before the launch the envs are bucketed by action (counting sort, warp-aggregated
+// atomics: leo_bucket_count_kernel + leo_bucket_fill_kernel) and a warp takes 32 slots of the permutation: the state is
+// gathered / scattered at the chunk boundaries (12 times per 1800 ticks), the tick loop diverges only in the at most three
+// warps that straddle a bucket boundary.  Per-env arithmetic does not depend on the lane an env runs in: results are
+// bit-identical with and without (tests/test_gpu_round2.py).  bucket[0..3] = sizes, bucket[4..7] = cursors.  Order of the
+// buckets in the permutation: action 2 (the desat chain: the slowest warps), 0, 1, unknown -- the work queue hands out the
+// long items first, so that the tail of a launch is made of the short ones.
+__device__ __forceinline__ int leo_action_class(int action) { return (action >= 0 && action <= 2) ? action : 3; }
+__global__ void __launch_bounds__(256)
+leo_bucket_count_kernel(int64_t n, const int32_t *__restrict__ actions, int *__restrict__ bucket)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cls = e < n ? leo_action_class(actions[e]) : -1;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if ((threadIdx.x & 31) == 0 && m) atomicAdd(&bucket[c], __popc(m));
+    }
+}
+__global__ void __launch_bounds__(256)
+leo_bucket_fill_kernel(int64_t n, const int32_t *__restrict__ actions, int *__restrict__ bucket, int32_t *__restrict__ perm)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int cls = e < n ? leo_action_class(actions[e]) : -1;
+    const int lane = threadIdx.x & 31;
+    const int n0 = bucket[0], n1 = bucket[1], n2 = bucket[2];
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+        if (!m) continue;
+        const int leader = __ffs(m) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&bucket[4 + c], __popc(m));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        const int first = c == 2 ? 0 : (c == 0 ? n2 : (c == 1 ? n2 + n0 : n0 + n1 + n2));     // slowest bucket first in the queue
+        if (cls == c) perm[first + base + __popc(m & ((1u << lane) - 1))] = (int32_t)e;
+    }
+}
 
 __device__ __forceinline__ void chunk_publish(int *p, int v)
 {
@@ -174,8 +215,9 @@ leo_step_kernel(const __grid_constant__ LeoParams P, const __grid_constant__ Leo
         } else {
             g = blockIdx.x * (LEO_BLOCK / 32) + warp;
         }
-        const int64_t e = (int64_t)g * LEO_LANES + lane;
-        const bool valid = lane < LEO_LANES && e < n;
+        const int64_t slot = (int64_t)g * LEO_LANES + lane;
+        const bool valid = lane < LEO_LANES && slot < n;
+        const int64_t e = (valid && sc.perm) ? (int64_t)sc.perm[slot] : slot;     // envs of one action per warp (see LeoSched)
         leo::StepOut o;
         o.done = 0; o.reason = 0; o.reward = 0.;
         for (int c = c_first; c < c_end; c++) {
@@ -322,6 +364,7 @@ struct bskenv_handle {
     double *S, *ics, *stats;
     int64_t *I;
     int *sched;                 // work queue head of the step kernel
+    int32_t *perm; int *bucket; // lane assignment of the throughput organisation (envs bucketed by action), bucket sizes / cursors
     double *d_eph[2];           // device copies of the ephemeris tables (Sun position, Earth orientation angles)
     int sm_count;
     // host-buffer entry points: page-locked staging (only for pageable caller buffers), own stream, ordering events
@@ -370,7 +413,7 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
     const bool small = grid <= h->sm_count * LEO_SMALL_BLOCKS;  // at most LEO_SMALL_BLOCKS blocks per SM: the 255-register build
     LeoSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
-    sc.n_chunks = leo_host::step_chunks(h->P); sc.progress = h->sched + 4;
+    sc.n_chunks = leo_host::step_chunks(h->P); sc.progress = h->sched + 4; sc.perm = nullptr;
     if (grid > resident) {
         sc.dynamic = 1;
         grid = resident;
@@ -409,6 +452,14 @@ static int launch_step(bskenv_handle *h, const int32_t *act, double *obs, double
         h->launches++;
         if (st != h->own_stream || !st) CU_TRY(h, note_launch(h, st));
         return BSKENV_OK;
+    }
+    if (!small && h->organisation != BSKENV_ORG_THREAD_INDEX) {      // bucket the envs by action (LeoSched)
+        const int bgrid = (int)((h->n + 255) / 256);
+        CU_TRY(h, cudaMemsetAsync(h->bucket, 0, sizeof(int) * 8, st));
+        leo_bucket_count_kernel<<<bgrid, 256, 0, st>>>(h->n, act, h->bucket);
+        leo_bucket_fill_kernel<<<bgrid, 256, 0, st>>>(h->n, act, h->bucket, h->perm);
+        sc.perm = h->perm;
+        h->launches += 2;
     }
 #define LEO_STR_(x) #x
 #define LEO_STR(x) LEO_STR_(x)
@@ -462,7 +513,7 @@ double bskenv_flops_per_step(const bskenv_handle *h) { return h ? leo_host::flop
 int bskenv_set_organisation(bskenv_handle *h, int organisation)
 {
     if (!h) return BSKENV_EINVAL;
-    if (organisation < BSKENV_ORG_AUTO || organisation > BSKENV_ORG_SPLIT) { h->err = "bskenv_set_organisation: unknown organisation"; return BSKENV_EINVAL; }
+    if (organisation < BSKENV_ORG_AUTO || organisation > BSKENV_ORG_THREAD_INDEX) { h->err = "bskenv_set_organisation: unknown organisation"; return BSKENV_EINVAL; }
     h->organisation = organisation;
     return BSKENV_OK;
 }
@@ -488,7 +539,7 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     leo_host::build_params_f(h->P, h->PF);
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0; h->kernel_name = nullptr; h->organisation = BSKENV_ORG_AUTO;
-    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr; h->bucket = nullptr;
     h->d_eph[0] = h->d_eph[1] = nullptr;
     for (int k = 0; k < 8; k++) { h->h_stage[k] = nullptr; h->pend_user[k] = nullptr; h->pend_bytes[k] = 0; }
     h->host_pending = 0; h->own_stream = nullptr; h->ev_last = nullptr; h->ev_valid = 0;
@@ -496,6 +547,8 @@ int bskenv_create(const bskenv_config *cfg, int device, int64_t n_envs, int64_t 
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_last, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaMalloc(&h->sched, sizeof(int) * (size_t)(4 + (n_envs + LEO_LANES - 1) / LEO_LANES));
+    if (e == cudaSuccess) e = cudaMalloc(&h->perm, sizeof(int32_t) * h->stride);
+    if (e == cudaSuccess) e = cudaMalloc(&h->bucket, sizeof(int) * 8);
     if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(double) * LEO_ND * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->I, sizeof(int64_t) * LEO_NI * h->stride);
     if (e == cudaSuccess) e = cudaMalloc(&h->ics, sizeof(double) * 19 * h->stride);
@@ -517,7 +570,7 @@ int bskenv_destroy(bskenv_handle *h)
 {
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm); cudaFree(h->bucket);
     cudaFree(h->d_eph[0]); cudaFree(h->d_eph[1]);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     for (int k = 0; k < 8; k++) cudaFreeHost(h->h_stage[k]);

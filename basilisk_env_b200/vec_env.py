@@ -279,7 +279,8 @@ class LeoPowerAttVecEnv:
 
     def set_organisation(self, organisation):
         """Work organisation of the step kernel (include/bskenv.h: bskenv_set_organisation): "auto" (by batch size), "thread"
-        (one thread per env) or "split" (two warps per group of 32 envs: the small-batch organisation).  Same arithmetic."""
+        (one thread per env; large batches bucketed by action), "split" (two warps per group of 32 envs: the small-batch
+        organisation) or "thread_index" (one thread per env, lanes in index order: no bucketing).  Same arithmetic."""
         org = ORGANISATIONS[organisation] if isinstance(organisation, str) else int(organisation)
         self._check(self._L.bskenv_set_organisation(self._h, org), "bskenv_set_organisation")
 
@@ -287,7 +288,7 @@ class LeoPowerAttVecEnv:
         return float(self._L.bskenv_flops_per_step(self._h))
 
 
-ORGANISATIONS = {"auto": 0, "thread": 1, "split": 2}
+ORGANISATIONS = {"auto": 0, "thread": 1, "split": 2, "thread_index": 3}
 _FIELD_WIDTH = {"r_BN_N": 3, "v_BN_N": 3, "sigma_BN": 3, "omega_BN_B": 3, "Omega": 4, "u_current": 4,
                 "extTorquePntB_B": 3, "att_guidance": 12, "att_reference": 9, "commandedControlTorque": 3,
                 "rwTorqueCommand": 4, "wheelDeltaH": 3, "ThrustOnCmd": 8, "thrOnTimeRemaining": 8, "OnTimeRequest": 8,

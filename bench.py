@@ -261,7 +261,8 @@ def main():
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - e0) * 1e3
     t_mark1 = time.perf_counter()
-    launches = env.launch_count() - l0 - W - min(W, 3)
+    # kernels per decision step (large batches: bucket count + bucket fill + step kernel) x the 2K steps of the timed regions
+    launches = (env.launch_count() - l0) // (W + K + min(W, 3) + K) * 2 * K
     kernel_name = env.kernel_name()
     clocks = sampler.stop(t_mark0, t_mark1) if sampler else None
     checksum = float(outs[1].sum())

@@ -192,7 +192,10 @@ const char *bskenv_kernel_name(const bskenv_handle *h);
  * with each other); the choice only moves time.
  *   BSKENV_ORG_AUTO    pick by batch size (default)
  *   BSKENV_ORG_THREAD  one thread per env, one warp per 32 envs (throughput organisation; `north_star`: "thread ... owns
- *                      one spacecraft")
+ *                      one spacecraft").  Batches beyond two blocks per SM are bucketed by action before the launch (a
+ *                      warp takes 32 envs of one mode: the flight software of the three modes differs, leoPowerAttitude-
+ *                      Simulator.py:543-588)
+ *   BSKENV_ORG_THREAD_INDEX  the same without the bucketing: lanes in env-index order (measurement / test switch)
  *   BSKENV_ORG_SPLIT   two warps per group of 32 envs: a dynamics warp (RK4 and everything the next tick depends on) and a
  *                      companion warp (flight software, eclipse / panel / battery) on another SM sub-partition, handing
  *                      state over in shared memory once per tick -- the small-batch organisation (BASELINE configs[1]:
@@ -203,6 +206,7 @@ const char *bskenv_kernel_name(const bskenv_handle *h);
 #define BSKENV_ORG_AUTO 0
 #define BSKENV_ORG_THREAD 1
 #define BSKENV_ORG_SPLIT 2
+#define BSKENV_ORG_THREAD_INDEX 3
 int bskenv_set_organisation(bskenv_handle *h, int organisation);
 
 /* FP64 FMA-pipe microbenchmark used as the roofline denominator (MEASURED_PEAKS.json has none):

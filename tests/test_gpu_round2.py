@@ -190,6 +190,40 @@ def test_queued_work_items_equal_static_shards_and_oracle(bsk, orc):
         parity.compare_state(batch.envs[k].state(), Sn[:, e], In[:, e], f"queued path vs oracle, env {e}")
 
 
+def test_action_bucketed_lanes_equal_index_order(bsk):
+    """Throughput organisation: batches beyond two blocks per SM are bucketed by action before the launch (a warp takes 32 envs
+    of one mode, gathered through a permutation; bskenv.cu: LeoSched).  Per-env arithmetic does not depend on the lane an env
+    runs in: against lanes in index order ("thread_index") everything is bit-identical -- a ragged batch (60001 envs, queued
+    path), in-kernel auto-reset (max_length = 4 ends every episode within the run), per-env episode records, and an action outside {0, 1, 2}
+    (keeps the tasks in force, SIM:543-588 has no branch for it: fourth bucket)."""
+    import torch
+    n, steps = 60001, 6
+    g = torch.Generator("cuda").manual_seed(3)
+    acts = torch.randint(0, 3, (steps, n), dtype=torch.int32, device="cuda", generator=g)
+    acts[2, ::7] = 5
+    acts[4] = 2                                           # one bucket takes everything
+    res = {}
+    for org in ("thread", "thread_index"):
+        env = _vec(n, seed=13, auto_reset=True, organisation=org, max_length=4)
+        env.reset()
+        outs = []
+        for t in range(steps):
+            o, r, d, info = env.step(acts[t])
+            outs.append([x.clone() for x in (o, r, d, info["done_reason"], info["terminal_obs"], info["episode_r"], info["episode_l"])])
+        S, I = env.get_state()
+        res[org] = (outs, S.clone(), I.clone(), env.episode_stats(), env.kernel_name())
+        env.close()
+    a, b = res["thread"], res["thread_index"]
+    assert a[4] == b[4] and a[4].startswith("leo_step_kernel")
+    for t in range(steps):
+        for x, y in zip(a[0][t], b[0][t]):
+            assert torch.equal(x, y), t
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert a[3]["episodes"] == b[3]["episodes"] >= n and a[3]["env_steps"] == b[3]["env_steps"] == n * steps
+    for k in ("wheel_failures", "power_failures", "orbit_decays", "max_length_ends"):
+        assert a[3][k] == b[3][k], k
+
+
 def _perigee_altitude(rows):
     mu = 3.986004415e14
     r, v = rows[:, 0:3], rows[:, 3:6]
