@@ -32,7 +32,7 @@ D2H_BYTES_PER_ENV = 5 * 8 + 8 + 1 + 1   # obs[5] f64, reward f64, done u8, done_
 # ALGORITHMIC bytes per env-step: persistent state read + written once, plus the step I/O
 STATE_BYTES_PER_ENV = (89 + 22) * 8
 # the ncu capture of the shipped build whose executed-flop count the roofline numerator is checked against
-FLOP_CAPTURE = "profiles/ncu_leo_r02c.md: 1.9483e6 per env-step"     # the ncu capture of the shipped build the flop model is checked against
+FLOP_CAPTURE = "profiles/ncu_leo_r02f.md: 1.9484e6 per env-step"     # the ncu capture of the shipped build the flop model is checked against
 
 
 def parse():
@@ -303,7 +303,8 @@ def main():
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                          "traffic_note": "ncu capture at 131072 envs (profiles/traffic.json); above the algorithmic bytes by design: the "
-                                         "interval runs as 6 chunks with a state round trip each (DESIGN.md section 5), < 2 % of HBM bandwidth",
+                                         "interval runs as 6 chunks with a state round trip each, gathered through the action-bucket permutation "
+                                         "(DESIGN.md section 5), < 2 % of HBM bandwidth",
                          "kernel": kernel_name, "kernel_ms": kern_ms, "flop_per_env_step": flops,
                          "flop_source": "operation list of the kernel as built (bskenv_flops_per_step), equal to the executed "
                                         f"2*DFMA+DMUL+DADD count of ncu ({FLOP_CAPTURE}); the un-fused "
