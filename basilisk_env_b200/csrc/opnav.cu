@@ -19,6 +19,9 @@
 #include "opnav_core.cuh"
 #include "opnav_host.h"
 
+#ifndef ON_NZBUF_MAX_FRAC
+#define ON_NZBUF_MAX_FRAC 0.45   // of the free device memory, for the noise buffer of the three-kernel interval
+#endif
 #ifndef ON_MIN_BLOCKS
 #define ON_MIN_BLOCKS 3
 #endif
@@ -133,6 +136,51 @@ opnav_pass1_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S
             opnav::MeasBuf mb;                                  // this env's column of the hand-over buffer
             mb.p = mbuf + e; mb.stride = stride;
             opnav::opnav_pass1(P, S, I, stride, e, actions[e], scr.c, scr.w, mb);
+        }
+        __syncwarp();
+    }
+}
+
+// Three-kernel form (opnav_core.cuh: opnav_pass0 / opnav_pass1_fed): the noise walk of the whole interval first, one thread per
+// slot of the lane permutation, a plain grid (every slot costs the same: no queue), registers allocated for ON_NOISE_BLOCKS
+// blocks per SM; it writes the slot-major noise buffer that opnav_dyn_kernel -- the first pass without the walk -- consumes one
+// tick ahead through its shared scratch.
+#ifndef ON_NOISE_BLOCKS
+#define ON_NOISE_BLOCKS 6      // 80 registers: 113664 slots are exactly one wave of 148 SMs x 6 blocks x 128 threads
+#endif
+struct OnScratchN { opnav::Walk w; };                                    // 15 doubles per thread (odd stride: conflict-free)
+struct OnScratchD { opnav::Cold c; double feed[30]; };                   // 19 + 2 x 15 = 49 doubles per thread
+__global__ void __launch_bounds__(ON_BLOCK, ON_NOISE_BLOCKS)
+opnav_noise_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, const int64_t *__restrict__ I, int64_t stride, int64_t n,
+                   const int32_t *__restrict__ perm, double *__restrict__ nzbuf)
+{
+    extern __shared__ double on_smem[];
+    OnScratchN &scr = *reinterpret_cast<OnScratchN *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratchN) / sizeof(double)));
+    const int64_t slot = (int64_t)blockIdx.x * ON_BLOCK + threadIdx.x;
+    if (slot >= n) return;
+    opnav::opnav_pass0(P, S, I, stride, (int64_t)perm[slot], scr.w, nzbuf + slot, stride);
+}
+
+template <int MINB>
+__global__ void ON_STEP_BOUNDS(MINB)
+opnav_dyn_kernel(const __grid_constant__ OpNavParams P, double *__restrict__ S, int64_t *__restrict__ I, int64_t stride, int64_t n,
+                 const int32_t *__restrict__ actions, const OnSched sc, const int32_t *__restrict__ perm, double *__restrict__ mbuf,
+                 const double *__restrict__ nzbuf)
+{
+    extern __shared__ double on_smem[];
+    OnScratchD &scr = *reinterpret_cast<OnScratchD *>(on_smem + (size_t)threadIdx.x * (sizeof(OnScratchD) / sizeof(double)));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (bool more = true; more; more = sc.dynamic != 0) {
+        int g;
+        if (!on_next_group(sc, &sc.sched[0], lane, warp, g)) break;
+        const int64_t slot = (int64_t)g * 32 + lane;
+        if (slot < n) {
+            const int64_t e = (int64_t)perm[slot];
+            opnav::MeasBuf mb;
+            mb.p = mbuf + e; mb.stride = stride;
+            opnav::NoiseFeed nf;
+            nf.g = nzbuf + slot; nf.stride = stride; nf.buf = scr.feed;
+            opnav::opnav_pass1_fed(P, S, I, stride, e, actions[e], scr.c, nf, mb);
         }
         __syncwarp();
     }
@@ -271,6 +319,8 @@ struct bskenv_opnav_handle {
     int *sched;
     int32_t *perm;              // lane assignment of the step kernel (envs bucketed by task set)
     double *mbuf;               // measurements of the interval, first pass -> second pass: [slot][ON_MEAS_W][stride]
+    double *nzbuf;              // noise walk of the interval, noise kernel -> dynamics kernel: [ticks_per_step + 1][15][stride]
+    int noise_split;            // -1 undecided, 0 fused first pass, 1 three-kernel form (nzbuf allocated)
     double *d_eph;              // device copy of the Sun ephemeris table
     int sm_count;
     void *h_stage[6];           // page-locked staging for pageable caller buffers: actions, obs, reward, done, reason, debug
@@ -302,6 +352,11 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
     const int64_t set2 = (int64_t)h->sm_count * 2 * ON_BLOCK, set3 = (int64_t)h->sm_count * 3 * ON_BLOCK;
     const int64_t n2 = (h->n + set2 - 1) / set2, n3 = (h->n + set3 - 1) / set3;
     const int minb1 = (ON_MIN_BLOCKS == 3 && n3 * 379 < n2 * 302) ? 3 : 2, minb2 = ON_MIN_BLOCKS == 3 ? 3 : 2;
+#ifdef ON_DYN_FORCE_MINB
+    const int minb1_dyn = ON_DYN_FORCE_MINB;
+#else
+    const int minb1_dyn = minb1;
+#endif
     const int full = (int)((groups + wpb - 1) / wpb);
     OnSched sc;
     sc.sched = h->sched; sc.n_groups = (int)groups; sc.dynamic = 0;
@@ -324,7 +379,38 @@ static int opnav_launch_step(bskenv_opnav_handle *h, const int32_t *act, double 
         ON_TRY(h, cudaFuncSetAttribute(opnav_pass2_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b));
         attr_set[h->device & 63] = true;
     }
-    if (minb1 == 3) opnav_pass1_kernel<3><<<grid1, ON_BLOCK, smem_a, st>>>(h->P, h->S, h->I, h->stride, h->n, act, s1, h->perm, h->mbuf);
+    if (h->noise_split < 0) {
+        // Three-kernel form: OPT-IN (BSKENV_OPNAV_NOISE_SPLIT=1), and only when the noise buffer fits -- 120 B per env-tick, at most
+        // ON_NZBUF_MAX_FRAC of the free device memory (113664 envs x 3001 ticks = 40.9 GB).  Measured on a B200: 118.6 against
+        // 122.4 ms per 113664 envs (+3 %), 83.1 against 89.1 ms per 75776 envs (+7 %), bit-identical -- for 40.9 GB of memory and
+        // 84 GB of DRAM traffic per interval against 1.75 GB: not the default.
+        h->noise_split = 0;
+        const char *split = getenv("BSKENV_OPNAV_NOISE_SPLIT");
+        size_t free_b = 0, total_b = 0;
+        const size_t need = sizeof(double) * 15 * (size_t)(h->P.ticks_per_step + 1) * (size_t)h->stride;
+        if (h->P.nav_noise && split && split[0] == '1' && cudaMemGetInfo(&free_b, &total_b) == cudaSuccess &&
+            (double)need <= ON_NZBUF_MAX_FRAC * (double)free_b) {
+            if (cudaMalloc(&h->nzbuf, need) == cudaSuccess) h->noise_split = 1;
+            else { cudaGetLastError(); h->nzbuf = nullptr; }
+        }
+    }
+    if (h->noise_split == 1) {
+        const size_t smem_n = sizeof(OnScratchN) * ON_BLOCK, smem_d = sizeof(OnScratchD) * ON_BLOCK;
+        static bool attr_d[64] = {false};
+        if (!attr_d[h->device & 63]) {
+            ON_TRY(h, cudaFuncSetAttribute(opnav_dyn_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+            ON_TRY(h, cudaFuncSetAttribute(opnav_dyn_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+            attr_d[h->device & 63] = true;
+        }
+        opnav_noise_kernel<<<(int)((h->n + ON_BLOCK - 1) / ON_BLOCK), ON_BLOCK, smem_n, st>>>(h->P, h->S, h->I, h->stride, h->n, h->perm, h->nzbuf);
+        OnSched sd = sc;
+        const int rd = h->sm_count * minb1_dyn, gridd = full > rd ? rd : full;
+        sd.dynamic = full > rd;
+        if (minb1_dyn == 3) opnav_dyn_kernel<3><<<gridd, ON_BLOCK, smem_d, st>>>(h->P, h->S, h->I, h->stride, h->n, act, sd, h->perm, h->mbuf, h->nzbuf);
+        else opnav_dyn_kernel<2><<<gridd, ON_BLOCK, smem_d, st>>>(h->P, h->S, h->I, h->stride, h->n, act, sd, h->perm, h->mbuf, h->nzbuf);
+        h->launches += 1;
+    }
+    else if (minb1 == 3) opnav_pass1_kernel<3><<<grid1, ON_BLOCK, smem_a, st>>>(h->P, h->S, h->I, h->stride, h->n, act, s1, h->perm, h->mbuf);
     else opnav_pass1_kernel<2><<<grid1, ON_BLOCK, smem_a, st>>>(h->P, h->S, h->I, h->stride, h->n, act, s1, h->perm, h->mbuf);
     if (minb2 == 3)
         opnav_pass2_kernel<3><<<grid2, ON_BLOCK, smem_b, st>>>(h->P, h->S, h->I, h->ics, h->stride, h->n, act, obs, rew, done, reason, debug,
@@ -363,7 +449,7 @@ int bskenv_opnav_create(const bskenv_opnav_config *cfg, int device, int64_t n_en
     if (!perr.empty()) { g_opnav_create_error = "bskenv_opnav_create: " + perr; delete h; return BSKENV_EINVAL; }
     h->P.first_env_index = first_env_index;
     h->device = device; h->n = n_envs; h->stride = (n_envs + 31) / 32 * 32; h->launches = 0;
-    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr; h->d_eph = nullptr; h->mbuf = nullptr;
+    h->S = h->ics = h->stats = nullptr; h->I = nullptr; h->sched = nullptr; h->perm = nullptr; h->d_eph = nullptr; h->mbuf = nullptr; h->nzbuf = nullptr; h->noise_split = -1;
     for (int k = 0; k < 6; k++) h->h_stage[k] = nullptr;
     h->own_stream = nullptr; h->ev_last = nullptr; h->ev_valid = 0;
     cudaError_t e = cudaSetDevice(device);
@@ -397,7 +483,7 @@ int bskenv_opnav_destroy(bskenv_opnav_handle *h)
 {
     if (!h) return BSKENV_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm); cudaFree(h->d_eph); cudaFree(h->mbuf);
+    cudaFree(h->S); cudaFree(h->I); cudaFree(h->ics); cudaFree(h->stats); cudaFree(h->sched); cudaFree(h->perm); cudaFree(h->d_eph); cudaFree(h->mbuf); cudaFree(h->nzbuf);
     if (h->own_stream) { cudaStreamSynchronize(h->own_stream); cudaStreamDestroy(h->own_stream); }
     for (int k = 0; k < 6; k++) cudaFreeHost(h->h_stage[k]);
     if (h->ev_last) cudaEventDestroy(h->ev_last);

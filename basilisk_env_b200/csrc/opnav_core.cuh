@@ -1042,6 +1042,81 @@ ON_HD void opnav_pass1(const OpNavParams &P, double *S, int64_t *I, int64_t stri
     d.finish_state(S, I, stride, e, c, mb.p, mb.stride, n_m);
 }
 
+// THREE-KERNEL form of the interval (opnav.cu: opnav_noise_kernel, opnav_dyn_kernel, opnav_pass2_kernel).  The noise walk
+// depends on nothing but its own Philox stream, so the first pass itself splits: `opnav_pass0` advances the 15 error states
+// through the interval and leaves them, tick by tick, in a slot-major global buffer (15 doubles per env-tick: 360 KB per env
+// and interval -- HBM is 180 GB); `opnav_pass1_fed` is the first pass with the walk replaced by that feed, double-buffered in
+// the per-thread shared scratch one tick ahead (cp.async on the device: no registers, no exposed load latency).  Same
+// arithmetic per role as opnav_pass1: results are bit-identical.  Each kernel gets the register allocation and residency
+// of its own working set (the walk: 15 states and a Philox block; the dynamics: truth, flight software, Sun nodes).
+ON_HD void opnav_pass0(const OpNavParams &P, double *S, const int64_t *I, int64_t stride, int64_t e, Walk &w, double *nz, int64_t nz_stride)
+{
+    NoiseRole nzr;
+    nzr.load(P, S, I, stride, e, w);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int64_t k = nzr.k_first; k <= nzr.k_last; k++) {
+        nzr.tick(P, k);
+        double *q = nz + (k - nzr.k_first) * 15 * nz_stride;
+#pragma unroll
+        for (int i = 0; i < 15; i++) q[(int64_t)i * nz_stride] = nzr.nerr[i];
+    }
+    nzr.finish(S, stride, e);
+}
+
+struct NoiseFeed {
+    const double *g;              // this slot's column of the noise buffer: value i of local tick kl at g[(kl * 15 + i) * stride]
+    int64_t stride;
+    double *buf;                  // [2][15] in the per-thread scratch
+    ON_HD void prefetch(int64_t kl) const
+    {
+        double *dst = buf + (kl & 1) * 15;
+        const double *src = g + kl * 15 * stride;
+#if defined(__CUDA_ARCH__)
+        const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+#pragma unroll
+        for (int i = 0; i < 15; i++)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" : : "r"(d + 8u * i), "l"(src + (int64_t)i * stride) : "memory");
+#else
+        for (int i = 0; i < 15; i++) dst[i] = src[(int64_t)i * stride];
+#endif
+    }
+    ON_HD const double *get(int64_t kl) const
+    {
+#if defined(__CUDA_ARCH__)
+        asm volatile("cp.async.wait_all;" : : : "memory");
+#endif
+        return buf + (kl & 1) * 15;
+    }
+};
+
+ON_HD void opnav_pass1_fed(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, Cold &c, NoiseFeed nf, MeasBuf mb)
+{
+    DynRole d;
+    d.load(P, S, I, stride, e, action, c);
+    int n_m = 0;
+    nf.prefetch(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int64_t k = d.k_first; k <= d.k_last; k++) {
+        Meas m;
+        const int64_t kl = k - d.k_first;
+        const double *nerr = nf.get(kl);
+        if (k < d.k_last) nf.prefetch(kl + 1);
+        d.tick(P, k, c, nerr, m);
+        if (m.valid) {
+            n_m++;
+            double *q = mb.p + (int64_t)n_m * ON_MEAS_W * mb.stride;
+            q[0] = (double)k;
+            for (int i = 0; i < 3; i++) q[(1 + i) * mb.stride] = m.obs[i];
+            for (int i = 0; i < 6; i++) q[(4 + i) * mb.stride] = m.R[i];
+        }
+    }
+    d.finish_state(S, I, stride, e, c, mb.p, mb.stride, n_m);
+}
+
 // observation (ONS:263-293) and opNavEnv.step epilogue (ONE:100-125, :139-152); fx = filter position estimate, psig = sqrt of the
 // first three covariance diagonal entries; the truth comes back from the state the first pass stored
 ON_HD void opnav_finish_obs(const OpNavParams &P, double *S, int64_t *I, int64_t stride, int64_t e, int action, const double (&fx)[3],

@@ -289,3 +289,36 @@ def test_opnav_queued_three_block_builds_equal_static_two_block_shards(bsk):
     big.close()
     for p in parts:
         p.close()
+
+
+def test_opnav_three_kernel_interval_is_bit_identical(bsk, monkeypatch):
+    """Opt-in three-kernel form of the interval (BSKENV_OPNAV_NOISE_SPLIT=1; opnav_core.cuh: opnav_pass0 / opnav_pass1_fed): the
+    noise walk of the whole interval first, into a slot-major buffer (120 B per env-tick), then the dynamics / flight-software
+    pass fed from it one tick ahead through shared memory (cp.async), then the filter.  Same arithmetic per role as the default
+    two-kernel interval: outputs, episode records and state are bit-identical over four intervals with auto-reset, a ragged
+    batch and the queued work distribution (60001 envs; 21.6 GB of noise buffer)."""
+    import torch
+    from basilisk_env_b200.opnav_env import OpNavVecEnv
+    n, steps = 60001, 4
+    g = torch.Generator("cuda").manual_seed(4)
+    acts = torch.randint(0, 2, (steps, n), dtype=torch.int32, device="cuda", generator=g)
+    res = {}
+    for name in ("default", "split"):
+        monkeypatch.setenv("BSKENV_OPNAV_NOISE_SPLIT", "1" if name == "split" else "0")
+        env = OpNavVecEnv(n, device=0, auto_reset=True, sample_orbit=1, camera_reenable=1, noise_seed=7, max_length=2)
+        env.reset(seed=3)
+        outs = []
+        l0 = env.launch_count()
+        for t in range(steps):
+            o, r, d, info = env.step(acts[t])
+            outs.append([x.clone() for x in (o, r, d, info["done_reason"], info["full_states"], info["episode_r"], info["episode_l"])])
+        S, I = env.get_state()
+        res[name] = (outs, S.clone(), I.clone(), (env.launch_count() - l0) // steps)
+        env.close()
+    a, b = res["default"], res["split"]
+    assert a[3] == 2 and b[3] == 3                        # kernels per decision interval
+    for t in range(steps):
+        for x, y in zip(a[0][t], b[0][t]):
+            assert torch.equal(x, y), t
+    assert torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert int(sum(o[2].sum() for o in a[0])) >= n        # max_length = 2: every env finished an episode and was reset in the kernel
