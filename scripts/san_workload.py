@@ -36,6 +36,10 @@ env = LeoPowerAttVecEnv(60000, device=0, auto_reset=True, step_duration=6.0, max
 env.reset()
 for t in range(3):
     env.step(torch.full((60000,), t % 3, dtype=torch.int32, device="cuda"))
+# ... and with mixed actions: the envs are bucketed by action (leo_bucket_*_kernel), the step kernel gathers through the permutation
+gq = torch.Generator(device="cuda"); gq.manual_seed(1)
+for t in range(2):
+    env.step(torch.randint(0, 4, (60000,), dtype=torch.int32, device="cuda", generator=gq))
 print("leo queue+chunks", env.episode_stats()); env.close()
 # round 2: zero-copy host buffers (the kernel reads / writes page-locked host memory), per-env episode record, async / wait,
 # the stable-baselines adapter; batches of 200 envs run the small-batch organisation (MINB = 1), 60000 the throughput one
@@ -69,3 +73,13 @@ on.reset(seed=9)
 for t in range(3):
     on.step(torch.randint(0, 2, (60000,), dtype=torch.int32, device="cuda"))
 print("opnav two kernels + queues", on.episode_stats()["episodes"]); on.close()
+
+# opNav three-kernel interval (opt-in): noise kernel -> slot-major buffer -> dynamics kernel fed through cp.async -> filter
+os.environ["BSKENV_OPNAV_NOISE_SPLIT"] = "1"
+on = OpNavVecEnv(333, device=0, auto_reset=True, step_duration_min=2.0, max_length=2, camera_reenable=1, sample_orbit=1)
+on.reset(seed=8)
+for t in range(4):
+    on.step(torch.randint(0, 2, (333,), dtype=torch.int32, device="cuda"))
+assert on.launch_count() == 12
+print("opnav three-kernel", on.episode_stats()); on.close()
+os.environ["BSKENV_OPNAV_NOISE_SPLIT"] = "0"

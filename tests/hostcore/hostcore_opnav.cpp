@@ -63,6 +63,16 @@ void hco_step(HCO *h, const int32_t *actions, double *obs, double *reward, uint8
         std::vector<double> mbuf((size_t)opnav::opnav_meas_slots(h->P) * ON_MEAS_W);
         opnav::MeasBuf mb;
         mb.p = mbuf.data(); mb.stride = 1;
+        if (getenv("HCO_NOISE_SPLIT") && getenv("HCO_NOISE_SPLIT")[0] == '1') {
+            // the three-kernel form of the interval (opnav.cu: opnav_noise_kernel / opnav_dyn_kernel / opnav_pass2_kernel), back to back
+            std::vector<double> nz((size_t)(h->P.ticks_per_step + 1) * 15);
+            double feed[30];
+            opnav::opnav_pass0(h->P, h->S.data(), h->I.data(), h->n, e, w, nz.data(), 1);
+            opnav::NoiseFeed nf;
+            nf.g = nz.data(); nf.stride = 1; nf.buf = feed;
+            opnav::opnav_pass1_fed(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], c, nf, mb);
+            opnav::opnav_pass2(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o, f, mb);
+        } else
         opnav::opnav_step_env(h->P, h->S.data(), h->I.data(), h->n, e, actions[e], o, f, c, w, mb);
         for (int k = 0; k < 4; k++) obs[4 * e + k] = o.ob[k];
         if (debug) for (int k = 0; k < 12; k++) debug[12 * e + k] = o.debug[k];

@@ -200,3 +200,24 @@ def test_sun_table_replaces_the_analytic_series():
     hc0, _ = _run(rows, acts, **kw)
     S1, _ = hc.state(); S0, _ = hc0.state()
     assert np.abs(S1[par.F("sigma_BN"):par.F("sigma_BN") + 3] - S0[par.F("sigma_BN"):par.F("sigma_BN") + 3]).max() > 1e-3
+
+
+def test_three_pass_interval_is_bit_identical_to_the_fused_first_pass(monkeypatch):
+    """The opt-in three-kernel form of the interval (opnav_core.cuh: opnav_pass0 -> noise buffer -> opnav_pass1_fed -> opnav_pass2;
+    GPU: tests/test_opnav_gpu.py::test_opnav_three_kernel_interval_is_bit_identical) run back to back on the host: same bits as
+    the default two-pass interval, observations, rewards, flags and the whole state, over three intervals incl. the first tick."""
+    rows = par.sample_rows(on, 6, seed=5)
+    acts = np.array([[0, 1, 0, 1, 0, 0], [1, 1, 0, 0, 0, 1], [0, 0, 1, 1, 1, 0]], np.int32)
+    res = {}
+    for name in ("fused", "split"):
+        monkeypatch.setenv("HCO_NOISE_SPLIT", "1" if name == "split" else "0")
+        hc = HostCoreOpNav(len(rows), noise_seed=9, camera_reenable=1)
+        hc.reset_ics(rows)
+        outs = [hc.step(a) for a in acts]
+        res[name] = (outs, hc.state())
+    for a, b in zip(res["fused"][0], res["split"][0]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(res["fused"][1][0], res["split"][1][0])
+    np.testing.assert_array_equal(res["fused"][1][1], res["split"][1][1])
+    assert np.abs(res["split"][1][0]).sum() > 0
