@@ -398,6 +398,18 @@ def side_stress(n, torch, dev, peak_tf, steps=5, warmup=3):
             out[key]["roofline"] = {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s",
                                     "frac": tf / peak_tf if peak_tf else None, "kernel_ms": ms, "flop_per_env_step": flops}
         env.close()
+    # steady state, as the headline measures it: auto-reset on, i.i.d. actions, a longer warm-up (the first intervals after a common
+    # reset are slower: every env spins its wheels up at once); the no-reset runs above exist for the precision comparison
+    env = LeoPowerAttVecEnv(n, device=dev.index, seed=17, use_j2=1, rw_set=1, auto_reset=True)
+    env.reset()
+    acts2 = torch.randint(0, 3, (13, n), dtype=torch.int32, device=dev, generator=g)
+    total_ms, per = time_device_steps(env, acts2, steps, 8, torch, None, 1)
+    ms = float(np.mean(per))
+    tf = env.flops_per_step() * n / (ms * 1e-3) / 1e12
+    out["fp64_steady_state"] = {"value": n * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps, "kernel": env.kernel_name(),
+                                "warmup": 8, "auto_reset": True,
+                                "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": tf / peak_tf if peak_tf else None}}
+    env.close()
     d0, i0, dn0 = states["fp64"]; d1, i1, dn1 = states["mixed"]
 
     def q(x):
