@@ -511,6 +511,25 @@ def side_opnav(n, torch, dev, peak_tf, steps=3, warmup=3, cpu_seconds=4.0):
                    "d2h_bytes_per_step": OPNAV_D2H_BYTES_PER_ENV * n,
                    "api": "bskenv_opnav_step_host with page-locked host buffers (env.host_buffers)"},
            "gpu_launches": int(launches), "episode_stats": stats, "checksum": float(outs[0].sum())}
+    # the opt-in three-kernel interval (noise walk in a kernel of its own, 120 B of device buffer per env-tick):
+    # same actions, same results bit for bit -- measured beside the default, not the headline
+    prev = os.environ.get("BSKENV_OPNAV_NOISE_SPLIT")
+    os.environ["BSKENV_OPNAV_NOISE_SPLIT"] = "1"
+    try:
+        env = OpNavVecEnv(n, device=dev.index, seed=5, auto_reset=True, sample_orbit=1, camera_reenable=1)
+        env.reset()
+        l0 = env.launch_count()
+        t_ms, per3 = time_device_steps(env, acts, steps, warmup, torch, None, 1)
+        k3 = (env.launch_count() - l0) // (warmup + steps)
+        out["three_kernel_interval"] = {"value": n * steps / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / steps, "kernels_per_step": int(k3),
+                                        "noise_buffer_bytes": 15 * 8 * 3001 * ((n + 31) // 32 * 32) if k3 == 3 else 0,
+                                        "enabled_by": "BSKENV_OPNAV_NOISE_SPLIT=1 (falls back to two kernels when the buffer does not fit)"}
+        env.close()
+    finally:
+        if prev is None:
+            del os.environ["BSKENV_OPNAV_NOISE_SPLIT"]
+        else:
+            os.environ["BSKENV_OPNAV_NOISE_SPLIT"] = prev
     if cpu_seconds > 0:
         cb = opnav_cpu_arm(2, cpu_seconds)
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "build_flags")}
