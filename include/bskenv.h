@@ -272,7 +272,10 @@ int bskenv_opnav_reset_ics(bskenv_opnav_handle *h, const double *ics_dev /* [n*1
                            double *obs_dev, void *stream);
 int bskenv_opnav_reset_init(bskenv_opnav_handle *h, const uint8_t *mask_dev, double *obs_dev, void *stream);
 int bskenv_opnav_get_ics(bskenv_opnav_handle *h, double *ics_dev, void *stream);
-/* step(): ONE launch = one decision interval for every env.  Caller-owned device buffers:
+/* step(): ONE call = one decision interval for every env (two kernels: noise walk + dynamics / flight software, then the
+ * filter; three -- the noise walk in a kernel of its own, feeding the dynamics through a device buffer of 120 B per env-tick,
+ * allocated at the first step -- when the environment variable BSKENV_OPNAV_NOISE_SPLIT=1 is set at that time and the buffer
+ * fits in 45 % of the free device memory; same results bit for bit).  Caller-owned device buffers:
  *   actions int32[n]; obs double[n*4]; reward double[n]; done uint8[n]; done_reason uint8[n];
  *   debug double[n*12] (may be NULL: info['full_states']); term_obs double[n*4] (may be NULL; auto_reset only). */
 int bskenv_opnav_step(bskenv_opnav_handle *h, const int32_t *actions_dev, double *obs_dev, double *reward_dev,
